@@ -1,0 +1,140 @@
+"""ctypes binding of ``libalg_b200.so`` (the C ABI declared in ``include/alg_b200.h``).
+
+There is no CPU fallback: if the shared library is missing the import of any
+compute entry point raises, and every call checks the status code and raises
+``RuntimeError`` with ``alg_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libalg_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+ALG_F32, ALG_BF16, ALG_F16 = 0, 1, 2
+EPI_NONE, EPI_GELU_TANH, EPI_GATE_RESIDUAL, EPI_RESIDUAL, EPI_GELU_ERF, EPI_SILU = range(6)
+
+
+class UniPCStep(C.Structure):
+    _fields_ = [
+        ("n_pass", C.c_int32), ("cfg_fp32", C.c_int32), ("guidance", C.c_float), ("sigma_t", C.c_float),
+        ("use_corrector", C.c_int32), ("order_c", C.c_int32), ("c_ratio", C.c_float), ("c_a", C.c_float),
+        ("c_b", C.c_float), ("c_rk_inv", C.c_float), ("c_rho0", C.c_float), ("c_rho_last", C.c_float),
+        ("order_p", C.c_int32), ("p_ratio", C.c_float), ("p_a", C.c_float), ("p_b", C.c_float),
+        ("p_rk_inv", C.c_float), ("p_rho0", C.c_float),
+    ]
+
+
+class Gemm(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("B", C.c_void_p), ("D", C.c_void_p), ("bias", C.c_void_p), ("R", C.c_void_p),
+        ("gate", C.c_void_p), ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("lda", C.c_int64),
+        ("ldb", C.c_int64), ("ldd", C.c_int64), ("rows_per_batch", C.c_int64), ("gate_ld", C.c_int64),
+        ("epilogue", C.c_int32), ("bias_per_row", C.c_int32), ("out_f32", C.c_int32),
+    ]
+
+
+class Attention(C.Structure):
+    _fields_ = [
+        ("Q", C.c_void_p), ("K", C.c_void_p), ("Vt", C.c_void_p), ("O", C.c_void_p), ("batch", C.c_int32),
+        ("heads", C.c_int32), ("head_dim", C.c_int32), ("n_q", C.c_int64), ("n_kv", C.c_int64),
+        ("q_bs", C.c_int64), ("q_rs", C.c_int64), ("k_bs", C.c_int64), ("k_rs", C.c_int64), ("v_bs", C.c_int64),
+        ("v_rs", C.c_int64), ("o_bs", C.c_int64), ("o_rs", C.c_int64), ("scale", C.c_float),
+        ("accumulate", C.c_int32),
+    ]
+
+
+class WanConfig(C.Structure):
+    _fields_ = [
+        ("num_heads", C.c_int32), ("head_dim", C.c_int32), ("in_channels", C.c_int32), ("out_channels", C.c_int32),
+        ("text_dim", C.c_int32), ("freq_dim", C.c_int32), ("ffn_dim", C.c_int32), ("num_layers", C.c_int32),
+        ("image_dim", C.c_int32), ("text_len", C.c_int32), ("patch_t", C.c_int32), ("patch_h", C.c_int32),
+        ("patch_w", C.c_int32), ("rope_max_seq_len", C.c_int32), ("eps", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/alg_b200.h declares
+SIGNATURES = {
+    "alg_abi_version": (C.c_int, []),
+    "alg_last_error": (C.c_char_p, []),
+    "alg_check_device": (C.c_int, []),
+    "alg_launch_count": (C.c_int64, []),
+    "alg_lowpass_down_up": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "alg_lowpass_gaussian": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]),
+    "alg_gaussian_kernel1d": (C.c_int, [C.c_int, C.c_double, C.c_int, C.POINTER(C.c_float)]),
+    "alg_cfg_unipc_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(UniPCStep), C.c_void_p]),
+    "alg_cfg_ddim_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "alg_cfg_euler_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "alg_gemm_bf16": (C.c_int, [C.POINTER(Gemm), C.c_void_p]),
+    "alg_attention_bf16": (C.c_int, [C.POINTER(Attention), C.c_void_p]),
+    "alg_wan_create": (C.c_int, [C.POINTER(WanConfig), C.POINTER(C.c_void_p)]),
+    "alg_wan_destroy": (None, [C.c_void_p]),
+    "alg_wan_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int]),
+    "alg_wan_weights_complete": (C.c_int, [C.c_void_p]),
+    "alg_wan_set_debug_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "alg_wan_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "alg_wan_forward": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j", str(os.cpu_count() or 4)]
+    r = subprocess.run(cmd, capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libalg_b200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(alg_b200 has no CPU or PyTorch fallback)"
+            )
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.alg_abi_version() != 1:
+            raise RuntimeError("libalg_b200.so ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise RuntimeError(lib().alg_last_error().decode() or f"alg_b200 call failed with status {status}")
+
+
+def launch_count() -> int:
+    return int(lib().alg_launch_count())
+
+
+def dtype_code(dt) -> int:
+    import torch
+
+    try:
+        return {torch.float32: ALG_F32, torch.bfloat16: ALG_BF16, torch.float16: ALG_F16}[dt]
+    except KeyError:
+        raise TypeError(f"alg_b200 supports float32 / bfloat16 / float16 tensors, got {dt}") from None
+
+
+def stream_ptr(device=None) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("alg_b200 operators need CUDA tensors (there is no CPU fallback)")

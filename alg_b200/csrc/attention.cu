@@ -1,0 +1,349 @@
+// Non-causal flash attention forward on tcgen05 / TMEM (SURVEY kernel K8).
+//
+// Replaces F.scaled_dot_product_attention inside the DiT (reference call site wan:910; Wan self-attention
+// N = 32 760 tokens, 40 heads x 128).  One CTA owns TWO 128-row query tiles of one (batch, head) and streams the
+// K / V^T tiles of that head through a TMA-fed shared-memory ring:
+//
+//   warp 8  : TMA producer      Q0, Q1 once; K_j and V^T_j double-buffered (SWIZZLE_128B, K-major)
+//   warp 9  : MMA issuer        S_i = Q_i K_j^T   (tcgen05.mma SS, 128 x 128 x D   -> TMEM S_i)
+//                               O_i += P_i V_j    (tcgen05.mma TS, A = P_i in TMEM -> TMEM O_i)
+//   warps 0-3 / 4-7 : softmax warpgroup for tile 0 / 1 (one query row per thread):
+//                               tcgen05.ld S -> online softmax in fp32 (exp2, lazy rescale of O in TMEM only when
+//                               the running max grows by > 2^8) -> bf16 P written back over S with tcgen05.st
+//
+// The two tiles ping-pong: while one warpgroup does softmax, the tensor core runs the other tile's MMAs.
+// TMEM (512 columns): S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,256+D)  O1 [384,384+D).
+// V is consumed TRANSPOSED ([head_dim, n_kv], produced directly by the V projection GEMM with swapped operands) so
+// that both MMAs use K-major operands.
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace alg {
+namespace attn {
+using namespace tc;
+
+constexpr int BQ = 128;   // query rows per tile (two tiles per CTA)
+constexpr int BKV = 128;  // keys per pipeline step
+constexpr int kThreads = 320;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+template <int D>
+struct Cfg {
+  static constexpr int kBytesQ = BQ * D * 2;     // one query tile
+  static constexpr int kBytesK = BKV * D * 2;    // one K stage
+  static constexpr int kBytesV = D * BKV * 2;    // one V^T stage
+  static constexpr int kStages = 2;
+  static constexpr int kSmemBytes = 2 * kBytesQ + kStages * (kBytesK + kBytesV) + 1024 + 256;
+  static constexpr int kSubQK = BQ * 128;  // bytes of one [128 rows][64 elem] swizzle sub-tile
+  static constexpr int kSubV = D * 128;    // bytes of one [D rows][64 kv] sub-tile
+};
+
+struct Params {
+  __nv_bfloat16* O;
+  int64_t o_bs, o_rs;
+  int n_q, n_kv, heads;
+  float scale_log2;  // scale * log2(e)
+  int accumulate;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+    attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const Params p) {
+  using C = Cfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2][BQ x D]
+  uint8_t* sK = sQ + 2 * C::kBytesQ;                    // [stages][BKV x D]
+  uint8_t* sV = sK + C::kStages * C::kBytesK;           // [stages][D x BKV]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::kStages * C::kBytesV);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* k_full = bars + 1;      // 2
+  uint64_t* k_empty = bars + 3;     // 2
+  uint64_t* v_full = bars + 5;      // 2
+  uint64_t* v_empty = bars + 7;     // 2
+  uint64_t* s_full = bars + 9;      // 2
+  uint64_t* p_full = bars + 11;     // 2
+  uint64_t* o_full = bars + 13;     // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * BQ;
+  const int n_tiles = (p.n_kv + BKV - 1) / BKV;
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    if (lane == 0) {  // ===== TMA producer =====
+      mbar_arrive_expect_tx(q_full, 2 * C::kBytesQ);
+      for (int i = 0; i < 2; ++i)
+        for (int s = 0; s < D / 64; ++s)
+          tma_load_3d(sQ + i * C::kBytesQ + s * C::kSubQK, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], C::kBytesK);
+        for (int s = 0; s < D / 64; ++s)
+          tma_load_3d(sK + st * C::kBytesK + s * C::kSubQK, &tmK, &k_full[st], head * D + s * 64, j * BKV, batch);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], C::kBytesV);
+        for (int s = 0; s < BKV / 64; ++s)
+          tma_load_3d(sV + st * C::kBytesV + s * C::kSubV, &tmV, &v_full[st], j * BKV + s * 64, head * D, batch);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
+      constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D);
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      auto issue_s = [&](int i, int st) {  // S_i = Q_i K^T
+        const uint32_t d = tmem_base + i * 128;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * C::kSubQK + (ks & 3) * 32;
+          mma_ss(d, make_smem_desc_sw128(q_addr + i * C::kBytesQ + off),
+                 make_smem_desc_sw128(k_addr + st * C::kBytesK + off), idesc_s, ks != 0);
+        }
+      };
+      auto issue_pv = [&](int i, int st, bool acc) {  // O_i (+)= P_i V
+        const uint32_t d = tmem_base + 256 + i * 128;
+        const uint32_t a = tmem_base + i * 128;
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * C::kSubV + (ks & 3) * 32;
+          mma_ts(d, a + ks * 8, make_smem_desc_sw128(v_addr + st * C::kBytesV + off), idesc_o, (acc || ks != 0));
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      tc_commit(&s_full[0]);
+      issue_s(1, 0);
+      tc_commit(&s_full[1]);
+      tc_commit(&k_empty[0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int nst = (j + 1) & 1;
+        const uint32_t nph = ((j + 1) >> 1) & 1;
+        const bool more = j + 1 < n_tiles;
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(&p_full[i], j & 1);
+          if (i == 0) mbar_wait(&v_full[st], ph);
+          tc_fence_after();
+          issue_pv(i, st, j > 0);
+          if (i == 1) tc_commit(&v_empty[st]);
+          if (more) {
+            if (i == 0) {
+              mbar_wait(&k_full[nst], nph);
+              tc_fence_after();
+            }
+            issue_s(i, nst);
+            tc_commit(&s_full[i]);
+            if (i == 1) tc_commit(&k_empty[nst]);
+          } else {
+            tc_commit(&o_full[i]);
+          }
+        }
+      }
+    }
+  } else {  // ===== softmax warpgroups =====
+    const int i = warp >> 2;  // query tile
+    const int quad = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + i * 128;
+    const uint32_t t_o = tmem_base + lane_base + 256 + i * 128;
+    const int row = q0 + i * BQ + quad * 32 + lane;
+    float m_used = -INFINITY, l = 0.f;
+    const float c = p.scale_log2;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[i], j & 1);
+      tc_fence_after();
+      float s[128];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) tmem_ld32(t_s + ch * 32, reinterpret_cast<uint32_t*>(s) + ch * 32);
+      tmem_ld_wait();
+      const int valid = p.n_kv - j * BKV;
+      if (valid < BKV) {  // ragged last key tile: TMA zero-filled the tail, mask it out
+#pragma unroll
+        for (int k = 0; k < 128; ++k)
+          if (k >= valid) s[k] = -INFINITY;
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int k = 1; k < 128; ++k) mx = fmaxf(mx, s[k]);
+      mx *= c;
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const float m_new = fmaxf(m_used, mx);
+        const bool need = (m_new - m_used) > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {  // warp-uniform: tcgen05.ld/st are warp collectives
+          const float f = ex2(m_used - m_new);
+          l *= f;
+          m_used = m_new;
+#pragma unroll 1
+          for (int ch = 0; ch < D / 16; ++ch) {
+            uint32_t o[16];
+            tmem_ld16(t_o + ch * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * f);
+            tmem_st16(t_o + ch * 16, o);
+          }
+        }
+      }
+      const float neg_m = -m_used;
+      float sum = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float a = ex2(fmaf(s[ch * 32 + 2 * k], c, neg_m));
+          const float b = ex2(fmaf(s[ch * 32 + 2 * k + 1], c, neg_m));
+          sum += a + b;
+          __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          pk[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        tmem_st16(t_s + ch * 16, pk);  // P (bf16 pairs) overwrites the first 64 columns of S
+      }
+      l += sum;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[i]);
+    }
+    // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------------
+    mbar_wait(&o_full[i], 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = p.O + (int64_t)batch * p.o_bs + (int64_t)row * p.o_rs + head * D;
+#pragma unroll
+    for (int ch = 0; ch < D / 32; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(t_o + ch * 32, o);
+      tmem_ld_wait();
+      if (row < p.n_q) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+          uint4 prev;
+          if (p.accumulate) prev = *reinterpret_cast<const uint4*>(orow + ch * 32 + g * 8);
+          const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(o[g * 8 + 2 * e]) * inv;
+            float y = __uint_as_float(o[g * 8 + 2 * e + 1]) * inv;
+            if (p.accumulate) {  // hidden_states(text) + hidden_states_img: both already bf16 tensors
+              float2 q = __bfloat1622float2(ph[e]);
+              x = bf16_round(x) + q.x;
+              y = bf16_round(y) + q.y;
+            }
+            h[e] = __floats2bfloat162_rn(x, y);
+          }
+          *reinterpret_cast<uint4*>(orow + ch * 32 + g * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D>
+static int launch(const alg_attention_t* a, cudaStream_t st) {
+  using C = Cfg<D>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_done = true;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t hd = (uint64_t)a->heads * D;
+  {
+    uint64_t dims[3] = {hd, (uint64_t)a->n_q, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->q_rs, (uint64_t)a->q_bs};
+    uint32_t box[3] = {64, BQ, 1};
+    if (int rc = make_tmap_bf16(&tmQ, a->Q, 3, dims, strides, box)) return rc;
+  }
+  {
+    uint64_t dims[3] = {hd, (uint64_t)a->n_kv, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->k_rs, (uint64_t)a->k_bs};
+    uint32_t box[3] = {64, BKV, 1};
+    if (int rc = make_tmap_bf16(&tmK, a->K, 3, dims, strides, box)) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a->n_kv, hd, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->v_rs, (uint64_t)a->v_bs};
+    uint32_t box[3] = {64, (uint32_t)D, 1};
+    if (int rc = make_tmap_bf16(&tmV, a->Vt, 3, dims, strides, box)) return rc;
+  }
+  Params p;
+  p.O = reinterpret_cast<__nv_bfloat16*>(a->O);
+  p.o_bs = a->o_bs;
+  p.o_rs = a->o_rs;
+  p.n_q = (int)a->n_q;
+  p.n_kv = (int)a->n_kv;
+  p.heads = a->heads;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.accumulate = a->accumulate;
+  dim3 grid((unsigned)((a->n_q + 2 * BQ - 1) / (2 * BQ)), (unsigned)a->heads, (unsigned)a->batch);
+  attention_kernel<D><<<grid, kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace attn
+}  // namespace alg
+
+extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
+  using namespace alg;
+  ALG_REQUIRE(a && a->Q && a->K && a->Vt && a->O, "attention: null pointer");
+  ALG_REQUIRE(a->head_dim == 64 || a->head_dim == 128, "attention: head_dim must be 64 or 128");
+  ALG_REQUIRE(a->batch > 0 && a->heads > 0 && a->n_q > 0 && a->n_kv > 0, "attention: empty problem");
+  ALG_REQUIRE(a->batch <= 65535 && a->heads <= 65535, "attention: batch/heads exceed the grid limits");
+  ALG_REQUIRE(a->q_rs % 8 == 0 && a->k_rs % 8 == 0 && a->v_rs % 8 == 0 && a->o_rs % 8 == 0 && a->q_bs % 8 == 0 &&
+                  a->k_bs % 8 == 0 && a->v_bs % 8 == 0 && a->o_bs % 8 == 0,
+              "attention: strides must be multiples of 8 elements (16 bytes)");
+  ALG_REQUIRE(a->v_rs >= a->n_kv, "attention: Vt row stride smaller than n_kv");
+  ALG_REQUIRE((reinterpret_cast<uintptr_t>(a->O) & 15) == 0, "attention: O must be 16-byte aligned");
+  if (int rc = alg_check_device()) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return a->head_dim == 128 ? attn::launch<128>(a, st) : attn::launch<64>(a, st);
+}

@@ -1,0 +1,338 @@
+// HBM-bound kernels of the Wan DiT forward: patch gather, LayerNorm(+modulate), RMSNorm(+RoPE),
+// timestep embedding, modulation tables, unpatchify.  All fp32 statistics, bf16 activations, with the
+// intermediate roundings placed where diffusers' WanTransformer3DModel places them.
+#include "dit_kernels.cuh"
+
+namespace alg {
+namespace dit {
+
+constexpr int kRowThreads = 256;
+constexpr int kMaxChunks = 4;  // 8 bf16 per chunk per thread -> d <= 8192
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // protect `red` from the previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kRowThreads / 32; ++i) t += red[i];
+  return t;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 t = __bfloat1622float2(h[e]);
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void patch_gather_kernel(const CondPtrs cond, int n_pass, int lat_ch, int cond_ch, int T, int H, int W, __nv_bfloat16* __restrict__ A) {
+  const int ph = H / 2, pw = W / 2;
+  const int64_t N = (int64_t)T * ph * pw;
+  const int Kdim = (lat_ch + cond_ch) * 4;
+  const int64_t total = (int64_t)n_pass * N * Kdim;
+  const int64_t plane = (int64_t)H * W;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Kdim);
+    const int64_t tok = idx / Kdim;
+    const int pss = (int)(tok / N);
+    const int64_t n = tok - (int64_t)pss * N;
+    const int c = k >> 2, i = (k >> 1) & 1, j = k & 1;
+    const int t = (int)(n / (ph * pw));
+    const int rem = (int)(n - (int64_t)t * ph * pw);
+    const int y = rem / pw, x = rem - y * pw;
+    const float* src = c < lat_ch ? cond.lat[pss] + (int64_t)c * T * plane : cond.p[pss] + (int64_t)(c - lat_ch) * T * plane;
+    A[idx] = __float2bfloat16_rn(src[(int64_t)t * plane + (int64_t)(2 * y + i) * W + 2 * x + j]);
+  }
+}
+
+int patch_gather(CondPtrs cond_dev, int n_pass, int lat_ch, int cond_ch, int T, int H, int W,
+                 __nv_bfloat16* A, cudaStream_t st) {
+  const int64_t total = (int64_t)n_pass * T * (H / 2) * (W / 2) * (lat_ch + cond_ch) * 4;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  patch_gather_kernel<<<grid, 256, 0, st>>>(cond_dev, n_pass, lat_ch, cond_ch, T, H, W, A);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads)
+    layer_norm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int d, float eps,
+                      const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ scale,
+                      const float* __restrict__ shift) {
+  __shared__ float red[kRowThreads / 32];
+  const int64_t row = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
+  uint4* orow = reinterpret_cast<uint4*>(out + row * d);
+  const int chunks = d / 8;
+  float v[kMaxChunks][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ci = threadIdx.x + c * kRowThreads;
+    if (ci < chunks) {
+      unpack8(xr[ci], v[c]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[c][e];
+    }
+  }
+  const float mean = block_sum(sum, red) / (float)d;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ci = threadIdx.x + c * kRowThreads;
+    if (ci < chunks) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float t = v[c][e] - mean;
+        sq += t * t;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum(sq, red) / (float)d + eps);
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ci = threadIdx.x + c * kRowThreads;
+    if (ci < chunks) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int col = ci * 8 + e;
+        float y = __fmul_rn(__fsub_rn(v[c][e], mean), rstd);
+        if (w) y = __fadd_rn(__fmul_rn(y, w[col]), b[col]);
+        if (scale) y = __fadd_rn(__fmul_rn(y, __fadd_rn(1.0f, scale[col])), shift[col]);
+        o[e] = y;
+      }
+      orow[ci] = pack8(o);
+    }
+  }
+}
+
+int layer_norm(const __nv_bfloat16* x, __nv_bfloat16* out, int64_t rows, int d, float eps, const float* w,
+               const float* b, const float* scale, const float* shift, cudaStream_t st) {
+  ALG_REQUIRE(d % 8 == 0 && d <= kRowThreads * 8 * kMaxChunks, "layer_norm: d must be a multiple of 8 and <= 8192");
+  ALG_REQUIRE(rows <= 0x7fffffff, "layer_norm: too many rows");
+  if (rows == 0) return 0;
+  layer_norm_kernel<<<(unsigned)rows, kRowThreads, 0, st>>>(x, out, d, eps, w, b, scale, shift);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads)
+    rms_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int d, int head_dim, float eps,
+                         const __nv_bfloat16* __restrict__ w, RopeTables rope, int use_rope) {
+  __shared__ float red[kRowThreads / 32];
+  const int64_t row = blockIdx.x;
+  uint4* xr = reinterpret_cast<uint4*>(x + row * d);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  const int chunks = d / 8;
+  float v[kMaxChunks][8];
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ci = threadIdx.x + c * kRowThreads;
+    if (ci < chunks) {
+      unpack8(xr[ci], v[c]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sq += v[c][e] * v[c][e];
+    }
+  }
+  const float rstd = rsqrtf(block_sum(sq, red) / (float)d + eps);
+  int t = 0, y = 0, xx = 0;
+  if (use_rope) {
+    const int64_t N = (int64_t)rope.ppf * rope.pph * rope.ppw;
+    const int n = (int)(row % N);
+    t = n / (rope.pph * rope.ppw);
+    const int rem = n - t * rope.pph * rope.ppw;
+    y = rem / rope.ppw;
+    xx = rem - y * rope.ppw;
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ci = threadIdx.x + c * kRowThreads;
+    if (ci < chunks) {
+      float wv[8], o[8];
+      unpack8(wr[ci], wv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float h = bf16_round(__fmul_rn(v[c][e], rstd));  // hidden_states.to(weight.dtype)
+        o[e] = bf16_round(__fmul_rn(h, wv[e]));                  // * weight (bf16 tensor op)
+      }
+      if (use_rope) {
+        const int pair0 = ((ci * 8) % head_dim) >> 1;  // 4 complex pairs per chunk, never straddling a head
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int pi = pair0 + q;
+          const double* cs;
+          if (pi < rope.n_t) cs = rope.t + ((int64_t)t * rope.n_t + pi) * 2;
+          else if (pi < rope.n_t + rope.n_h) cs = rope.h + ((int64_t)y * rope.n_h + (pi - rope.n_t)) * 2;
+          else cs = rope.w + ((int64_t)xx * rope.n_w + (pi - rope.n_t - rope.n_h)) * 2;
+          const double cr = cs[0], si = cs[1];
+          const double re = (double)o[2 * q], im = (double)o[2 * q + 1];
+          o[2 * q] = (float)(re * cr - im * si);  // complex128 multiply, then .type_as(bf16) in pack8
+          o[2 * q + 1] = (float)(re * si + im * cr);
+        }
+      }
+      xr[ci] = pack8(o);
+    }
+  }
+}
+
+int rms_norm_rope(__nv_bfloat16* x, int64_t rows, int d, int head_dim, float eps, const __nv_bfloat16* w,
+                  const RopeTables* rope, cudaStream_t st) {
+  ALG_REQUIRE(d % 8 == 0 && d <= kRowThreads * 8 * kMaxChunks && head_dim % 8 == 0, "rms_norm: unsupported width");
+  ALG_REQUIRE(rows <= 0x7fffffff, "rms_norm: too many rows");
+  if (rows == 0) return 0;
+  RopeTables r{};
+  if (rope) r = *rope;
+  rms_norm_rope_kernel<<<(unsigned)rows, kRowThreads, 0, st>>>(x, d, head_dim, eps, w, r, rope != nullptr);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void timestep_sinusoid_kernel(float timestep, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    // exponent = -log(10000) * arange(half) / half ; emb = t * exp(exponent) ; [cos | sin]
+    const float exponent = (-9.210340371976184f * (float)i) / (float)half;
+    const float e = timestep * expf(exponent);
+    out[i] = cosf(e);
+    out[half + i] = sinf(e);
+  }
+}
+int timestep_sinusoid(float timestep, int dim, float* out, cudaStream_t st) {
+  timestep_sinusoid_kernel<<<1, 128, 0, st>>>(timestep, dim, out);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void gemv_f32_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ x,
+                                float* __restrict__ out, int out_f, int in_f, int act) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= out_f) return;
+  const float* wr = W + (int64_t)warp * in_f;
+  float acc = 0.f;
+  if ((in_f & 3) == 0) {
+    const float4* w4 = reinterpret_cast<const float4*>(wr);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int i = lane; i < in_f / 4; i += 32) {
+      const float4 a = __ldg(w4 + i), c = x4[i];
+      acc += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+    }
+  } else {
+    for (int i = lane; i < in_f; i += 32) acc += wr[i] * x[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    float v = acc + (b ? b[warp] : 0.f);
+    if (act == 1) v = v / (1.0f + expf(-v));
+    out[warp] = v;
+  }
+}
+int gemv_f32(const float* W, const float* b, const float* x, float* out, int out_f, int in_f, int act,
+             cudaStream_t st) {
+  const int warps_per_block = 8;
+  gemv_f32_kernel<<<(out_f + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(W, b, x, out, out_f,
+                                                                                                   in_f, act);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void temb_finish_kernel(const float* __restrict__ v, __nv_bfloat16* __restrict__ temb,
+                                   __nv_bfloat16* __restrict__ silu_temb, int d) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d; i += gridDim.x * blockDim.x) {
+    const __nv_bfloat16 t = __float2bfloat16_rn(v[i]);
+    const float f = __bfloat162float(t);
+    temb[i] = t;
+    silu_temb[i] = __float2bfloat16_rn(f / (1.0f + expf(-f)));
+  }
+}
+int temb_finish(const float* v, __nv_bfloat16* temb, __nv_bfloat16* silu_temb, int d, cudaStream_t st) {
+  temb_finish_kernel<<<(d + 255) / 256, 256, 0, st>>>(v, temb, silu_temb, d);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void add_table_kernel(const float* __restrict__ table, const __nv_bfloat16* __restrict__ src,
+                                 float* __restrict__ mod, int rows, int d, int broadcast) {
+  const int total = rows * d;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % d;
+    mod[i] = __fadd_rn(table[i], __bfloat162float(src[broadcast ? c : i]));
+  }
+}
+int add_table(const float* table, const __nv_bfloat16* src, float* mod, int rows, int d, int broadcast,
+              cudaStream_t st) {
+  add_table_kernel<<<(rows * d + 255) / 256, 256, 0, st>>>(table, src, mod, rows, d, broadcast);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ proj, __nv_bfloat16* __restrict__ out, int n_pass,
+                                  int C, int T, int H, int W) {
+  const int ph = H / 2, pw = W / 2;
+  const int64_t N = (int64_t)T * ph * pw;
+  const int64_t total = (int64_t)n_pass * C * T * H * W;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H); r /= H;
+    const int t = (int)(r % T); r /= T;
+    const int c = (int)(r % C);
+    const int pss = (int)(r / C);
+    const int64_t n = ((int64_t)t * ph + (y >> 1)) * pw + (x >> 1);
+    const int k = (((y & 1) * 2) + (x & 1)) * C + c;
+    out[idx] = proj[((int64_t)pss * N + n) * (4 * C) + k];
+  }
+}
+int unpatchify(const __nv_bfloat16* proj, __nv_bfloat16* out, int n_pass, int C, int T, int H, int W,
+               cudaStream_t st) {
+  const int64_t total = (int64_t)n_pass * C * T * H * W;
+  unpatchify_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(proj, out, n_pass, C, T, H, W);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void copy_rows_kernel(const __nv_bfloat16* __restrict__ src, int64_t src_ld, __nv_bfloat16* __restrict__ dst,
+                                 int64_t dst_ld, int64_t rows, int d) {
+  const int chunks = d / 8;
+  const int64_t total = rows * chunks;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / chunks;
+    const int c = (int)(idx - r * chunks);
+    reinterpret_cast<uint4*>(dst + r * dst_ld)[c] = reinterpret_cast<const uint4*>(src + r * src_ld)[c];
+  }
+}
+int copy_rows(const __nv_bfloat16* src, int64_t src_ld, __nv_bfloat16* dst, int64_t dst_ld, int64_t rows, int d,
+              cudaStream_t st) {
+  ALG_REQUIRE(d % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0, "copy_rows: widths must be multiples of 8");
+  const int64_t total = rows * (d / 8);
+  if (total == 0) return 0;
+  copy_rows_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, d);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace dit
+}  // namespace alg

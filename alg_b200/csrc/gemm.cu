@@ -1,0 +1,411 @@
+// bf16 GEMM  D = epilogue(A * B^T + bias)  on tcgen05 tensor cores (SURVEY kernel K6).
+//
+// Replaces every nn.Linear of the DiT (cuBLASLt in the reference; call site wan:910).
+//   * A [M, K] and B [N, K] (nn.Linear.weight layout) are both K-major: TMA loads 64-element
+//     (128-byte, SWIZZLE_128B) K-slabs into a 4-stage shared-memory ring
+//   * one elected thread issues tcgen05.mma (128 x BN x 16), accumulating in TMEM
+//   * two TMEM accumulator stages: the epilogue warps drain tile i (tcgen05.ld -> bias / GELU /
+//     gate*x + residual -> global) while the tensor core already works on tile i + 1
+//   * persistent CTAs (one per SM), grouped tile order so a wave re-uses A and B out of L2
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (warp % 4 selects the TMEM lane quadrant it may read).
+#include <algorithm>
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace alg {
+namespace tc {
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode_fn();
+  ALG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  ALG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA: base address must be 16-byte aligned");
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) {
+      gstride[i - 1] = strides_elems[i] * 2;
+      ALG_REQUIRE(gstride[i - 1] % 16 == 0, "TMA: row stride must be a multiple of 16 bytes");
+    }
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bdim,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ALG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return 0;
+}
+
+}  // namespace tc
+
+namespace gemm {
+using namespace tc;
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr int kGroupM = 16;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBytesA = BM * BK * 2;
+  static constexpr int kBytesB = BN * BK * 2;
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32)
+  static constexpr int kSmemBytes = kStages * (kBytesA + kBytesB) + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct Params {
+  void* D;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* R;
+  const float* gate;
+  int64_t M, N, K, ldd, rows_per_batch, gate_ld;
+  int epilogue, bias_per_row, out_f32;
+  int m_tiles, n_tiles, k_blocks;
+};
+
+__device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
+  const int per_group = kGroupM * n_tiles;
+  const int g = t / per_group;
+  const int first_m = g * kGroupM;
+  const int gsize = min(m_tiles - first_m, kGroupM);
+  const int local = t - g * per_group;
+  m_blk = first_m + local % gsize;
+  n_blk = local / gsize;
+}
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
+  const float inner = kBeta * (x + kKappa * x * x * x);
+  const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * inner));  // tanh(inner)
+  return 0.5f * x * (1.0f + t);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::kStages * C::kBytesA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * (C::kBytesA + C::kBytesB));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(t, p.m_tiles, p.n_tiles, m_blk, n_blk);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], C::kBytesA + C::kBytesB);
+          tma_load_2d(sA + stage * C::kBytesA, &tmA, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sB + stage * C::kBytesB, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * C::kBytesA);
+          const uint32_t b_addr = smem_u32(sB + stage * C::kBytesB);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            mma_ss(d_tmem, make_smem_desc_sw128(a_addr + k * UMMA_K * 2), make_smem_desc_sw128(b_addr + k * UMMA_K * 2),
+                   idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty[stage]);  // slot is free once these MMAs have read it
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {  // ===== epilogue warps 2..5 =====
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      int m_blk, n_blk;
+      tile_coords(t, p.m_tiles, p.n_tiles, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int64_t safe_row = row_ok ? row : 0;
+      float row_bias = 0.f;
+      if (p.bias && p.bias_per_row && row_ok) row_bias = __bfloat162float(p.bias[row]);
+      const float* gate_row = nullptr;
+      if (p.epilogue == ALG_EPI_GATE_RESIDUAL) gate_row = p.gate + (safe_row / p.rows_per_batch) * p.gate_ld;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int64_t col0 = (int64_t)n_blk * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const bool full_chunk = col0 + 32 <= p.N;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        // ---- bias -------------------------------------------------------------------------
+        if (p.bias) {
+          if (p.bias_per_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += row_bias;
+          } else if (full_chunk) {
+            const uint4* b4 = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u = __ldg(b4 + g);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __bfloat1622float2(h[e]);
+                v[g * 8 + 2 * e] += f.x;
+                v[g * 8 + 2 * e + 1] += f.y;
+              }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
+          }
+        }
+        // ---- activation / residual --------------------------------------------------------
+        if (p.epilogue != ALG_EPI_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);  // the nn.Linear output tensor is bf16
+          if (p.epilogue == ALG_EPI_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+          } else if (p.epilogue == ALG_EPI_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+          } else if (p.epilogue == ALG_EPI_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+          } else {  // RESIDUAL / GATE_RESIDUAL
+            const __nv_bfloat16* rrow = p.R + row * p.ldd + col0;
+            const bool gated = p.epilogue == ALG_EPI_GATE_RESIDUAL;
+            if (full_chunk) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 u = *reinterpret_cast<const uint4*>(rrow + g * 8);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+                if (gated) {
+                  g0 = __ldg(reinterpret_cast<const float4*>(gate_row + col0 + g * 8));
+                  g1 = __ldg(reinterpret_cast<const float4*>(gate_row + col0 + g * 8 + 4));
+                }
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __bfloat1622float2(h[e]);
+                  const int j = g * 8 + 2 * e;
+                  v[j] = __fadd_rn(f.x, gated ? __fmul_rn(v[j], gg[2 * e]) : v[j]);
+                  v[j + 1] = __fadd_rn(f.y, gated ? __fmul_rn(v[j + 1], gg[2 * e + 1]) : v[j + 1]);
+                }
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) {
+                  const float x = __bfloat162float(rrow[j]);
+                  const float y = gated ? __fmul_rn(v[j], gate_row[col0 + j]) : v[j];
+                  v[j] = __fadd_rn(x, y);
+                }
+            }
+          }
+        }
+        // ---- store ------------------------------------------------------------------------
+        if (p.out_f32) {
+          float* drow = reinterpret_cast<float*>(p.D) + row * p.ldd + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(drow + g * 4) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) drow[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.D) + row * p.ldd + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(drow + g * 8) = u;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) drow[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN>
+static int launch(const alg_gemm_t* g, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    ALG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_done = true;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)g->K, (uint64_t)g->M}, strides[2] = {1, (uint64_t)g->lda};
+    uint32_t box[2] = {BK, BM};
+    if (int rc = make_tmap_bf16(&tmA, g->A, 2, dims, strides, box)) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)g->K, (uint64_t)g->N}, strides[2] = {1, (uint64_t)g->ldb};
+    uint32_t box[2] = {BK, BN};
+    if (int rc = make_tmap_bf16(&tmB, g->B, 2, dims, strides, box)) return rc;
+  }
+  Params p;
+  p.D = g->D;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(g->bias);
+  p.R = reinterpret_cast<const __nv_bfloat16*>(g->R);
+  p.gate = g->gate;
+  p.M = g->M;
+  p.N = g->N;
+  p.K = g->K;
+  p.ldd = g->ldd;
+  p.rows_per_batch = g->rows_per_batch > 0 ? g->rows_per_batch : g->M;
+  p.gate_ld = g->gate_ld;
+  p.epilogue = g->epilogue;
+  p.bias_per_row = g->bias_per_row;
+  p.out_f32 = g->out_f32;
+  p.m_tiles = (int)((g->M + BM - 1) / BM);
+  p.n_tiles = (int)((g->N + BN - 1) / BN);
+  p.k_blocks = (int)((g->K + BK - 1) / BK);
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = std::min(tiles, num_sms());
+  gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmB, p);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace gemm
+}  // namespace alg
+
+extern "C" int alg_gemm_bf16(const alg_gemm_t* g, void* stream) {
+  using namespace alg;
+  ALG_REQUIRE(g && g->A && g->B && g->D, "gemm: null pointer");
+  ALG_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "gemm: empty problem");
+  ALG_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
+  ALG_REQUIRE(g->lda >= g->K && g->ldb >= g->K && g->ldd >= g->N, "gemm: leading dimension too small");
+  ALG_REQUIRE(g->ldd % (g->out_f32 ? 4 : 8) == 0, "gemm: ldd must keep rows 16-byte aligned");
+  ALG_REQUIRE((reinterpret_cast<uintptr_t>(g->D) & 15) == 0, "gemm: D must be 16-byte aligned");
+  ALG_REQUIRE(g->epilogue >= ALG_EPI_NONE && g->epilogue <= ALG_EPI_SILU, "gemm: unknown epilogue");
+  if (g->epilogue == ALG_EPI_RESIDUAL || g->epilogue == ALG_EPI_GATE_RESIDUAL) {
+    ALG_REQUIRE(g->R && !g->out_f32, "gemm: residual epilogues need R and bf16 output");
+    ALG_REQUIRE((reinterpret_cast<uintptr_t>(g->R) & 15) == 0, "gemm: R must be 16-byte aligned");
+  }
+  if (g->epilogue == ALG_EPI_GATE_RESIDUAL)
+    ALG_REQUIRE(g->gate && g->gate_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g->gate) & 15) == 0,
+                "gemm: gate must be 16-byte aligned fp32 with gate_ld % 4 == 0");
+  if (g->bias && !g->bias_per_row)
+    ALG_REQUIRE((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  if (int rc = alg_check_device()) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (g->N % 256 == 0 || g->N > 512) return gemm::launch<256>(g, st);
+  if (g->N % 128 == 0 || g->N > 128) return gemm::launch<128>(g, st);
+  return gemm::launch<64>(g, st);
+}

@@ -1,0 +1,210 @@
+/*
+ * alg_b200.h -- C ABI of libalg_b200.so, the sm_100a implementation of the ALG
+ * (Adaptive Low-pass Guidance) per-step denoise loop.
+ *
+ * The reference (choi403/ALG @ 3657bfd) has no FFI of its own: its hot path is
+ * Python calling PyTorch/diffusers.  Each entry point below therefore names the
+ * reference call site it replaces (file:line under /root/reference); the
+ * Python-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no PyTorch types cross this boundary
+ *   - every pointer argument is a DEVICE pointer unless its name ends in _host
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all work is enqueued on it, nothing synchronises unless stated
+ *   - return value: 0 = OK, non-zero = error; text via alg_last_error()
+ *   - not thread-safe per handle; one engine handle per device / process
+ */
+#ifndef ALG_B200_H_
+#define ALG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALG_B200_ABI_VERSION 1
+
+typedef enum { ALG_F32 = 0, ALG_BF16 = 1, ALG_F16 = 2 } alg_dtype_t;
+
+int alg_abi_version(void);
+/* Thread-local message of the last failing call in this thread ("" if none). */
+const char* alg_last_error(void);
+/* 0 when the current device is sm_100 (B200); non-zero + message otherwise. */
+int alg_check_device(void);
+
+/* ------------------------------------------------------------------------- */
+/* Low-pass filters: lp_utils.apply_low_pass_filter (lp_utils.py:8-60)       */
+/* ------------------------------------------------------------------------- */
+
+/* lp_utils.py:49-54 -- two F.interpolate(bilinear, antialias=True) calls
+ * (H,W)->(h1,w1)->(H,W) on `planes` independent H x W images (the 5-D view of
+ * lp_utils.py:31-35 flattens to planes = B*C*K).  The intermediate small image
+ * is rounded to `dtype` exactly where the reference materialises it.
+ * in/out: [planes, H, W] contiguous, same dtype; out may alias in. */
+int alg_lowpass_down_up(const void* in, void* out, int64_t planes, int H, int W, int h1, int w1,
+                        int dtype, void* stream);
+
+/* lp_utils.py:40-47 -> torchvision gaussian_blur: reflect pad k/2, dense k x k
+ * depthwise conv with the outer-product Gaussian; the 1-D and 2-D weights are
+ * built and rounded in `dtype` like the reference (bf16 weights sum to 0.99902
+ * at k=13, sigma=15).  ksize odd, 1 <= ksize <= 63, ksize/2 < min(H, W).
+ * out must NOT alias in. */
+int alg_lowpass_gaussian(const void* in, void* out, int64_t planes, int H, int W, int ksize,
+                         double sigma, int dtype, void* stream);
+
+/* The dtype-faithful 1-D Gaussian taps used above, written to host memory. */
+int alg_gaussian_kernel1d(int ksize, double sigma, int dtype, float* taps_host);
+
+/* ------------------------------------------------------------------------- */
+/* Fused CFG combine + scheduler.step                                         */
+/* ------------------------------------------------------------------------- */
+
+/* Host-computed scalars of one UniPC (bh2, predict-x0, flow-sigma) step. */
+typedef struct {
+  int32_t n_pass;         /* 1: no CFG; 2: u + w (t - u); 3: u0 + w (t - u)                */
+  int32_t cfg_fp32;       /* 0: CFG in the noise dtype (Wan: three bf16 roundings, wan:919-924); 1: fp32 */
+  float guidance;         /* w                                                           */
+  float sigma_t;          /* convert_model_output: x0 = x - sigma_t * v                   */
+  int32_t use_corrector;  /* step_index > 0                                              */
+  int32_t order_c;        /* corrector order (1 or 2)                                    */
+  float c_ratio;          /* sigma_t / sigma_s0                                          */
+  float c_a;              /* alpha_t * h_phi_1                                           */
+  float c_b;              /* alpha_t * B_h                                               */
+  float c_rk_inv;         /* 1 / r_k           (order_c == 2)                            */
+  float c_rho0;           /* rhos_c[0]         (order_c == 2)                            */
+  float c_rho_last;       /* rhos_c[-1]                                                  */
+  int32_t order_p;        /* predictor order (1 or 2)                                    */
+  float p_ratio, p_a, p_b, p_rk_inv, p_rho0;
+} alg_unipc_step_t;
+
+/* wan:919-927 -- CFG combine + UniPCMultistepScheduler.step in one pass.
+ *   noise      [n_pass, E]  noise_dtype (bf16 for Wan)       read
+ *   x          [E] fp32     latents                           read, x_out written (may alias)
+ *   last_sample[E] fp32     previous (corrected) sample       read if use_corrector, then overwritten
+ *   m_prev0    [E] fp32     model_outputs[-1] of last step    read if corrector or order 2
+ *   m_prev1    [E] fp32     model_outputs[-2] of last step    read if order_c == 2; OVERWRITTEN with
+ *                           this step's x0 prediction (caller swaps the two pointers afterwards) */
+int alg_cfg_unipc_step(const void* noise, int noise_dtype, const float* x, float* x_out, float* last_sample,
+                       const float* m_prev0, float* m_prev1, int64_t E, const alg_unipc_step_t* p,
+                       void* stream);
+
+/* cog:1091-1123 -- fp32 CFG + CogVideoXDDIMScheduler.step (v-prediction) + cast back.
+ *   noise [n_pass, E] noise_dtype; x, x_out [E] sample_dtype (bf16 for Cog).
+ *   sqrt_alpha_t, sqrt_beta_t, a, b are the fp64 scalars of the scheduler rounded to fp32
+ *   the way ATen passes CPU scalars to CUDA kernels. */
+int alg_cfg_ddim_step(const void* noise, int noise_dtype, const void* x, void* x_out, int sample_dtype,
+                      int64_t E, int n_pass, float guidance, float sqrt_alpha_t, float sqrt_beta_t,
+                      float a, float b, void* stream);
+
+/* hy:1254-1270 -- (true-)CFG + FlowMatchEulerDiscreteScheduler.step on frames 1.. + re-prepend
+ * of the conditioning frame.  Layout [C, T, HW]; noise holds all T frames (frame 0 ignored).
+ *   x_out[c, 0] = first_frame[c, 0];  x_out[c, f>0] = fp32(noise_dtype(x + noise_dtype(dt * v)))  */
+int alg_cfg_euler_step(const void* noise, int noise_dtype, const float* x, float* x_out,
+                       const float* first_frame, int C, int T, int64_t HW, int n_pass, float guidance,
+                       float dt, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Tensor-core building blocks (tcgen05 / TMEM / TMA); used by the DiT engine */
+/* and exported so parity tests can drive them directly.                      */
+/* ------------------------------------------------------------------------- */
+
+typedef enum {
+  ALG_EPI_NONE = 0,          /* D = acc (+bias)                                               */
+  ALG_EPI_GELU_TANH = 1,     /* D = gelu_tanh(bf16(acc + bias))                               */
+  ALG_EPI_GATE_RESIDUAL = 2, /* D = bf16(fp32(R) + fp32(bf16(acc + bias)) * gate[row/rows_per_batch, col]) */
+  ALG_EPI_RESIDUAL = 3,      /* D = bf16(fp32(R) + fp32(bf16(acc + bias)))                    */
+  ALG_EPI_GELU_ERF = 4,      /* D = gelu(bf16(acc + bias)), exact erf form                    */
+  ALG_EPI_SILU = 5           /* D = silu(bf16(acc + bias))                                    */
+} alg_epilogue_t;
+
+typedef struct {
+  const void* A;      /* [M, K] bf16, row-major, lda elements between rows                     */
+  const void* B;      /* [N, K] bf16, row-major (nn.Linear.weight layout), ldb                 */
+  void* D;            /* [M, N] bf16 (or fp32 when out_f32), ldd                               */
+  const void* bias;   /* bf16 [N] (or [M] when bias_per_row), may be NULL                      */
+  const void* R;      /* residual, bf16 [M, N] with ldd; RESIDUAL / GATE_RESIDUAL only         */
+  const float* gate;  /* fp32 [M / rows_per_batch, gate_ld] (GATE_RESIDUAL only)               */
+  int64_t M, N, K;
+  int64_t lda, ldb, ldd;
+  int64_t rows_per_batch;
+  int64_t gate_ld;
+  int32_t epilogue;
+  int32_t bias_per_row;
+  int32_t out_f32;
+} alg_gemm_t;
+
+/* D = epilogue(A * B^T + bias): every nn.Linear of the DiT (SURVEY kernel K6). */
+int alg_gemm_bf16(const alg_gemm_t* g, void* stream);
+
+typedef struct {
+  const void* Q;   /* bf16; element (b, n, h, d) at Q + b*q_bs + n*q_rs + h*head_dim + d          */
+  const void* K;   /* bf16; (b, n, h, d) at K + b*k_bs + n*k_rs + h*head_dim + d                  */
+  const void* Vt;  /* bf16, transposed values: (b, h, d, n) at Vt + b*v_bs + (h*head_dim + d)*v_rs + n */
+  void* O;         /* bf16; same addressing as Q with o_bs / o_rs                                 */
+  int32_t batch, heads, head_dim; /* head_dim in {64, 128}                                        */
+  int64_t n_q, n_kv;
+  int64_t q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs; /* in elements                          */
+  float scale;                    /* 1/sqrt(head_dim)                                             */
+  int32_t accumulate;             /* 1: O += result (Wan text + image cross-attention sum)        */
+} alg_attention_t;
+
+/* Non-causal softmax(Q K^T * scale) V, fp32 softmax, bf16 in/out (SURVEY kernel K8;
+ * replaces F.scaled_dot_product_attention inside the DiT, wan:910). */
+int alg_attention_bf16(const alg_attention_t* a, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Wan2.1 I2V DiT engine: WanTransformer3DModel.forward (call site wan:910-917) */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+  int32_t num_heads, head_dim, in_channels, out_channels;
+  int32_t text_dim, freq_dim, ffn_dim, num_layers, image_dim, text_len;
+  int32_t patch_t, patch_h, patch_w;
+  int32_t rope_max_seq_len;
+  float eps;
+} alg_wan_config_t;
+
+typedef struct alg_wan_engine alg_wan_engine_t;
+
+int alg_wan_create(const alg_wan_config_t* cfg, alg_wan_engine_t** out);
+void alg_wan_destroy(alg_wan_engine_t* e);
+
+/* Register one parameter by its diffusers state_dict name (e.g.
+ * "blocks.0.attn1.to_q.weight").  The engine keeps the POINTER: the caller owns
+ * the memory and must keep it alive.  dtype must be bf16, except fp32 for the
+ * modules diffusers keeps in fp32 (time_embedder, scale_shift_table, norm2). */
+int alg_wan_set_weight(alg_wan_engine_t* e, const char* name, const void* ptr, int64_t numel, int dtype);
+/* 0 when every parameter of the configured model has been registered. */
+int alg_wan_weights_complete(alg_wan_engine_t* e);
+
+/* Scratch bytes needed for a forward of n_pass samples on a [T, H, W] latent grid. */
+int alg_wan_workspace_bytes(alg_wan_engine_t* e, int n_pass, int T, int H, int W, int n_img_tokens,
+                            size_t* bytes);
+
+/* wan:882-917 -- model-input assembly + DiT forward for the 2 or 3 CFG passes.
+ *   latents[p][16, T, H, W] fp32           per pass (the loop passes the SAME pointer n_pass times: never replicated)
+ *   cond[p]   [20, T, H, W] fp32           per pass: condition / lp_image_latents
+ *   text[p]   [text_len, text_dim] bf16    per pass: negative / positive prompt embeds
+ *   image     [n_img_tokens, image_dim] bf16 (shared)
+ *   timestep  the scheduler's int64 timestep value
+ *   noise_out [n_pass, 16, T, H, W] bf16
+ * The fp32 -> bf16 cast and the channel concat (wan:886-891) happen inside the patch gather. */
+int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents, const float* const* cond, const void* const* text,
+                    const void* image, int n_img_tokens, int n_pass, int T, int H, int W, int64_t timestep,
+                    void* noise_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Debug / parity hook: when a device buffer is set, every forward appends to it (while space lasts), in order:
+ * the patch embedding [n_pass*N, d] bf16, temb [d] bf16, timestep_proj [6d] bf16, then the residual stream
+ * [n_pass*N, d] bf16 after each block.  Pass NULL to switch it off. */
+int alg_wan_set_debug_buffer(alg_wan_engine_t* e, void* buf, size_t bytes);
+
+/* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
+int64_t alg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALG_B200_H_ */
