@@ -7,6 +7,7 @@
 // resampling operators (W-down, H-down, W-up, H-up) there and writes the plane back once:
 // algorithmic traffic = read once + write once.  Planes too large for shared memory take a
 // generic four-pass path through global scratch.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -28,7 +29,17 @@ struct Band {  // CSR-ish resampling operator: out[i] = sum_k w[off[i] + k] * in
   int max_band = 0;
 };
 
-static Band make_band(int in_size, int out_size) {
+// For 16-bit tensors ATen's CUDA kernel keeps the taps in the tensor dtype (UpSample.cuh:_compute_weights:
+// `wt_ptr[j] = scalar_t(w)`, then `wt_ptr[j] /= total_w`), so they are rounded here the same way.
+static int aa_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ALG_AA_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+static Band make_band(int in_size, int out_size, int dt) {
   Band b;
   const float scale = (float)in_size / (float)out_size;
   const float support = scale >= 1.0f ? scale : 1.0f;
@@ -50,7 +61,14 @@ static Band make_band(int in_size, int out_size) {
       ws[j] = v > 0.f ? v : 0.f;
       total += ws[j];
     }
-    for (int j = 0; j < n; ++j) b.w.push_back(total != 0.f ? ws[j] / total : 0.f);
+    for (int j = 0; j < n; ++j) {
+      float w = host_round(ws[j], dt);
+      if (total != 0.f) {
+        const float tot = (dt != ALG_F32 && aa_variant() == 1) ? host_round(total, dt) : total;
+        w = host_round(w / tot, dt);
+      }
+      b.w.push_back(w);
+    }
     b.start.push_back(xmin);
     b.off.push_back((int)b.w.size());
     if (n > b.max_band) b.max_band = n;
@@ -67,13 +85,13 @@ struct DownUpTables {
 };
 
 static std::mutex g_tab_mu;
-static std::map<std::tuple<int, int, int, int, int>, DownUpTables> g_tables;
+static std::map<std::tuple<int, int, int, int, int, int>, DownUpTables> g_tables;
 
-static int get_tables(int H, int W, int h1, int w1, DownUpTables* out) {
+static int get_tables(int H, int W, int h1, int w1, int dt, DownUpTables* out) {
   int dev = 0;
   ALG_CUDA_OK(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_tab_mu);
-  auto key = std::make_tuple(dev, H, W, h1, w1);
+  auto key = std::make_tuple(dev, H, W, h1, w1, dt);
   auto it = g_tables.find(key);
   if (it != g_tables.end()) {
     *out = it->second;
@@ -88,7 +106,7 @@ static int get_tables(int H, int W, int h1, int w1, DownUpTables* out) {
     g_tables.clear();
   }
   // order: 0 = W-down (W -> w1), 1 = H-down (H -> h1), 2 = W-up (w1 -> W), 3 = H-up (h1 -> H)
-  Band bands[4] = {make_band(W, w1), make_band(H, h1), make_band(w1, W), make_band(h1, H)};
+  Band bands[4] = {make_band(W, w1, dt), make_band(H, h1, dt), make_band(w1, W, dt), make_band(h1, H, dt)};
   std::vector<int> ints;
   std::vector<float> ws;
   DownUpTables t;
@@ -116,6 +134,7 @@ struct BandPtr {
 };
 
 // dst[r][j] = sum_k w * src[r][start_j + k]      (resample along the contiguous axis)
+template <int DT>
 __device__ __forceinline__ void pass_w(const float* __restrict__ src, float* __restrict__ dst, int rows, int in_w,
                                        int out_w, BandPtr b) {
   for (int idx = threadIdx.x; idx < rows * out_w; idx += blockDim.x) {
@@ -124,7 +143,7 @@ __device__ __forceinline__ void pass_w(const float* __restrict__ src, float* __r
     const float* p = src + r * in_w + s;
     float acc = 0.f;
     for (int k = 0; k < n; ++k) acc = fmaf(b.w[o + k], p[k], acc);
-    dst[idx] = acc;
+    dst[idx] = Elem<DT>::round(acc);  // ATen keeps the row-pass result in a scalar_t buffer
   }
 }
 // dst[i][c] = sum_k w * src[start_i + k][c]       (resample along the strided axis)
@@ -177,11 +196,11 @@ __global__ void __launch_bounds__(256) down_up_fused_kernel(const void* __restri
       for (int i = threadIdx.x; i < HW; i += blockDim.x) A[i] = (float)src[i];
     }
     __syncthreads();
-    pass_w(A, B, H, W, w1, bw_down);  // t1 [H, w1]
+    pass_w<DT>(A, B, H, W, w1, bw_down);  // t1 [H, w1]
     __syncthreads();
     pass_h<DT, true, false>(B, A, w1, h1, bh_down);  // small [h1, w1], rounded to dtype (reference materialises it)
     __syncthreads();
-    pass_w(A, B, h1, w1, W, bw_up);  // t2 [h1, W]
+    pass_w<DT>(A, B, h1, w1, W, bw_up);  // t2 [h1, W]
     __syncthreads();
     pass_h<DT, false, true>(B, dst, W, H, bh_up);  // out [H, W]
     __syncthreads();
@@ -221,13 +240,13 @@ static int down_up_generic(const void* in, void* out, int64_t planes, int H, int
   ALG_CUDA_OK(cudaMallocAsync(&sm, sizeof(float) * planes * h1 * w1, st));
   ALG_CUDA_OK(cudaMallocAsync(&t2, sizeof(float) * planes * h1 * W, st));
   auto grid = [](int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 16); };
-  resample_pass_kernel<DT, ALG_F32, true, false><<<grid(planes * H * w1), 256, 0, st>>>(
+  resample_pass_kernel<DT, ALG_F32, true, true><<<grid(planes * H * w1), 256, 0, st>>>(
       in, t1, planes, H, W, H, w1, t.ints + t.s_off[0], t.ints + t.o_off[0], t.weights + t.w_off[0], DT);
   ALG_LAUNCH_OK();
   resample_pass_kernel<ALG_F32, ALG_F32, false, true><<<grid(planes * h1 * w1), 256, 0, st>>>(
       t1, sm, planes, H, w1, h1, w1, t.ints + t.s_off[1], t.ints + t.o_off[1], t.weights + t.w_off[1], DT);
   ALG_LAUNCH_OK();
-  resample_pass_kernel<ALG_F32, ALG_F32, true, false><<<grid(planes * h1 * W), 256, 0, st>>>(
+  resample_pass_kernel<ALG_F32, ALG_F32, true, true><<<grid(planes * h1 * W), 256, 0, st>>>(
       sm, t2, planes, h1, w1, h1, W, t.ints + t.s_off[2], t.ints + t.o_off[2], t.weights + t.w_off[2], DT);
   ALG_LAUNCH_OK();
   resample_pass_kernel<ALG_F32, DT, false, false><<<grid(planes * H * W), 256, 0, st>>>(
@@ -243,7 +262,7 @@ template <int DT>
 static int down_up_dispatch(const void* in, void* out, int64_t planes, int H, int W, int h1, int w1,
                             cudaStream_t st) {
   DownUpTables t;
-  if (int rc = get_tables(H, W, h1, w1, &t)) return rc;
+  if (int rc = get_tables(H, W, h1, w1, DT, &t)) return rc;
   const int64_t a_elems = std::max<int64_t>((int64_t)H * W, (int64_t)h1 * w1);
   const int64_t b_elems = std::max<int64_t>((int64_t)H * w1, (int64_t)h1 * W);
   const size_t smem = (size_t)(a_elems + b_elems) * sizeof(float);

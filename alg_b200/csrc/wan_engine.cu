@@ -42,12 +42,47 @@ struct alg_wan_engine {
   int n_t = 0, n_h = 0, n_w = 0;
   void* debug_buf = nullptr;
   size_t debug_bytes = 0;
+  // optional per-class device timing (CUDA events on the launching stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
   int dim() const { return cfg.num_heads * cfg.head_dim; }
 };
 
 namespace {
 using namespace alg;
 typedef __nv_bfloat16 bf16;
+
+enum { PROF_SELF_ATTN = 0, PROF_CROSS_ATTN = 1, PROF_GEMM = 2, PROF_ELEMENTWISE = 3, PROF_NUM = 4 };
+thread_local alg_wan_engine* tl_engine = nullptr;  // engine whose forward is running on this thread (profiling)
+
+cudaEvent_t take_event(alg_wan_engine* e) {
+  if (e->ev_used == e->ev_pool.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    e->ev_pool.push_back(ev);
+  }
+  return e->ev_pool[e->ev_used++];
+}
+struct ProfScope {  // times everything enqueued on `st` during its lifetime as one span of class `cls`
+  alg_wan_engine* e;
+  cudaStream_t st;
+  alg_wan_engine::Span sp;
+  ProfScope(alg_wan_engine* e_, cudaStream_t st_, int cls) : e(e_), st(st_) {
+    if (!e || !e->profiling) return;
+    sp.cls = cls;
+    sp.a = take_event(e);
+    sp.b = take_event(e);
+    cudaEventRecord(sp.a, st);
+  }
+  ~ProfScope() {
+    if (!e || !e->profiling) return;
+    cudaEventRecord(sp.b, st);
+    e->spans.push_back(sp);
+  }
+};
 
 struct Bump {
   char* base;
@@ -65,6 +100,7 @@ struct Bump {
 int gemm(cudaStream_t st, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, int64_t M,
          int64_t N, int64_t K, const void* bias, int epi = ALG_EPI_NONE, const void* R = nullptr,
          const float* gate = nullptr, int bias_per_row = 0) {
+  ProfScope ps(tl_engine, st, PROF_GEMM);
   alg_gemm_t g{};
   g.A = A; g.B = B; g.D = D; g.bias = bias; g.R = R; g.gate = gate;
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldd = ldd;
@@ -74,6 +110,7 @@ int gemm(cudaStream_t st, const void* A, int64_t lda, const void* B, int64_t ldb
 
 int attention(cudaStream_t st, const bf16* Q, const bf16* K, const bf16* Vt, bf16* O, int batch, int heads, int hd,
               int64_t n_q, int64_t n_kv, int64_t kv_pad, int accumulate) {
+  ProfScope ps(tl_engine, st, n_q == n_kv ? PROF_SELF_ATTN : PROF_CROSS_ATTN);
   alg_attention_t a{};
   const int64_t d = (int64_t)heads * hd;
   a.Q = Q; a.K = K; a.Vt = Vt; a.O = O;
@@ -90,6 +127,11 @@ inline int64_t pad8(int64_t n) { return (n + 7) & ~int64_t(7); }
 #define ALG_TRY(expr)          \
   do {                         \
     if (int _rc = (expr)) return _rc; \
+  } while (0)
+#define ALG_TRY_EW(expr)                            \
+  do {                                              \
+    ProfScope _ps(tl_engine, st, PROF_ELEMENTWISE); \
+    if (int _rc = (expr)) return _rc;               \
   } while (0)
 
 int resolve(alg_wan_engine* e) {
@@ -258,6 +300,7 @@ extern "C" int alg_wan_create(const alg_wan_config_t* cfg, alg_wan_engine_t** ou
 
 extern "C" void alg_wan_destroy(alg_wan_engine_t* e) {
   if (!e) return;
+  for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
   cudaFree(e->rope_t);
   cudaFree(e->rope_h);
   cudaFree(e->rope_w);
@@ -315,6 +358,10 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
   ALG_REQUIRE((n_img > 0) == (c.image_dim > 0 && image != nullptr), "wan_forward: image tokens / image_dim mismatch");
   ALG_TRY(resolve(e));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  struct TlGuard {
+    TlGuard(alg_wan_engine* x) { tl_engine = x; }
+    ~TlGuard() { tl_engine = nullptr; }
+  } tl_guard(e);
   const int64_t d = e->dim();
   const int heads = c.num_heads, hd = c.head_dim;
   const int lat_ch = c.out_channels, cond_ch = c.in_channels - c.out_channels;
@@ -355,15 +402,15 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
     cp.lat[p] = latents[p];
     cp.p[p] = cond[p];
   }
-  ALG_TRY(dit::patch_gather(cp, n_pass, lat_ch, cond_ch, T, H, W, Apatch, st));
+  ALG_TRY_EW(dit::patch_gather(cp, n_pass, lat_ch, cond_ch, T, H, W, Apatch, st));
   ALG_TRY(gemm(st, Apatch, pk, e->patch_w, pk, x, d, M, d, pk, e->patch_b));
   debug_dump(x, (size_t)M * d * 2);
 
   // ---- 2. condition embedder --------------------------------------------------------------------------
-  ALG_TRY(dit::timestep_sinusoid((float)timestep, c.freq_dim, sinus, st));
-  ALG_TRY(dit::gemv_f32(e->te1_w, e->te1_b, sinus, te_h, (int)d, c.freq_dim, 1, st));
-  ALG_TRY(dit::gemv_f32(e->te2_w, e->te2_b, te_h, te_o, (int)d, (int)d, 0, st));
-  ALG_TRY(dit::temb_finish(te_o, temb, silu_temb, (int)d, st));
+  ALG_TRY_EW(dit::timestep_sinusoid((float)timestep, c.freq_dim, sinus, st));
+  ALG_TRY_EW(dit::gemv_f32(e->te1_w, e->te1_b, sinus, te_h, (int)d, c.freq_dim, 1, st));
+  ALG_TRY_EW(dit::gemv_f32(e->te2_w, e->te2_b, te_h, te_o, (int)d, (int)d, 0, st));
+  ALG_TRY_EW(dit::temb_finish(te_o, temb, silu_temb, (int)d, st));
   ALG_TRY(gemm(st, silu_temb, d, e->tp_w, d, tproj, 6 * d, 1, 6 * d, d, e->tp_b));
   for (int p = 0; p < n_pass; ++p) {
     int same = -1;
@@ -371,20 +418,20 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
       if (text[r] == text[p]) same = r;
     bf16* dst = ctx_text + (int64_t)p * txt * d;
     if (same >= 0) {  // [neg, neg, pos]: embed each distinct prompt once
-      ALG_TRY(dit::copy_rows(ctx_text + (int64_t)same * txt * d, d, dst, d, txt, (int)d, st));
+      ALG_TRY_EW(dit::copy_rows(ctx_text + (int64_t)same * txt * d, d, dst, d, txt, (int)d, st));
     } else {
       ALG_TRY(gemm(st, text[p], c.text_dim, e->tx1_w, c.text_dim, txt_h, d, txt, d, c.text_dim, e->tx1_b, ALG_EPI_GELU_TANH));
       ALG_TRY(gemm(st, txt_h, d, e->tx2_w, d, dst, d, txt, d, d, e->tx2_b));
     }
   }
   if (n_img > 0) {
-    ALG_TRY(dit::layer_norm((const bf16*)image, img_n, ni, c.image_dim, 1e-5f, e->in1_w, e->in1_b, nullptr, nullptr, st));
+    ALG_TRY_EW(dit::layer_norm((const bf16*)image, img_n, ni, c.image_dim, 1e-5f, e->in1_w, e->in1_b, nullptr, nullptr, st));
     ALG_TRY(gemm(st, img_n, c.image_dim, e->if1_w, c.image_dim, img_h, c.image_dim, ni, c.image_dim, c.image_dim,
                  e->if1_b, ALG_EPI_GELU_ERF));
     ALG_TRY(gemm(st, img_h, c.image_dim, e->if2_w, c.image_dim, img_p, d, ni, d, c.image_dim, e->if2_b));
-    ALG_TRY(dit::layer_norm(img_p, ctx_img, ni, (int)d, 1e-5f, e->in2_w, e->in2_b, nullptr, nullptr, st));
+    ALG_TRY_EW(dit::layer_norm(img_p, ctx_img, ni, (int)d, 1e-5f, e->in2_w, e->in2_b, nullptr, nullptr, st));
     for (int p = 1; p < n_pass; ++p)
-      ALG_TRY(dit::copy_rows(ctx_img, d, ctx_img + (int64_t)p * ni * d, d, ni, (int)d, st));
+      ALG_TRY_EW(dit::copy_rows(ctx_img, d, ctx_img + (int64_t)p * ni * d, d, ni, (int)d, st));
   }
   debug_dump(temb, (size_t)d * 2);
   debug_dump(tproj, (size_t)6 * d * 2);
@@ -394,32 +441,32 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
   // ---- 3. transformer blocks --------------------------------------------------------------------------
   for (int l = 0; l < c.num_layers; ++l) {
     const BlockW& b = e->blocks[l];
-    ALG_TRY(dit::add_table(b.table, tproj, mod, 6, (int)d, 0, st));
+    ALG_TRY_EW(dit::add_table(b.table, tproj, mod, 6, (int)d, 0, st));
     const float *shift = mod, *scale = mod + d, *gate = mod + 2 * d, *c_shift = mod + 3 * d, *c_scale = mod + 4 * d,
                 *c_gate = mod + 5 * d;
     // self-attention
-    ALG_TRY(dit::layer_norm(x, h, M, (int)d, c.eps, nullptr, nullptr, scale, shift, st));
+    ALG_TRY_EW(dit::layer_norm(x, h, M, (int)d, c.eps, nullptr, nullptr, scale, shift, st));
     ALG_TRY(gemm(st, h, d, b.attn1.q_w, d, q, d, M, d, d, b.attn1.q_b));
     ALG_TRY(gemm(st, h, d, b.attn1.k_w, d, k, d, M, d, d, b.attn1.k_b));
     for (int p = 0; p < n_pass; ++p)  // V^T = W_v h^T + b_v: swapped operands, bias per row
       ALG_TRY(gemm(st, b.attn1.v_w, d, h + (int64_t)p * N * d, d, vt + (int64_t)p * d * Npad, Npad, d, N, d, b.attn1.v_b,
                    ALG_EPI_NONE, nullptr, nullptr, 1));
-    ALG_TRY(dit::rms_norm_rope(q, M, (int)d, hd, c.eps, (const bf16*)b.attn1.norm_q, &rope, st));
-    ALG_TRY(dit::rms_norm_rope(k, M, (int)d, hd, c.eps, (const bf16*)b.attn1.norm_k, &rope, st));
+    ALG_TRY_EW(dit::rms_norm_rope(q, M, (int)d, hd, c.eps, (const bf16*)b.attn1.norm_q, &rope, st));
+    ALG_TRY_EW(dit::rms_norm_rope(k, M, (int)d, hd, c.eps, (const bf16*)b.attn1.norm_k, &rope, st));
     ALG_TRY(attention(st, q, k, vt, ao, n_pass, heads, hd, N, N, Npad, 0));
     ALG_TRY(gemm(st, ao, d, b.attn1.o_w, d, x, d, M, d, d, b.attn1.o_b, ALG_EPI_GATE_RESIDUAL, x, gate));
     // cross-attention (text keys = last text_len context tokens, image keys = the rest)
-    ALG_TRY(dit::layer_norm(x, h, M, (int)d, c.eps, b.norm2_w, b.norm2_b, nullptr, nullptr, st));
+    ALG_TRY_EW(dit::layer_norm(x, h, M, (int)d, c.eps, b.norm2_w, b.norm2_b, nullptr, nullptr, st));
     ALG_TRY(gemm(st, h, d, b.attn2.q_w, d, q, d, M, d, d, b.attn2.q_b));
-    ALG_TRY(dit::rms_norm_rope(q, M, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_q, nullptr, st));
+    ALG_TRY_EW(dit::rms_norm_rope(q, M, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_q, nullptr, st));
     ALG_TRY(gemm(st, ctx_text, d, b.attn2.k_w, d, k_text, d, n_pass * txt, d, d, b.attn2.k_b));
-    ALG_TRY(dit::rms_norm_rope(k_text, n_pass * txt, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_k, nullptr, st));
+    ALG_TRY_EW(dit::rms_norm_rope(k_text, n_pass * txt, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_k, nullptr, st));
     for (int p = 0; p < n_pass; ++p)
       ALG_TRY(gemm(st, b.attn2.v_w, d, ctx_text + (int64_t)p * txt * d, d, vt_text + (int64_t)p * d * txt_pad, txt_pad, d,
                    txt, d, b.attn2.v_b, ALG_EPI_NONE, nullptr, nullptr, 1));
     if (n_img > 0) {
       ALG_TRY(gemm(st, ctx_img, d, b.attn2.add_k_w, d, k_img, d, n_pass * ni, d, d, b.attn2.add_k_b));
-      ALG_TRY(dit::rms_norm_rope(k_img, n_pass * ni, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_added_k, nullptr, st));
+      ALG_TRY_EW(dit::rms_norm_rope(k_img, n_pass * ni, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_added_k, nullptr, st));
       for (int p = 0; p < n_pass; ++p)
         ALG_TRY(gemm(st, b.attn2.add_v_w, d, ctx_img + (int64_t)p * ni * d, d, vt_img + (int64_t)p * d * ni_pad, ni_pad, d,
                      ni, d, b.attn2.add_v_b, ALG_EPI_NONE, nullptr, nullptr, 1));
@@ -428,16 +475,44 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
     ALG_TRY(attention(st, q, k_text, vt_text, ao, n_pass, heads, hd, N, txt, txt_pad, n_img > 0 ? 1 : 0));
     ALG_TRY(gemm(st, ao, d, b.attn2.o_w, d, x, d, M, d, d, b.attn2.o_b, ALG_EPI_RESIDUAL, x));
     // feed-forward
-    ALG_TRY(dit::layer_norm(x, h, M, (int)d, c.eps, nullptr, nullptr, c_scale, c_shift, st));
+    ALG_TRY_EW(dit::layer_norm(x, h, M, (int)d, c.eps, nullptr, nullptr, c_scale, c_shift, st));
     ALG_TRY(gemm(st, h, d, b.ffn1_w, d, ffn, c.ffn_dim, M, c.ffn_dim, d, b.ffn1_b, ALG_EPI_GELU_TANH));
     ALG_TRY(gemm(st, ffn, c.ffn_dim, b.ffn2_w, c.ffn_dim, x, d, M, d, c.ffn_dim, b.ffn2_b, ALG_EPI_GATE_RESIDUAL, x, c_gate));
     debug_dump(x, (size_t)M * d * 2);
   }
 
   // ---- 4. output norm, projection, unpatchify ------------------------------------------------------------
-  ALG_TRY(dit::add_table(e->head_table, temb, mod, 2, (int)d, 1, st));
-  ALG_TRY(dit::layer_norm(x, h, M, (int)d, c.eps, nullptr, nullptr, mod + d, mod, st));
+  ALG_TRY_EW(dit::add_table(e->head_table, temb, mod, 2, (int)d, 1, st));
+  ALG_TRY_EW(dit::layer_norm(x, h, M, (int)d, c.eps, nullptr, nullptr, mod + d, mod, st));
   ALG_TRY(gemm(st, h, d, e->proj_w, d, proj, pop, M, po, d, e->proj_b));
-  ALG_TRY(dit::unpatchify(proj, (bf16*)noise_out, n_pass, c.out_channels, T, H, W, st));
+  ALG_TRY_EW(dit::unpatchify(proj, (bf16*)noise_out, n_pass, c.out_channels, T, H, W, st));
+  return 0;
+}
+
+extern "C" int alg_wan_profile(alg_wan_engine_t* e, int enable) {
+  using namespace alg;
+  ALG_REQUIRE(e, "wan_profile: null engine");
+  e->profiling = enable != 0;
+  e->spans.clear();
+  e->ev_used = 0;
+  return 0;
+}
+
+extern "C" int alg_wan_profile_read(alg_wan_engine_t* e, float* ms_per_class, int32_t* launches_per_class, int n_classes) {
+  using namespace alg;
+  ALG_REQUIRE(e && ms_per_class && launches_per_class && n_classes >= PROF_NUM, "wan_profile_read: bad arguments");
+  for (int i = 0; i < n_classes; ++i) {
+    ms_per_class[i] = 0.f;
+    launches_per_class[i] = 0;
+  }
+  for (const auto& sp : e->spans) {
+    ALG_CUDA_OK(cudaEventSynchronize(sp.b));
+    float ms = 0.f;
+    ALG_CUDA_OK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    ms_per_class[sp.cls] += ms;
+    launches_per_class[sp.cls] += 1;
+  }
+  e->spans.clear();
+  e->ev_used = 0;
   return 0;
 }

@@ -306,7 +306,9 @@ class FlowMatchEulerDiscreteScheduler(_ConfigMixin):
             raise NotImplementedError("HunyuanVideo loop: batch 1, fp32 latents container")
         E = sample.numel()
         n_pass = _as_passes(noise_pred, E)
-        dt = float(self.sigmas[self._step_index + 1] - self.sigmas[self._step_index])
+        # diffusers keeps FlowMatchEuler sigmas ON THE DEVICE: `dt * model_output` is then a 0-dim CUDA tensor times a
+        # bf16 tensor, and ATen casts the 0-dim operand to the result dtype (bf16) before multiplying
+        dt = float((self.sigmas[self._step_index + 1] - self.sigmas[self._step_index]).to(noise_pred.dtype))
         noise_pred, sample, first_frame = noise_pred.contiguous(), sample.contiguous(), first_frame.contiguous()
         if out is None:
             out = torch.empty_like(sample)

@@ -149,8 +149,12 @@ class WanTransformer3DModel:
         return dict(self._state)
 
     def to(self, device=None, dtype=None):
-        if device is not None and torch.device(device) != self.device and self._state:
-            self.load_state_dict({k: v.to(device) for k, v in self._state.items()})
+        if device is not None and self._state:
+            dev = torch.device(device)
+            if dev.type == "cuda" and dev.index is None:
+                dev = torch.device("cuda", torch.cuda.current_device())
+            if dev != self.device:
+                self.load_state_dict({k: v.to(dev) for k, v in self._state.items()})
         return self
 
     def __del__(self):
@@ -165,6 +169,18 @@ class WanTransformer3DModel:
         self._debug = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         _lib.check(_lib.lib().alg_wan_set_debug_buffer(self._handle, self._debug.data_ptr(), nbytes))
         return self._debug
+
+    PROFILE_CLASSES = ("self_attention", "cross_attention", "gemm", "elementwise")
+
+    def profile(self, enable: bool = True):
+        """Per-kernel-class device timing of the forwards that follow (CUDA events on the launching stream)."""
+        _lib.check(_lib.lib().alg_wan_profile(self._handle, int(enable)))
+
+    def profile_read(self) -> Dict[str, dict]:
+        ms = (C.c_float * 4)()
+        n = (C.c_int32 * 4)()
+        _lib.check(_lib.lib().alg_wan_profile_read(self._handle, ms, n, 4))
+        return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(self.PROFILE_CLASSES)}
 
     def forward_passes(self, latents: Sequence[torch.Tensor], cond: Sequence[torch.Tensor],
                        text: Sequence[torch.Tensor], image: Optional[torch.Tensor], timestep: int,

@@ -1,0 +1,350 @@
+"""bench.py -- video frames/sec of the ALG denoise loop, Wan-I2V-14B 480p / 81 frames / 50 steps (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A "step" is one iteration of the denoise loop (wan:844-927): low-pass filter of the conditioning latent, the 2- or
+3-pass DiT forward, the CFG combine and the UniPC update, for ONE video sample per GPU (independent samples shard
+across GPUs: weak scaling, no data-path collective; NCCL only broadcasts the weights at init).  K timed steps sample
+the real 50-step schedule uniformly (index floor(k*50/K)), which keeps its 10:40 mix of 3-pass : 2-pass steps for
+K = 5, 10, 25, 50; frames/sec = N_gpus * 81 / (50 * mean step time).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+NUM_FRAMES, STEPS_PER_VIDEO, HEIGHT, WIDTH = 81, 50, 480, 832
+T_LAT, H_LAT, W_LAT = 21, 60, 104
+ALG = dict(use_low_pass_guidance=True, lp_filter_type="down_up", lp_filter_in_latent=True, lp_blur_sigma=15.0,
+           lp_blur_kernel_size=0.02734375, lp_resize_factor=0.4, lp_strength_schedule_type="interval",
+           schedule_blur_kernel_size=False, schedule_interval_start_time=0.0, schedule_interval_end_time=0.20,
+           schedule_linear_start_weight=1.0, schedule_linear_end_weight=0.0, schedule_linear_end_time=0.5,
+           schedule_exp_decay_rate=10.0)
+GUIDANCE = 5.0
+FLOW_SHIFT = 5.0  # run.py:63 compares int 480 to '480' => always 5.0 (quirk q1): measure the as-shipped behaviour
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def step_indices(k):
+    return [int(i * STEPS_PER_VIDEO / k) for i in range(k)]
+
+
+def n_pass_of(idx):
+    import lp_utils
+    s = lp_utils.get_lp_strength(idx, STEPS_PER_VIDEO, ALG["lp_strength_schedule_type"], 0.0, 0.20, 1.0, 0.0, 0.5, 10.0)
+    return 3 if s != 0.0 else 2
+
+
+def forward_flops(n_tok, d=5120, ffn=13824, layers=40, ctx=769, text_dim=4096):
+    """Algorithmic FLOPs of one sample-forward."""
+    self_attn = 4 * n_tok * n_tok * d
+    per_layer = 8 * n_tok * d * d + self_attn + 4 * n_tok * d * d + 4 * ctx * d * d + 4 * n_tok * ctx * d + 4 * n_tok * d * ffn
+    return layers * per_layer, layers * self_attn
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent (NVML) SM clock + throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            names = {N.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     N.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", N.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                     N.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self.stop_flag:
+                self.samples.append(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as ex:  # pragma: no cover
+            self.reasons.add(f"nvml_unavailable:{type(ex).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ======================================================================================================
+# reference arm / cpu_baseline: the oracle port of the loop on host cores, bounded sample + FLOP extrapolation
+# ======================================================================================================
+def cpu_sample(steps, warmup, threads=None, sample_frames=3, layers=1):
+    """Time the CPU restatement (oracle/) of one 2-pass denoise step on a BOUNDED sample: `sample_frames` latent
+    frames (of 21) through `layers` transformer block(s) (of 40) at full width, fp32, all host threads; scale to the
+    full step by algorithmic FLOPs.  Returns (frames_per_sec_extrapolated, seconds_per_sample_step, description)."""
+    from oracle import lp_oracle, sched_oracle, wan_oracle as W
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = W.WanConfig(num_layers=layers)
+    sd = W.make_weights(cfg, seed=0, device="cpu", dtype=torch.float32)
+    g = torch.Generator().manual_seed(42)
+    lat = torch.randn(1, 16, sample_frames, H_LAT, W_LAT, generator=g)
+    cond = torch.randn(1, 20, sample_frames, H_LAT, W_LAT, generator=g)
+    pos = torch.randn(1, 512, 4096, generator=g)
+    neg = torch.randn(1, 512, 4096, generator=g)
+    img = torch.randn(1, 257, 1280, generator=g)
+    sched = sched_oracle.UniPCOracle(flow_shift=FLOW_SHIFT)
+    sched.set_timesteps(STEPS_PER_VIDEO)
+
+    def one_step(i):
+        import numpy as np
+        lp = torch.from_numpy(lp_oracle.apply_low_pass_filter(cond.numpy(), "down_up", 0.0, 0.0, 0.4))
+        x = torch.cat([torch.cat([lat] * 2), torch.cat([cond, lp])], dim=1)
+        t = sched.timesteps[i].expand(2)
+        noise = W.forward(sd, cfg, x, t, torch.cat([neg, pos]), img.repeat(2, 1, 1))
+        sched.step_index = i
+        sched.model_outputs = [lat, lat]
+        sched.last_sample = lat
+        sched.this_order, sched.lower_order_nums = 2, 2
+        return sched.step(sched_oracle.cfg_combine(noise.bfloat16(), GUIDANCE), lat)
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            one_step(1)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            one_step(1 + k)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+    n_s = sample_frames * (H_LAT // 2) * (W_LAT // 2)
+    n_f = T_LAT * (H_LAT // 2) * (W_LAT // 2)
+    f_sample = 2 * forward_flops(n_s, layers=layers)[0]
+    f_video = sum(n_pass_of(i) for i in range(STEPS_PER_VIDEO)) * forward_flops(n_f)[0]
+    sec_video = dt * f_video / f_sample
+    desc = (f"oracle port (PyTorch fp32, {threads} threads): one 2-pass denoise step on {sample_frames}/21 latent frames "
+            f"({n_s} tokens) x {layers}/40 blocks = {f_sample:.3e} FLOP in {dt:.2f} s; extrapolated by FLOPs to the "
+            f"{f_video:.3e} FLOP video")
+    return NUM_FRAMES / sec_video, dt, desc, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fps, dt, desc, threads = cpu_sample(args.steps, args.warmup)
+    line = {
+        "metric": "video frames/sec (Wan-I2V-14B 480p, 81 frames, 50 steps, ALG down_up)", "value": fps * args.gpus,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": "Wan-I2V-14B 480x832, 81 frames, 50 steps, ALG down_up f=0.4 interval[0,0.2], gs 5 "
+                               "(BASELINE.json configs[1]); CPU bounded sample, FLOP-extrapolated"},
+        "cpu_baseline": {"value": fps * args.gpus, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": fps * args.gpus, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================
+# this repo's arm
+# ======================================================================================================
+def synthetic_inputs(device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    lat = torch.randn(1, 16, T_LAT, H_LAT, W_LAT, generator=g, device=device)
+    mask = torch.zeros(1, 4, T_LAT, H_LAT, W_LAT, device=device)
+    mask[:, :, 0] = 1  # wan:436-447: ones on latent frame 0
+    cond = torch.cat([mask, torch.randn(1, 16, T_LAT, H_LAT, W_LAT, generator=g, device=device)], dim=1)
+    n_tok = 64 + seed % 200
+
+    def text():
+        e = torch.randn(1, 512, 4096, generator=g, device=device)
+        e[:, n_tok:] = 0  # Wan zero-pads beyond the prompt length (wan:214-217)
+        return e.bfloat16()
+
+    return lat, cond, text(), text(), torch.randn(1, 257, 1280, generator=g, device=device).bfloat16()
+
+
+def broadcast_weights(sd, src=0):
+    """NCCL over NVLink: rank `src` owns the seeded weights, everyone else receives them (init only)."""
+    import torch.distributed as dist
+    for name in sorted(sd):
+        dist.broadcast(sd[name], src=src)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from alg_b200 import _lib, wan
+    from alg_b200.schedulers import UniPCMultistepScheduler
+    from pipeline_wan_image2video_lowpass import WanImageToVideoPipeline
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.check(_lib.lib().alg_check_device())
+
+    cfg = dict(wan.WAN_I2V_14B)
+    if world > 1 and rank != 0:  # allocate, then receive rank 0's weights over NVLink
+        sd = {k: torch.empty(s, device=device, dtype=torch.float32 if any(f in k for f in wan.FP32_KEYS) else torch.bfloat16)
+              for k, s in wan.parameter_shapes(cfg).items()}
+    else:
+        sd = wan.synthetic_state_dict(cfg, seed=0, device=device)
+    if world > 1:
+        broadcast_weights(sd)
+    transformer = wan.WanTransformer3DModel(**cfg).load_state_dict(sd)
+    pipe = WanImageToVideoPipeline.from_pretrained("synthetic", transformer=transformer, synthetic=True)
+    pipe.scheduler = UniPCMultistepScheduler.from_config(pipe.scheduler.config, flow_shift=FLOW_SHIFT)
+    pipe.to(device)
+    pipe._guidance_scale = GUIDANCE
+    sched = pipe.scheduler
+    sched.set_timesteps(STEPS_PER_VIDEO, device=device)
+    ts = sched.timesteps.tolist()
+    lat0, cond, pos, neg, img = synthetic_inputs(device, 42 + rank)
+    image_rgb = torch.zeros(1, 3, HEIGHT, WIDTH, device=device)
+
+    def step(idx, latents):
+        # jump to schedule position idx (the multistep history buffers hold the previous timed step's values:
+        # identical work, the numbers only matter to the parity tests)
+        sched._step_index = idx
+        sched.lower_order_nums = min(idx, 2)
+        sched.this_order = min(idx, 2) or None
+        sched._have_last = idx > 0 and sched._state is not None
+        out, _ = pipe.denoise_step(idx, ts[idx], latents, cond, image_rgb, pos, neg, img, None, NUM_FRAMES,
+                                   STEPS_PER_VIDEO, ALG)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    idxs = step_indices(args.steps)
+    with torch.no_grad():
+        lat = lat0
+        for w in range(args.warmup):
+            lat = step((0, 10, 11)[w % 3], lat0)
+        # ---------------- device-timed region: inputs resident in HBM ------------------------------------
+        transformer.profile(True)
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        launches0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for idx in idxs:
+            lat = step(idx, lat0)
+        e1.record()
+        barrier()
+        sampler.stop_flag = True
+        launches = _lib.launch_count() - launches0
+        ms_total = e0.elapsed_time(e1)
+        prof = transformer.profile_read()
+        transformer.profile(False)
+        # ---------------- end-to-end region: host buffers in, host result out, every step ----------------
+        host_in = [t.cpu().pin_memory() for t in (lat0, cond, pos, neg, img)]
+        host_out = torch.empty_like(lat0, device="cpu").pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in host_in)
+        d2h = host_out.numel() * host_out.element_size()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for idx in idxs:
+            l_d, c_d, p_d, n_d, i_d = (t.to(device, non_blocking=True) for t in host_in)
+            sched._step_index = idx
+            sched.lower_order_nums = min(idx, 2)
+            sched.this_order = min(idx, 2) or None
+            out, _ = pipe.denoise_step(idx, ts[idx], l_d, c_d, image_rgb, p_d, n_d, i_d, None, NUM_FRAMES, STEPS_PER_VIDEO, ALG)
+            host_out.copy_(out, non_blocking=True)
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+
+    t_dev = torch.tensor([ms_total, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = (float(v) for v in t_dev.tolist())
+    ms_step = ms_total / args.steps
+    fps = world * NUM_FRAMES / (STEPS_PER_VIDEO * ms_step / 1e3)
+    fps_e2e = world * NUM_FRAMES / (STEPS_PER_VIDEO * (ms_e2e / args.steps) / 1e3)
+
+    if rank == 0:
+        hbm, tf_burst, tf_sust, src = peaks()
+        n_tok = T_LAT * (H_LAT // 2) * (W_LAT // 2)
+        sa = prof["self_attention"]
+        passes = sum(n_pass_of(i) for i in idxs)
+        # one self-attention launch covers all passes of a step x 40 heads: flops = 4 * B * heads * N^2 * d_head
+        flops_launch = {p: 4 * p * n_tok * n_tok * 5120 for p in (2, 3)}
+        flops_total = sum(40 * flops_launch[n_pass_of(i)] for i in idxs)
+        achieved = flops_total / (sa["ms"] / 1e3) / 1e12 if sa["ms"] > 0 else None
+        total_flops = passes * forward_flops(n_tok)[0]
+        roofline = {"kernel": "attention_kernel<128> (DiT self-attention, N=32760, 40 heads x 128)", "bound": "tensor",
+                    "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s",
+                    "frac": achieved / tf_sust if achieved else None, "peak_kind": f"bf16_tflops_sustained ({src}); kernel timed inside a long step",
+                    "frac_of_burst_peak": achieved / tf_burst if achieved else None, "traffic": None,
+                    "launches": sa["launches"], "avg_launch_ms": sa["ms"] / max(sa["launches"], 1),
+                    "share_of_step": sa["ms"] / ms_total,
+                    "per_class_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+                    "whole_step_tflops": total_flops / (ms_total / 1e3) / 1e12}
+        cpu = None
+        if world == 1 or True:
+            try:
+                c_fps, c_dt, c_desc, c_thr = cpu_sample(steps=1, warmup=1)
+                cpu = {"value": c_fps, "unit": "frames/s", "cores": c_thr, "kind": "port", "sample": c_desc}
+            except Exception as ex:  # pragma: no cover
+                cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+        line = {
+            "metric": "video frames/sec (Wan-I2V-14B 480p, 81 frames, 50 steps, ALG down_up)", "value": fps,
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Wan-I2V-14B 480x832, 81 frames, 50 steps, ALG down_up f=0.4 interval[0,0.2], gs 5, UniPC "
+                                   "flow_shift 5.0 (BASELINE.json configs[1]); one sample per GPU",
+                       "step_sampling": f"schedule indices {idxs} ({passes} sample-forwards in {args.steps} steps; full video = 110 in 50)",
+                       "weights": "seeded random init at the true 16.4 B-parameter architecture (no checkpoints offline)",
+                       "l2": "inputs_exceed_l2 (32.8 GB of weights stream through the 126 MB L2 every step)",
+                       "parallelism": f"dp{world} (independent samples; NCCL weight broadcast at init only)"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

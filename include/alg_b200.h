@@ -201,6 +201,12 @@ int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents, const floa
  * [n_pass*N, d] bf16 after each block.  Pass NULL to switch it off. */
 int alg_wan_set_debug_buffer(alg_wan_engine_t* e, void* buf, size_t bytes);
 
+/* Device timing per kernel class, measured with CUDA events on the launching stream around every launch of the
+ * forward (classes: 0 self-attention, 1 cross-attention, 2 GEMM, 3 HBM-bound elementwise).  Enable, run forwards,
+ * then read: the read synchronises on the recorded events, returns summed milliseconds + launch counts and resets. */
+int alg_wan_profile(alg_wan_engine_t* e, int enable);
+int alg_wan_profile_read(alg_wan_engine_t* e, float* ms_per_class, int32_t* launches_per_class, int n_classes);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 int64_t alg_launch_count(void);
 

@@ -17,11 +17,14 @@ decides where bf16 roundings happen -- anchored on the reference's call sites:
   * Hy:   ``FlowMatchEulerDiscreteScheduler.from_config(flow_shift, invert_sigmas)`` run.py:82-86;
           ``sigmas = linspace(1, 0, N+1)[:-1]`` hy:1111; ``step(noise[:, :, 1:], t, latents[:, :, 1:])`` hy:1265
 
-Division convention: where upstream divides a CUDA tensor by a 0-dim CPU tensor
-(``(mi - m0) / rk``) ATen's CUDA kernel multiplies by the reciprocal
-(``div_true_kernel_cuda`` CPU-scalar fast path).  The reference runs on CUDA,
-so the oracle restates that (``_div_scalar``); it differs from a true division
-by at most 1 ulp.
+CUDA-scalar convention.  The reference runs on CUDA, where ATen treats a 0-dim CPU
+tensor (or Python number) operand of a CUDA tensor op as a *scalar at opmath (fp32)
+precision*: ``sigma_t * bf16_tensor`` is ``bf16(fp32(sigma_t) * fp32(x))``, and
+``tensor / scalar`` multiplies by the fp32 reciprocal (``div_true_kernel_cuda``).  Plain
+PyTorch ops on CPU tensors would instead round the scalar to the tensor dtype first, so
+this CPU restatement spells the CUDA behaviour out (``_smul`` / ``_div_scalar``); on CUDA
+tensors the same helpers fall through to the plain ops, which is how the ``-m gpu`` tests
+check that the spelling-out is faithful (measured: bit-identical).
 """
 from __future__ import annotations
 
@@ -31,8 +34,21 @@ import numpy as np
 import torch
 
 
-def _div_scalar(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
-    return x * (torch.tensor(1.0, dtype=torch.float32) / s.to(torch.float32))
+def _f32(s) -> torch.Tensor:
+    return torch.as_tensor(s).detach().to("cpu", torch.float32)
+
+
+def _smul(s, x: torch.Tensor) -> torch.Tensor:
+    """``scalar * tensor`` the way ATen's CUDA kernels compute it (scalar enters at fp32, result in x.dtype)."""
+    if x.is_cuda:
+        return s * x
+    return (x.to(torch.float32) * _f32(s)).to(x.dtype)
+
+
+def _div_scalar(x: torch.Tensor, s) -> torch.Tensor:
+    if x.is_cuda:
+        return x / s
+    return x * (torch.tensor(1.0, dtype=torch.float32) / _f32(s))
 
 
 # ----------------------------------------------------------------------------
@@ -102,7 +118,7 @@ class UniPCOracle:
         use_corrector = i > 0 and self.last_sample is not None
         # convert_model_output (flow_prediction, predict_x0): 0-dim fp32 * bf16 tensor -> bf16
         sigma_t = self.sigmas[i]
-        x0_pred = sample - sigma_t * model_output
+        x0_pred = sample - _smul(sigma_t, model_output)
         if use_corrector:
             sample = self._uni_c(x0_pred, self.last_sample, sample, self.this_order)
         for k in range(self.solver_order - 1):
@@ -126,14 +142,14 @@ class UniPCOracle:
         lambdas_prev = [self._lambda(i - k) for k in range(1, order)]
         alpha_t, sigma_t, sigma_s0, h_phi_1, B_h, rks, R, b = self._bh(self.sigmas[i + 1], self.sigmas[i], lambdas_prev, order)
         D1s = [_div_scalar(self.model_outputs[-(k + 1)] - m0, rks[k - 1]) for k in range(1, order)]
-        x_t_ = sigma_t / sigma_s0 * x - alpha_t * h_phi_1 * m0
+        x_t_ = _smul(sigma_t / sigma_s0, x) - _smul(alpha_t * h_phi_1, m0)
         if D1s:
             assert order == 2
             rhos_p = torch.tensor([0.5], dtype=x.dtype)
-            pred_res = rhos_p[0] * D1s[0]
+            pred_res = _smul(rhos_p[0], D1s[0])
         else:
-            pred_res = 0
-        x_t = x_t_ - alpha_t * B_h * pred_res
+            pred_res = torch.zeros((), dtype=x.dtype, device=x.device)
+        x_t = x_t_ - _smul(alpha_t * B_h, pred_res)
         return x_t.to(x.dtype)
 
     def _uni_c(self, model_t, x, this_sample, order):
@@ -146,15 +162,15 @@ class UniPCOracle:
             rhos_c = torch.tensor([0.5], dtype=x.dtype)
         else:
             rhos_c = torch.linalg.solve(R, b).to(x.dtype)
-        x_t_ = sigma_t / sigma_s0 * x - alpha_t * h_phi_1 * m0
+        x_t_ = _smul(sigma_t / sigma_s0, x) - _smul(alpha_t * h_phi_1, m0)
         if D1s:
-            corr_res = rhos_c[0] * D1s[0]
+            corr_res = _smul(rhos_c[0], D1s[0])
             for k in range(1, len(D1s)):
-                corr_res = corr_res + rhos_c[k] * D1s[k]
+                corr_res = corr_res + _smul(rhos_c[k], D1s[k])
         else:
             corr_res = 0
         D1_t = model_t - m0
-        x_t = x_t_ - alpha_t * B_h * (corr_res + rhos_c[-1] * D1_t)
+        x_t = x_t_ - _smul(alpha_t * B_h, corr_res + _smul(rhos_c[-1], D1_t))
         return x_t.to(x.dtype)
 
 
@@ -194,9 +210,9 @@ class CogDDIMOracle:
 
     def step(self, model_output: torch.Tensor, t: int, sample: torch.Tensor) -> torch.Tensor:
         a_t, b_t, a, b = self.coeffs(int(t))
-        # 0-dim fp64 tensors do not promote dimensioned tensors: arithmetic runs in sample.dtype
-        pred_x0 = (a_t ** 0.5) * sample - (b_t ** 0.5) * model_output
-        return a * sample + b * pred_x0
+        # 0-dim fp64 tensors do not promote dimensioned tensors: each product stays in its tensor's dtype
+        pred_x0 = _smul(a_t ** 0.5, sample) - _smul(b_t ** 0.5, model_output)
+        return _smul(a, sample) + _smul(b, pred_x0)
 
 
 # ----------------------------------------------------------------------------
@@ -230,7 +246,13 @@ class FlowEulerOracle:
     def step(self, model_output: torch.Tensor, sample: torch.Tensor) -> torch.Tensor:
         sample = sample.to(torch.float32)
         dt = self.sigmas[self.step_index + 1] - self.sigmas[self.step_index]
-        prev = sample + dt * model_output
+        if model_output.is_cuda:
+            prev = sample + dt.to(model_output.device) * model_output
+        else:
+            # upstream keeps `sigmas` on the device, so dt is a 0-dim CUDA tensor: ATen casts it to the result dtype
+            # (that of model_output) before the multiply -- unlike the CPU-scalar path of `_smul`
+            dt_r = dt.to(model_output.dtype).to(torch.float32)
+            prev = sample + (model_output.to(torch.float32) * dt_r).to(model_output.dtype)
         self.step_index += 1
         return prev.to(model_output.dtype)
 
@@ -244,6 +266,6 @@ def cfg_combine(noise_pred: torch.Tensor, guidance_scale: float, fp32: bool = Fa
         noise_pred = noise_pred.float()
     if noise_pred.shape[0] == 3:
         u0, u, t = noise_pred.chunk(3)
-        return u0 + guidance_scale * (t - u)
+        return u0 + _smul(guidance_scale, t - u)
     u, t = noise_pred.chunk(2)
-    return u + guidance_scale * (t - u)
+    return u + _smul(guidance_scale, t - u)

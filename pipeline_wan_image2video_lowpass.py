@@ -1,0 +1,413 @@
+"""Wan2.1 image-to-video pipeline with Adaptive Low-pass Guidance -- B200-native drop-in.
+
+Same module name, class name, constructor and ``__call__`` signature as the reference's
+``pipeline_wan_image2video_lowpass.WanImageToVideoPipeline`` (reference file:line cited per method), but the per-step
+work runs in ``libalg_b200.so``:
+
+    low-pass filter of the conditioning latent  -> alg_lowpass_down_up / alg_lowpass_gaussian   (wan:869-880)
+    model-input assembly + DiT forward (2-3 passes) -> alg_wan_forward                          (wan:882-917)
+    CFG combine + UniPC scheduler.step          -> alg_cfg_unipc_step                           (wan:919-927)
+
+The ``[latents]*3`` / ``cat`` / ``.to(bf16)`` model input of the reference is never materialised: the engine gathers
+patches straight from the fp32 ``latents`` and the fp32 ``condition`` / low-passed condition.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional, Union
+
+import PIL.Image
+import torch
+
+import lp_utils
+from alg_b200.pipeline_utils import (DiffusionPipelineBase, MultiPipelineCallbacks, PipelineCallback,
+                                     SyntheticImageEncoder, SyntheticTextEncoder, SyntheticVideoVAE, VideoProcessor,
+                                     WanPipelineOutput, randn_tensor)
+from alg_b200.schedulers import UniPCMultistepScheduler
+from alg_b200.wan import WAN_I2V_14B, WanTransformer3DModel
+
+PipelineImageInput = Union[PIL.Image.Image, torch.Tensor, List[PIL.Image.Image]]
+
+WAN_VAE_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508, 0.4134, -0.0715, 0.5517, -0.3632,
+                -0.1922, -0.9497, 0.2503, -0.2921]
+WAN_VAE_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743, 3.2687, 2.1526, 2.8652, 1.5579, 1.6382,
+               1.1253, 2.8251, 1.9160]
+
+
+def retrieve_latents(encoder_output, generator=None, sample_mode: str = "sample"):
+    if hasattr(encoder_output, "latent_dist") and sample_mode == "sample":
+        return encoder_output.latent_dist.sample(generator)
+    if hasattr(encoder_output, "latent_dist") and sample_mode == "argmax":
+        return encoder_output.latent_dist.mode()
+    if hasattr(encoder_output, "latents"):
+        return encoder_output.latents
+    raise AttributeError("Could not access latents of provided encoder_output")
+
+
+class WanImageToVideoPipeline(DiffusionPipelineBase):
+    """Image-to-video generation with Wan2.1 + ALG on the native sm_100a engine (reference class: wan:128-183)."""
+
+    model_cpu_offload_seq = "text_encoder->image_encoder->transformer->vae"
+    _callback_tensor_inputs = ["latents", "prompt_embeds", "negative_prompt_embeds"]
+
+    def __init__(self, tokenizer, text_encoder, image_encoder, image_processor, transformer: WanTransformer3DModel, vae,
+                 scheduler):
+        self.register_modules(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, image_encoder=image_encoder,
+                              transformer=transformer, scheduler=scheduler, image_processor=image_processor)
+        downs = getattr(getattr(vae, "config", None), "temperal_downsample", None)
+        self.vae_scale_factor_temporal = 2 ** sum(downs) if downs is not None else 4
+        self.vae_scale_factor_spatial = 2 ** len(downs) if downs is not None else 8
+        self.video_processor = VideoProcessor(vae_scale_factor=self.vae_scale_factor_spatial)
+
+    # ------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, vae=None, image_encoder=None, transformer=None,
+                        torch_dtype=torch.bfloat16, cache_dir=None, synthetic: Optional[bool] = None, seed: int = 0,
+                        device="cuda", **config_overrides):
+        """run.py:56-61.  Offline there are no checkpoints: ``synthetic=True`` (or ``ALG_SYNTHETIC=1``) builds the
+        true Wan2.1-I2V-14B architecture with seeded random weights directly on ``device``."""
+        import os
+
+        if synthetic is None:
+            synthetic = os.environ.get("ALG_SYNTHETIC", "0") == "1" or str(pretrained_model_name_or_path).startswith("synthetic")
+        if not synthetic:
+            raise NotImplementedError(
+                f"loading real checkpoints ({pretrained_model_name_or_path!r}) needs the diffusers-safetensors weight "
+                "mapper, which is the next scope item (SURVEY 8(f).2); pass synthetic=True or set ALG_SYNTHETIC=1")
+        if transformer is None:
+            transformer = WanTransformer3DModel.from_synthetic(seed=seed, device=device, **config_overrides)
+        if vae is None:
+            vae = SyntheticVideoVAE(z_dim=16, latents_mean=WAN_VAE_MEAN, latents_std=WAN_VAE_STD, dtype=torch.float32)
+        text_dim = transformer.config.text_dim
+        image_dim = transformer.config.image_dim
+        pipe = cls(tokenizer=None, text_encoder=SyntheticTextEncoder(text_dim, torch_dtype),
+                   image_encoder=image_encoder or SyntheticImageEncoder(257, image_dim), image_processor=None,
+                   transformer=transformer, vae=vae, scheduler=UniPCMultistepScheduler(flow_shift=3.0))
+        return pipe
+
+    # ------------------------------------------------------------------------------------------------
+    # once-per-video conditioning (wan:185-316).  Real encoders are out of scope; synthetic ones stand in.
+    def _embed_text(self, prompt, num_videos_per_prompt, max_sequence_length, device, dtype):
+        prompt = [prompt] if isinstance(prompt, str) else prompt
+        emb = self.text_encoder.embed(prompt, max_sequence_length).to(device=device, dtype=dtype or torch.bfloat16)
+        b, s, _ = emb.shape
+        return emb.repeat(1, num_videos_per_prompt, 1).view(b * num_videos_per_prompt, s, -1)
+
+    def encode_image(self, image, device=None):
+        device = device or self._execution_device
+        t = image if torch.is_tensor(image) else self.video_processor.preprocess(image)
+        return self.image_encoder.embed(t).to(device)
+
+    def encode_prompt(self, prompt, negative_prompt=None, do_classifier_free_guidance: bool = True,
+                      num_videos_per_prompt: int = 1, prompt_embeds=None, negative_prompt_embeds=None,
+                      max_sequence_length: int = 226, device=None, dtype=None):
+        device = device or self._execution_device
+        prompt = [prompt] if isinstance(prompt, str) else prompt
+        batch_size = len(prompt) if prompt is not None else prompt_embeds.shape[0]
+        if prompt_embeds is None:
+            prompt_embeds = self._embed_text(prompt, num_videos_per_prompt, max_sequence_length, device, dtype)
+        if do_classifier_free_guidance and negative_prompt_embeds is None:
+            negative_prompt = negative_prompt or ""
+            negative_prompt = batch_size * [negative_prompt] if isinstance(negative_prompt, str) else negative_prompt
+            if prompt is not None and type(prompt) is not type(negative_prompt):
+                raise TypeError(f"`negative_prompt` should be the same type to `prompt`, but got {type(negative_prompt)} !="
+                                f" {type(prompt)}.")
+            if batch_size != len(negative_prompt):
+                raise ValueError(f"`negative_prompt`: {negative_prompt} has batch size {len(negative_prompt)}, but `prompt`:"
+                                 f" {prompt} has batch size {batch_size}. Please make sure that passed `negative_prompt` matches"
+                                 " the batch size of `prompt`.")
+            negative_prompt_embeds = self._embed_text(negative_prompt, num_videos_per_prompt, max_sequence_length, device, dtype)
+        return prompt_embeds, negative_prompt_embeds
+
+    # ------------------------------------------------------------------------------------------------
+    def check_inputs(self, prompt, negative_prompt, image, height, width, prompt_embeds=None,
+                     negative_prompt_embeds=None, image_embeds=None, callback_on_step_end_tensor_inputs=None):
+        """Same ValueErrors, in the same order, as wan:318-370."""
+        if image is not None and image_embeds is not None:
+            raise ValueError(f"Cannot forward both `image`: {image} and `image_embeds`: {image_embeds}. Please make sure to"
+                             " only forward one of the two.")
+        if image is None and image_embeds is None:
+            raise ValueError("Provide either `image` or `prompt_embeds`. Cannot leave both `image` and `image_embeds` undefined.")
+        if image is not None and not isinstance(image, torch.Tensor) and not isinstance(image, PIL.Image.Image):
+            raise ValueError(f"`image` has to be of type `torch.Tensor` or `PIL.Image.Image` but is {type(image)}")
+        if height % 16 != 0 or width % 16 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 16 but are {height} and {width}.")
+        if callback_on_step_end_tensor_inputs is not None:
+            bad = [k for k in callback_on_step_end_tensor_inputs if k not in self._callback_tensor_inputs]
+            if bad:
+                raise ValueError(f"`callback_on_step_end_tensor_inputs` has to be in {self._callback_tensor_inputs}, but found {bad}")
+        if prompt is not None and prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `prompt`: {prompt} and `prompt_embeds`: {prompt_embeds}. Please make sure to"
+                             " only forward one of the two.")
+        if negative_prompt is not None and negative_prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `negative_prompt`: {negative_prompt} and `negative_prompt_embeds`: "
+                             f"{negative_prompt_embeds}. Please make sure to only forward one of the two.")
+        if prompt is None and prompt_embeds is None:
+            raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and `prompt_embeds` undefined.")
+        if prompt is not None and not isinstance(prompt, (str, list)):
+            raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
+        if negative_prompt is not None and not isinstance(negative_prompt, (str, list)):
+            raise ValueError(f"`negative_prompt` has to be of type `str` or `list` but is {type(negative_prompt)}")
+
+    # ------------------------------------------------------------------------------------------------
+    def _latent_norm(self, device, dtype):
+        z = self.vae.config.z_dim
+        mean = torch.tensor(self.vae.config.latents_mean).view(1, z, 1, 1, 1).to(device, dtype)
+        inv_std = 1.0 / torch.tensor(self.vae.config.latents_std).view(1, z, 1, 1, 1).to(device, dtype)
+        return mean, inv_std
+
+    def _first_frame_mask(self, batch_size, num_frames, latent_height, latent_width, device, keep_last=False):
+        """4-channel temporal mask of wan:436-447: ones on the conditioned frame(s), folded 4 frames -> 1 latent frame."""
+        m = torch.ones(batch_size, 1, num_frames, latent_height, latent_width)
+        m[:, :, 1:(num_frames - 1 if keep_last else num_frames)] = 0
+        first = torch.repeat_interleave(m[:, :, 0:1], dim=2, repeats=self.vae_scale_factor_temporal)
+        m = torch.concat([first, m[:, :, 1:, :]], dim=2)
+        m = m.view(batch_size, -1, self.vae_scale_factor_temporal, latent_height, latent_width).transpose(1, 2)
+        return m.to(device)
+
+    def prepare_latents(self, image, batch_size, num_channels_latents=16, height=480, width=832, num_frames=81,
+                        dtype=None, device=None, generator=None, latents=None, last_image=None):
+        """Initial noise + [mask | normalised VAE latent of (image, zeros...)] condition (wan:372-449)."""
+        t_lat = (num_frames - 1) // self.vae_scale_factor_temporal + 1
+        h_lat, w_lat = height // self.vae_scale_factor_spatial, width // self.vae_scale_factor_spatial
+        shape = (batch_size, num_channels_latents, t_lat, h_lat, w_lat)
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an effective batch"
+                             f" size of {batch_size}. Make sure the batch size matches the length of the generators.")
+        if latents is None:
+            latents = randn_tensor(shape, generator=generator, device=device, dtype=dtype)
+        else:
+            latents = latents.to(device=device, dtype=dtype)
+        image = image.unsqueeze(2)
+        pad = image.new_zeros(image.shape[0], image.shape[1], num_frames - (1 if last_image is None else 2), height, width)
+        clip = [image, pad] if last_image is None else [image, pad, last_image.unsqueeze(2)]
+        video_condition = torch.cat(clip, dim=2).to(device=device, dtype=self.vae.dtype)
+        mean, inv_std = self._latent_norm(latents.device, latents.dtype)
+        if isinstance(generator, list):
+            cond = torch.cat([retrieve_latents(self.vae.encode(video_condition), sample_mode="argmax") for _ in generator])
+        else:
+            cond = retrieve_latents(self.vae.encode(video_condition), sample_mode="argmax").repeat(batch_size, 1, 1, 1, 1)
+        cond = (cond.to(dtype) - mean) * inv_std
+        mask = self._first_frame_mask(batch_size, num_frames, h_lat, w_lat, cond.device, keep_last=last_image is not None)
+        return latents, torch.concat([mask, cond], dim=1)
+
+    def prepare_lp(self, lp_filter_type, lp_blur_sigma, lp_blur_kernel_size, lp_resize_factor, generator, num_frames,
+                   use_low_pass_guidance, lp_filter_in_latent, orig_image_latents, orig_image_tensor):
+        """Low-passed copy of the image condition (wan:451-559).  In-latent: one CUDA launch on the 20-channel
+        ``condition``.  Pixel space: filter RGB, then VAE-encode + ``sample(generator)`` every call (RNG order kept)."""
+        if not use_low_pass_guidance:
+            return None
+        if lp_filter_in_latent:
+            lp = lp_utils.apply_low_pass_filter(orig_image_latents, filter_type=lp_filter_type, blur_sigma=lp_blur_sigma,
+                                                blur_kernel_size=lp_blur_kernel_size, resize_factor=lp_resize_factor)
+            # wan:550-556 tests size(1) (channels) against patch_size[0] == 1: a no-op for every Wan checkpoint (quirk q7)
+            assert lp.size(1) % self.transformer.config.patch_size[0] == 0
+            return lp.to(dtype=orig_image_latents.dtype)
+        image_lp = lp_utils.apply_low_pass_filter(orig_image_tensor, filter_type=lp_filter_type, blur_sigma=lp_blur_sigma,
+                                                  blur_kernel_size=lp_blur_kernel_size, resize_factor=lp_resize_factor)
+        frame = image_lp.unsqueeze(2)
+        b, _, height, width = orig_image_tensor.shape
+        clip = torch.cat([frame, frame.new_zeros(b, frame.shape[1], num_frames - 1, height, width)], dim=2)
+        mean, inv_std = self._latent_norm(image_lp.device, image_lp.dtype)
+        encoded = self.vae.encode(clip).latent_dist.sample(generator=generator)
+        cond = (encoded - mean) * inv_std
+        mask = self._first_frame_mask(b, num_frames, height // self.vae_scale_factor_spatial,
+                                      width // self.vae_scale_factor_spatial, cond.device)
+        return torch.concat([mask, cond], dim=1).to(dtype=orig_image_latents.dtype)
+
+    # ------------------------------------------------------------------------------------------------
+    @property
+    def guidance_scale(self):
+        return self._guidance_scale
+
+    @property
+    def do_classifier_free_guidance(self):
+        return self._guidance_scale > 1
+
+    @property
+    def num_timesteps(self):
+        return self._num_timesteps
+
+    @property
+    def current_timestep(self):
+        return self._current_timestep
+
+    @property
+    def interrupt(self):
+        return self._interrupt
+
+    @property
+    def attention_kwargs(self):
+        return self._attention_kwargs
+
+    # ------------------------------------------------------------------------------------------------
+    def denoise_step(self, i, t, latents, condition, image, prompt_embeds, negative_prompt_embeds, image_embeds,
+                     generator, num_frames, num_inference_steps, alg: Dict[str, Any]):
+        """One iteration of wan:844-927 for a single sample: returns (new latents, bf16 noise prediction of all passes)."""
+        guidance_scale = self._guidance_scale
+        if not self.do_classifier_free_guidance:
+            # the reference leaves latent_model_input undefined here (NameError, quirk q2); fail with a clear message
+            raise ValueError("WanImageToVideoPipeline needs guidance_scale > 1 (the reference has no unguided branch)")
+        lp_latents, strength = None, 0.0
+        if alg["use_low_pass_guidance"]:
+            strength = lp_utils.get_lp_strength(
+                step_index=i, total_steps=num_inference_steps,
+                lp_strength_schedule_type=alg["lp_strength_schedule_type"],
+                schedule_interval_start_time=alg["schedule_interval_start_time"],
+                schedule_interval_end_time=alg["schedule_interval_end_time"],
+                schedule_linear_start_weight=alg["schedule_linear_start_weight"],
+                schedule_linear_end_weight=alg["schedule_linear_end_weight"],
+                schedule_linear_end_time=alg["schedule_linear_end_time"],
+                schedule_exp_decay_rate=alg["schedule_exp_decay_rate"])
+            sigma = alg["lp_blur_sigma"] * strength
+            ksize = alg["lp_blur_kernel_size"] * strength if alg["schedule_blur_kernel_size"] else alg["lp_blur_kernel_size"]
+            factor = 1.0 - (1.0 - alg["lp_resize_factor"]) * strength
+            lp_latents = self.prepare_lp(lp_filter_type=alg["lp_filter_type"], lp_blur_sigma=sigma,
+                                         lp_blur_kernel_size=ksize, lp_resize_factor=factor, generator=generator,
+                                         num_frames=num_frames, use_low_pass_guidance=True,
+                                         lp_filter_in_latent=alg["lp_filter_in_latent"], orig_image_latents=condition,
+                                         orig_image_tensor=image)
+        if alg["use_low_pass_guidance"] and strength != 0.0:  # three passes: uncond(orig), uncond(LP), text(LP)
+            conds = [condition[0], lp_latents[0], lp_latents[0]]
+            texts = [negative_prompt_embeds[0], negative_prompt_embeds[0], prompt_embeds[0]]
+        else:  # vanilla CFG
+            conds = [condition[0], condition[0]]
+            texts = [negative_prompt_embeds[0], prompt_embeds[0]]
+        noise_pred = self.transformer.forward_passes([latents[0]] * len(conds), conds, texts, image_embeds[0], int(t))
+        latents = self.scheduler.step_cfg(noise_pred, guidance_scale, latents)
+        return latents, noise_pred
+
+    @torch.no_grad()
+    def __call__(
+        self,
+        image: PipelineImageInput,
+        prompt: Union[str, List[str]] = None,
+        negative_prompt: Union[str, List[str]] = None,
+        height: int = 480,
+        width: int = 832,
+        num_frames: int = 81,
+        num_inference_steps: int = 50,
+        guidance_scale: float = 5.0,
+        num_videos_per_prompt: Optional[int] = 1,
+        generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+        latents: Optional[torch.Tensor] = None,
+        prompt_embeds: Optional[torch.Tensor] = None,
+        negative_prompt_embeds: Optional[torch.Tensor] = None,
+        image_embeds: Optional[torch.Tensor] = None,
+        last_image: Optional[torch.Tensor] = None,
+        output_type: Optional[str] = "np",
+        return_dict: bool = True,
+        attention_kwargs: Optional[Dict[str, Any]] = None,
+        callback_on_step_end: Optional[
+            Union[Callable[[int, int, Dict], None], PipelineCallback, MultiPipelineCallbacks]
+        ] = None,
+        callback_on_step_end_tensor_inputs: List[str] = ["latents"],
+        max_sequence_length: int = 512,
+        use_low_pass_guidance: bool = False,
+        lp_filter_type: str = "none",
+        lp_filter_in_latent: bool = False,
+        lp_blur_sigma: float = 15.0,
+        lp_blur_kernel_size: float = 0.02734375,
+        lp_resize_factor: float = 0.25,
+        lp_strength_schedule_type: str = "none",
+        schedule_blur_kernel_size: bool = False,
+        schedule_interval_start_time: float = 0.0,
+        schedule_interval_end_time: float = 0.05,
+        schedule_linear_start_weight: float = 1.0,
+        schedule_linear_end_weight: float = 0.0,
+        schedule_linear_end_time: float = 0.5,
+        schedule_exp_decay_rate: float = 10.0,
+    ):
+        """Generate a video (wan:587-970).  Arguments, defaults and return type are those of the reference."""
+        if isinstance(callback_on_step_end, (PipelineCallback, MultiPipelineCallbacks)):
+            callback_on_step_end_tensor_inputs = callback_on_step_end.tensor_inputs
+        self.check_inputs(prompt, negative_prompt, image, height, width, prompt_embeds, negative_prompt_embeds,
+                          image_embeds, callback_on_step_end_tensor_inputs)
+        if num_frames % self.vae_scale_factor_temporal != 1:
+            num_frames = num_frames // self.vae_scale_factor_temporal * self.vae_scale_factor_temporal + 1
+        num_frames = max(num_frames, 1)
+        self._guidance_scale = guidance_scale
+        self._attention_kwargs = attention_kwargs
+        self._current_timestep = None
+        self._interrupt = False
+        device = self._execution_device
+
+        if prompt is not None and isinstance(prompt, str):
+            batch_size = 1
+        elif prompt is not None and isinstance(prompt, list):
+            batch_size = len(prompt)
+        else:
+            batch_size = prompt_embeds.shape[0]
+        if batch_size * num_videos_per_prompt != 1:
+            raise NotImplementedError("the native loop runs one sample per GPU (independent samples shard across GPUs)")
+
+        prompt_embeds, negative_prompt_embeds = self.encode_prompt(
+            prompt=prompt, negative_prompt=negative_prompt, do_classifier_free_guidance=self.do_classifier_free_guidance,
+            num_videos_per_prompt=num_videos_per_prompt, prompt_embeds=prompt_embeds,
+            negative_prompt_embeds=negative_prompt_embeds, max_sequence_length=max_sequence_length, device=device)
+        transformer_dtype = self.transformer.dtype
+        prompt_embeds = prompt_embeds.to(device, transformer_dtype)
+        if negative_prompt_embeds is not None:
+            negative_prompt_embeds = negative_prompt_embeds.to(device, transformer_dtype)
+        if image_embeds is None:
+            if last_image is None:
+                image_embeds = self.encode_image(image, device)
+            else:
+                image_embeds = self.encode_image([image, last_image], device)
+                image_embeds = image_embeds.reshape(-1, 2 * image_embeds.shape[1], image_embeds.shape[2])
+        image_embeds = image_embeds.repeat(batch_size, 1, 1).to(device, transformer_dtype)
+
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        timesteps = self.scheduler.timesteps
+        timesteps_host = timesteps.tolist()
+
+        num_channels_latents = self.vae.config.z_dim
+        if image is not None:
+            image = self.video_processor.preprocess(image, height=height, width=width).to(device, dtype=torch.float32)
+        else:
+            image = torch.zeros(1, 3, height, width, device=device)
+        if last_image is not None:
+            last_image = self.video_processor.preprocess(last_image, height=height, width=width).to(device, dtype=torch.float32)
+        latents, condition = self.prepare_latents(image, batch_size * num_videos_per_prompt, num_channels_latents, height,
+                                                  width, num_frames, torch.float32, device, generator, latents, last_image)
+
+        alg = dict(use_low_pass_guidance=use_low_pass_guidance, lp_filter_type=lp_filter_type,
+                   lp_filter_in_latent=lp_filter_in_latent, lp_blur_sigma=lp_blur_sigma,
+                   lp_blur_kernel_size=lp_blur_kernel_size, lp_resize_factor=lp_resize_factor,
+                   lp_strength_schedule_type=lp_strength_schedule_type, schedule_blur_kernel_size=schedule_blur_kernel_size,
+                   schedule_interval_start_time=schedule_interval_start_time,
+                   schedule_interval_end_time=schedule_interval_end_time,
+                   schedule_linear_start_weight=schedule_linear_start_weight,
+                   schedule_linear_end_weight=schedule_linear_end_weight, schedule_linear_end_time=schedule_linear_end_time,
+                   schedule_exp_decay_rate=schedule_exp_decay_rate)
+
+        num_warmup_steps = len(timesteps) - num_inference_steps * self.scheduler.order
+        self._num_timesteps = len(timesteps)
+        with self.progress_bar(total=num_inference_steps) as progress_bar:
+            for i, t_host in enumerate(timesteps_host):
+                if self.interrupt:
+                    continue
+                t = timesteps[i]
+                self._current_timestep = t
+                latents, _ = self.denoise_step(i, t_host, latents, condition, image, prompt_embeds, negative_prompt_embeds,
+                                               image_embeds, generator, num_frames, num_inference_steps, alg)
+                if callback_on_step_end is not None:
+                    scope = dict(latents=latents, prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds)
+                    outputs = callback_on_step_end(self, i, t, {k: scope[k] for k in callback_on_step_end_tensor_inputs})
+                    latents = outputs.pop("latents", latents)
+                    prompt_embeds = outputs.pop("prompt_embeds", prompt_embeds)
+                    negative_prompt_embeds = outputs.pop("negative_prompt_embeds", negative_prompt_embeds)
+                if i == len(timesteps) - 1 or ((i + 1) > num_warmup_steps and (i + 1) % self.scheduler.order == 0):
+                    progress_bar.update()
+        self._current_timestep = None
+
+        if output_type != "latent":
+            z = latents.to(self.vae.dtype)
+            mean, inv_std = self._latent_norm(z.device, z.dtype)
+            video = self.vae.decode(z / inv_std + mean, return_dict=False)[0]
+            video = self.video_processor.postprocess_video(video, output_type=output_type)
+        else:
+            video = latents
+        self.maybe_free_model_hooks()
+        if not return_dict:
+            return (video,)
+        return WanPipelineOutput(frames=video)

@@ -78,6 +78,25 @@ def sec_lowpass():
     print("down_up 8192 planes ms", ms, "GB/s", 2 * x.numel() * 4 / ms / 1e6)
 
 
+def sec_aa():
+    import torch
+    import torch.nn.functional as F
+    from alg_b200 import lowpass
+    print("ALG_AA_VARIANT", os.environ.get("ALG_AA_VARIANT"))
+    torch.manual_seed(0)
+    for dt in (torch.bfloat16, torch.float16):
+        for shape, f in (((1, 16, 13, 60, 90), 0.25), ((1, 4, 2, 60, 104), 0.4), ((2, 3, 31, 45), 0.6), ((1, 2, 64, 64), 0.5)):
+            x = torch.randn(shape, device="cuda").to(dt)
+            y = lowpass.apply_low_pass_filter(x, "down_up", 0.0, 0.0, f)
+            H, W = shape[-2:]
+            h1, w1 = max(1, int(round(H * f))), max(1, int(round(W * f)))
+            v = x.reshape(-1, 1, H, W)
+            small = F.interpolate(v, size=(h1, w1), mode="bilinear", antialias=True)
+            r = F.interpolate(small, size=(H, W), mode="bilinear", antialias=True).view(shape)
+            d = y.float() - r.float()
+            print(dt, shape, f, "frac_ne", float((d != 0).float().mean()), "max", float(d.abs().max()), "rel", _rel(y, r))
+
+
 def sec_sched():
     import torch
     from alg_b200 import schedulers as S

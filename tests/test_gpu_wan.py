@@ -1,0 +1,150 @@
+"""Native Wan DiT engine + ALG loop vs the oracle restatement (eager PyTorch), through the pipeline / C ABI.
+
+Tolerance protocol: two independent bf16 implementations of a DiT differ by ~1e-2 in noise_pred, so
+the engine is required to be no further from an fp32 evaluation (same bf16-rounded weights) than eager PyTorch bf16
+is (x1.5 slack), and per-step latents teacher-forced within 1e-3 relative L2 of the oracle loop."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(seed=0, **over):
+    import __graft_entry__ as G
+    from alg_b200 import wan
+    cfg, model, inputs, alg = G.tiny_problem("cuda", seed)
+    if over:
+        cfg = dict(cfg, **over)
+        model = wan.WanTransformer3DModel.from_synthetic(seed=seed + 3, device="cuda", **cfg)
+    return cfg, model, inputs, alg
+
+
+def _oracle_forward(cfg, sd, lat, conds, texts, img, t, fp32=False):
+    from oracle import wan_oracle as W
+    ocfg = W.WanConfig(**cfg)
+    n = len(conds)
+    x = torch.cat([torch.stack([lat] * n), torch.stack(conds)], dim=1).bfloat16()
+    text = torch.stack(texts)
+    im = img[None].repeat(n, 1, 1)
+    tt = torch.tensor([t] * n, device=x.device)
+    if fp32:
+        sd = {k: v.float() for k, v in sd.items()}
+        x, text, im = x.float(), text.float(), im.float()
+    return W.forward(sd, ocfg, x, tt, text, im)
+
+
+@pytest.mark.parametrize("n_pass", [2, 3])
+@pytest.mark.parametrize("over", [{}, {"num_attention_heads": 3, "ffn_dim": 1000, "num_layers": 3}])
+def test_forward_matches_oracle(n_pass, over):
+    cfg, model, inp, _ = _problem(1, **over)
+    lat, c0 = inp["latents"][0], inp["condition"][0]
+    c1 = torch.randn_like(c0)
+    conds = [c0, c1, c1][:n_pass] if n_pass == 3 else [c0, c0]
+    texts = ([inp["negative_prompt_embeds"][0]] * (n_pass - 1)) + [inp["prompt_embeds"][0]]
+    img = inp["image_embeds"][0]
+    out = model.forward_passes([lat] * n_pass, conds, texts, img, 987)
+    sd = model.state_dict()
+    ref16 = _oracle_forward(cfg, sd, lat, conds, texts, img, 987)
+    ref32 = _oracle_forward(cfg, sd, lat, conds, texts, img, 987, fp32=True)
+    e_eng, e_torch = rel_l2(out, ref32), rel_l2(ref16, ref32)
+    assert e_eng < max(1.5 * e_torch, 2e-3), (e_eng, e_torch)
+    assert rel_l2(out, ref16) < 2e-2
+    # diffusers-style call on the pre-batched bf16 input gives the same result (wan:910-917 signature)
+    x = torch.cat([torch.stack([lat] * n_pass), torch.stack(conds)], dim=1).bfloat16()
+    out2 = model(hidden_states=x, timestep=torch.tensor([987] * n_pass, device="cuda"),
+                 encoder_hidden_states=torch.stack(texts), encoder_hidden_states_image=img[None].repeat(n_pass, 1, 1),
+                 return_dict=False)[0]
+    assert torch.equal(out2, out)
+
+
+def test_forward_full_width_one_block():
+    """True Wan width (40 heads x 128, ffn 13824, text 4096, image 1280), one block, 1 560 tokens."""
+    from alg_b200 import wan
+    cfg = dict(wan.WAN_I2V_14B, num_layers=1)
+    cfg.pop("cross_attn_norm"); cfg.pop("qk_norm"); cfg.pop("added_kv_proj_dim")
+    model = wan.WanTransformer3DModel.from_synthetic(seed=5, device="cuda", num_layers=1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    T, H, W = 1, 60, 104
+    lat = torch.randn(16, T, H, W, generator=g, device="cuda")
+    c0 = torch.randn(20, T, H, W, generator=g, device="cuda")
+    neg, pos = (torch.randn(512, 4096, generator=g, device="cuda").bfloat16() for _ in range(2))
+    img = torch.randn(257, 1280, generator=g, device="cuda").bfloat16()
+    out = model.forward_passes([lat, lat], [c0, c0], [neg, pos], img, 500)
+    ocfg = {k: v for k, v in cfg.items()}
+    sd = model.state_dict()
+    ref16 = _oracle_forward(ocfg, sd, lat, [c0, c0], [neg, pos], img, 500)
+    ref32 = _oracle_forward(ocfg, sd, lat, [c0, c0], [neg, pos], img, 500, fp32=True)
+    e_eng, e_torch = rel_l2(out, ref32), rel_l2(ref16, ref32)
+    assert e_eng < max(1.5 * e_torch, 2e-3), (e_eng, e_torch)
+
+
+def test_loop_teacher_forced_per_step_latents():
+    """Per-step latent relative L2 <= 1e-3 (north_star), both sides consuming the oracle's x_i."""
+    import __graft_entry__ as G
+    from alg_b200.schedulers import UniPCMultistepScheduler
+    from pipeline_wan_image2video_lowpass import WanImageToVideoPipeline
+    cfg, model, inp, alg = _problem(2)
+    steps = 6
+    ref, per_step = G.oracle_loop(cfg, model.state_dict(), inp, alg, steps, 5.0)
+    xs = [inp["latents"]] + [p[0] for p in per_step]
+    pipe = WanImageToVideoPipeline.from_pretrained("synthetic", transformer=model, synthetic=True)
+    pipe.scheduler = UniPCMultistepScheduler.from_config(pipe.scheduler.config, flow_shift=5.0)
+    pipe.to("cuda")
+    pipe._guidance_scale = 5.0
+    sched = pipe.scheduler
+    sched.set_timesteps(steps, device="cuda")
+    image = torch.zeros(1, 3, 128, 192, device="cuda")
+    n3 = 0
+    for i, t in enumerate(sched.timesteps.tolist()):
+        x_next, npred = pipe.denoise_step(i, t, xs[i], inp["condition"], image, inp["prompt_embeds"],
+                                          inp["negative_prompt_embeds"], inp["image_embeds"], None, 9, steps, alg)
+        n3 += npred.shape[0] == 3
+        assert npred.shape[0] == per_step[i][1].shape[0]
+        # scheduler history is the engine's own, so after step 0 this also accumulates a little multistep state error
+        assert rel_l2(x_next, xs[i + 1]) < 1e-3, (i, rel_l2(x_next, xs[i + 1]))
+    assert n3 == 3  # interval [0, 0.4] of 6 steps -> steps 0, 1, 2 run three passes
+
+
+def test_pipeline_call_surface_and_callbacks():
+    import inspect
+    from pipeline_wan_image2video_lowpass import WanImageToVideoPipeline
+    cfg, model, inp, alg = _problem(3)
+    pipe = WanImageToVideoPipeline.from_pretrained("synthetic", transformer=model, synthetic=True).to("cuda")
+    pipe.set_progress_bar_config(disable=True)
+    names = list(inspect.signature(pipe.__call__).parameters)
+    assert names[:8] == ["image", "prompt", "negative_prompt", "height", "width", "num_frames", "num_inference_steps", "guidance_scale"]
+    assert len(names) == 35 and names[-1] == "schedule_exp_decay_rate"
+    seen = []
+
+    def cb(p, i, t, kw):
+        seen.append((i, int(t), kw["latents"].shape))
+        if i == 1:
+            p._interrupt = True
+        return {}
+
+    kw = dict(image=None, image_embeds=inp["image_embeds"], prompt_embeds=inp["prompt_embeds"],
+              negative_prompt_embeds=inp["negative_prompt_embeds"], height=128, width=192, num_frames=9,
+              num_inference_steps=4, output_type="latent", callback_on_step_end=cb)
+    out = pipe(generator=torch.Generator("cuda").manual_seed(42), **kw, **alg)
+    assert [s[0] for s in seen] == [0, 1] and out.frames.shape == (1, 16, 3, 16, 24)
+    frames = pipe(generator=torch.Generator("cuda").manual_seed(42), **dict(kw, callback_on_step_end=None, output_type="np",
+                                                                          num_inference_steps=2), **alg).frames
+    assert frames.shape == (1, 9, 128, 192, 3)
+    with pytest.raises(ValueError, match="divisible by 16"):
+        pipe(**dict(kw, height=100), **alg)
+    with pytest.raises(ValueError, match="guidance_scale > 1"):
+        pipe(**dict(kw, guidance_scale=1.0), **alg)
+    with pytest.raises(ValueError, match="Cannot forward both `prompt`"):
+        pipe(**dict(kw, prompt="x"), **alg)
+    # prompts through the (synthetic) text encoder, PIL image through the (synthetic) VAE / image encoder
+    from PIL import Image
+    out = pipe(image=Image.new("RGB", (200, 130), (120, 30, 60)), prompt="a red bus", negative_prompt="blurry", height=128,
+               width=192, num_frames=9, num_inference_steps=2, output_type="latent", max_sequence_length=32, **alg)
+    assert torch.isfinite(out.frames).all()
+
+
+def test_smoke_entry():
+    import __graft_entry__ as G
+    G.smoke()
