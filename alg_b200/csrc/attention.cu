@@ -16,6 +16,8 @@
 // V is consumed TRANSPOSED ([head_dim, n_kv], produced directly by the V projection GEMM with swapped operands) so
 // that both MMAs use K-major operands.
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 #include "tc_common.cuh"
 
@@ -27,6 +29,9 @@ constexpr int BQ = 128;   // query rows per tile (two tiles per CTA)
 constexpr int BKV = 128;  // keys per pipeline step
 constexpr int kThreads = 320;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+#ifndef ALG_ATTN_POLY_DEFAULT
+#define ALG_ATTN_POLY_DEFAULT 4
+#endif
 
 template <int D>
 struct Cfg {
@@ -53,7 +58,32 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int D>
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+  return r;
+}
+// 2^x for a pair on the FMA pipe instead of MUFU (relieves the 16/clk/SM ex2 unit, which at 128 x 128 exps per
+// 128 x 128 x 128 MMA pair is exactly as busy as the tensor pipe): Cody-Waite split x = n + f, |f| <= 0.5, degree-3
+// minimax 2^f (7.5e-5 relative, below the bf16 rounding of P), exponent patched in with integer adds.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);  // 1.5 * 2^23: low mantissa bits of t hold rint(x)
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(make_float2(0.0551716685295105f, 0.0551716685295105f), f,
+                        make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return p;
+}
+
+// POLY = 0: every exp2 on MUFU; POLY = n > 0: one pair in every n pairs of a row goes through ex2_poly2.
+template <int D, int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Params p) {
@@ -90,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
@@ -189,23 +219,31 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int row = q0 + i * BQ + quad * 32 + lane;
     float m_used = -INFINITY, l = 0.f;
     const float c = p.scale_log2;
-    for (int j = 0; j < n_tiles; ++j) {
+    // one key tile of online softmax; `ragged` (compile-time) is the last, partially filled tile -- kept out of the
+    // main loop body, where the compiler would otherwise if-convert the mask into 255 always-executed selects
+    auto softmax_step = [&](const int j, auto ragged) {
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
       float s[128];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) tmem_ld32(t_s + ch * 32, reinterpret_cast<uint32_t*>(s) + ch * 32);
       tmem_ld_wait();
-      const int valid = p.n_kv - j * BKV;
-      if (valid < BKV) {  // ragged last key tile: TMA zero-filled the tail, mask it out
+      if constexpr (decltype(ragged)::value) {  // TMA zero-filled the tail of the tile: mask it out
+        const int valid = p.n_kv - j * BKV;
 #pragma unroll
         for (int k = 0; k < 128; ++k)
           if (k >= valid) s[k] = -INFINITY;
       }
-      float mx = s[0];
+// row max: four independent FMNMX3 chains (a single dependent chain of 127 max ops costs ~500 cycles)
+      float mc[4];
 #pragma unroll
-      for (int k = 1; k < 128; ++k) mx = fmaxf(mx, s[k]);
-      mx *= c;
+      for (int g = 0; g < 4; ++g) {
+        float m = s[g * 32];
+#pragma unroll
+        for (int k = 1; k + 1 < 32; k += 2) m = max3(m, s[g * 32 + k], s[g * 32 + k + 1]);
+        mc[g] = fmaxf(m, s[g * 32 + 31]);
+      }
+      float mx = fmaxf(max3(mc[0], mc[1], mc[2]), mc[3]) * c;
       if (j == 0) {
         m_used = mx;
       } else {
@@ -226,26 +264,38 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
       }
-      const float neg_m = -m_used;
-      float sum = 0.f;
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_used, -m_used);
+      float2 sum0 = make_float2(0.f, 0.f), sum1 = sum0;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t pk[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float a = ex2(fmaf(s[ch * 32 + 2 * k], c, neg_m));
-          const float b = ex2(fmaf(s[ch * 32 + 2 * k + 1], c, neg_m));
-          sum += a + b;
-          __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          const float2 x = __ffma2_rn(make_float2(s[ch * 32 + 2 * k], s[ch * 32 + 2 * k + 1]), c2, nm2);
+          float2 e;
+          if (POLY > 0 && (k % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
+            e = ex2_poly2(x);
+          } else {
+            e.x = ex2(x.x);
+            e.y = ex2(x.y);
+          }
+          if (k & 1) sum1 = __fadd2_rn(sum1, e);
+          else sum0 = __fadd2_rn(sum0, e);
+          __nv_bfloat162 h = __floats2bfloat162_rn(e.x, e.y);
           pk[k] = *reinterpret_cast<uint32_t*>(&h);
         }
         tmem_st16(t_s + ch * 16, pk);  // P (bf16 pairs) overwrites the first 64 columns of S
       }
-      l += sum;
+      l += (sum0.x + sum0.y) + (sum1.x + sum1.y);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[i]);
-    }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[i]);
+    };
+    const int n_full = p.n_kv / BKV;
+#pragma unroll 1
+    for (int j = 0; j < n_full; ++j) softmax_step(j, std::false_type{});
+    if (n_full < n_tiles) softmax_step(n_full, std::true_type{});
     // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------------
     mbar_wait(&o_full[i], 0);
     tc_fence_after();
@@ -289,12 +339,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-template <int D>
+template <int D, int POLY>
 static int launch(const alg_attention_t* a, cudaStream_t st) {
   using C = Cfg<D>;
   static bool attr_done = false;
   if (!attr_done) {
-    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_done = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -324,7 +374,7 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
   dim3 grid((unsigned)((a->n_q + 2 * BQ - 1) / (2 * BQ)), (unsigned)a->heads, (unsigned)a->batch);
-  attention_kernel<D><<<grid, kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  attention_kernel<D, POLY><<<grid, kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
   ALG_LAUNCH_OK();
   return 0;
 }
@@ -345,5 +395,19 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   ALG_REQUIRE((reinterpret_cast<uintptr_t>(a->O) & 15) == 0, "attention: O must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return a->head_dim == 128 ? attn::launch<128>(a, st) : attn::launch<64>(a, st);
+  static int poly = -1;  // tuning knob: share of exp2 evaluated on the FMA pipe (1 pair in `poly`), default from profiling
+  if (poly < 0) {
+    const char* e = getenv("ALG_ATTN_POLY");
+    poly = e ? atoi(e) : ALG_ATTN_POLY_DEFAULT;
+  }
+  if (a->head_dim == 128) {
+    switch (poly) {
+      case 0: return attn::launch<128, 0>(a, st);
+      case 2: return attn::launch<128, 2>(a, st);
+      case 3: return attn::launch<128, 3>(a, st);
+      case 4: return attn::launch<128, 4>(a, st);
+      default: return attn::launch<128, 8>(a, st);
+    }
+  }
+  return poly == 0 ? attn::launch<64, 0>(a, st) : attn::launch<64, 4>(a, st);
 }

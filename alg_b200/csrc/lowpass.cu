@@ -23,28 +23,23 @@ float host_round_f16(float f) { return __half2float(__float2half_rn(f)); }
 // --------------------------------------------------------------------------------------------
 // ATen anti-aliased triangle-filter weights (align_corners = false), fp32 like the CUDA kernel
 // --------------------------------------------------------------------------------------------
-struct Band {  // CSR-ish resampling operator: out[i] = sum_k w[off[i] + k] * in[start[i] + k]
-  std::vector<int> start, off;
-  std::vector<float> w;
-  int max_band = 0;
+struct Band {  // banded resampling operator: out[i] = sum_{k < cnt[i]} w[i * stride + k] * in[start[i] + k]
+  std::vector<int> start, cnt;
+  std::vector<float> w;  // [n_out][stride], zero padded
+  int stride = 1;
 };
 
-// For 16-bit tensors ATen's CUDA kernel keeps the taps in the tensor dtype (UpSample.cuh:_compute_weights:
-// `wt_ptr[j] = scalar_t(w)`, then `wt_ptr[j] /= total_w`), so they are rounded here the same way.
-static int aa_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ALG_AA_VARIANT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
+// ATen's CUDA kernel (UpSampleBilinear2d.cu: upsample_gen2d_aa_out_frame, _compute_weights_span, _compute_weights)
+// computes the taps in fp32, stores them in the tensor dtype (`wt_ptr[j] = scalar_t(w)`) and normalises in place with
+// `wt_ptr[j] /= total_w` -- for a 16-bit scalar_t that is scalar_t / scalar_t, i.e. the fp32 total is itself rounded to
+// the tensor dtype before the divide (torch/include/ATen/native/cuda/UpSample.cuh:322-347): rounded here the same way.
 static Band make_band(int in_size, int out_size, int dt) {
   Band b;
   const float scale = (float)in_size / (float)out_size;
   const float support = scale >= 1.0f ? scale : 1.0f;
-  const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
-  b.off.push_back(0);
+  const float invscale = scale >= 1.0f ? (float)(1.0 / (double)scale) : 1.0f;
+  std::vector<std::vector<float>> rows(out_size);
+  int max_band = 1;
   for (int i = 0; i < out_size; ++i) {
     const float center = scale * ((float)i + 0.5f);
     int xmin = (int)(center - support + 0.5f);
@@ -53,35 +48,39 @@ static Band make_band(int in_size, int out_size, int dt) {
     if (xmax > in_size) xmax = in_size;
     int n = xmax - xmin;
     if (n < 0) n = 0;
+    const float xmin_m_center = (float)xmin - center;
     float total = 0.f;
     std::vector<float> ws(n);
     for (int j = 0; j < n; ++j) {
-      float x = ((float)(j + xmin) - center + 0.5f) * invscale;
+      float x = ((float)j + xmin_m_center + 0.5f) * invscale;
       float v = 1.0f - fabsf(x);
       ws[j] = v > 0.f ? v : 0.f;
       total += ws[j];
     }
     for (int j = 0; j < n; ++j) {
       float w = host_round(ws[j], dt);
-      if (total != 0.f) {
-        const float tot = (dt != ALG_F32 && aa_variant() == 1) ? host_round(total, dt) : total;
-        w = host_round(w / tot, dt);
-      }
-      b.w.push_back(w);
+      if (total != 0.f) w = host_round(w / host_round(total, dt), dt);
+      ws[j] = w;
     }
     b.start.push_back(xmin);
-    b.off.push_back((int)b.w.size());
-    if (n > b.max_band) b.max_band = n;
+    b.cnt.push_back(n);
+    if (n > max_band) max_band = n;
+    rows[i] = ws;
   }
+  b.stride = max_band | 1;  // odd stride: column-parallel reads of the table spread over the banks
+  b.w.assign((size_t)out_size * b.stride, 0.f);
+  for (int i = 0; i < out_size; ++i)
+    for (size_t k = 0; k < rows[i].size(); ++k) b.w[(size_t)i * b.stride + k] = rows[i][k];
   return b;
 }
 
 // Device tables of one (H, W, h1, w1) geometry: 4 operators packed in one allocation.
 struct DownUpTables {
-  int* ints = nullptr;      // [start | off] x 4
+  int* ints = nullptr;  // [start | cnt] x 4
   float* weights = nullptr;
-  // element offsets into ints / weights
-  int s_off[4], o_off[4], w_off[4];
+  int n_ints = 0, n_weights = 0;
+  // element offsets into ints / weights, and the per-operator weight row stride
+  int s_off[4], c_off[4], w_off[4], stride[4];
 };
 
 static std::mutex g_tab_mu;
@@ -113,11 +112,14 @@ static int get_tables(int H, int W, int h1, int w1, int dt, DownUpTables* out) {
   for (int i = 0; i < 4; ++i) {
     t.s_off[i] = (int)ints.size();
     ints.insert(ints.end(), bands[i].start.begin(), bands[i].start.end());
-    t.o_off[i] = (int)ints.size();
-    ints.insert(ints.end(), bands[i].off.begin(), bands[i].off.end());
+    t.c_off[i] = (int)ints.size();
+    ints.insert(ints.end(), bands[i].cnt.begin(), bands[i].cnt.end());
     t.w_off[i] = (int)ws.size();
+    t.stride[i] = bands[i].stride;
     ws.insert(ws.end(), bands[i].w.begin(), bands[i].w.end());
   }
+  t.n_ints = (int)ints.size();
+  t.n_weights = (int)ws.size();
   ALG_CUDA_OK(cudaMalloc(&t.ints, ints.size() * sizeof(int)));
   ALG_CUDA_OK(cudaMalloc(&t.weights, ws.size() * sizeof(float)));
   ALG_CUDA_OK(cudaMemcpy(t.ints, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -129,54 +131,93 @@ static int get_tables(int H, int W, int h1, int w1, int dt, DownUpTables* out) {
 
 struct BandPtr {
   const int* start;
-  const int* off;
+  const int* cnt;
   const float* w;
+  int stride;
 };
 
+constexpr int kRegTaps = 8;  // taps cached in registers; longer bands read the rest from the table
+
+// One tap of interpolate_aa_single_dim (UpSample.cuh:349-365): taps and samples are widened to fp32 and summed with
+// `output += t * wts` (an FMA chain under nvcc's default contraction), for every tensor dtype.
+template <int DT>
+__device__ __forceinline__ float tap(float acc, float w, float x, bool first) {
+  return first ? w * x : fmaf(w, x, acc);
+}
+
 // dst[r][j] = sum_k w * src[r][start_j + k]      (resample along the contiguous axis)
+// thread (tx, ty): columns j = tx + 32 m with that column's taps in registers, rows r = ty + 8 m'.
 template <int DT>
 __device__ __forceinline__ void pass_w(const float* __restrict__ src, float* __restrict__ dst, int rows, int in_w,
                                        int out_w, BandPtr b) {
-  for (int idx = threadIdx.x; idx < rows * out_w; idx += blockDim.x) {
-    int r = idx / out_w, j = idx - r * out_w;
-    int s = b.start[j], o = b.off[j], n = b.off[j + 1] - o;
-    const float* p = src + r * in_w + s;
-    float acc = 0.f;
-    for (int k = 0; k < n; ++k) acc = fmaf(b.w[o + k], p[k], acc);
-    dst[idx] = Elem<DT>::round(acc);  // ATen keeps the row-pass result in a scalar_t buffer
-  }
-}
-// dst[i][c] = sum_k w * src[start_i + k][c]       (resample along the strided axis)
-template <int DT, bool ROUND, bool TO_GLOBAL>
-__device__ __forceinline__ void pass_h(const float* __restrict__ src, void* __restrict__ dst, int cols, int out_h,
-                                       BandPtr b) {
-  for (int idx = threadIdx.x; idx < out_h * cols; idx += blockDim.x) {
-    int i = idx / cols, c = idx - i * cols;
-    int s = b.start[i], o = b.off[i], n = b.off[i + 1] - o;
-    const float* p = src + s * cols + c;
-    float acc = 0.f;
-    for (int k = 0; k < n; ++k) acc = fmaf(b.w[o + k], p[k * cols], acc);
-    if (TO_GLOBAL) {
-      Elem<DT>::store(dst, idx, acc);
-    } else {
-      reinterpret_cast<float*>(dst)[idx] = ROUND ? Elem<DT>::round(acc) : acc;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
+  for (int j = tx; j < out_w; j += 32) {
+    const int s = b.start[j], n = b.cnt[j];
+    const float* wt = b.w + j * b.stride;
+    float w[kRegTaps];
+#pragma unroll
+    for (int k = 0; k < kRegTaps; ++k) w[k] = k < n ? wt[k] : 0.f;
+    for (int r = ty; r < rows; r += ny) {
+      const float* p = src + r * in_w + s;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kRegTaps; ++k)
+        if (k < n) acc = tap<DT>(acc, w[k], p[k], k == 0);
+      for (int k = kRegTaps; k < n; ++k) acc = tap<DT>(acc, wt[k], p[k], false);
+      dst[r * out_w + j] = Elem<DT>::round(acc);  // ATen keeps the row-pass result in a scalar_t buffer
     }
   }
 }
+// dst[i][c] = sum_k w * src[start_i + k][c]       (resample along the strided axis)
+// thread (tx, ty): output rows i = ty + 8 m (taps warp-uniform, in registers), columns c = tx + 32 m'.
+template <int DT, bool ROUND, bool TO_GLOBAL>
+__device__ __forceinline__ void pass_h(const float* __restrict__ src, void* __restrict__ dst, int cols, int out_h,
+                                       BandPtr b) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
+  for (int i = ty; i < out_h; i += ny) {
+    const int s = b.start[i], n = b.cnt[i];
+    const float* wt = b.w + i * b.stride;
+    float w[kRegTaps];
+#pragma unroll
+    for (int k = 0; k < kRegTaps; ++k) w[k] = k < n ? wt[k] : 0.f;
+    for (int c = tx; c < cols; c += 32) {
+      const float* p = src + s * cols + c;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kRegTaps; ++k)
+        if (k < n) acc = tap<DT>(acc, w[k], p[k * cols], k == 0);
+      for (int k = kRegTaps; k < n; ++k) acc = tap<DT>(acc, wt[k], p[k * cols], false);
+      if (TO_GLOBAL) {
+        Elem<DT>::store(dst, (size_t)i * cols + c, acc);
+      } else {
+        reinterpret_cast<float*>(dst)[i * cols + c] = ROUND ? Elem<DT>::round(acc) : acc;
+      }
+    }
+  }
+}
+
+struct DownUpGeom {
+  int s_off[4], c_off[4], w_off[4], stride[4];
+  int n_ints, n_weights;
+};
 
 template <int DT>
 __global__ void __launch_bounds__(256) down_up_fused_kernel(const void* __restrict__ in, void* __restrict__ out,
                                                             int64_t planes, int H, int W, int h1, int w1,
                                                             const int* __restrict__ ints,
-                                                            const float* __restrict__ weights, int4 s_off, int4 o_off,
-                                                            int4 w_off, int bufA_elems) {
+                                                            const float* __restrict__ weights, DownUpGeom g,
+                                                            int bufA_elems, int bufB_elems) {
   extern __shared__ __align__(16) float smem[];
-  float* A = smem;               // in [H, W]      -> small [h1, w1]
-  float* B = smem + bufA_elems;  // t1 [H, w1]     -> t2 [h1, W]
-  BandPtr bw_down{ints + s_off.x, ints + o_off.x, weights + w_off.x};
-  BandPtr bh_down{ints + s_off.y, ints + o_off.y, weights + w_off.y};
-  BandPtr bw_up{ints + s_off.z, ints + o_off.z, weights + w_off.z};
-  BandPtr bh_up{ints + s_off.w, ints + o_off.w, weights + w_off.w};
+  float* A = smem;                           // in [H, W]      -> small [h1, w1]
+  float* B = smem + bufA_elems;              // t1 [H, w1]     -> t2 [h1, W]
+  float* sw = B + bufB_elems;                // operator taps
+  int* si = reinterpret_cast<int*>(sw + g.n_weights);  // operator starts / counts
+  for (int i = threadIdx.x; i < g.n_weights; i += blockDim.x) sw[i] = weights[i];
+  for (int i = threadIdx.x; i < g.n_ints; i += blockDim.x) si[i] = ints[i];
+  BandPtr bw_down{si + g.s_off[0], si + g.c_off[0], sw + g.w_off[0], g.stride[0]};
+  BandPtr bh_down{si + g.s_off[1], si + g.c_off[1], sw + g.w_off[1], g.stride[1]};
+  BandPtr bw_up{si + g.s_off[2], si + g.c_off[2], sw + g.w_off[2], g.stride[2]};
+  BandPtr bh_up{si + g.s_off[3], si + g.c_off[3], sw + g.w_off[3], g.stride[3]};
   using T = typename Elem<DT>::type;
   const int HW = H * W;
   for (int64_t plane = blockIdx.x; plane < planes; plane += gridDim.x) {
@@ -189,8 +230,12 @@ __global__ void __launch_bounds__(256) down_up_fused_kernel(const void* __restri
       for (int i = threadIdx.x; i < HW / VEC; i += blockDim.x) {
         uint4 v = __ldg(s4 + i);
         const T* e = reinterpret_cast<const T*>(&v);
+        if (VEC == 4) {
+          *reinterpret_cast<float4*>(A + i * 4) = make_float4((float)e[0], (float)e[1], (float)e[2], (float)e[3]);
+        } else {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) A[i * VEC + k] = (float)e[k];
+          for (int k = 0; k < VEC; ++k) A[i * VEC + k] = (float)e[k];
+        }
       }
     } else {
       for (int i = threadIdx.x; i < HW; i += blockDim.x) A[i] = (float)src[i];
@@ -211,7 +256,7 @@ __global__ void __launch_bounds__(256) down_up_fused_kernel(const void* __restri
 template <int DT_IN, int DT_OUT, bool ALONG_W, bool ROUND_BF>
 __global__ void resample_pass_kernel(const void* __restrict__ in, void* __restrict__ out, int64_t planes, int in_h,
                                      int in_w, int out_h, int out_w, const int* __restrict__ start,
-                                     const int* __restrict__ off, const float* __restrict__ w, int round_dt) {
+                                     const int* __restrict__ cnt, const float* __restrict__ w, int stride, int round_dt) {
   int64_t total = planes * out_h * out_w;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -219,13 +264,16 @@ __global__ void resample_pass_kernel(const void* __restrict__ in, void* __restri
     int rem = (int)(idx - plane * (int64_t)out_h * out_w);
     int i = rem / out_w, j = rem - i * out_w;
     const size_t base = (size_t)plane * in_h * in_w;
+    const int o = ALONG_W ? j : i;
+    const int s = start[o], n = cnt[o];
+    const float* wt = w + (size_t)o * stride;
     float acc = 0.f;
-    if (ALONG_W) {
-      int s = start[j], o = off[j], n = off[j + 1] - o;
-      for (int k = 0; k < n; ++k) acc = fmaf(w[o + k], Elem<DT_IN>::load(in, base + (size_t)i * in_w + s + k), acc);
-    } else {
-      int s = start[i], o = off[i], n = off[i + 1] - o;
-      for (int k = 0; k < n; ++k) acc = fmaf(w[o + k], Elem<DT_IN>::load(in, base + (size_t)(s + k) * in_w + j), acc);
+    for (int k = 0; k < n; ++k) {
+      const float x = ALONG_W ? Elem<DT_IN>::load(in, base + (size_t)i * in_w + s + k)
+                              : Elem<DT_IN>::load(in, base + (size_t)(s + k) * in_w + j);
+      if (round_dt == ALG_BF16) acc = tap<ALG_BF16>(acc, wt[k], x, k == 0);
+      else if (round_dt == ALG_F16) acc = tap<ALG_F16>(acc, wt[k], x, k == 0);
+      else acc = tap<ALG_F32>(acc, wt[k], x, k == 0);
     }
     if (ROUND_BF) acc = round_dt == ALG_BF16 ? Elem<ALG_BF16>::round(acc) : (round_dt == ALG_F16 ? Elem<ALG_F16>::round(acc) : acc);
     Elem<DT_OUT>::store(out, idx, acc);
@@ -241,16 +289,16 @@ static int down_up_generic(const void* in, void* out, int64_t planes, int H, int
   ALG_CUDA_OK(cudaMallocAsync(&t2, sizeof(float) * planes * h1 * W, st));
   auto grid = [](int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 16); };
   resample_pass_kernel<DT, ALG_F32, true, true><<<grid(planes * H * w1), 256, 0, st>>>(
-      in, t1, planes, H, W, H, w1, t.ints + t.s_off[0], t.ints + t.o_off[0], t.weights + t.w_off[0], DT);
+      in, t1, planes, H, W, H, w1, t.ints + t.s_off[0], t.ints + t.c_off[0], t.weights + t.w_off[0], t.stride[0], DT);
   ALG_LAUNCH_OK();
   resample_pass_kernel<ALG_F32, ALG_F32, false, true><<<grid(planes * h1 * w1), 256, 0, st>>>(
-      t1, sm, planes, H, w1, h1, w1, t.ints + t.s_off[1], t.ints + t.o_off[1], t.weights + t.w_off[1], DT);
+      t1, sm, planes, H, w1, h1, w1, t.ints + t.s_off[1], t.ints + t.c_off[1], t.weights + t.w_off[1], t.stride[1], DT);
   ALG_LAUNCH_OK();
   resample_pass_kernel<ALG_F32, ALG_F32, true, true><<<grid(planes * h1 * W), 256, 0, st>>>(
-      sm, t2, planes, h1, w1, h1, W, t.ints + t.s_off[2], t.ints + t.o_off[2], t.weights + t.w_off[2], DT);
+      sm, t2, planes, h1, w1, h1, W, t.ints + t.s_off[2], t.ints + t.c_off[2], t.weights + t.w_off[2], t.stride[2], DT);
   ALG_LAUNCH_OK();
   resample_pass_kernel<ALG_F32, DT, false, false><<<grid(planes * H * W), 256, 0, st>>>(
-      t2, out, planes, h1, W, H, W, t.ints + t.s_off[3], t.ints + t.o_off[3], t.weights + t.w_off[3], DT);
+      t2, out, planes, h1, W, H, W, t.ints + t.s_off[3], t.ints + t.c_off[3], t.weights + t.w_off[3], t.stride[3], DT);
   ALG_LAUNCH_OK();
   ALG_CUDA_OK(cudaFreeAsync(t1, st));
   ALG_CUDA_OK(cudaFreeAsync(sm, st));
@@ -265,7 +313,7 @@ static int down_up_dispatch(const void* in, void* out, int64_t planes, int H, in
   if (int rc = get_tables(H, W, h1, w1, DT, &t)) return rc;
   const int64_t a_elems = std::max<int64_t>((int64_t)H * W, (int64_t)h1 * w1);
   const int64_t b_elems = std::max<int64_t>((int64_t)H * w1, (int64_t)h1 * W);
-  const size_t smem = (size_t)(a_elems + b_elems) * sizeof(float);
+  const size_t smem = (size_t)(a_elems + b_elems + t.n_weights + t.n_ints) * sizeof(float);
   if (smem > 200 * 1024) return down_up_generic<DT>(in, out, planes, H, W, h1, w1, t, st);
   static bool attr_set[3] = {false, false, false};
   if (!attr_set[DT]) {
@@ -274,11 +322,17 @@ static int down_up_dispatch(const void* in, void* out, int64_t planes, int H, in
   }
   const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
   const int grid = (int)std::min<int64_t>(planes, (int64_t)148 * ctas_per_sm);
-  int4 s_off{t.s_off[0], t.s_off[1], t.s_off[2], t.s_off[3]};
-  int4 o_off{t.o_off[0], t.o_off[1], t.o_off[2], t.o_off[3]};
-  int4 w_off{t.w_off[0], t.w_off[1], t.w_off[2], t.w_off[3]};
-  down_up_fused_kernel<DT><<<grid, 256, smem, st>>>(in, out, planes, H, W, h1, w1, t.ints, t.weights, s_off, o_off,
-                                                    w_off, (int)a_elems);
+  DownUpGeom g;
+  for (int i = 0; i < 4; ++i) {
+    g.s_off[i] = t.s_off[i];
+    g.c_off[i] = t.c_off[i];
+    g.w_off[i] = t.w_off[i];
+    g.stride[i] = t.stride[i];
+  }
+  g.n_ints = t.n_ints;
+  g.n_weights = t.n_weights;
+  down_up_fused_kernel<DT><<<grid, 256, smem, st>>>(in, out, planes, H, W, h1, w1, t.ints, t.weights, g, (int)a_elems,
+                                                    (int)b_elems);
   ALG_LAUNCH_OK();
   return 0;
 }

@@ -52,6 +52,8 @@ def apply_low_pass_filter(
     planes = src.numel() // (H * W) if H * W else 0
     dt = _lib.dtype_code(src.dtype)
     out = torch.empty_like(src)
+    if planes == 0:
+        return out.view(tensor.shape)  # empty batch: nothing to launch
     L = _lib.lib()
     stream = _lib.stream_ptr(src.device)
     with torch.cuda.device(src.device):

@@ -198,7 +198,7 @@ class SyntheticVideoVAE(torch.nn.Module):
             scale_factor_temporal=temporal, scale_factor_spatial=spatial,
             latents_mean=latents_mean or [0.0] * z_dim, latents_std=latents_std or [1.0] * z_dim,
             block_out_channels=[1] * (int(math.log2(spatial)) + 1), temporal_compression_ratio=temporal,
-            temperal_downsample=[True] * int(math.log2(temporal)))
+            temperal_downsample=[False] * (int(math.log2(spatial)) - int(math.log2(temporal))) + [True] * int(math.log2(temporal)))
         self.to(dtype)
 
     @property

@@ -54,7 +54,7 @@ def test_down_up_matches_torch_and_oracle_fp32(shape, f):
     h1, w1 = max(1, int(round(H * f))), max(1, int(round(W * f)))
     v = x.reshape(-1, 1, H, W)
     r = F.interpolate(F.interpolate(v, size=(h1, w1), mode="bilinear", antialias=True), size=(H, W), mode="bilinear", antialias=True)
-    assert rel_l2(y, r.view(shape)) < 2e-6
+    assert rel_l2(y, r.view(shape)) < 4e-6  # two fp32 evaluation orders of the same taps (ATen itself is 1.8e-6 off fp64)
     if x.numel() < 1_000_000:
         o = lp_oracle.apply_low_pass_filter(x.cpu().numpy(), "down_up", 0.0, 0.0, f)
         assert rel_l2(y, torch.from_numpy(o)) < 2e-6
