@@ -2,17 +2,22 @@
 //
 // Replaces F.scaled_dot_product_attention inside the DiT (reference call site wan:910; Wan self-attention
 // N = 32 760 tokens, 40 heads x 128).  One CTA owns TWO 128-row query tiles of one (batch, head) and streams the
-// K / V^T tiles of that head through a TMA-fed shared-memory ring:
+// K / V^T tiles of that head, 64 keys per step, through a TMA-fed shared-memory ring:
 //
-//   warp 8  : TMA producer      Q0, Q1 once; K_j and V^T_j double-buffered (SWIZZLE_128B, K-major)
-//   warp 9  : MMA issuer        S_i = Q_i K_j^T   (tcgen05.mma SS, 128 x 128 x D   -> TMEM S_i)
-//                               O_i += P_i V_j    (tcgen05.mma TS, A = P_i in TMEM -> TMEM O_i)
+//   warp 8  : TMA producer      Q0, Q1 once; K_j and V^T_j rings (SWIZZLE_128B, K-major), 4 stages each
+//   warp 9  : MMA issuer        S_i(j) = Q_i K_j^T   (tcgen05.mma SS, 128 x 64 x D    -> TMEM S_i[j & 1])
+//                               O_i   += P_i(j) V_j  (tcgen05.mma TS, A = P_i in TMEM -> TMEM O_i)
 //   warps 0-3 / 4-7 : softmax warpgroup for tile 0 / 1 (one query row per thread):
-//                               tcgen05.ld S -> online softmax in fp32 (exp2, lazy rescale of O in TMEM only when
-//                               the running max grows by > 2^8) -> bf16 P written back over S with tcgen05.st
+//                               tcgen05.ld S -> online softmax in fp32 (exp2; O in TMEM is rescaled only when the
+//                               running max grows by > 2^8) -> bf16 P written back over S with tcgen05.st
 //
-// The two tiles ping-pong: while one warpgroup does softmax, the tensor core runs the other tile's MMAs.
-// TMEM (512 columns): S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,256+D)  O1 [384,384+D).
+// S is double-buffered in TMEM and issued TWO steps ahead (S_i(j+2) right behind P_i(j) V_j), so a softmax warpgroup
+// never waits for the tensor pipe in steady state: when it has published P_i(j), S_i(j+1) is already complete.  The
+// first version of this kernel used 128-key steps with a single S buffer per tile, which made every step a serial
+// chain  softmax -> PV -> S -> softmax  and capped the tensor pipe at ~56 % busy (profiles/r01_attention.md).
+//
+// TMEM (512 columns): S0 [0,64) [64,128)   S1 [128,192) [192,256)   O0 [256,256+D)   O1 [384,384+D).
+// P_i(j) (bf16 pairs) overwrites the first 32 columns of the S buffer it was computed from.
 // V is consumed TRANSPOSED ([head_dim, n_kv], produced directly by the V projection GEMM with swapped operands) so
 // that both MMAs use K-major operands.
 #include <algorithm>
@@ -25,9 +30,10 @@ namespace alg {
 namespace attn {
 using namespace tc;
 
-constexpr int BQ = 128;   // query rows per tile (two tiles per CTA)
-constexpr int BKV = 128;  // keys per pipeline step
+constexpr int BQ = 128;  // query rows per tile (two tiles per CTA)
+constexpr int BKV = 64;  // keys per pipeline step
 constexpr int kThreads = 320;
+constexpr int kStages = 4;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef ALG_ATTN_POLY_DEFAULT
 #define ALG_ATTN_POLY_DEFAULT 4
@@ -35,13 +41,12 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 template <int D>
 struct Cfg {
-  static constexpr int kBytesQ = BQ * D * 2;     // one query tile
-  static constexpr int kBytesK = BKV * D * 2;    // one K stage
-  static constexpr int kBytesV = D * BKV * 2;    // one V^T stage
-  static constexpr int kStages = 2;
-  static constexpr int kSmemBytes = 2 * kBytesQ + kStages * (kBytesK + kBytesV) + 1024 + 256;
-  static constexpr int kSubQK = BQ * 128;  // bytes of one [128 rows][64 elem] swizzle sub-tile
-  static constexpr int kSubV = D * 128;    // bytes of one [D rows][64 kv] sub-tile
+  static constexpr int kBytesQ = BQ * D * 2;   // one query tile
+  static constexpr int kBytesK = BKV * D * 2;  // one K stage  [64 keys][D]
+  static constexpr int kBytesV = D * BKV * 2;  // one V^T stage [D][64 keys]
+  static constexpr int kSmemBytes = 2 * kBytesQ + kStages * (kBytesK + kBytesV) + 1024 + 512;
+  static constexpr int kSubQ = BQ * 128;   // bytes of one [128 rows][64 elem] swizzle sub-tile of Q
+  static constexpr int kSubK = BKV * 128;  // bytes of one [64 keys][64 elem] sub-tile of K
 };
 
 struct Params {
@@ -57,7 +62,6 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
@@ -90,37 +94,44 @@ __global__ void __launch_bounds__(kThreads, 1)
   using C = Cfg<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // [2][BQ x D]
-  uint8_t* sK = sQ + 2 * C::kBytesQ;                    // [stages][BKV x D]
-  uint8_t* sV = sK + C::kStages * C::kBytesK;           // [stages][D x BKV]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::kStages * C::kBytesV);
-  uint64_t* q_full = bars;          // 1
-  uint64_t* k_full = bars + 1;      // 2
-  uint64_t* k_empty = bars + 3;     // 2
-  uint64_t* v_full = bars + 5;      // 2
-  uint64_t* v_empty = bars + 7;     // 2
-  uint64_t* s_full = bars + 9;      // 2
-  uint64_t* p_full = bars + 11;     // 2
-  uint64_t* o_full = bars + 13;     // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint8_t* sQ = smem;                          // [2][BQ x D]
+  uint8_t* sK = sQ + 2 * C::kBytesQ;           // [stages][BKV x D]
+  uint8_t* sV = sK + kStages * C::kBytesK;     // [stages][D x BKV]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * C::kBytesV);
+  uint64_t* q_full = bars;                     // 1
+  uint64_t* k_full = bars + 1;                 // kStages
+  uint64_t* k_empty = k_full + kStages;        // kStages
+  uint64_t* v_full = k_empty + kStages;        // kStages
+  uint64_t* v_empty = v_full + kStages;        // kStages
+  uint64_t* s_full = v_empty + kStages;        // [tile][buffer] = 4
+  uint64_t* p_full = s_full + 4;               // [tile][buffer] = 4 (a softmax warpgroup may run one step ahead of
+                                               // the MMA warp's wait: one barrier per S buffer keeps the parity unambiguous)
+  uint64_t* o_done = p_full + 4;               // 2: committed behind every PV (the rare O-rescale path waits on it)
+  uint64_t* o_full = o_done + 2;               // 2: committed behind the last PV only (epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, batch = blockIdx.z;
   const int q0 = blockIdx.x * 2 * BQ;
-  const int n_tiles = (p.n_kv + BKV - 1) / BKV;
+  const int n_steps = (p.n_kv + BKV - 1) / BKV;
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], 4);  // one arrival per softmax warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&o_done[i], 1);
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
@@ -135,77 +146,80 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    if (lane == 0) {  // ===== TMA producer =====
+    if (elect_one()) {  // ===== TMA producer: Q0 Q1 | K0 K1 | V0 K2 | V1 K3 | ... (the order the MMA warp consumes) =====
       mbar_arrive_expect_tx(q_full, 2 * C::kBytesQ);
       for (int i = 0; i < 2; ++i)
         for (int s = 0; s < D / 64; ++s)
-          tma_load_3d(sQ + i * C::kBytesQ + s * C::kSubQK, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
+          tma_load_3d(sQ + i * C::kBytesQ + s * C::kSubQ, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
+      auto load_k = [&](int j) {
+        const int st = j % kStages;
+        mbar_wait(&k_empty[st], ((j / kStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], C::kBytesK);
         for (int s = 0; s < D / 64; ++s)
-          tma_load_3d(sK + st * C::kBytesK + s * C::kSubQK, &tmK, &k_full[st], head * D + s * 64, j * BKV, batch);
-        mbar_wait(&v_empty[st], ph ^ 1);
+          tma_load_3d(sK + st * C::kBytesK + s * C::kSubK, &tmK, &k_full[st], head * D + s * 64, j * BKV, batch);
+      };
+      auto load_v = [&](int j) {
+        const int st = j % kStages;
+        mbar_wait(&v_empty[st], ((j / kStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[st], C::kBytesV);
-        for (int s = 0; s < BKV / 64; ++s)
-          tma_load_3d(sV + st * C::kBytesV + s * C::kSubV, &tmV, &v_full[st], j * BKV + s * 64, head * D, batch);
+        tma_load_3d(sV + st * C::kBytesV, &tmV, &v_full[st], j * BKV, head * D, batch);
+      };
+      load_k(0);
+      if (n_steps > 1) load_k(1);
+      for (int j = 0; j < n_steps; ++j) {
+        load_v(j);
+        if (j + 2 < n_steps) load_k(j + 2);
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {  // ===== MMA issuer =====
+    if (elect_one()) {  // ===== MMA issuer.  elect.sync (not `lane == 0`) tells ptxas that a single lane runs this region, so the
+                        // descriptors stay in uniform registers; otherwise every UTCHMMA is wrapped in an ELECT / R2UR loop =====
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
       constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D);
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      auto issue_s = [&](int i, int st) {  // S_i = Q_i K^T
-        const uint32_t d = tmem_base + i * 128;
+      auto issue_s = [&](int i, int j) {  // S_i(j) = Q_i K_j^T into buffer j & 1
+        const uint32_t d = tmem_base + i * 128 + (j & 1) * 64;
+        const uint32_t kb = k_addr + (j % kStages) * C::kBytesK;
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t off = (ks >> 2) * C::kSubQK + (ks & 3) * 32;
-          mma_ss(d, make_smem_desc_sw128(q_addr + i * C::kBytesQ + off),
-                 make_smem_desc_sw128(k_addr + st * C::kBytesK + off), idesc_s, ks != 0);
+          mma_ss(d, make_smem_desc_sw128(q_addr + i * C::kBytesQ + (ks >> 2) * C::kSubQ + (ks & 3) * 32),
+                 make_smem_desc_sw128(kb + (ks >> 2) * C::kSubK + (ks & 3) * 32), idesc_s, ks != 0);
         }
+        tc_commit(&s_full[i * 2 + (j & 1)]);
       };
-      auto issue_pv = [&](int i, int st, bool acc) {  // O_i (+)= P_i V
+      auto issue_pv = [&](int i, int j) {  // O_i (+)= P_i(j) V_j
         const uint32_t d = tmem_base + 256 + i * 128;
-        const uint32_t a = tmem_base + i * 128;
+        const uint32_t a = tmem_base + i * 128 + (j & 1) * 64;
+        const uint32_t vb = v_addr + (j % kStages) * C::kBytesV;
 #pragma unroll
-        for (int ks = 0; ks < BKV / 16; ++ks) {
-          const uint32_t off = (ks >> 2) * C::kSubV + (ks & 3) * 32;
-          mma_ts(d, a + ks * 8, make_smem_desc_sw128(v_addr + st * C::kBytesV + off), idesc_o, (acc || ks != 0));
-        }
+        for (int ks = 0; ks < BKV / 16; ++ks)
+          mma_ts(d, a + ks * 8, make_smem_desc_sw128(vb + ks * 32), idesc_o, (j > 0 || ks != 0));
+        tc_commit(&o_done[i]);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      tc_commit(&s_full[0]);
-      issue_s(1, 0);
-      tc_commit(&s_full[1]);
-      tc_commit(&k_empty[0]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int nst = (j + 1) & 1;
-        const uint32_t nph = ((j + 1) >> 1) & 1;
-        const bool more = j + 1 < n_tiles;
+      for (int j = 0; j < 2 && j < n_steps; ++j) {
+        mbar_wait(&k_full[j % kStages], 0);
+        tc_fence_after();
+        issue_s(0, j);
+        issue_s(1, j);
+        tc_commit(&k_empty[j % kStages]);
+      }
+      for (int j = 0; j < n_steps; ++j) {
+        const int jn = j + 2;
         for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_full[i], j & 1);
-          if (i == 0) mbar_wait(&v_full[st], ph);
+          mbar_wait(&p_full[i * 2 + (j & 1)], (j >> 1) & 1);
+          if (i == 0) mbar_wait(&v_full[j % kStages], (j / kStages) & 1);
           tc_fence_after();
-          issue_pv(i, st, j > 0);
-          if (i == 1) tc_commit(&v_empty[st]);
-          if (more) {
+          issue_pv(i, j);
+          if (i == 1) tc_commit(&v_empty[j % kStages]);
+          if (j == n_steps - 1) tc_commit(&o_full[i]);
+          if (jn < n_steps) {
             if (i == 0) {
-              mbar_wait(&k_full[nst], nph);
+              mbar_wait(&k_full[jn % kStages], (jn / kStages) & 1);
               tc_fence_after();
             }
-            issue_s(i, nst);
-            tc_commit(&s_full[i]);
-            if (i == 1) tc_commit(&k_empty[nst]);
-          } else {
-            tc_commit(&o_full[i]);
+            issue_s(i, jn);  // reuses the S buffer whose P was consumed by the PV just issued (in-order tensor pipe)
+            if (i == 1) tc_commit(&k_empty[jn % kStages]);
           }
         }
       }
@@ -219,37 +233,41 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int row = q0 + i * BQ + quad * 32 + lane;
     float m_used = -INFINITY, l = 0.f;
     const float c = p.scale_log2;
-    // one key tile of online softmax; `ragged` (compile-time) is the last, partially filled tile -- kept out of the
-    // main loop body, where the compiler would otherwise if-convert the mask into 255 always-executed selects
+    // one 64-key step of online softmax; `ragged` (compile-time) is the last, partially filled step -- kept out of the
+    // main loop body, where the compiler would otherwise if-convert the mask into always-executed selects
     auto softmax_step = [&](const int j, auto ragged) {
-      mbar_wait(&s_full[i], j & 1);
+      const uint32_t t_sj = t_s + (j & 1) * 64;
+      mbar_wait(&s_full[i * 2 + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
-      float s[128];
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) tmem_ld32(t_s + ch * 32, reinterpret_cast<uint32_t*>(s) + ch * 32);
+      float s[64];
+      tmem_ld32(t_sj, reinterpret_cast<uint32_t*>(s));
+      tmem_ld32(t_sj + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tmem_ld_wait();
       if constexpr (decltype(ragged)::value) {  // TMA zero-filled the tail of the tile: mask it out
         const int valid = p.n_kv - j * BKV;
 #pragma unroll
-        for (int k = 0; k < 128; ++k)
+        for (int k = 0; k < 64; ++k)
           if (k >= valid) s[k] = -INFINITY;
       }
-// row max: four independent FMNMX3 chains (a single dependent chain of 127 max ops costs ~500 cycles)
+      // row max: four independent FMNMX3 chains (one dependent chain of max ops is pure latency)
       float mc[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float m = s[g * 32];
+        float m = s[g * 16];
 #pragma unroll
-        for (int k = 1; k + 1 < 32; k += 2) m = max3(m, s[g * 32 + k], s[g * 32 + k + 1]);
-        mc[g] = fmaxf(m, s[g * 32 + 31]);
+        for (int k = 1; k + 1 < 16; k += 2) m = max3(m, s[g * 16 + k], s[g * 16 + k + 1]);
+        mc[g] = fmaxf(m, s[g * 16 + 15]);
       }
-      float mx = fmaxf(max3(mc[0], mc[1], mc[2]), mc[3]) * c;
+      const float mx = fmaxf(max3(mc[0], mc[1], mc[2]), mc[3]) * c;
       if (j == 0) {
         m_used = mx;
       } else {
         const float m_new = fmaxf(m_used, mx);
         const bool need = (m_new - m_used) > kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {  // warp-uniform: tcgen05.ld/st are warp collectives
+          // S runs two steps ahead of PV: O_i may still be receiving P_i(j-1) V_(j-1)
+          mbar_wait(&o_done[i], (j - 1) & 1);
+          tc_fence_after();
           const float f = ex2(m_used - m_new);
           l *= f;
           m_used = m_new;
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_used, -m_used);
       float2 sum0 = make_float2(0.f, 0.f), sum1 = sum0;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < 2; ++ch) {
         uint32_t pk[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -284,18 +302,18 @@ __global__ void __launch_bounds__(kThreads, 1)
           __nv_bfloat162 h = __floats2bfloat162_rn(e.x, e.y);
           pk[k] = *reinterpret_cast<uint32_t*>(&h);
         }
-        tmem_st16(t_s + ch * 16, pk);  // P (bf16 pairs) overwrites the first 64 columns of S
+        tmem_st16(t_sj + ch * 16, pk);  // P (bf16 pairs) overwrites the first 32 columns of this S buffer
       }
       l += (sum0.x + sum0.y) + (sum1.x + sum1.y);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i]);
+      if (lane == 0) mbar_arrive(&p_full[i * 2 + (j & 1)]);
     };
     const int n_full = p.n_kv / BKV;
 #pragma unroll 1
     for (int j = 0; j < n_full; ++j) softmax_step(j, std::false_type{});
-    if (n_full < n_tiles) softmax_step(n_full, std::true_type{});
+    if (n_full < n_steps) softmax_step(n_full, std::true_type{});
     // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------------
     mbar_wait(&o_full[i], 0);
     tc_fence_after();
@@ -361,7 +379,7 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   }
   {
     uint64_t dims[3] = {(uint64_t)a->n_kv, hd, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->v_rs, (uint64_t)a->v_bs};
-    uint32_t box[3] = {64, (uint32_t)D, 1};
+    uint32_t box[3] = {BKV, (uint32_t)D, 1};
     if (int rc = make_tmap_bf16(&tmV, a->Vt, 3, dims, strides, box)) return rc;
   }
   Params p;
@@ -395,7 +413,7 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   ALG_REQUIRE((reinterpret_cast<uintptr_t>(a->O) & 15) == 0, "attention: O must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static int poly = -1;  // tuning knob: share of exp2 evaluated on the FMA pipe (1 pair in `poly`), default from profiling
+  static int poly = -1;  // tuning knob: share of exp2 evaluated on the FMA pipe (1 pair in `poly`); default from profiling
   if (poly < 0) {
     const char* e = getenv("ALG_ATTN_POLY");
     poly = e ? atoi(e) : ALG_ATTN_POLY_DEFAULT;
@@ -404,7 +422,6 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
     switch (poly) {
       case 0: return attn::launch<128, 0>(a, st);
       case 2: return attn::launch<128, 2>(a, st);
-      case 3: return attn::launch<128, 3>(a, st);
       case 4: return attn::launch<128, 4>(a, st);
       default: return attn::launch<128, 8>(a, st);
     }

@@ -11,6 +11,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (warp % 4 selects the TMEM lane quadrant it may read).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== TMA producer =====
+    if (elect_one()) {  // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -159,7 +160,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
+    if (elect_one()) {  // ===== MMA issuer: elect.sync tells ptxas a single lane runs this region, so descriptors stay in
+                        // uniform registers (a plain lane == 0 test wraps every UTCHMMA in an ELECT / R2UR loop) =====
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -405,6 +407,13 @@ extern "C" int alg_gemm_bf16(const alg_gemm_t* g, void* stream) {
     ALG_REQUIRE((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static int force_bn = -1;  // experiment knob
+  if (force_bn < 0) {
+    const char* e = getenv("ALG_GEMM_BN");
+    force_bn = e ? atoi(e) : 0;
+  }
+  if (force_bn == 128) return gemm::launch<128>(g, st);
+  if (force_bn == 64) return gemm::launch<64>(g, st);
   if (g->N % 256 == 0 || g->N > 512) return gemm::launch<256>(g, st);
   if (g->N % 128 == 0 || g->N > 128) return gemm::launch<128>(g, st);
   return gemm::launch<64>(g, st);
