@@ -82,13 +82,14 @@ def test_forward_full_width_one_block():
 
 def test_loop_teacher_forced_per_step_latents():
     """Per-step latent relative L2 <= 1e-3 (north_star), both sides consuming the oracle's x_i.  The per-step error is
-    |delta sigma| x (bf16 noise_pred difference, amplified by the CFG scale), so it is asserted on a 16-step schedule
-    (3.2x coarser than the 50-step contract) rather than on a 6-step one."""
+    |delta sigma| x (bf16 noise_pred difference, amplified by the CFG scale), so it is asserted on the 50-step schedule
+    the contract is quoted on (BASELINE.json configs[1]), with the shipped ALG interval [0, 0.2]."""
     import __graft_entry__ as G
     from alg_b200.schedulers import UniPCMultistepScheduler
     from pipeline_wan_image2video_lowpass import WanImageToVideoPipeline
     cfg, model, inp, alg = _problem(2)
-    steps = 16
+    steps = 50
+    alg = dict(alg, schedule_interval_end_time=0.2)
     ref, per_step = G.oracle_loop(cfg, model.state_dict(), inp, alg, steps, 5.0)
     xs = [inp["latents"]] + [p[0] for p in per_step]
     pipe = WanImageToVideoPipeline.from_pretrained("synthetic", transformer=model, synthetic=True)
@@ -106,7 +107,7 @@ def test_loop_teacher_forced_per_step_latents():
         assert npred.shape[0] == per_step[i][1].shape[0]
         # scheduler history is the engine's own, so after step 0 this also accumulates a little multistep state error
         assert rel_l2(x_next, xs[i + 1]) < 1e-3, (i, rel_l2(x_next, xs[i + 1]))
-    assert n3 == 7  # interval [0, 0.4] of 16 steps (step_norm = i / 15) -> steps 0..6 run three passes
+    assert n3 == 10  # interval [0, 0.2] of 50 steps -> steps 0..9 run three passes (SURVEY section 4 KAT)
 
 
 def test_pipeline_call_surface_and_callbacks():
