@@ -15,6 +15,9 @@ LIB_PATH = os.path.join(_HERE, "libalg_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ALG_F32, ALG_BF16, ALG_F16 = 0, 1, 2
+ABI_VERSION = 2
+NORM_NONE, NORM_RMS, NORM_LAYER = 0, 1, 2
+EW_ADD, EW_SILU, EW_COPY, EW_GELU_TANH = 0, 1, 2, 3
 EPI_NONE, EPI_GELU_TANH, EPI_GATE_RESIDUAL, EPI_RESIDUAL, EPI_GELU_ERF, EPI_SILU = range(6)
 
 
@@ -34,6 +37,33 @@ class Gemm(C.Structure):
         ("gate", C.c_void_p), ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("lda", C.c_int64),
         ("ldb", C.c_int64), ("ldd", C.c_int64), ("rows_per_batch", C.c_int64), ("gate_ld", C.c_int64),
         ("epilogue", C.c_int32), ("bias_per_row", C.c_int32), ("out_f32", C.c_int32),
+        ("gate_dtype", C.c_int32), ("gate_round", C.c_int32), ("gate_split_row", C.c_int64), ("gate_alt", C.c_void_p),
+    ]
+
+
+class LayerNorm(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("d", C.c_int32), ("eps", C.c_float),
+        ("weight", C.c_void_p), ("bias", C.c_void_p), ("affine_dtype", C.c_int32), ("mod_dtype", C.c_int32),
+        ("scale", C.c_void_p), ("shift", C.c_void_p), ("scale_alt", C.c_void_p), ("shift_alt", C.c_void_p),
+        ("rows_per_batch", C.c_int64), ("mod_batch_stride", C.c_int64), ("split_row", C.c_int64),
+        ("chain_bf16", C.c_int32),
+    ]
+
+
+class HeadNormRope(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("rows", C.c_int64), ("ld", C.c_int64), ("heads", C.c_int32), ("head_dim", C.c_int32),
+        ("norm_kind", C.c_int32), ("eps", C.c_float), ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("cos", C.c_void_p), ("sin", C.c_void_p), ("rows_per_batch", C.c_int64), ("rope_row0", C.c_int64),
+        ("rope_rows", C.c_int64),
+    ]
+
+
+class PatchSrc(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p), ("ptr_t0", C.c_void_p), ("dtype", C.c_int32), ("channels", C.c_int32),
+        ("sc", C.c_int64), ("st", C.c_int64), ("sy", C.c_int64), ("sc_t0", C.c_int64),
     ]
 
 
@@ -70,6 +100,14 @@ SIGNATURES = {
     "alg_cfg_euler_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "alg_gemm_bf16": (C.c_int, [C.POINTER(Gemm), C.c_void_p]),
     "alg_attention_bf16": (C.c_int, [C.POINTER(Attention), C.c_void_p]),
+    "alg_layer_norm": (C.c_int, [C.POINTER(LayerNorm), C.c_void_p]),
+    "alg_head_norm_rope": (C.c_int, [C.POINTER(HeadNormRope), C.c_void_p]),
+    "alg_patch_gather": (C.c_int, [C.POINTER(PatchSrc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "alg_unpatchify": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
+    "alg_timestep_embedding": (C.c_int, [C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "alg_elementwise_bf16": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "alg_mean_rows_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "alg_copy_rows_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "alg_wan_create": (C.c_int, [C.POINTER(WanConfig), C.POINTER(C.c_void_p)]),
     "alg_wan_destroy": (None, [C.c_void_p]),
     "alg_wan_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int]),
@@ -106,7 +144,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.alg_abi_version() != 1:
+        if l.alg_abi_version() != ABI_VERSION:
             raise RuntimeError("libalg_b200.so ABI version mismatch")
         _lib = l
     return _lib

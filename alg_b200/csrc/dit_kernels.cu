@@ -1,4 +1,4 @@
-// HBM-bound kernels of the Wan DiT forward: patch gather, LayerNorm(+modulate), RMSNorm(+RoPE),
+// HBM-bound kernels of the Wan DiT forward: patch gather, RMSNorm(+RoPE) (LayerNorm lives in dit_ops.cu),
 // timestep embedding, modulation tables, unpatchify.  All fp32 statistics, bf16 activations, with the
 // intermediate roundings placed where diffusers' WanTransformer3DModel places them.
 #include "dit_kernels.cuh"
@@ -66,69 +66,6 @@ int patch_gather(CondPtrs cond_dev, int n_pass, int lat_ch, int cond_ch, int T, 
   const int64_t total = (int64_t)n_pass * T * (H / 2) * (W / 2) * (lat_ch + cond_ch) * 4;
   const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
   patch_gather_kernel<<<grid, 256, 0, st>>>(cond_dev, n_pass, lat_ch, cond_ch, T, H, W, A);
-  ALG_LAUNCH_OK();
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowThreads)
-    layer_norm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int d, float eps,
-                      const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ scale,
-                      const float* __restrict__ shift) {
-  __shared__ float red[kRowThreads / 32];
-  const int64_t row = blockIdx.x;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
-  uint4* orow = reinterpret_cast<uint4*>(out + row * d);
-  const int chunks = d / 8;
-  float v[kMaxChunks][8];
-  float sum = 0.f;
-#pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int ci = threadIdx.x + c * kRowThreads;
-    if (ci < chunks) {
-      unpack8(xr[ci], v[c]);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sum += v[c][e];
-    }
-  }
-  const float mean = block_sum(sum, red) / (float)d;
-  float sq = 0.f;
-#pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int ci = threadIdx.x + c * kRowThreads;
-    if (ci < chunks) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float t = v[c][e] - mean;
-        sq += t * t;
-      }
-    }
-  }
-  const float rstd = rsqrtf(block_sum(sq, red) / (float)d + eps);
-#pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int ci = threadIdx.x + c * kRowThreads;
-    if (ci < chunks) {
-      float o[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int col = ci * 8 + e;
-        float y = __fmul_rn(__fsub_rn(v[c][e], mean), rstd);
-        if (w) y = __fadd_rn(__fmul_rn(y, w[col]), b[col]);
-        if (scale) y = __fadd_rn(__fmul_rn(y, __fadd_rn(1.0f, scale[col])), shift[col]);
-        o[e] = y;
-      }
-      orow[ci] = pack8(o);
-    }
-  }
-}
-
-int layer_norm(const __nv_bfloat16* x, __nv_bfloat16* out, int64_t rows, int d, float eps, const float* w,
-               const float* b, const float* scale, const float* shift, cudaStream_t st) {
-  ALG_REQUIRE(d % 8 == 0 && d <= kRowThreads * 8 * kMaxChunks, "layer_norm: d must be a multiple of 8 and <= 8192");
-  ALG_REQUIRE(rows <= 0x7fffffff, "layer_norm: too many rows");
-  if (rows == 0) return 0;
-  layer_norm_kernel<<<(unsigned)rows, kRowThreads, 0, st>>>(x, out, d, eps, w, b, scale, shift);
   ALG_LAUNCH_OK();
   return 0;
 }

@@ -14,10 +14,6 @@ struct CondPtrs {
 int patch_gather(CondPtrs cond, int n_pass, int lat_ch, int cond_ch, int T, int H, int W,
                  __nv_bfloat16* A, cudaStream_t st);
 
-// out = bf16( LN_fp32(x) [* w + b] [* (1 + scale) + shift] );  scale/shift fp32 [d] (batch-invariant), may be null
-int layer_norm(const __nv_bfloat16* x, __nv_bfloat16* out, int64_t rows, int d, float eps, const float* w,
-               const float* b, const float* scale, const float* shift, cudaStream_t st);
-
 // diffusers RMSNorm over the full row (across heads) with bf16 weight, then (optionally) Wan RoPE in fp64 on
 // adjacent pairs of every head.  In place.  rope tables: cos/sin doubles [max_pos][n_t | n_h | n_w] per axis.
 struct RopeTables {

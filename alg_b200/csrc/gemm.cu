@@ -77,9 +77,10 @@ struct Params {
   void* D;
   const __nv_bfloat16* bias;
   const __nv_bfloat16* R;
-  const float* gate;
-  int64_t M, N, K, ldd, rows_per_batch, gate_ld;
-  int epilogue, bias_per_row, out_f32;
+  const void* gate;
+  const void* gate_alt;
+  int64_t M, N, K, ldd, rows_per_batch, gate_ld, gate_split_row;
+  int epilogue, bias_per_row, out_f32, gate_bf16, gate_round;
   int m_tiles, n_tiles, k_blocks;
 };
 
@@ -206,8 +207,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int64_t safe_row = row_ok ? row : 0;
       float row_bias = 0.f;
       if (p.bias && p.bias_per_row && row_ok) row_bias = __bfloat162float(p.bias[row]);
-      const float* gate_row = nullptr;
-      if (p.epilogue == ALG_EPI_GATE_RESIDUAL) gate_row = p.gate + (safe_row / p.rows_per_batch) * p.gate_ld;
+      const char* gate_row = nullptr;  // fp32 or bf16 [N] gate vector of this row's sample (alt vector below split_row)
+      if (p.epilogue == ALG_EPI_GATE_RESIDUAL) {
+        const int64_t b = safe_row / p.rows_per_batch, r_in = safe_row - b * p.rows_per_batch;
+        gate_row = reinterpret_cast<const char*>(r_in < p.gate_split_row ? p.gate_alt : p.gate) +
+                   b * p.gate_ld * (p.gate_bf16 ? 2 : 4);
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int64_t col0 = (int64_t)n_blk * BN + c * 32;
@@ -264,25 +269,50 @@ __global__ void __launch_bounds__(kThreads, 1)
               for (int g = 0; g < 4; ++g) {
                 uint4 u = *reinterpret_cast<const uint4*>(rrow + g * 8);
                 const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-                float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+                float gg[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
                 if (gated) {
-                  g0 = __ldg(reinterpret_cast<const float4*>(gate_row + col0 + g * 8));
-                  g1 = __ldg(reinterpret_cast<const float4*>(gate_row + col0 + g * 8 + 4));
+                  if (p.gate_bf16) {
+                    const uint4 gu = __ldg(reinterpret_cast<const uint4*>(gate_row + (col0 + g * 8) * 2));
+                    const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gu);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f = __bfloat1622float2(gh[e]);
+                      gg[2 * e] = f.x;
+                      gg[2 * e + 1] = f.y;
+                    }
+                  } else {
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate_row + (col0 + g * 8) * 4));
+                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate_row + (col0 + g * 8 + 4) * 4));
+                    gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w;
+                    gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+                  }
                 }
-                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   float2 f = __bfloat1622float2(h[e]);
                   const int j = g * 8 + 2 * e;
-                  v[j] = __fadd_rn(f.x, gated ? __fmul_rn(v[j], gg[2 * e]) : v[j]);
-                  v[j + 1] = __fadd_rn(f.y, gated ? __fmul_rn(v[j + 1], gg[2 * e + 1]) : v[j + 1]);
+                  float y0 = gated ? __fmul_rn(v[j], gg[2 * e]) : v[j];
+                  float y1 = gated ? __fmul_rn(v[j + 1], gg[2 * e + 1]) : v[j + 1];
+                  if (gated && p.gate_round) {  // eager bf16 `x + gate * y`: the product is a bf16 tensor
+                    y0 = bf16_round(y0);
+                    y1 = bf16_round(y1);
+                  }
+                  v[j] = __fadd_rn(f.x, y0);
+                  v[j + 1] = __fadd_rn(f.y, y1);
                 }
               }
             } else {
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) {
                   const float x = __bfloat162float(rrow[j]);
-                  const float y = gated ? __fmul_rn(v[j], gate_row[col0 + j]) : v[j];
+                  float y = v[j];
+                  if (gated) {
+                    const float gv = p.gate_bf16
+                                         ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gate_row)[col0 + j])
+                                         : reinterpret_cast<const float*>(gate_row)[col0 + j];
+                    y = __fmul_rn(y, gv);
+                    if (p.gate_round) y = bf16_round(y);
+                  }
                   v[j] = __fadd_rn(x, y);
                 }
             }
@@ -371,6 +401,10 @@ static int launch(const alg_gemm_t* g, cudaStream_t st) {
   p.ldd = g->ldd;
   p.rows_per_batch = g->rows_per_batch > 0 ? g->rows_per_batch : g->M;
   p.gate_ld = g->gate_ld;
+  p.gate_alt = g->gate_alt;
+  p.gate_split_row = g->gate_alt ? g->gate_split_row : 0;
+  p.gate_bf16 = g->gate_dtype == ALG_BF16;
+  p.gate_round = g->gate_round;
   p.epilogue = g->epilogue;
   p.bias_per_row = g->bias_per_row;
   p.out_f32 = g->out_f32;
@@ -401,8 +435,13 @@ extern "C" int alg_gemm_bf16(const alg_gemm_t* g, void* stream) {
     ALG_REQUIRE((reinterpret_cast<uintptr_t>(g->R) & 15) == 0, "gemm: R must be 16-byte aligned");
   }
   if (g->epilogue == ALG_EPI_GATE_RESIDUAL)
-    ALG_REQUIRE(g->gate && g->gate_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g->gate) & 15) == 0,
-                "gemm: gate must be 16-byte aligned fp32 with gate_ld % 4 == 0");
+  {
+    ALG_REQUIRE(g->gate_dtype == ALG_F32 || g->gate_dtype == ALG_BF16, "gemm: gate dtype must be f32 or bf16");
+    ALG_REQUIRE(g->gate && g->gate_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(g->gate) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(g->gate_alt) & 15) == 0,
+                "gemm: gate vectors must be 16-byte aligned with gate_ld % 8 == 0");
+    ALG_REQUIRE(g->gate_split_row == 0 || g->gate_alt, "gemm: gate_split_row needs gate_alt");
+  }
   if (g->bias && !g->bias_per_row)
     ALG_REQUIRE((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;

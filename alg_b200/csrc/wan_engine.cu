@@ -122,6 +122,17 @@ int attention(cudaStream_t st, const bf16* Q, const bf16* K, const bf16* Vt, bf1
   return alg_attention_bf16(&a, st);
 }
 
+// FP32LayerNorm (+affine | +AdaLN modulate) of the Wan block: the shared LayerNorm kernel in its fp32-chain mode
+int layer_norm(cudaStream_t st, const bf16* x, bf16* out, int64_t rows, int d, float eps, const float* w, const float* b,
+               const float* scale, const float* shift) {
+  alg_layer_norm_t p{};
+  p.x = x; p.out = out; p.rows = rows; p.d = d; p.eps = eps;
+  p.weight = w; p.bias = b; p.affine_dtype = ALG_F32;
+  p.scale = scale; p.shift = shift; p.mod_dtype = ALG_F32;
+  p.rows_per_batch = rows > 0 ? rows : 1;
+  return alg_layer_norm(&p, st);
+}
+
 inline int64_t pad8(int64_t n) { return (n + 7) & ~int64_t(7); }
 
 #define ALG_TRY(expr)          \
@@ -425,11 +436,11 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
     }
   }
   if (n_img > 0) {
-    ALG_TRY_EW(dit::layer_norm((const bf16*)image, img_n, ni, c.image_dim, 1e-5f, e->in1_w, e->in1_b, nullptr, nullptr, st));
+    ALG_TRY_EW(layer_norm(st, (const bf16*)image, img_n, ni, c.image_dim, 1e-5f, e->in1_w, e->in1_b, nullptr, nullptr));
     ALG_TRY(gemm(st, img_n, c.image_dim, e->if1_w, c.image_dim, img_h, c.image_dim, ni, c.image_dim, c.image_dim,
                  e->if1_b, ALG_EPI_GELU_ERF));
     ALG_TRY(gemm(st, img_h, c.image_dim, e->if2_w, c.image_dim, img_p, d, ni, d, c.image_dim, e->if2_b));
-    ALG_TRY_EW(dit::layer_norm(img_p, ctx_img, ni, (int)d, 1e-5f, e->in2_w, e->in2_b, nullptr, nullptr, st));
+    ALG_TRY_EW(layer_norm(st, img_p, ctx_img, ni, (int)d, 1e-5f, e->in2_w, e->in2_b, nullptr, nullptr));
     for (int p = 1; p < n_pass; ++p)
       ALG_TRY_EW(dit::copy_rows(ctx_img, d, ctx_img + (int64_t)p * ni * d, d, ni, (int)d, st));
   }
@@ -445,7 +456,7 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
     const float *shift = mod, *scale = mod + d, *gate = mod + 2 * d, *c_shift = mod + 3 * d, *c_scale = mod + 4 * d,
                 *c_gate = mod + 5 * d;
     // self-attention
-    ALG_TRY_EW(dit::layer_norm(x, h, M, (int)d, c.eps, nullptr, nullptr, scale, shift, st));
+    ALG_TRY_EW(layer_norm(st, x, h, M, (int)d, c.eps, nullptr, nullptr, scale, shift));
     ALG_TRY(gemm(st, h, d, b.attn1.q_w, d, q, d, M, d, d, b.attn1.q_b));
     ALG_TRY(gemm(st, h, d, b.attn1.k_w, d, k, d, M, d, d, b.attn1.k_b));
     for (int p = 0; p < n_pass; ++p)  // V^T = W_v h^T + b_v: swapped operands, bias per row
@@ -456,7 +467,7 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
     ALG_TRY(attention(st, q, k, vt, ao, n_pass, heads, hd, N, N, Npad, 0));
     ALG_TRY(gemm(st, ao, d, b.attn1.o_w, d, x, d, M, d, d, b.attn1.o_b, ALG_EPI_GATE_RESIDUAL, x, gate));
     // cross-attention (text keys = last text_len context tokens, image keys = the rest)
-    ALG_TRY_EW(dit::layer_norm(x, h, M, (int)d, c.eps, b.norm2_w, b.norm2_b, nullptr, nullptr, st));
+    ALG_TRY_EW(layer_norm(st, x, h, M, (int)d, c.eps, b.norm2_w, b.norm2_b, nullptr, nullptr));
     ALG_TRY(gemm(st, h, d, b.attn2.q_w, d, q, d, M, d, d, b.attn2.q_b));
     ALG_TRY_EW(dit::rms_norm_rope(q, M, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_q, nullptr, st));
     ALG_TRY(gemm(st, ctx_text, d, b.attn2.k_w, d, k_text, d, n_pass * txt, d, d, b.attn2.k_b));
@@ -475,7 +486,7 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
     ALG_TRY(attention(st, q, k_text, vt_text, ao, n_pass, heads, hd, N, txt, txt_pad, n_img > 0 ? 1 : 0));
     ALG_TRY(gemm(st, ao, d, b.attn2.o_w, d, x, d, M, d, d, b.attn2.o_b, ALG_EPI_RESIDUAL, x));
     // feed-forward
-    ALG_TRY_EW(dit::layer_norm(x, h, M, (int)d, c.eps, nullptr, nullptr, c_scale, c_shift, st));
+    ALG_TRY_EW(layer_norm(st, x, h, M, (int)d, c.eps, nullptr, nullptr, c_scale, c_shift));
     ALG_TRY(gemm(st, h, d, b.ffn1_w, d, ffn, c.ffn_dim, M, c.ffn_dim, d, b.ffn1_b, ALG_EPI_GELU_TANH));
     ALG_TRY(gemm(st, ffn, c.ffn_dim, b.ffn2_w, c.ffn_dim, x, d, M, d, c.ffn_dim, b.ffn2_b, ALG_EPI_GATE_RESIDUAL, x, c_gate));
     debug_dump(x, (size_t)M * d * 2);
@@ -483,7 +494,7 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
 
   // ---- 4. output norm, projection, unpatchify ------------------------------------------------------------
   ALG_TRY_EW(dit::add_table(e->head_table, temb, mod, 2, (int)d, 1, st));
-  ALG_TRY_EW(dit::layer_norm(x, h, M, (int)d, c.eps, nullptr, nullptr, mod + d, mod, st));
+  ALG_TRY_EW(layer_norm(st, x, h, M, (int)d, c.eps, nullptr, nullptr, mod + d, mod));
   ALG_TRY(gemm(st, h, d, e->proj_w, d, proj, pop, M, po, d, e->proj_b));
   ALG_TRY_EW(dit::unpatchify(proj, (bf16*)noise_out, n_pass, c.out_channels, T, H, W, st));
   return 0;

@@ -16,9 +16,13 @@ from . import _lib
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = _lib.EPI_NONE,
          residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
-         bias_per_row: bool = False, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16) -> torch.Tensor:
-    """``epilogue(a @ w.T + bias)``: a [M, K] bf16, w [N, K] bf16 (nn.Linear layout).  See alg_gemm_bf16."""
-    _lib.require_cuda(a, w, bias, residual, gate, out)
+         bias_per_row: bool = False, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
+         gate_alt: Optional[torch.Tensor] = None, gate_split_row: int = 0, gate_round: bool = False) -> torch.Tensor:
+    """``epilogue(a @ w.T + bias)``: a [M, K] bf16, w [N, K] bf16 (nn.Linear layout).  See alg_gemm_bf16.
+
+    ``gate`` fp32 or bf16, [N] or [batches, N]; ``gate_alt`` replaces it for rows whose index inside their sample is
+    below ``gate_split_row``; ``gate_round`` rounds ``gate * y`` to bf16 before the residual add (eager bf16 chain)."""
+    _lib.require_cuda(a, w, bias, residual, gate, out, gate_alt)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
     M, K = a.shape
@@ -40,6 +44,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     g.epilogue = epilogue
     g.bias_per_row = int(bias_per_row)
     g.out_f32 = int(out.dtype == torch.float32)
+    if gate is not None:
+        assert gate.dtype in (torch.float32, torch.bfloat16) and gate.stride(-1) == 1
+        g.gate_dtype = _lib.dtype_code(gate.dtype)
+        g.gate_round = int(gate_round)
+        if gate_alt is not None:
+            assert gate_alt.dtype == gate.dtype and gate_alt.stride(-1) == 1
+            assert gate_alt.dim() == 1 or gate.dim() == 1 or gate_alt.stride(0) == gate.stride(0)
+            g.gate_alt = gate_alt.data_ptr()
+            g.gate_split_row = int(gate_split_row)
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.stride(0) == out.stride(0)
     with torch.cuda.device(a.device):
@@ -73,3 +86,149 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, n_kv: Optio
     with torch.cuda.device(q.device):
         _lib.check(_lib.lib().alg_attention_bf16(C.byref(a), _lib.stream_ptr(q.device)))
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# HBM-bound DiT building blocks (alg_layer_norm, alg_head_norm_rope, alg_patch_gather, ...)
+# ------------------------------------------------------------------------------------------------------
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _launch(fn, device, *args):
+    with torch.cuda.device(device):
+        _lib.check(fn(*args, _lib.stream_ptr(device)))
+
+
+def layer_norm(x: torch.Tensor, *, eps: float, weight=None, bias=None, scale=None, shift=None, scale_alt=None,
+               shift_alt=None, rows_per_batch: int = 0, split_row: int = 0, chain_bf16: bool = False,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm over the rows of x [rows, d] bf16 (+affine) (+AdaLN modulate).  See alg_layer_norm."""
+    _lib.require_cuda(x, weight, bias, scale, shift, scale_alt, shift_alt, out)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
+    rows, d = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.is_contiguous() and out.shape == x.shape and out.dtype == torch.bfloat16
+    p = _lib.LayerNorm()
+    p.x, p.out, p.rows, p.d, p.eps = x.data_ptr(), out.data_ptr(), rows, d, eps
+    if weight is not None:
+        assert weight.dtype == bias.dtype and weight.numel() == d and weight.is_contiguous() and bias.is_contiguous()
+        p.weight, p.bias, p.affine_dtype = weight.data_ptr(), bias.data_ptr(), _lib.dtype_code(weight.dtype)
+    if scale is not None:
+        assert scale.dtype == shift.dtype and scale.stride(-1) == 1 and shift.stride(-1) == 1
+        p.scale, p.shift, p.mod_dtype = scale.data_ptr(), shift.data_ptr(), _lib.dtype_code(scale.dtype)
+        p.rows_per_batch = rows_per_batch or max(rows, 1)
+        if scale.dim() == 2 and scale.shape[0] > 1:
+            assert shift.stride(0) == scale.stride(0)
+            p.mod_batch_stride = scale.stride(0)
+        if scale_alt is not None:
+            assert scale_alt.dtype == scale.dtype and shift_alt.dtype == scale.dtype
+            if scale.dim() == 2 and scale.shape[0] > 1:
+                assert scale_alt.stride(0) == scale.stride(0) and shift_alt.stride(0) == scale.stride(0)
+            p.scale_alt, p.shift_alt, p.split_row = scale_alt.data_ptr(), shift_alt.data_ptr(), int(split_row)
+    p.chain_bf16 = int(chain_bf16)
+    _launch(_lib.lib().alg_layer_norm, x.device, C.byref(p))
+    return out
+
+
+def head_norm_rope(x: torch.Tensor, heads: int, head_dim: int, *, norm_kind: int = _lib.NORM_NONE, weight=None,
+                   bias=None, eps: float = 1e-6, cos=None, sin=None, rows_per_batch: int = 0, rope_row0: int = 0,
+                   rope_rows: int = 0) -> torch.Tensor:
+    """In-place per-head q/k norm + rotary embedding on x [rows, >= heads*head_dim] bf16.  See alg_head_norm_rope."""
+    _lib.require_cuda(x, weight, bias, cos, sin)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    p = _lib.HeadNormRope()
+    p.x, p.rows, p.ld, p.heads, p.head_dim = x.data_ptr(), x.shape[0], x.stride(0), heads, head_dim
+    p.norm_kind, p.eps, p.weight, p.bias = norm_kind, eps, _ptr(weight), _ptr(bias)
+    if weight is not None:
+        assert weight.dtype == torch.bfloat16 and weight.numel() == head_dim
+    if cos is not None:
+        assert cos.dtype == sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+        assert cos.shape[-1] == head_dim and cos.shape == sin.shape
+        p.cos, p.sin = cos.data_ptr(), sin.data_ptr()
+        p.rope_rows = rope_rows or cos.shape[0]
+        assert p.rope_rows <= cos.shape[0]
+    p.rows_per_batch, p.rope_row0 = rows_per_batch or x.shape[0], rope_row0
+    _launch(_lib.lib().alg_head_norm_rope, x.device, C.byref(p))
+    return x
+
+
+def patch_gather(passes, out: torch.Tensor) -> torch.Tensor:
+    """Model-input assembly + 2x2 im2col.  ``passes``: per CFG pass, a list of sources; a source is a [C, T, H, W] tensor
+    view (stride(-1) == 1, any float dtype) or a tuple (view, frame0_view [C, 1, H, W]).  out [n_pass*N, >= 4*C_total] bf16."""
+    n_pass, n_src = len(passes), len(passes[0])
+    arr = (_lib.PatchSrc * (n_pass * n_src))()
+    keep = []
+    T = H = W = None
+    for pi, srcs in enumerate(passes):
+        assert len(srcs) == n_src
+        for si, s in enumerate(srcs):
+            t, t0 = s if isinstance(s, tuple) else (s, None)
+            _lib.require_cuda(t, t0)
+            assert t.dim() == 4 and t.stride(3) == 1
+            Cc, T_, H_, W_ = t.shape
+            assert (T, H, W) in ((None, None, None), (T_, H_, W_))
+            T, H, W = T_, H_, W_
+            d = arr[pi * n_src + si]
+            d.ptr, d.dtype, d.channels = t.data_ptr(), _lib.dtype_code(t.dtype), Cc
+            d.sc, d.st, d.sy = t.stride(0), t.stride(1), t.stride(2)
+            if t0 is not None:
+                assert t0.dtype == t.dtype and t0.stride(-1) == 1 and t0.stride(-2) == t.stride(2) and t0.shape[0] == Cc
+                d.ptr_t0, d.sc_t0 = t0.data_ptr(), t0.stride(0)
+            keep.append((t, t0))
+    assert out.dtype == torch.bfloat16 and out.dim() == 2 and out.stride(1) == 1
+    _launch(_lib.lib().alg_patch_gather, out.device, arr, n_pass, n_src, T, H, W, out.data_ptr(), out.stride(0))
+    return out
+
+
+def unpatchify(proj: torch.Tensor, out: torch.Tensor, channel_major: bool) -> torch.Tensor:
+    """proj [n_pass*N, >= 4*C] bf16 -> out, a [n_pass, C, T, H, W] bf16 view (stride(-1) == 1).  See alg_unpatchify."""
+    _lib.require_cuda(proj, out)
+    assert proj.dtype == out.dtype == torch.bfloat16 and out.dim() == 5 and out.stride(4) == 1 and proj.stride(1) == 1
+    n_pass, Cc, T, H, W = out.shape
+    _launch(_lib.lib().alg_unpatchify, out.device, proj.data_ptr(), proj.stride(0), out.data_ptr(), n_pass, Cc, T, H, W,
+            out.stride(0), out.stride(1), out.stride(2), out.stride(3), int(channel_major))
+    return out
+
+
+def timestep_embedding(t: float, dim: int, dtype, device) -> torch.Tensor:
+    out = torch.empty(dim, device=device, dtype=dtype)
+    _lib.require_cuda(out)
+    _launch(_lib.lib().alg_timestep_embedding, out.device, float(t), dim, out.data_ptr(), _lib.dtype_code(dtype))
+    return out
+
+
+def _ew(op, a, b=None, out=None):
+    _lib.require_cuda(a, b, out)
+    assert a.dtype == torch.bfloat16 and a.is_contiguous() and (b is None or (b.shape == a.shape and b.is_contiguous()))
+    if out is None:
+        out = torch.empty_like(a)
+    _launch(_lib.lib().alg_elementwise_bf16, a.device, op, a.data_ptr(), _ptr(b), out.data_ptr(), a.numel())
+    return out
+
+
+def add(a, b, out=None):
+    return _ew(_lib.EW_ADD, a, b, out)
+
+
+def silu(a, out=None):
+    return _ew(_lib.EW_SILU, a, None, out)
+
+
+def mean_rows(x: torch.Tensor) -> torch.Tensor:
+    """bf16 [rows, d] -> bf16 [d], fp32 accumulation."""
+    _lib.require_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty(x.shape[1], device=x.device, dtype=torch.bfloat16)
+    _launch(_lib.lib().alg_mean_rows_bf16, x.device, x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.data_ptr())
+    return out
+
+
+def copy_rows(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[r, :d] = src[r, :d] (bf16 2-D views with unit inner stride)."""
+    _lib.require_cuda(src, dst)
+    assert src.dtype == dst.dtype == torch.bfloat16 and src.shape == dst.shape and src.stride(1) == dst.stride(1) == 1
+    _launch(_lib.lib().alg_copy_rows_bf16, src.device, src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0),
+            src.shape[0], src.shape[1])
+    return dst

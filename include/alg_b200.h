@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ALG_B200_ABI_VERSION 1
+#define ALG_B200_ABI_VERSION 2
 
 typedef enum { ALG_F32 = 0, ALG_BF16 = 1, ALG_F16 = 2 } alg_dtype_t;
 
@@ -126,7 +126,7 @@ typedef struct {
   void* D;            /* [M, N] bf16 (or fp32 when out_f32), ldd                               */
   const void* bias;   /* bf16 [N] (or [M] when bias_per_row), may be NULL                      */
   const void* R;      /* residual, bf16 [M, N] with ldd; RESIDUAL / GATE_RESIDUAL only         */
-  const float* gate;  /* fp32 [M / rows_per_batch, gate_ld] (GATE_RESIDUAL only)               */
+  const void* gate;   /* fp32 (or bf16, see gate_dtype) [M / rows_per_batch, gate_ld] (GATE_RESIDUAL only) */
   int64_t M, N, K;
   int64_t lda, ldb, ldd;
   int64_t rows_per_batch;
@@ -134,6 +134,12 @@ typedef struct {
   int32_t epilogue;
   int32_t bias_per_row;
   int32_t out_f32;
+  /* --- ABI 2: gating variants of ALG_EPI_GATE_RESIDUAL (CogVideoX / HunyuanVideo blocks) --- */
+  int32_t gate_dtype;        /* ALG_F32 (Wan: fp32 gate, one rounding) or ALG_BF16 (gate is a bf16 tensor)        */
+  int32_t gate_round;        /* 1: D = bf16(R + bf16(gate * bf16(acc + bias))) -- eager bf16 `x + gate * y`       */
+  int64_t gate_split_row;    /* rows with (row % rows_per_batch) < gate_split_row use gate_alt (0 = unused)       */
+  const void* gate_alt;      /* Cog: text rows use enc_gate (cog DiT block); Hy: first-frame rows use the
+                                token-replace gate (hy DiT block, image_condition_type token_replace)            */
 } alg_gemm_t;
 
 /* D = epilogue(A * B^T + bias): every nn.Linear of the DiT (SURVEY kernel K6). */
@@ -154,6 +160,96 @@ typedef struct {
 /* Non-causal softmax(Q K^T * scale) V, fp32 softmax, bf16 in/out (SURVEY kernel K8;
  * replaces F.scaled_dot_product_attention inside the DiT, wan:910). */
 int alg_attention_bf16(const alg_attention_t* a, void* stream);
+
+
+/* ------------------------------------------------------------------------- */
+/* HBM-bound DiT building blocks shared by the CogVideoX and HunyuanVideo     */
+/* forwards (call sites cog:1082-1090, hy:1243-1252).  The host side that     */
+/* sequences them mirrors diffusers' modules (alg_b200/cogvideox.py,          */
+/* alg_b200/hunyuan.py); all arithmetic is in these kernels.                  */
+/* ------------------------------------------------------------------------- */
+
+/* LayerNorm over the rows of a bf16 [rows, d] matrix (+ affine) (+ AdaLN modulate).
+ *   chain_bf16 = 0: out = bf16( LN(x)[*w+b] [* (1 + scale) + shift] ), everything in fp32 (Wan FP32LayerNorm path)
+ *   chain_bf16 = 1: y = bf16(LN(x)[*w+b]);  out = bf16( bf16(y * bf16(1 + scale)) + shift )  -- the eager bf16 op chain of
+ *                   CogVideoXLayerNormZero / AdaLayerNormZero(Single) / AdaLayerNorm(Continuous)
+ * Modulation vectors are [d] per sample: sample b = row / rows_per_batch reads scale + b * mod_batch_stride; rows whose
+ * index inside the sample is < split_row read scale_alt / shift_alt instead (Cog text rows; Hy first-frame tokens). */
+typedef struct {
+  const void* x;
+  void* out;
+  int64_t rows;
+  int32_t d;
+  float eps;
+  const void* weight; /* NULL: no affine */
+  const void* bias;
+  int32_t affine_dtype; /* ALG_F32 or ALG_BF16 */
+  int32_t mod_dtype;    /* ALG_F32 or ALG_BF16 */
+  const void* scale;    /* NULL: no modulation */
+  const void* shift;
+  const void* scale_alt;
+  const void* shift_alt;
+  int64_t rows_per_batch;
+  int64_t mod_batch_stride;
+  int64_t split_row;
+  int32_t chain_bf16;
+} alg_layer_norm_t;
+int alg_layer_norm(const alg_layer_norm_t* p, void* stream);
+
+typedef enum { ALG_NORM_NONE = 0, ALG_NORM_RMS = 1, ALG_NORM_LAYER = 2 } alg_head_norm_t;
+
+/* Per-head q/k normalisation + rotary embedding, in place on bf16 [rows, heads * head_dim] (row stride ld).
+ *   ALG_NORM_RMS   : h = bf16(x * rsqrt(mean(x^2) + eps)); y = bf16(h * w)            (diffusers RMSNorm, Hy qk_norm)
+ *   ALG_NORM_LAYER : y = bf16(LN(x) * w + b) over head_dim                            (Cog attention norm_q / norm_k)
+ * RoPE (diffusers apply_rotary_emb, use_real, adjacent pairs): y = bf16(y * cos + rot(y) * sin) in fp32 for rows whose
+ * index inside the sample lies in [rope_row0, rope_row0 + rope_rows); cos / sin fp32 [rope_rows, head_dim]. */
+typedef struct {
+  void* x;
+  int64_t rows, ld;
+  int32_t heads, head_dim;
+  int32_t norm_kind;
+  float eps;
+  const void* weight; /* bf16 [head_dim] */
+  const void* bias;   /* bf16 [head_dim], ALG_NORM_LAYER only */
+  const float* cos;   /* NULL: no RoPE */
+  const float* sin;
+  int64_t rows_per_batch, rope_row0, rope_rows;
+} alg_head_norm_rope_t;
+int alg_head_norm_rope(const alg_head_norm_rope_t* p, void* stream);
+
+/* One source of the patch gather: `channels` planes of a [.., T, H, W] grid with element strides sc (channel), st (frame),
+ * sy (row); x stride is 1.  ptr_t0 (optional) replaces frame 0 (hy:1171 first-frame token replacement), strides sc_t0 / sy. */
+typedef struct {
+  const void* ptr;
+  const void* ptr_t0;
+  int32_t dtype;
+  int32_t channels;
+  int64_t sc, st, sy, sc_t0;
+} alg_patch_src_t;
+
+/* Model-input assembly fused with the 2x2 im2col of the patch embedding (wan:882-891, cog:1059-1075, hy:1168-1195):
+ * A[(p*N + n), (c, i, j)] = bf16(src_c[t, 2y+i, 2x+j]), channels = concatenation of the n_src sources of pass p.
+ * srcs_host: n_pass * n_src descriptors (host memory).  The replicated / concatenated / cast model input is never built. */
+int alg_patch_gather(const alg_patch_src_t* srcs_host, int n_pass, int n_src, int T, int H, int W, void* A, int64_t lda,
+                     void* stream);
+
+/* proj [n_pass*N, ld] bf16 (N = T*(H/2)*(W/2)) -> out bf16, element (p, c, t, y, x) at out + p*s_pass + c*sc + t*st + y*sy + x.
+ * channel_major = 0: proj column (i*2 + j)*C + c  (Wan);  1: column c*4 + i*2 + j  (CogVideoX, HunyuanVideo). */
+int alg_unpatchify(const void* proj, int64_t ld, void* out, int n_pass, int C, int T, int H, int W, int64_t s_pass,
+                   int64_t sc, int64_t st, int64_t sy, int channel_major, void* stream);
+
+/* diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0): out[dim] = [cos | sin], dtype f32/bf16 */
+int alg_timestep_embedding(float timestep, int dim, void* out, int dtype, void* stream);
+
+typedef enum { ALG_EW_ADD = 0, ALG_EW_SILU = 1, ALG_EW_COPY = 2, ALG_EW_GELU_TANH = 3 } alg_ew_op_t;
+/* Tiny bf16 vector ops of the conditioning path: out = bf16(a + b) | bf16(silu(a)) | a.  b may be NULL unless ADD. */
+int alg_elementwise_bf16(int op, const void* a, const void* b, void* out, int64_t n, void* stream);
+
+/* out[d] = bf16( sum_r x[r, :] / rows ) with fp32 accumulation (HunyuanVideo token-refiner pooled text projection). */
+int alg_mean_rows_bf16(const void* x, int64_t rows, int d, int64_t ld, void* out, void* stream);
+
+/* dst[r, 0:d] = src[r, 0:d] for rows rows, bf16, 16-byte vectorised (sequence concat). */
+int alg_copy_rows_bf16(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int d, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Wan2.1 I2V DiT engine: WanTransformer3DModel.forward (call site wan:910-917) */

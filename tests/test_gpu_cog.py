@@ -1,0 +1,143 @@
+"""CogVideoX: native DiT sequencing (alg_b200/cogvideox.py over the C ABI) + ALG loop vs the oracle restatement.
+
+Tolerance protocol as for Wan: the engine must be no further from an fp32 evaluation of the same
+bf16-rounded weights than eager PyTorch bf16 is (x1.5 slack); per-step latents teacher-forced; since CogVideoX keeps
+its latents in bf16 (cog:1123) the per-step bar is one bf16 rounding of the state: rel-L2 <= 2^-8."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(num_attention_heads=2, attention_head_dim=64, time_embed_dim=64, text_embed_dim=64, num_layers=2,
+            sample_width=12, sample_height=8, sample_frames=9, max_text_seq_length=16)
+ALG = dict(use_low_pass_guidance=True, lp_filter_type="down_up", lp_filter_in_latent=True, lp_blur_sigma=15.0,
+           lp_blur_kernel_size=0.02734375, lp_resize_factor=0.25, lp_strength_schedule_type="interval",
+           schedule_blur_kernel_size=False, schedule_interval_start_time=0.0, schedule_interval_end_time=0.3,
+           schedule_linear_start_weight=1.0, schedule_linear_end_weight=0.0, schedule_linear_end_time=0.5,
+           schedule_exp_decay_rate=10.0)
+
+
+def _model(seed=0, **over):
+    from alg_b200 import cogvideox
+    cfg = dict(TINY, **over)
+    return cfg, cogvideox.CogVideoXTransformer3DModel.from_synthetic(seed=seed, device="cuda", **cfg)
+
+
+def _ocfg(cfg):
+    from oracle import cog_oracle as Co
+    keys = Co.CogConfig.__dataclass_fields__
+    return Co.CogConfig(**{k: v for k, v in cfg.items() if k in keys})
+
+
+@pytest.mark.parametrize("n_pass,frames", [(2, 3), (3, 3), (1, 5)])
+@pytest.mark.parametrize("over", [{}, {"num_attention_heads": 3, "num_layers": 3, "time_embed_dim": 128}])
+def test_forward_matches_oracle(n_pass, frames, over):
+    from oracle import cog_oracle as Co
+    cfg, model = _model(1, **over)
+    ocfg = _ocfg(cfg)
+    g = torch.Generator(device="cuda").manual_seed(n_pass)
+    H, W = 8, 12
+    x = torch.randn(n_pass, frames, 32, H, W, generator=g, device="cuda").bfloat16()
+    text = torch.randn(n_pass, 16, 64, generator=g, device="cuda").bfloat16()
+    t = torch.tensor([601] * n_pass, device="cuda")
+    rope = tuple(r.cuda() for r in Co.rotary_tables(ocfg, H // 2, W // 2, frames))
+    out = model(x, text, t, image_rotary_emb=rope, return_dict=False)[0]
+    sd = model.state_dict()
+    ref16 = Co.forward(sd, ocfg, x, text, t, rope)
+    ref32 = Co.forward({k: v.float() for k, v in sd.items()}, ocfg, x.float(), text.float(), t, rope)
+    e_eng, e_torch = rel_l2(out, ref32), rel_l2(ref16, ref32)
+    assert e_eng < max(1.5 * e_torch, 3e-3), (e_eng, e_torch)
+    assert rel_l2(out, ref16) < 2e-2
+
+
+def test_forward_full_width_one_block():
+    """True CogVideoX-5b width (48 heads x 64, ff 12288, text 4096, 226 text tokens), one block, 2 latent frames at 60 x 90."""
+    from alg_b200 import cogvideox
+    from oracle import cog_oracle as Co
+    model = cogvideox.CogVideoXTransformer3DModel.from_synthetic(seed=5, device="cuda", num_layers=1, sample_frames=5)
+    ocfg = Co.CogConfig(num_layers=1, sample_frames=5)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    Fr, H, W = 2, 60, 90
+    x = torch.randn(2, Fr, 32, H, W, generator=g, device="cuda").bfloat16()
+    text = torch.randn(2, 226, 4096, generator=g, device="cuda").bfloat16()
+    t = torch.tensor([999, 999], device="cuda")
+    rope = tuple(r.cuda() for r in Co.rotary_tables(ocfg, H // 2, W // 2, Fr))
+    out = model(x, text, t, image_rotary_emb=rope, return_dict=False)[0]
+    sd = model.state_dict()
+    ref16 = Co.forward(sd, ocfg, x, text, t, rope)
+    ref32 = Co.forward({k: v.float() for k, v in sd.items()}, ocfg, x.float(), text.float(), t, rope)
+    e_eng, e_torch = rel_l2(out, ref32), rel_l2(ref16, ref32)
+    assert e_eng < max(1.5 * e_torch, 3e-3), (e_eng, e_torch)
+
+
+def _pipe(model):
+    from pipeline_cogvideox_image2video_lowpass import CogVideoXImageToVideoPipeline
+    pipe = CogVideoXImageToVideoPipeline.from_pretrained("synthetic", transformer=model, synthetic=True).to("cuda")
+    pipe.set_progress_bar_config(disable=True)
+    return pipe
+
+
+@pytest.mark.parametrize("mode", ["latent_down_up", "pixel_gaussian"])
+def test_loop_teacher_forced_per_step_latents(mode):
+    """cog:1005-1140 against oracle/cog_oracle.denoise_loop, both sides consuming the oracle's x_i (teacher-forced)."""
+    from alg_b200 import lowpass
+    from oracle import cog_oracle as Co, sched_oracle
+    cfg, model = _model(2)
+    ocfg = _ocfg(cfg)
+    pipe = _pipe(model)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    Fr, H, W, steps, gs = 3, 8, 12, 10, 6.0
+    lat0 = torch.randn(1, Fr, 16, H, W, generator=g, device="cuda").bfloat16()
+    img_lat = torch.cat([torch.randn(1, 1, 16, H, W, generator=g, device="cuda"), torch.zeros(1, Fr - 1, 16, H, W, device="cuda")], 1).bfloat16()
+    image_rgb = torch.rand(1, 3, H * 8, W * 8, generator=g, device="cuda").bfloat16() * 2 - 1
+    pos, neg = (torch.randn(1, 16, 64, generator=g, device="cuda").bfloat16() for _ in range(2))
+    alg = dict(ALG) if mode == "latent_down_up" else dict(ALG, lp_filter_type="gaussian_blur", lp_filter_in_latent=False,
+                                                          lp_blur_kernel_size=0.2, lp_blur_sigma=3.0)
+    rope = tuple(r.cuda() for r in Co.rotary_tables(ocfg, H // 2, W // 2, Fr))
+    sd = model.state_dict()
+    g_ref, g_mine = (torch.Generator(device="cuda").manual_seed(11) for _ in range(2))
+
+    def prepare_lp_ref(kind, sigma, k, f):  # the reference's prepare_lp with the real (CUDA) filter; VAE = the pipeline's stub
+        return pipe.prepare_lp(kind, sigma, k, f, g_ref, 9, True, alg["lp_filter_in_latent"], img_lat, image_rgb)
+
+    per_step = []
+    sched = sched_oracle.CogDDIMOracle()
+    Co.denoise_loop(lambda x, text, t: Co.forward(sd, ocfg, x, text, t.cuda(), rope), sched, lat0, img_lat, pos, neg, steps, gs,
+                    alg, prepare_lp_ref, lowpass.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
+    xs = [lat0] + [p[0] for p in per_step]
+    pipe.scheduler.set_timesteps(steps, device="cuda")
+    n3 = 0
+    for i, t in enumerate(pipe.scheduler.timesteps.tolist()):
+        x_next, npred = pipe.denoise_step(i, t, xs[i], img_lat, image_rgb, pos, neg, rope, g_mine, 9, steps, alg, gs)
+        n3 += npred.shape[0] == 3
+        assert npred.shape == per_step[i][1].shape
+        assert rel_l2(x_next, xs[i + 1]) < 2 ** -8, (i, rel_l2(x_next, xs[i + 1]))
+    assert n3 == 3  # interval [0, 0.3] of 10 steps: step_norm = i / 9 <= 0.3 for i = 0, 1, 2
+
+
+def test_pipeline_call_surface():
+    import inspect
+    from PIL import Image
+    cfg, model = _model(3)
+    pipe = _pipe(model)
+    names = list(inspect.signature(pipe.__call__).parameters)
+    assert names[:9] == ["image", "prompt", "negative_prompt", "height", "width", "num_frames", "num_inference_steps",
+                         "timesteps", "guidance_scale"]
+    assert len(names) == 37 and names[-1] == "schedule_exp_decay_rate"
+    img = Image.new("RGB", (100, 70), (10, 200, 90))
+    kw = dict(image=img, prompt="a boat", negative_prompt="blurry", num_frames=9, num_inference_steps=3, max_sequence_length=16)
+    seen = []
+    out = pipe(**kw, output_type="latent", generator=torch.Generator("cuda").manual_seed(42),
+               callback_on_step_end=lambda p, i, t, k: (seen.append(i), {})[1], **ALG)
+    assert out.frames.shape == (1, 3, 16, 8, 12) and out.frames.dtype == torch.bfloat16 and seen == [0, 1, 2]
+    assert torch.isfinite(out.frames.float()).all()
+    frames = pipe(**kw, output_type="np", **dict(ALG, use_low_pass_guidance=False)).frames
+    assert frames.shape == (1, 9, 64, 96, 3)
+    with pytest.raises(ValueError, match="divisible by 8"):
+        pipe(**dict(kw, height=100), **ALG)
+    with pytest.raises(ValueError, match="needs guidance_scale > 1"):
+        pipe(**kw, guidance_scale=1.0, **ALG)
+    with pytest.raises(ValueError, match="does not support custom"):
+        pipe(**kw, timesteps=[999, 500], **ALG)

@@ -22,15 +22,33 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(_lib.SIGNATURES)
-    assert _lib.lib().alg_abi_version() == 1
+    assert _lib.lib().alg_abi_version() == _lib.ABI_VERSION
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc sees include/alg_b200.h == the ctypes mirror in _lib.py."""
+    import subprocess
+
     from alg_b200 import _lib
 
-    assert ctypes.sizeof(_lib.UniPCStep) == 18 * 4
-    assert ctypes.sizeof(_lib.Gemm) == 6 * 8 + 8 * 8 + 3 * 4 + 4  # padded to 8
-    assert ctypes.sizeof(_lib.WanConfig) == 15 * 4
+    pairs = {"alg_unipc_step_t": _lib.UniPCStep, "alg_gemm_t": _lib.Gemm, "alg_attention_t": _lib.Attention,
+             "alg_wan_config_t": _lib.WanConfig, "alg_layer_norm_t": _lib.LayerNorm,
+             "alg_head_norm_rope_t": _lib.HeadNormRope, "alg_patch_src_t": _lib.PatchSrc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "alg_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append("return 0; }")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
 
 
 def test_gaussian_taps_are_dtype_faithful():
