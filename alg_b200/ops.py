@@ -192,8 +192,11 @@ def unpatchify(proj: torch.Tensor, out: torch.Tensor, channel_major: bool) -> to
     return out
 
 
-def timestep_embedding(t: float, dim: int, dtype, device) -> torch.Tensor:
-    out = torch.empty(dim, device=device, dtype=dtype)
+def timestep_embedding(t: float, dim: int, dtype, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0) of one scalar -> [dim]."""
+    if out is None:
+        out = torch.empty(dim, device=device, dtype=dtype)
+    assert out.numel() == dim and out.is_contiguous() and out.dtype == dtype
     _lib.require_cuda(out)
     _launch(_lib.lib().alg_timestep_embedding, out.device, float(t), dim, out.data_ptr(), _lib.dtype_code(dtype))
     return out

@@ -66,6 +66,26 @@ def load_image(image):
     return image.convert("RGB")
 
 
+def write_video(path, frames, fps):
+    """run.py:121-133 replacement: frames = list of PIL images or an array [T, H, W, 3] in [0, 1] (or uint8) -> mp4.
+
+    ``torchvision.io.write_video`` no longer exists in this image's torchvision and there is no ffmpeg binary / PyAV;
+    OpenCV's FFMPEG-backed VideoWriter is what is available (mp4v fourcc)."""
+    import cv2
+
+    arr = np.stack([np.asarray(f) for f in frames]) if not isinstance(frames, np.ndarray) else frames
+    if arr.dtype != np.uint8:
+        arr = (np.clip(arr, 0, 1) * 255).round().astype(np.uint8)
+    t, h, w, _ = arr.shape
+    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"mp4v"), float(fps), (w, h))
+    if not vw.isOpened():
+        raise RuntimeError(f"cannot open a video writer for {path}")
+    for f in arr:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    vw.release()
+    return path
+
+
 class VideoProcessor:
     """preprocess: PIL / ndarray / tensor -> fp32 [B, 3, H, W] in [-1, 1]; postprocess_video: [B, C, T, H, W] -> np / pt / pil."""
 

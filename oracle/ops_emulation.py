@@ -156,11 +156,12 @@ def unpatchify(proj, out, channel_major):
     return out
 
 
-def timestep_embedding(t, dim, dtype, device):
+def timestep_embedding(t, dim, dtype, device, out=None):
     half = dim // 2
     exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=device) / half
     emb = float(t) * torch.exp(exponent)
-    return torch.cat([torch.cos(emb), torch.sin(emb)]).to(dtype)
+    r = torch.cat([torch.cos(emb), torch.sin(emb)]).to(dtype)
+    return r if out is None else out.copy_(r)
 
 
 def add(a, b, out=None):

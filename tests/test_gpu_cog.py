@@ -125,7 +125,7 @@ def test_pipeline_call_surface():
     names = list(inspect.signature(pipe.__call__).parameters)
     assert names[:9] == ["image", "prompt", "negative_prompt", "height", "width", "num_frames", "num_inference_steps",
                          "timesteps", "guidance_scale"]
-    assert len(names) == 37 and names[-1] == "schedule_exp_decay_rate"
+    assert len(names) == 36 and names[-1] == "schedule_exp_decay_rate"  # 22 standard + 14 ALG (cog:727-774)
     img = Image.new("RGB", (100, 70), (10, 200, 90))
     kw = dict(image=img, prompt="a boat", negative_prompt="blurry", num_frames=9, num_inference_steps=3, max_sequence_length=16)
     seen = []
@@ -141,3 +141,25 @@ def test_pipeline_call_surface():
         pipe(**kw, guidance_scale=1.0, **ALG)
     with pytest.raises(ValueError, match="does not support custom"):
         pipe(**kw, timesteps=[999, 500], **ALG)
+
+
+def test_run_py_end_to_end(tmp_path, monkeypatch):
+    """run.py's CLI / YAML flow (run.py:26-146) on a tiny synthetic CogVideoX: config -> pipe(**kwargs) -> mp4 on disk."""
+    import types
+    import yaml
+    from PIL import Image
+    import run
+    cfg, model = _model(4)
+    orig = run.CogVideoXImageToVideoPipeline.from_pretrained.__func__
+    monkeypatch.setattr(run.CogVideoXImageToVideoPipeline, "from_pretrained",
+                        classmethod(lambda cls, path, **kw: orig(cls, "synthetic", transformer=model, synthetic=True)))
+    conf = yaml.safe_load(open("configs/cogvideox_alg.yaml"))
+    assert "CogVideoX" in conf["model"]["path"]
+    conf["generation"].update(num_frames=9, num_inference_steps=3, height=64, width=96)
+    conf["generation"]["max_sequence_length"] = 16
+    cpath, ipath, opath = tmp_path / "c.yaml", tmp_path / "i.png", tmp_path / "o.mp4"
+    cpath.write_text(yaml.safe_dump(conf))
+    Image.new("RGB", (120, 80), (200, 30, 30)).save(ipath)
+    run.main(types.SimpleNamespace(config=str(cpath), image_path=str(ipath), prompt="a red bus", output_path=str(opath),
+                                   model_cache_dir=None))
+    assert opath.exists() and opath.stat().st_size > 1000

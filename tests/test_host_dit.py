@@ -60,3 +60,50 @@ def test_ops_fail_loudly_without_cuda():
         ops.layer_norm(x, eps=1e-5)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.head_norm_rope(x, 1, 64)
+
+
+HY_TINY = dict(num_attention_heads=2, attention_head_dim=128, num_layers=2, num_single_layers=2, num_refiner_layers=1,
+               text_embed_dim=64, pooled_projection_dim=32)
+
+
+def test_hunyuan_sequencer_matches_oracle(monkeypatch):
+    """Also checks that dropping the padded text tokens (the engine's form of the key-padding mask) is exact: the
+    oracle keeps them and builds diffusers' boolean masks."""
+    from alg_b200 import hunyuan
+    from oracle import hunyuan_oracle as Ho, ops_emulation as emu
+    monkeypatch.setattr(hunyuan, "ops", emu)
+    cfg = Ho.tiny_config()
+    sd = Ho.make_weights(cfg, dtype=torch.bfloat16, seed=2)
+    g = torch.Generator().manual_seed(0)
+    T, H, W = 3, 8, 16
+    x = torch.randn(2, 16, T, H, W, generator=g)
+    text = torch.randn(2, 12, 64, generator=g).bfloat16()
+    mask = torch.zeros(2, 12)
+    mask[0, :7] = 1
+    mask[1, :10] = 1
+    pooled = torch.randn(2, 32, generator=g).bfloat16()
+    t = torch.tensor([900.0, 900.0]).bfloat16()
+    gd = torch.tensor([6.0, 6.0]).bfloat16() * 1000.0
+    assert float(gd[0]) == 6016.0  # hy:1115-1119: bf16(6.0) * 1000 rounds to 6016
+    model = hunyuan.HunyuanVideoTransformer3DModel(**HY_TINY).load_state_dict(sd)
+    out = model(x, t, text, mask, pooled, gd, return_dict=False)[0]
+    ref = Ho.forward(sd, cfg, x.bfloat16(), t, text, mask, pooled, gd)
+    ref32 = Ho.forward({k: v.float() for k, v in sd.items()}, cfg, x.bfloat16().float(), t.float(), text.float(), mask,
+                       pooled.float(), gd.float())
+    assert rel_l2(out, ref) < 2e-3, rel_l2(out, ref)
+    assert rel_l2(out, ref32) < 1.2 * rel_l2(ref, ref32)
+    # first-frame pointer override == cat([first, latents[:, :, 1:]], dim=2) (hy:1171, 1232)
+    first = torch.randn(16, 1, H, W, generator=g)
+    o2 = model.forward_pass(x[0], first, text[0, :7].contiguous(), pooled[0], float(t[0]), float(gd[0]))
+    x2 = x[:1].clone()
+    x2[0, :, 0:1] = first
+    r2 = Ho.forward(sd, cfg, x2.bfloat16(), t[:1], text[:1], mask[:1], pooled[:1], gd[:1])
+    assert rel_l2(o2, r2[0]) < 2e-3
+
+
+def test_hunyuan_rope_table_matches_oracle():
+    from alg_b200 import embeddings
+    from oracle import hunyuan_oracle as Ho
+    cos, sin = embeddings.hunyuan_rotary_pos_embed(5, 6, 10)
+    rc, rs = Ho.rope_tables(Ho.HunyuanConfig(), 5, 6, 10)
+    assert cos.shape == (300, 128) and torch.equal(cos, rc) and torch.equal(sin, rs)
