@@ -182,22 +182,14 @@ def synthetic_inputs(device, seed):
     return lat, cond, text(), text(), torch.randn(1, 257, 1280, generator=g, device=device).bfloat16()
 
 
-def broadcast_weights(sd, src=0):
-    """NCCL over NVLink: rank `src` owns the seeded weights, everyone else receives them (init only)."""
-    import torch.distributed as dist
-    for name in sorted(sd):
-        dist.broadcast(sd[name], src=src)
-
-
 def run_ours(args):
     import torch.distributed as dist
     from alg_b200 import _lib, wan
+    from alg_b200 import distributed as D
     from alg_b200.schedulers import UniPCMultistepScheduler
     from pipeline_wan_image2video_lowpass import WanImageToVideoPipeline
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = D.env_rank()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -212,8 +204,7 @@ def run_ours(args):
               for k, s in wan.parameter_shapes(cfg).items()}
     else:
         sd = wan.synthetic_state_dict(cfg, seed=0, device=device)
-    if world > 1:
-        broadcast_weights(sd)
+    D.broadcast_state_dict(sd)  # NCCL over NVLink: rank 0 owns the seeded weights (init only, outside the timed region)
     transformer = wan.WanTransformer3DModel(**cfg).load_state_dict(sd)
     pipe = WanImageToVideoPipeline.from_pretrained("synthetic", transformer=transformer, synthetic=True)
     pipe.scheduler = UniPCMultistepScheduler.from_config(pipe.scheduler.config, flow_shift=FLOW_SHIFT)
@@ -222,7 +213,7 @@ def run_ours(args):
     sched = pipe.scheduler
     sched.set_timesteps(STEPS_PER_VIDEO, device=device)
     ts = sched.timesteps.tolist()
-    lat0, cond, pos, neg, img = synthetic_inputs(device, 42 + rank)
+    lat0, cond, pos, neg, img = synthetic_inputs(device, D.sample_seed(rank))
     image_rgb = torch.zeros(1, 3, HEIGHT, WIDTH, device=device)
 
     def step(idx, latents):
@@ -286,13 +277,10 @@ def run_ours(args):
         barrier()
         ms_e2e = f0.elapsed_time(f1)
 
-    t_dev = torch.tensor([ms_total, ms_e2e], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = (float(v) for v in t_dev.tolist())
+    ms_total, ms_e2e = D.max_over_ranks([ms_total, ms_e2e], device)
     ms_step = ms_total / args.steps
-    fps = world * NUM_FRAMES / (STEPS_PER_VIDEO * ms_step / 1e3)
-    fps_e2e = world * NUM_FRAMES / (STEPS_PER_VIDEO * (ms_e2e / args.steps) / 1e3) if ms_e2e > 0 else None
+    fps = D.aggregate_rate(NUM_FRAMES / STEPS_PER_VIDEO, world, ms_step)
+    fps_e2e = D.aggregate_rate(NUM_FRAMES / STEPS_PER_VIDEO, world, ms_e2e / args.steps) if ms_e2e > 0 else None
 
     if rank == 0:
         hbm, tf_burst, tf_sust, src = peaks()

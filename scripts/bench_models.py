@@ -1,0 +1,85 @@
+"""Full-size step timing of the other two BASELINE.json configs through the pipelines' denoise_step (device-timed):
+
+    python scripts/bench_models.py cog      # configs[2]: CogVideoX-5b-I2V 720x480, 49 frames, gaussian_blur in pixel space
+    python scripts/bench_models.py hunyuan  # configs[3]: HunyuanVideo-I2V 720p, 129 frames, interval schedule (single pass)
+
+Prints one JSON line per model: ms per 3-pass / 2-pass (Cog) or 1-pass (Hy) step, frames/s of the full schedule derived
+from them, and the model FLOP rate.  Synthetic weights at the true architecture (no checkpoints offline)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+
+def timed(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def cog(reps):
+    from pipeline_cogvideox_image2video_lowpass import CogVideoXImageToVideoPipeline
+    pipe = CogVideoXImageToVideoPipeline.from_pretrained("synthetic", synthetic=True).to("cuda")
+    steps, frames, H, W = 50, 49, 480, 720
+    alg = dict(use_low_pass_guidance=True, lp_filter_type="gaussian_blur", lp_filter_in_latent=False, lp_blur_sigma=15.0,
+               lp_blur_kernel_size=0.02734375, lp_resize_factor=0.25, lp_strength_schedule_type="interval",
+               schedule_blur_kernel_size=False, schedule_interval_start_time=0.0, schedule_interval_end_time=0.04,
+               schedule_linear_start_weight=1.0, schedule_linear_end_weight=0.0, schedule_linear_end_time=0.5,
+               schedule_exp_decay_rate=10.0)
+    g = torch.Generator(device="cuda").manual_seed(42)
+    lat = torch.randn(1, 13, 16, 60, 90, generator=g, device="cuda").bfloat16()
+    img_lat = torch.cat([torch.randn(1, 1, 16, 60, 90, generator=g, device="cuda"), torch.zeros(1, 12, 16, 60, 90, device="cuda")], 1).bfloat16()
+    rgb = (torch.rand(1, 3, H, W, generator=g, device="cuda") * 2 - 1).bfloat16()
+    pos, neg = (torch.randn(1, 226, 4096, generator=g, device="cuda").bfloat16() for _ in range(2))
+    rope = pipe._prepare_rotary_positional_embeddings(H, W, 13, "cuda")
+    pipe.scheduler.set_timesteps(steps, device="cuda")
+    ts = pipe.scheduler.timesteps.tolist()
+    with torch.no_grad():
+        ms3 = timed(lambda: pipe.denoise_step(0, ts[0], lat, img_lat, rgb, pos, neg, rope, g, frames, steps, alg, 6.0), reps)
+        ms2 = timed(lambda: pipe.denoise_step(10, ts[10], lat, img_lat, rgb, pos, neg, rope, g, frames, steps, alg, 6.0), reps)
+    sec_video = (2 * ms3 + 48 * ms2) / 1e3
+    fwd = 3.32e14  # FLOP per sample-forward at config 3
+    print(json.dumps({"model": "CogVideoX-5b-I2V 720x480 49f 50 steps, gaussian_blur pixel-space ALG (BASELINE configs[2])",
+                      "ms_step_3pass": ms3, "ms_step_2pass": ms2, "frames_per_s": frames / sec_video,
+                      "model_tflops_2pass": 2 * fwd / (ms2 / 1e3) / 1e12, "tokens": 17776}), flush=True)
+
+
+def hunyuan(reps):
+    from pipeline_hunyuan_video_image2video_lowpass import HunyuanVideoImageToVideoPipeline
+    pipe = HunyuanVideoImageToVideoPipeline.from_pretrained("synthetic", synthetic=True).to("cuda")
+    steps, frames = 30, 129
+    T, H, W = 33, 90, 160
+    alg = dict(use_low_pass_guidance=True, lp_filter_type="down_up", lp_filter_in_latent=True, lp_blur_sigma=15.0,
+               lp_blur_kernel_size=0.02734375, lp_resize_factor=0.625, lp_strength_schedule_type="interval",
+               schedule_blur_kernel_size=False, schedule_interval_start_time=0.0, schedule_interval_end_time=0.04,
+               schedule_linear_start_weight=1.0, schedule_linear_end_weight=0.0, schedule_linear_end_time=0.5,
+               schedule_exp_decay_rate=10.0)
+    g = torch.Generator(device="cuda").manual_seed(42)
+    lat = torch.randn(1, 16, T, H, W, generator=g, device="cuda")
+    img_lat = torch.randn(1, 16, 1, H, W, generator=g, device="cuda")
+    pos = (torch.randn(1, 400, 4096, generator=g, device="cuda").bfloat16(), torch.randn(1, 768, generator=g, device="cuda").bfloat16(), 180)
+    pipe.scheduler.set_timesteps(sigmas=np.linspace(1.0, 0.0, steps + 1)[:-1], device="cuda")
+    ts = pipe.scheduler.timesteps.float().cpu()
+    with torch.no_grad():
+        ms1 = timed(lambda: (setattr(pipe.scheduler, "_step_index", 0),
+                             pipe.denoise_step(0, ts[0], lat, img_lat, pos, None, 6016.0, frames, steps, alg, 1.0))[1], reps)
+    fwd = 1.21e16  # FLOP per sample-forward at config 4
+    print(json.dumps({"model": "HunyuanVideo-I2V 720x1280 129f 30 steps, down_up ALG, embedded guidance (BASELINE configs[3])",
+                      "ms_step_1pass": ms1, "frames_per_s": frames / (steps * ms1 / 1e3),
+                      "model_tflops": fwd / (ms1 / 1e3) / 1e12, "tokens": T * (H // 2) * (W // 2) + 180}), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "cog"
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    {"cog": cog, "hunyuan": hunyuan}[which](reps)
