@@ -32,11 +32,13 @@ using namespace tc;
 
 constexpr int BQ = 128;  // query rows per tile (two tiles per CTA)
 constexpr int BKV = 64;  // keys per pipeline step
-constexpr int kThreads = 320;
 constexpr int kStages = 4;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef ALG_ATTN_POLY_DEFAULT
 #define ALG_ATTN_POLY_DEFAULT 4
+#endif
+#ifndef ALG_ATTN_SPLIT_DEFAULT
+#define ALG_ATTN_SPLIT_DEFAULT 0
 #endif
 
 template <int D>
@@ -44,7 +46,8 @@ struct Cfg {
   static constexpr int kBytesQ = BQ * D * 2;   // one query tile
   static constexpr int kBytesK = BKV * D * 2;  // one K stage  [64 keys][D]
   static constexpr int kBytesV = D * BKV * 2;  // one V^T stage [D][64 keys]
-  static constexpr int kSmemBytes = 2 * kBytesQ + kStages * (kBytesK + kBytesV) + 1024 + 512;
+  static constexpr int kXchBytes = 2 * 2 * 2 * BQ * 4;  // SPLIT: [tile][step parity][half][row] partial row maxima
+  static constexpr int kSmemBytes = 2 * kBytesQ + kStages * (kBytesK + kBytesV) + 1024 + 512 + kXchBytes;
   static constexpr int kSubQ = BQ * 128;   // bytes of one [128 rows][64 elem] swizzle sub-tile of Q
   static constexpr int kSubK = BKV * 128;  // bytes of one [64 keys][64 elem] sub-tile of K
 };
@@ -86,12 +89,25 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   return p;
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // POLY = 0: every exp2 on MUFU; POLY = n > 0: one pair in every n pairs of a row goes through ex2_poly2.
-template <int D, int POLY>
-__global__ void __launch_bounds__(kThreads, 1)
+// SPLIT = 0: one thread per query row (8 softmax warps, 2 per SM sub-partition).
+// SPLIT = 1: TWO threads per query row -- warps w and w + 4 of a tile own the same 32 TMEM lanes and take the key
+//            columns [0, 32) / [32, 64) of every step (16 softmax warps, 4 per sub-partition, so the schedulers can hide
+//            the MUFU / FMA latencies the 2-warp version exposed: 0.44 IPC, profiles/r01_attention.md).  The halves
+//            exchange their partial row maxima through shared memory behind one 256-thread named barrier per step,
+//            keep partial row sums, and each rescales / writes half of the O columns.
+template <int D, int POLY, int SPLIT>
+__global__ void __launch_bounds__((SPLIT ? 18 : 10) * 32, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Params p) {
   using C = Cfg<D>;
+  constexpr int kSoftmaxWarps = SPLIT ? 16 : 8;
+  constexpr int kTmaWarp = kSoftmaxWarps, kMmaWarp = kSoftmaxWarps + 1;
+  constexpr int kWarpsPerTile = kSoftmaxWarps / 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                          // [2][BQ x D]
@@ -109,13 +125,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* o_done = p_full + 4;               // 2: committed behind every PV (the rare O-rescale path waits on it)
   uint64_t* o_full = o_done + 2;               // 2: committed behind the last PV only (epilogue)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // SPLIT only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, batch = blockIdx.z;
   const int q0 = blockIdx.x * 2 * BQ;
   const int n_steps = (p.n_kv + BKV - 1) / BKV;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
@@ -128,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);  // one arrival per softmax warp
+      mbar_init(&p_full[i], kWarpsPerTile);  // one arrival per softmax warp of the tile
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&o_done[i], 1);
@@ -136,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -145,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kTmaWarp) {
     if (elect_one()) {  // ===== TMA producer: Q0 Q1 | K0 K1 | V0 K2 | V1 K3 | ... (the order the MMA warp consumes) =====
       mbar_arrive_expect_tx(q_full, 2 * C::kBytesQ);
       for (int i = 0; i < 2; ++i)
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (j + 2 < n_steps) load_k(j + 2);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     if (elect_one()) {  // ===== MMA issuer.  elect.sync (not `lane == 0`) tells ptxas that a single lane runs this region, so the
                         // descriptors stay in uniform registers; otherwise every UTCHMMA is wrapped in an ELECT / R2UR loop =====
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
@@ -224,13 +241,17 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     }
-  } else {  // ===== softmax warpgroups =====
-    const int i = warp >> 2;  // query tile
-    const int quad = warp & 3;
+  } else {  // ===== softmax warps =====
+    constexpr int W = SPLIT ? BKV / 2 : BKV;      // key columns of a step owned by this thread
+    constexpr int OC = SPLIT ? D / 2 : D;         // O columns this thread rescales / writes
+    const int i = warp / kWarpsPerTile;           // query tile
+    const int hh = SPLIT ? (warp >> 2) & 1 : 0;   // column half (SPLIT)
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t t_s = tmem_base + lane_base + i * 128;
-    const uint32_t t_o = tmem_base + lane_base + 256 + i * 128;
-    const int row = q0 + i * BQ + quad * 32 + lane;
+    const uint32_t t_o = tmem_base + lane_base + 256 + i * 128 + hh * OC;
+    const int row_in_tile = quad * 32 + lane;
+    const int row = q0 + i * BQ + row_in_tile;
     float m_used = -INFINITY, l = 0.f;
     const float c = p.scale_log2;
     // one 64-key step of online softmax; `ragged` (compile-time) is the last, partially filled step -- kept out of the
@@ -239,32 +260,44 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t t_sj = t_s + (j & 1) * 64;
       mbar_wait(&s_full[i * 2 + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
-      float s[64];
-      tmem_ld32(t_sj, reinterpret_cast<uint32_t*>(s));
-      tmem_ld32(t_sj + 32, reinterpret_cast<uint32_t*>(s) + 32);
+      float s[W];
+      tmem_ld32(t_sj + hh * W, reinterpret_cast<uint32_t*>(s));
+      if constexpr (W == 64) tmem_ld32(t_sj + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tmem_ld_wait();
       if constexpr (decltype(ragged)::value) {  // TMA zero-filled the tail of the tile: mask it out
-        const int valid = p.n_kv - j * BKV;
+        const int valid = p.n_kv - j * BKV - hh * W;
 #pragma unroll
-        for (int k = 0; k < 64; ++k)
+        for (int k = 0; k < W; ++k)
           if (k >= valid) s[k] = -INFINITY;
       }
-      // row max: four independent FMNMX3 chains (one dependent chain of max ops is pure latency)
-      float mc[4];
+      // row max: independent FMNMX3 chains (one dependent chain of max ops is pure latency)
+      float mc[W / 16];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < W / 16; ++g) {
         float m = s[g * 16];
 #pragma unroll
         for (int k = 1; k + 1 < 16; k += 2) m = max3(m, s[g * 16 + k], s[g * 16 + k + 1]);
         mc[g] = fmaxf(m, s[g * 16 + 15]);
       }
-      const float mx = fmaxf(max3(mc[0], mc[1], mc[2]), mc[3]) * c;
+      float mraw;
+      if constexpr (SPLIT) {
+        // exchange the partial maxima of the two column halves: this also orders "both halves have read S(j)" before
+        // either half overwrites the buffer with P(j)
+        float* slot = xch + ((i * 2 + (j & 1)) * 2) * BQ;
+        const float mine = fmaxf(mc[0], mc[1]);
+        slot[hh * BQ + row_in_tile] = mine;
+        named_bar_sync(1 + i, kWarpsPerTile * 32);
+        mraw = fmaxf(mine, slot[(hh ^ 1) * BQ + row_in_tile]);
+      } else {
+        mraw = fmaxf(max3(mc[0], mc[1], mc[2]), mc[W / 16 - 1]);
+      }
+      const float mx = mraw * c;
       if (j == 0) {
         m_used = mx;
       } else {
         const float m_new = fmaxf(m_used, mx);
         const bool need = (m_new - m_used) > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {  // warp-uniform: tcgen05.ld/st are warp collectives
+        if (__any_sync(0xffffffffu, need)) {  // warp-uniform (and identical in both halves: same rows, same maxima)
           // S runs two steps ahead of PV: O_i may still be receiving P_i(j-1) V_(j-1)
           mbar_wait(&o_done[i], (j - 1) & 1);
           tc_fence_after();
@@ -272,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           l *= f;
           m_used = m_new;
 #pragma unroll 1
-          for (int ch = 0; ch < D / 16; ++ch) {
+          for (int ch = 0; ch < OC / 16; ++ch) {
             uint32_t o[16];
             tmem_ld16(t_o + ch * 16, o);
             tmem_ld_wait();
@@ -285,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_used, -m_used);
       float2 sum0 = make_float2(0.f, 0.f), sum1 = sum0;
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      for (int ch = 0; ch < W / 32; ++ch) {
         uint32_t pk[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -302,7 +335,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           __nv_bfloat162 h = __floats2bfloat162_rn(e.x, e.y);
           pk[k] = *reinterpret_cast<uint32_t*>(&h);
         }
-        tmem_st16(t_sj + ch * 16, pk);  // P (bf16 pairs) overwrites the first 32 columns of this S buffer
+        // P (bf16 pairs) overwrites the first 32 columns of this S buffer: 16 columns per 32 keys
+        tmem_st16(t_sj + hh * 16 + ch * 16, pk);
       }
       l += (sum0.x + sum0.y) + (sum1.x + sum1.y);
       tmem_st_wait();
@@ -314,13 +348,19 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll 1
     for (int j = 0; j < n_full; ++j) softmax_step(j, std::false_type{});
     if (n_full < n_steps) softmax_step(n_full, std::true_type{});
+    if constexpr (SPLIT) {  // row sum = sum of the two halves' partial sums (slot of the parity the last step did not use)
+      float* slot = xch + ((i * 2 + (n_steps & 1)) * 2) * BQ;
+      slot[hh * BQ + row_in_tile] = l;
+      named_bar_sync(1 + i, kWarpsPerTile * 32);
+      l += slot[(hh ^ 1) * BQ + row_in_tile];
+    }
     // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------------
     mbar_wait(&o_full[i], 0);
     tc_fence_after();
     const float inv = 1.0f / l;
-    __nv_bfloat16* orow = p.O + (int64_t)batch * p.o_bs + (int64_t)row * p.o_rs + head * D;
+    __nv_bfloat16* orow = p.O + (int64_t)batch * p.o_bs + (int64_t)row * p.o_rs + head * D + hh * OC;
 #pragma unroll
-    for (int ch = 0; ch < D / 32; ++ch) {
+    for (int ch = 0; ch < OC / 32; ++ch) {
       uint32_t o[32];
       tmem_ld32(t_o + ch * 32, o);
       tmem_ld_wait();
@@ -351,18 +391,19 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int D, int POLY>
+template <int D, int POLY, int SPLIT>
 static int launch(const alg_attention_t* a, cudaStream_t st) {
   using C = Cfg<D>;
+  constexpr int kThreads = (SPLIT ? 18 : 10) * 32;
   static bool attr_done = false;
   if (!attr_done) {
-    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_done = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -392,7 +433,7 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
   dim3 grid((unsigned)((a->n_q + 2 * BQ - 1) / (2 * BQ)), (unsigned)a->heads, (unsigned)a->batch);
-  attention_kernel<D, POLY><<<grid, kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  attention_kernel<D, POLY, SPLIT><<<grid, kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
   ALG_LAUNCH_OK();
   return 0;
 }
@@ -413,18 +454,32 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   ALG_REQUIRE((reinterpret_cast<uintptr_t>(a->O) & 15) == 0, "attention: O must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static int poly = -1;  // tuning knob: share of exp2 evaluated on the FMA pipe (1 pair in `poly`); default from profiling
+  static int poly = -1, split = -1;  // tuning knobs; defaults from profiling
   if (poly < 0) {
     const char* e = getenv("ALG_ATTN_POLY");
     poly = e ? atoi(e) : ALG_ATTN_POLY_DEFAULT;
+    e = getenv("ALG_ATTN_SPLIT");
+    split = e ? atoi(e) : ALG_ATTN_SPLIT_DEFAULT;
+  }
+#define ALG_ATTN_DISPATCH(DD)                                                       \
+  if (split) {                                                                      \
+    switch (poly) {                                                                 \
+      case 0: return attn::launch<DD, 0, 1>(a, st);                                 \
+      case 2: return attn::launch<DD, 2, 1>(a, st);                                 \
+      case 4: return attn::launch<DD, 4, 1>(a, st);                                 \
+      default: return attn::launch<DD, 8, 1>(a, st);                                \
+    }                                                                               \
+  } else {                                                                          \
+    switch (poly) {                                                                 \
+      case 0: return attn::launch<DD, 0, 0>(a, st);                                 \
+      case 2: return attn::launch<DD, 2, 0>(a, st);                                 \
+      case 4: return attn::launch<DD, 4, 0>(a, st);                                 \
+      default: return attn::launch<DD, 8, 0>(a, st);                                \
+    }                                                                               \
   }
   if (a->head_dim == 128) {
-    switch (poly) {
-      case 0: return attn::launch<128, 0>(a, st);
-      case 2: return attn::launch<128, 2>(a, st);
-      case 4: return attn::launch<128, 4>(a, st);
-      default: return attn::launch<128, 8>(a, st);
-    }
+    ALG_ATTN_DISPATCH(128)
   }
-  return poly == 0 ? attn::launch<64, 0>(a, st) : attn::launch<64, 4>(a, st);
+  ALG_ATTN_DISPATCH(64)
+#undef ALG_ATTN_DISPATCH
 }

@@ -32,7 +32,7 @@ def check(B, H, D, Nq, Nkv, scale_q=1.0):
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
     H = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    var = "poly=" + os.environ.get("ALG_ATTN_POLY", "default")
+    var = "poly=" + os.environ.get("ALG_ATTN_POLY", "default") + " split=" + os.environ.get("ALG_ATTN_SPLIT", "default")
     errs = [check(1, 2, 128, 1000, 2000, 4.0), check(2, 3, 128, 512, 1024), check(1, 2, 128, 300, 257), check(1, 2, 64, 700, 1000),
             check(1, 4, 128, 4096, 4096, 3.0)]
     B, D, N = 1, 128, 32760

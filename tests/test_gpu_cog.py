@@ -163,3 +163,41 @@ def test_run_py_end_to_end(tmp_path, monkeypatch):
     run.main(types.SimpleNamespace(config=str(cpath), image_path=str(ipath), prompt="a red bus", output_path=str(opath),
                                    model_cache_dir=None))
     assert opath.exists() and opath.stat().st_size > 1000
+
+
+def test_config1_full_architecture_two_steps():
+    """BASELINE.json configs[0] on the GPU: the TRUE CogVideoX-5b-I2V architecture (42 layers, 48 x 64, ff 12288, 226 text
+    tokens), 9 frames / 2 steps / gs 6, ALG down_up f=0.25 in latent with the shipped interval [0, 0.04] -> step 0 runs
+    three passes, step 1 two (SURVEY section 4 KAT), teacher-forced against the oracle loop (eager PyTorch bf16)."""
+    from alg_b200 import cogvideox, lowpass
+    from oracle import cog_oracle as Co, sched_oracle
+    model = cogvideox.CogVideoXTransformer3DModel.from_synthetic(seed=11, device="cuda")
+    ocfg = Co.CogConfig()
+    pipe = _pipe(model)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    Fr, H, W, steps, gs = 3, 60, 90, 2, 6.0
+    lat0 = torch.randn(1, Fr, 16, H, W, generator=g, device="cuda").bfloat16()
+    img_lat = torch.cat([torch.randn(1, 1, 16, H, W, generator=g, device="cuda"), torch.zeros(1, Fr - 1, 16, H, W, device="cuda")], 1).bfloat16()
+    pos, neg = (torch.randn(1, 226, 4096, generator=g, device="cuda").bfloat16() for _ in range(2))
+    alg = dict(ALG, schedule_interval_end_time=0.04)
+    rope = pipe._prepare_rotary_positional_embeddings(H * 8, W * 8, Fr, "cuda")
+    ref_rope = tuple(r.cuda() for r in Co.rotary_tables(ocfg, H // 2, W // 2, Fr))
+    assert torch.equal(rope[0], ref_rope[0]) and torch.equal(rope[1], ref_rope[1])
+    sd = model.state_dict()
+
+    def prepare_lp_ref(kind, sigma, k, f):
+        return pipe.prepare_lp(kind, sigma, k, f, None, 9, True, True, img_lat, None)
+
+    per_step = []
+    Co.denoise_loop(lambda x, text, t: Co.forward(sd, ocfg, x, text, t.cuda(), rope), sched_oracle.CogDDIMOracle(), lat0, img_lat,
+                    pos, neg, steps, gs, alg, prepare_lp_ref, lowpass.get_lp_strength,
+                    on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
+    xs = [lat0] + [p[0] for p in per_step]
+    pipe.scheduler.set_timesteps(steps, device="cuda")
+    shapes = []
+    for i, t in enumerate(pipe.scheduler.timesteps.tolist()):
+        x_next, npred = pipe.denoise_step(i, t, xs[i], img_lat, None, pos, neg, rope, None, 9, steps, alg, gs)
+        shapes.append(npred.shape[0])
+        assert rel_l2(npred, per_step[i][1]) < 3e-2, (i, rel_l2(npred, per_step[i][1]))
+        assert rel_l2(x_next, xs[i + 1]) < 2 ** -7, (i, rel_l2(x_next, xs[i + 1]))
+    assert shapes == [3, 2]
