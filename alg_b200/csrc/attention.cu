@@ -5,7 +5,8 @@
 // K / V^T tiles of that head, 64 keys per step, through a TMA-fed shared-memory ring:
 //
 //   warp 8  : TMA producer      Q0, Q1 once; K_j and V^T_j rings (SWIZZLE_128B, K-major), 4 stages each
-//   warp 9  : MMA issuer        S_i(j) = Q_i K_j^T   (tcgen05.mma SS, 128 x 64 x D    -> TMEM S_i[j & 1])
+//   warps 9, 10 : MMA issuers (one per query tile)
+//                               S_i(j) = Q_i K_j^T   (tcgen05.mma SS, 128 x 64 x D    -> TMEM S_i[j & 1])
 //                               O_i   += P_i(j) V_j  (tcgen05.mma TS, A = P_i in TMEM -> TMEM O_i)
 //   warps 0-3 / 4-7 : softmax warpgroup for tile 0 / 1 (one query row per thread):
 //                               tcgen05.ld S -> online softmax in fp32 (exp2; O in TMEM is rescaled only when the
@@ -35,7 +36,7 @@ constexpr int BKV = 64;  // keys per pipeline step
 constexpr int kStages = 4;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef ALG_ATTN_POLY_DEFAULT
-#define ALG_ATTN_POLY_DEFAULT 4
+#define ALG_ATTN_POLY_DEFAULT 8
 #endif
 #ifndef ALG_ATTN_SPLIT_DEFAULT
 #define ALG_ATTN_SPLIT_DEFAULT 0
@@ -89,6 +90,93 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   return p;
 }
 
+// ---- MMA issuer (one elected thread) -----------------------------------------------------------------------------
+// The first version rebuilt both 64-bit shared-memory descriptors for every tcgen05.mma and indexed stages / barriers
+// with runtime j % kStages: ~330 SASS instructions per 64-key step on ONE thread, i.e. ~1 460 cycles per step against
+// 1 024 cycles of tensor work -- the issuer, not the softmax, paced the kernel (profiles/r01_attention.md, a04).  Here the
+// step is unrolled over j % 4 so stage, S-buffer, barrier offsets and barrier parities are compile-time, and every
+// operand descriptor is (base low word) + (compile-time offset).
+struct MmaCtx {
+  uint32_t tmem, bar, q_lo, k_lo, v_lo;
+  int n_steps;
+};
+constexpr int kBarKFull = 1, kBarKEmpty = 1 + kStages, kBarVFull = 1 + 2 * kStages, kBarVEmpty = 1 + 3 * kStages,
+              kBarSFull = 1 + 4 * kStages, kBarPFull = kBarSFull + 4, kBarODone = kBarPFull + 4, kBarOFull = kBarODone + 2;
+static_assert(kStages == 4, "the issuer's compile-time parities assume four K/V stages");
+
+// NOTE on the S shape: with 64-key (N = 64) S MMAs both operands stream from shared memory at 6 KB per MMA; the tensor
+// core fetches 128 B/clk, so a 128x64x16 SS MMA takes 48 cycles instead of its 32-cycle floor (measured:
+// scripts/microbench/mma_rate.cu; TS and N >= 128 run at the floor).  A paired 128-key S MMA runs at the floor but needs
+// both S buffers of the tile at once, which serialises S -> softmax -> softmax -> PV per tile; measured slower
+// (1 120 vs 1 270 TFLOP/s, profiles/r01_attention.md) because the softmax warps, not the tensor pipe, pace the kernel.
+template <int D, int I, int BUF, int ST>
+__device__ __forceinline__ void issue_s(const MmaCtx& c) {  // S_I = Q_I K^T (stage ST) into S buffer BUF
+  using C = Cfg<D>;
+  constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
+  const uint32_t d = c.tmem + I * 128 + BUF * 64;
+#pragma unroll
+  for (int ks = 0; ks < D / 16; ++ks) {
+    const uint32_t qoff = (I * C::kBytesQ + (ks >> 2) * C::kSubQ + (ks & 3) * 32) >> 4;
+    const uint32_t koff = (ST * C::kBytesK + (ks >> 2) * C::kSubK + (ks & 3) * 32) >> 4;
+    mma_ss_lo(d, c.q_lo + qoff, c.k_lo + koff, idesc_s, ks != 0);
+  }
+  tc_commit_a(c.bar + 8 * (kBarSFull + I * 2 + BUF));
+}
+template <int D, int I, int BUF, int ST>
+__device__ __forceinline__ void issue_pv(const MmaCtx& c, uint32_t acc_first) {  // O_I (+)= P_I (buffer BUF) V (stage ST)
+  using C = Cfg<D>;
+  constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D);
+  const uint32_t d = c.tmem + 256 + I * 128, a = c.tmem + I * 128 + BUF * 64;
+#pragma unroll
+  for (int ks = 0; ks < BKV / 16; ++ks)
+    mma_ts_lo(d, a + ks * 8, c.v_lo + ((ST * C::kBytesV + ks * 32) >> 4), idesc_o, ks == 0 ? acc_first : 1u);
+  tc_commit_a(c.bar + 8 * (kBarODone + I));
+}
+// step j = 4 m + JJ of query tile I; ph = m & 1 (parity of the K/V stage ring at this step).  Each tile has its OWN issuer
+// warp: one thread issuing for both tiles still needed ~230 instructions (~1 000+ cycles) per step; two threads halve that,
+// and the tiles' MMA streams are independent (disjoint TMEM), sharing only the K/V stage barriers (two arrivals each).
+template <int D, int I, int JJ>
+__device__ __forceinline__ void mma_tile_step(const MmaCtx& c, const int j, const uint32_t ph) {
+  constexpr int BUF = JJ & 1, ST = JJ % kStages, STN = (JJ + 2) % kStages;
+  constexpr uint32_t p_par = (JJ >> 1) & 1;                      // ((4 m + JJ) >> 1) & 1
+  const uint32_t phn = (JJ + 2 >= kStages) ? (ph ^ 1u) : ph;     // parity of (j + 2) / kStages
+  const bool has_next = j + 2 < c.n_steps, last = j == c.n_steps - 1;
+  mbar_wait_a(c.bar + 8 * (kBarPFull + I * 2 + BUF), p_par);
+  mbar_wait_a(c.bar + 8 * (kBarVFull + ST), ph);
+  tc_fence_after();
+  issue_pv<D, I, BUF, ST>(c, j > 0);
+  tc_commit_a(c.bar + 8 * (kBarVEmpty + ST));
+  if (last) tc_commit_a(c.bar + 8 * (kBarOFull + I));
+  if (has_next) {
+    mbar_wait_a(c.bar + 8 * (kBarKFull + STN), phn);
+    tc_fence_after();
+    issue_s<D, I, BUF, STN>(c);  // reuses the S buffer whose P was consumed by the PV just issued (in-order tensor pipe)
+    tc_commit_a(c.bar + 8 * (kBarKEmpty + STN));
+  }
+}
+template <int D, int I>
+__device__ __forceinline__ void mma_tile_loop(const MmaCtx& c) {
+  mbar_wait_a(c.bar, 0);  // q_full
+  mbar_wait_a(c.bar + 8 * (kBarKFull + 0), 0);
+  tc_fence_after();
+  issue_s<D, I, 0, 0>(c);
+  tc_commit_a(c.bar + 8 * (kBarKEmpty + 0));
+  if (c.n_steps > 1) {
+    mbar_wait_a(c.bar + 8 * (kBarKFull + 1), 0);
+    tc_fence_after();
+    issue_s<D, I, 1, 1>(c);
+    tc_commit_a(c.bar + 8 * (kBarKEmpty + 1));
+  }
+  uint32_t ph = 0;
+#pragma unroll 1
+  for (int j0 = 0; j0 < c.n_steps; j0 += 4, ph ^= 1u) {
+    mma_tile_step<D, I, 0>(c, j0, ph);
+    if (j0 + 1 < c.n_steps) mma_tile_step<D, I, 1>(c, j0 + 1, ph);
+    if (j0 + 2 < c.n_steps) mma_tile_step<D, I, 2>(c, j0 + 2, ph);
+    if (j0 + 3 < c.n_steps) mma_tile_step<D, I, 3>(c, j0 + 3, ph);
+  }
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -101,12 +189,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 //            exchange their partial row maxima through shared memory behind one 256-thread named barrier per step,
 //            keep partial row sums, and each rescales / writes half of the O columns.
 template <int D, int POLY, int SPLIT>
-__global__ void __launch_bounds__((SPLIT ? 18 : 10) * 32, 1)
+__global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Params p) {
   using C = Cfg<D>;
   constexpr int kSoftmaxWarps = SPLIT ? 16 : 8;
-  constexpr int kTmaWarp = kSoftmaxWarps, kMmaWarp = kSoftmaxWarps + 1;
+  constexpr int kTmaWarp = kSoftmaxWarps, kMmaWarp = kSoftmaxWarps + 1;  // MMA issuers: kMmaWarp (tile 0), kMmaWarp + 1 (tile 1)
   constexpr int kWarpsPerTile = kSoftmaxWarps / 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -139,9 +227,9 @@ __global__ void __launch_bounds__((SPLIT ? 18 : 10) * 32, 1)
     mbar_init(q_full, 1);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], 2);  // one commit per issuer warp
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -188,58 +276,18 @@ __global__ void __launch_bounds__((SPLIT ? 18 : 10) * 32, 1)
         if (j + 2 < n_steps) load_k(j + 2);
       }
     }
-  } else if (warp == kMmaWarp) {
-    if (elect_one()) {  // ===== MMA issuer.  elect.sync (not `lane == 0`) tells ptxas that a single lane runs this region, so the
-                        // descriptors stay in uniform registers; otherwise every UTCHMMA is wrapped in an ELECT / R2UR loop =====
-      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
-      constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D);
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      auto issue_s = [&](int i, int j) {  // S_i(j) = Q_i K_j^T into buffer j & 1
-        const uint32_t d = tmem_base + i * 128 + (j & 1) * 64;
-        const uint32_t kb = k_addr + (j % kStages) * C::kBytesK;
-#pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          mma_ss(d, make_smem_desc_sw128(q_addr + i * C::kBytesQ + (ks >> 2) * C::kSubQ + (ks & 3) * 32),
-                 make_smem_desc_sw128(kb + (ks >> 2) * C::kSubK + (ks & 3) * 32), idesc_s, ks != 0);
-        }
-        tc_commit(&s_full[i * 2 + (j & 1)]);
-      };
-      auto issue_pv = [&](int i, int j) {  // O_i (+)= P_i(j) V_j
-        const uint32_t d = tmem_base + 256 + i * 128;
-        const uint32_t a = tmem_base + i * 128 + (j & 1) * 64;
-        const uint32_t vb = v_addr + (j % kStages) * C::kBytesV;
-#pragma unroll
-        for (int ks = 0; ks < BKV / 16; ++ks)
-          mma_ts(d, a + ks * 8, make_smem_desc_sw128(vb + ks * 32), idesc_o, (j > 0 || ks != 0));
-        tc_commit(&o_done[i]);
-      };
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < 2 && j < n_steps; ++j) {
-        mbar_wait(&k_full[j % kStages], 0);
-        tc_fence_after();
-        issue_s(0, j);
-        issue_s(1, j);
-        tc_commit(&k_empty[j % kStages]);
-      }
-      for (int j = 0; j < n_steps; ++j) {
-        const int jn = j + 2;
-        for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_full[i * 2 + (j & 1)], (j >> 1) & 1);
-          if (i == 0) mbar_wait(&v_full[j % kStages], (j / kStages) & 1);
-          tc_fence_after();
-          issue_pv(i, j);
-          if (i == 1) tc_commit(&v_empty[j % kStages]);
-          if (j == n_steps - 1) tc_commit(&o_full[i]);
-          if (jn < n_steps) {
-            if (i == 0) {
-              mbar_wait(&k_full[jn % kStages], (jn / kStages) & 1);
-              tc_fence_after();
-            }
-            issue_s(i, jn);  // reuses the S buffer whose P was consumed by the PV just issued (in-order tensor pipe)
-            if (i == 1) tc_commit(&k_empty[jn % kStages]);
-          }
-        }
-      }
+  } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
+    if (elect_one()) {  // ===== MMA issuers.  elect.sync (not `lane == 0`) tells ptxas that a single lane runs this region, so
+                        // the descriptors stay in uniform registers; otherwise every UTCHMMA is wrapped in an ELECT / R2UR loop =====
+      MmaCtx c;
+      c.tmem = tmem_base;
+      c.bar = smem_u32(bars);
+      c.q_lo = smem_desc_lo_sw128(smem_u32(sQ));
+      c.k_lo = smem_desc_lo_sw128(smem_u32(sK));
+      c.v_lo = smem_desc_lo_sw128(smem_u32(sV));
+      c.n_steps = n_steps;
+      if (warp == kMmaWarp) mma_tile_loop<D, 0>(c);
+      else mma_tile_loop<D, 1>(c);
     }
   } else {  // ===== softmax warps =====
     constexpr int W = SPLIT ? BKV / 2 : BKV;      // key columns of a step owned by this thread
@@ -400,7 +448,7 @@ __global__ void __launch_bounds__((SPLIT ? 18 : 10) * 32, 1)
 template <int D, int POLY, int SPLIT>
 static int launch(const alg_attention_t* a, cudaStream_t st) {
   using C = Cfg<D>;
-  constexpr int kThreads = (SPLIT ? 18 : 10) * 32;
+  constexpr int kThreads = (SPLIT ? 19 : 11) * 32;
   static bool attr_done = false;
   if (!attr_done) {
     ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));

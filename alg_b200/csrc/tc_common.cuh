@@ -37,32 +37,37 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// `_a` variants take the 32-bit shared-window address directly (the attention MMA issuer keeps one barrier base in a
+// register and adds compile-time offsets, instead of converting a generic pointer at every wait / commit)
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t addr, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(addr), "r"(parity)
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_a(smem_u32(bar), parity); }
 // Bounded wait: a pipeline bug traps (visible as a launch failure) instead of hanging the GPU box.
 #ifndef ALG_WATCHDOG_CYCLES
 #define ALG_WATCHDOG_CYCLES 20000000000ll
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+static __device__ __noinline__ void mbar_watchdog_trap(uint32_t addr, uint32_t parity) {
+  printf("alg_b200: mbarrier watchdog (block %d thread %d bar smem 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+         addr, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  if (mbar_try_wait_a(addr, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > ALG_WATCHDOG_CYCLES) {
-      printf("alg_b200: mbarrier watchdog (block %d thread %d bar smem 0x%x parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+  while (!mbar_try_wait_a(addr, parity)) {
+    if (clock64() - t0 > ALG_WATCHDOG_CYCLES) mbar_watchdog_trap(addr, parity);
   }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
 
 // ------------------------------------------------------------------------------------------------
 // TMA
@@ -104,6 +109,33 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void tc_commit_a(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+// Descriptor-halves variants: the high word of a SWIZZLE_128B K-major descriptor is a constant, and the low word of
+// desc(addr + delta) is desc_lo(addr) + (delta >> 4) -- so an issuer loop needs ONE add per operand instead of
+// rebuilding the 64-bit descriptor (mask, shift, or) for every MMA.
+constexpr uint32_t kDescHiSw128 = 0x40004040u;  // SBO 1024 B | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t smem_desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | 0x10000u; }
+__device__ __forceinline__ void mma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
