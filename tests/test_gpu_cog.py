@@ -182,7 +182,8 @@ def test_config1_full_architecture_two_steps():
     alg = dict(ALG, schedule_interval_end_time=0.04)
     rope = pipe._prepare_rotary_positional_embeddings(H * 8, W * 8, Fr, "cuda")
     ref_rope = tuple(r.cuda() for r in Co.rotary_tables(ocfg, H // 2, W // 2, Fr))
-    assert torch.equal(rope[0], ref_rope[0]) and torch.equal(rope[1], ref_rope[1])
+    # tables built on the GPU (pipeline) vs on the CPU (oracle): same formula, cos / sin differ by an ulp
+    assert (rope[0] - ref_rope[0]).abs().max() < 1e-5 and (rope[1] - ref_rope[1]).abs().max() < 1e-5
     sd = model.state_dict()
 
     def prepare_lp_ref(kind, sigma, k, f):
