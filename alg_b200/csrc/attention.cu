@@ -304,9 +304,12 @@ __global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
     const float c = p.scale_log2;
     // one 64-key step of online softmax; `ragged` (compile-time) is the last, partially filled step -- kept out of the
     // main loop body, where the compiler would otherwise if-convert the mask into always-executed selects
-    auto softmax_step = [&](const int j, auto ragged) {
-      const uint32_t t_sj = t_s + (j & 1) * 64;
-      mbar_wait(&s_full[i * 2 + (j & 1)], (j >> 1) & 1);
+    // barrier addresses of this tile's two S buffers; the loop is unrolled by two so the buffer index is compile-time
+    const uint32_t bar_s0 = smem_u32(&s_full[i * 2]), bar_p0 = smem_u32(&p_full[i * 2]);
+    auto softmax_step = [&](const int j, auto ragged, auto buf_c) {
+      constexpr int BUF = decltype(buf_c)::value;
+      const uint32_t t_sj = t_s + BUF * 64;
+      mbar_wait_a(bar_s0 + 8 * BUF, (j >> 1) & 1);
       tc_fence_after();
       float s[W];
       tmem_ld32(t_sj + hh * W, reinterpret_cast<uint32_t*>(s));
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
       if constexpr (SPLIT) {
         // exchange the partial maxima of the two column halves: this also orders "both halves have read S(j)" before
         // either half overwrites the buffer with P(j)
-        float* slot = xch + ((i * 2 + (j & 1)) * 2) * BQ;
+        float* slot = xch + ((i * 2 + BUF) * 2) * BQ;
         const float mine = fmaxf(mc[0], mc[1]);
         slot[hh * BQ + row_in_tile] = mine;
         named_bar_sync(1 + i, kWarpsPerTile * 32);
@@ -390,12 +393,23 @@ __global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i * 2 + (j & 1)]);
+      if (lane == 0) mbar_arrive_a(bar_p0 + 8 * BUF);
     };
     const int n_full = p.n_kv / BKV;
+    using B0 = std::integral_constant<int, 0>;
+    using B1 = std::integral_constant<int, 1>;
+    int j = 0;
 #pragma unroll 1
-    for (int j = 0; j < n_full; ++j) softmax_step(j, std::false_type{});
-    if (n_full < n_steps) softmax_step(n_full, std::true_type{});
+    for (; j + 1 < n_full; j += 2) {
+      softmax_step(j, std::false_type{}, B0{});
+      softmax_step(j + 1, std::false_type{}, B1{});
+    }
+    if (j < n_full) {  // odd number of full steps: one more on buffer 0, a ragged tail (if any) lands on buffer 1
+      softmax_step(j, std::false_type{}, B0{});
+      if (n_full < n_steps) softmax_step(n_full, std::true_type{}, B1{});
+    } else if (n_full < n_steps) {
+      softmax_step(n_full, std::true_type{}, B0{});
+    }
     if constexpr (SPLIT) {  // row sum = sum of the two halves' partial sums (slot of the parity the last step did not use)
       float* slot = xch + ((i * 2 + (n_steps & 1)) * 2) * BQ;
       slot[hh * BQ + row_in_tile] = l;
