@@ -90,16 +90,25 @@ __global__ void __launch_bounds__(kRowThreads)
       for (int e = 0; e < 8; ++e) sq += v[c][e] * v[c][e];
     }
   }
-  const float rstd = rsqrtf(block_sum(sq, red) / (float)d + eps);
-  int t = 0, y = 0, xx = 0;
+  // the row's head_dim / 2 (cos, sin) pairs are the same for every head: stage them once per block in shared memory
+  // instead of re-reading the fp64 tables for each of the 40 heads (the table reads were 4x the activation bytes)
+  __shared__ double2 cs_row[64];
   if (use_rope) {
     const int64_t N = (int64_t)rope.ppf * rope.pph * rope.ppw;
     const int n = (int)(row % N);
-    t = n / (rope.pph * rope.ppw);
+    const int t = n / (rope.pph * rope.ppw);
     const int rem = n - t * rope.pph * rope.ppw;
-    y = rem / rope.ppw;
-    xx = rem - y * rope.ppw;
+    const int y = rem / rope.ppw, xx = rem - y * rope.ppw;
+    const int pi = threadIdx.x;
+    if (pi < head_dim / 2) {
+      const double* cs;
+      if (pi < rope.n_t) cs = rope.t + ((int64_t)t * rope.n_t + pi) * 2;
+      else if (pi < rope.n_t + rope.n_h) cs = rope.h + ((int64_t)y * rope.n_h + (pi - rope.n_t)) * 2;
+      else cs = rope.w + ((int64_t)xx * rope.n_w + (pi - rope.n_t - rope.n_h)) * 2;
+      cs_row[pi] = make_double2(cs[0], cs[1]);
+    }
   }
+  const float rstd = rsqrtf(block_sum(sq, red) / (float)d + eps);  // its __syncthreads also publish cs_row
 #pragma unroll
   for (int c = 0; c < kMaxChunks; ++c) {
     const int ci = threadIdx.x + c * kRowThreads;
@@ -115,12 +124,8 @@ __global__ void __launch_bounds__(kRowThreads)
         const int pair0 = ((ci * 8) % head_dim) >> 1;  // 4 complex pairs per chunk, never straddling a head
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int pi = pair0 + q;
-          const double* cs;
-          if (pi < rope.n_t) cs = rope.t + ((int64_t)t * rope.n_t + pi) * 2;
-          else if (pi < rope.n_t + rope.n_h) cs = rope.h + ((int64_t)y * rope.n_h + (pi - rope.n_t)) * 2;
-          else cs = rope.w + ((int64_t)xx * rope.n_w + (pi - rope.n_t - rope.n_h)) * 2;
-          const double cr = cs[0], si = cs[1];
+          const double2 cs = cs_row[pair0 + q];
+          const double cr = cs.x, si = cs.y;
           const double re = (double)o[2 * q], im = (double)o[2 * q + 1];
           o[2 * q] = (float)(re * cr - im * si);  // complex128 multiply, then .type_as(bf16) in pack8
           o[2 * q + 1] = (float)(re * si + im * cr);

@@ -292,10 +292,16 @@ def run_ours(args):
         flops_total = sum(40 * flops_launch[n_pass_of(i)] for i in idxs)
         achieved = flops_total / (sa["ms"] / 1e3) / 1e12 if sa["ms"] > 0 else None
         total_flops = passes * forward_flops(n_tok)[0]
+        traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of this kernel (per head x heads)
+        tpath = os.path.join(ROOT, "profiles", "r01_attention_traffic.json")
+        if os.path.exists(tpath) and sa["launches"]:
+            heads_per_launch = 40 * passes / (sa["launches"] / 40)  # 40 layers -> launches / 40 steps-worth of launches
+            traffic = json.load(open(tpath))["dram_bytes_per_head"] * heads_per_launch
         roofline = {"kernel": "attention_kernel<128> (DiT self-attention, N=32760, 40 heads x 128)", "bound": "tensor",
                     "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s",
                     "frac": achieved / tf_sust if achieved else None, "peak_kind": f"bf16_tflops_sustained ({src}); kernel timed inside a long step",
-                    "frac_of_burst_peak": achieved / tf_burst if achieved else None, "traffic": None,
+                    "frac_of_burst_peak": achieved / tf_burst if achieved else None, "traffic": traffic,
+                    "traffic_unit": "bytes per launch (ncu dram__bytes_read + write per head x mean heads per launch)",
                     "launches": sa["launches"], "avg_launch_ms": sa["ms"] / max(sa["launches"], 1),
                     "share_of_step": sa["ms"] / ms_total,
                     "per_class_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
