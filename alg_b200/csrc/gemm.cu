@@ -57,6 +57,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 }  // namespace tc
 
+#ifndef ALG_GEMM_CLUSTER_DEFAULT
+#define ALG_GEMM_CLUSTER_DEFAULT 1
+#endif
+
 namespace gemm {
 using namespace tc;
 
@@ -101,10 +105,18 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return 0.5f * x * (1.0f + t);
 }
 
-template <int BN>
+// CL = 2: the kernel runs as 2-CTA clusters; the CTAs of a pair work on two M tiles of the SAME N tile, each loads half of
+// the B tile and TMA-multicasts it into both CTAs' shared memory, so a k-block costs a CTA 16 KB (A) + 16 KB (half of B)
+// of L2 -> SM traffic instead of 48 KB.  MMA / TMEM / epilogue stay per-CTA (cta_group::1); a stage is released to the
+// producers by BOTH CTAs' commits (multicast arrive), because each producer writes into both CTAs' shared memory.
+template <int BN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   using C = Cfg<BN>;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  const int cluster_id = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+  const int num_clusters = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
+  const int m_units = (p.m_tiles + CL - 1) / CL;  // scheduling unit = CL consecutive M tiles of one N tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -117,14 +129,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = m_units * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int i = 0; i < C::kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -138,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything lands in its shared memory
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -145,14 +158,19 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (elect_one()) {  // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int m_blk, n_blk;
-        tile_coords(t, p.m_tiles, p.n_tiles, m_blk, n_blk);
+        tile_coords(t, m_units, p.n_tiles, m_blk, n_blk);
+        m_blk = m_blk * CL + (int)crank;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], C::kBytesA + C::kBytesB);
           tma_load_2d(sA + stage * C::kBytesA, &tmA, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sB + stage * C::kBytesB, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if (CL > 1)  // this CTA's half of the B tile, multicast to the pair
+            tma_load_2d_mc(sB + stage * C::kBytesB + crank * (C::kBytesB / CL), &tmB, &full[stage], kb * BK,
+                           n_blk * BN + (int)crank * (BN / CL), (uint16_t)((1u << CL) - 1));
+          else
+            tma_load_2d(sB + stage * C::kBytesB, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -167,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -183,7 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1)
             mma_ss(d_tmem, make_smem_desc_sw128(a_addr + k * UMMA_K * 2), make_smem_desc_sw128(b_addr + k * UMMA_K * 2),
                    idesc, (kb | k) != 0);
           }
-          tc_commit(&empty[stage]);  // slot is free once these MMAs have read it
+          if (CL > 1) tc_commit_mc(&empty[stage], (uint16_t)((1u << CL) - 1));  // both producers write this slot
+          else tc_commit(&empty[stage]);  // slot is free once these MMAs have read it
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -195,9 +214,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else {  // ===== epilogue warps 2..5 =====
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       int m_blk, n_blk;
-      tile_coords(t, p.m_tiles, p.n_tiles, m_blk, n_blk);
+      tile_coords(t, m_units, p.n_tiles, m_blk, n_blk);
+      m_blk = m_blk * CL + (int)crank;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -354,6 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
@@ -371,12 +392,12 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN>
+template <int BN, int CL>
 static int launch(const alg_gemm_t* g, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    ALG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    ALG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_done = true;
   }
   CUtensorMap tmA, tmB;
@@ -387,7 +408,7 @@ static int launch(const alg_gemm_t* g, cudaStream_t st) {
   }
   {
     uint64_t dims[2] = {(uint64_t)g->K, (uint64_t)g->N}, strides[2] = {1, (uint64_t)g->ldb};
-    uint32_t box[2] = {BK, BN};
+    uint32_t box[2] = {BK, BN / CL};
     if (int rc = make_tmap_bf16(&tmB, g->B, 2, dims, strides, box)) return rc;
   }
   Params p;
@@ -411,9 +432,25 @@ static int launch(const alg_gemm_t* g, cudaStream_t st) {
   p.m_tiles = (int)((g->M + BM - 1) / BM);
   p.n_tiles = (int)((g->N + BN - 1) / BN);
   p.k_blocks = (int)((g->K + BK - 1) / BK);
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = std::min(tiles, num_sms());
-  gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmB, p);
+  const int units = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
+  if (CL == 1) {
+    const int grid = std::min(units, num_sms());
+    gemm_kernel<BN, CL><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmB, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(std::min(units, num_sms() / CL) * CL));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ALG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CL>, tmA, tmB, p));
+  }
   ALG_LAUNCH_OK();
   return 0;
 }
@@ -446,14 +483,20 @@ extern "C" int alg_gemm_bf16(const alg_gemm_t* g, void* stream) {
     ALG_REQUIRE((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static int force_bn = -1;  // experiment knob
+  static int force_bn = -1, cluster = -1;  // experiment knobs
   if (force_bn < 0) {
     const char* e = getenv("ALG_GEMM_BN");
     force_bn = e ? atoi(e) : 0;
+    e = getenv("ALG_GEMM_CLUSTER");
+    cluster = e ? atoi(e) : ALG_GEMM_CLUSTER_DEFAULT;
   }
-  if (force_bn == 128) return gemm::launch<128>(g, st);
-  if (force_bn == 64) return gemm::launch<64>(g, st);
-  if (g->N % 256 == 0 || g->N > 512) return gemm::launch<256>(g, st);
-  if (g->N % 128 == 0 || g->N > 128) return gemm::launch<128>(g, st);
-  return gemm::launch<64>(g, st);
+  if (force_bn == 128) return gemm::launch<128, 1>(g, st);
+  if (force_bn == 64) return gemm::launch<64, 1>(g, st);
+  if (g->N % 256 == 0 || g->N > 512) {
+    // CTA pairs with the B tile multicast pay off once there are enough M tiles to fill the machine with pairs
+    if (cluster == 2 && g->M >= 4 * gemm::BM * 74) return gemm::launch<256, 2>(g, st);
+    return gemm::launch<256, 1>(g, st);
+  }
+  if (g->N % 128 == 0 || g->N > 128) return gemm::launch<128, 1>(g, st);
+  return gemm::launch<64, 1>(g, st);
 }
