@@ -1,0 +1,118 @@
+"""Reading diffusers-format checkpoints from a LOCAL directory (the real-checkpoint loader).
+
+The engines name their parameters exactly like the diffusers state dicts, so loading a checkpoint is reading the
+``<repo>/transformer/*.safetensors`` shards (+ ``config.json``) and handing the tensors to ``load_state_dict``; the
+scheduler comes from ``<repo>/scheduler/scheduler_config.json``.  Used by the three pipelines' ``from_pretrained`` when
+``pretrained_model_name_or_path`` is a directory (run.py:46-81 passes a hub id + ``cache_dir``; there is no network here,
+so only local snapshots can work).  VAE and the text / image encoders are not built.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+
+WEIGHTS_NAME = "diffusion_pytorch_model.safetensors"
+INDEX_NAME = WEIGHTS_NAME + ".index.json"
+
+
+def resolve_snapshot(path: str, cache_dir: Optional[str] = None) -> Optional[str]:
+    """A local directory that looks like a diffusers pipeline snapshot, or None.  Accepts the directory itself or a hub id
+    whose snapshot sits in the HF cache layout under ``cache_dir`` (models--org--name/snapshots/<rev>/)."""
+    if os.path.isdir(path) and os.path.isdir(os.path.join(path, "transformer")):
+        return path
+    if cache_dir:
+        root = os.path.join(cache_dir, "models--" + path.replace("/", "--"), "snapshots")
+        if os.path.isdir(root):
+            for rev in sorted(os.listdir(root)):
+                cand = os.path.join(root, rev)
+                if os.path.isdir(os.path.join(cand, "transformer")):
+                    return cand
+    return None
+
+
+def read_config(folder: str, name: str = "config.json") -> dict:
+    with open(os.path.join(folder, name)) as f:
+        cfg = json.load(f)
+    return {k: v for k, v in cfg.items() if not k.startswith("_")}  # drop _class_name / _diffusers_version / ...
+
+
+def load_safetensors_dir(folder: str, device="cpu") -> Dict[str, torch.Tensor]:
+    """All tensors of a (possibly sharded) ``diffusion_pytorch_model`` checkpoint, loaded straight onto ``device``."""
+    from safetensors import safe_open
+
+    index = os.path.join(folder, INDEX_NAME)
+    if os.path.exists(index):
+        with open(index) as f:
+            shards = sorted(set(json.load(f)["weight_map"].values()))
+    elif os.path.exists(os.path.join(folder, WEIGHTS_NAME)):
+        shards = [WEIGHTS_NAME]
+    else:
+        shards = sorted(f for f in os.listdir(folder) if f.endswith(".safetensors"))
+    if not shards:
+        raise FileNotFoundError(f"no .safetensors weights under {folder}")
+    sd: Dict[str, torch.Tensor] = {}
+    for shard in shards:
+        with safe_open(os.path.join(folder, shard), framework="pt", device=str(device)) as f:
+            for k in f.keys():
+                sd[k] = f.get_tensor(k)
+    return sd
+
+
+def load_transformer(snapshot: str, device="cuda") -> Tuple[dict, Dict[str, torch.Tensor]]:
+    folder = os.path.join(snapshot, "transformer")
+    return read_config(folder), load_safetensors_dir(folder, device)
+
+
+def scheduler_config(snapshot: str) -> dict:
+    folder = os.path.join(snapshot, "scheduler")
+    return read_config(folder, "scheduler_config.json") if os.path.isdir(folder) else {}
+
+
+def save_transformer(snapshot: str, config: dict, state_dict: Dict[str, torch.Tensor], class_name: str,
+                     max_shard_bytes: int = 1 << 30) -> None:
+    """Write ``<snapshot>/transformer`` in the diffusers layout (sharded safetensors + index).  Used by the tests to build
+    synthetic checkpoints; also lets a synthetic model be frozen to disk."""
+    from safetensors.torch import save_file
+
+    folder = os.path.join(snapshot, "transformer")
+    os.makedirs(folder, exist_ok=True)
+    with open(os.path.join(folder, "config.json"), "w") as f:
+        json.dump(dict(config, _class_name=class_name, _diffusers_version="0.34.0.dev0"), f, indent=2, default=list)
+    shards, cur, size = [], {}, 0
+    for k, v in state_dict.items():
+        nb = v.numel() * v.element_size()
+        if cur and size + nb > max_shard_bytes:
+            shards.append(cur)
+            cur, size = {}, 0
+        cur[k] = v.detach().cpu().contiguous()
+        size += nb
+    shards.append(cur)
+    if len(shards) == 1:
+        save_file(shards[0], os.path.join(folder, WEIGHTS_NAME))
+        return
+    weight_map = {}
+    for i, sh in enumerate(shards):
+        name = f"diffusion_pytorch_model-{i + 1:05d}-of-{len(shards):05d}.safetensors"
+        save_file(sh, os.path.join(folder, name))
+        weight_map.update({k: name for k in sh})
+    with open(os.path.join(folder, INDEX_NAME), "w") as f:
+        json.dump({"metadata": {}, "weight_map": weight_map}, f)
+
+
+def build_from_snapshot(model_cls, scheduler_cls, snapshot: str, device="cuda"):
+    """(transformer, scheduler) of a local diffusers snapshot: real DiT weights into the native engine, the scheduler from
+    its ``scheduler_config.json`` (unknown keys are ignored like diffusers' ``from_config`` does)."""
+    cfg, sd = load_transformer(snapshot, device)
+    if isinstance(cfg.get("patch_size"), list):
+        cfg["patch_size"] = tuple(cfg["patch_size"])
+    if isinstance(cfg.get("rope_axes_dim"), list):
+        cfg["rope_axes_dim"] = tuple(cfg["rope_axes_dim"])
+    transformer = model_cls(**cfg).load_state_dict(sd)
+    return transformer, scheduler_cls.from_config(scheduler_config(snapshot))
+
+
+AUX_MESSAGE = ("the VAE and the text / image encoders are not built (SURVEY 8(f).1, 8(f).3): pass real `vae=` / encoder objects, "
+               "or allow_synthetic_aux=True for shape-only stand-ins (latent-space runs with your own prompt_embeds)")

@@ -114,6 +114,25 @@ class CogVideoXTransformer3DModel:
 
     # ---- construction -------------------------------------------------------------------------------
     @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: str = "transformer", torch_dtype=None,
+                        cache_dir=None, device="cuda"):
+        """run.py:72-77 surface: real weights from a LOCAL diffusers snapshot (directory, or hub id resolved in cache_dir)."""
+        import os
+
+        from . import checkpoint
+
+        snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir)
+        if snap is None:
+            raise FileNotFoundError(f"no local diffusers snapshot for {pretrained_model_name_or_path!r} (there is no network: "
+                                    "pass a directory, or a hub id present under cache_dir)")
+        folder = os.path.join(snap, subfolder)
+        cfg = checkpoint.read_config(folder)
+        for k in ("patch_size", "rope_axes_dim"):
+            if isinstance(cfg.get(k), list):
+                cfg[k] = tuple(cfg[k])
+        return cls(**cfg).load_state_dict(checkpoint.load_safetensors_dir(folder, device))
+
+    @classmethod
     def from_synthetic(cls, seed: int = 0, device="cuda", **config):
         m = cls(**config)
         return m.load_state_dict(synthetic_state_dict(m._cfg, seed=seed, device=device))

@@ -85,23 +85,35 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, transformer=None, vae=None, torch_dtype=torch.bfloat16,
-                        cache_dir=None, synthetic: Optional[bool] = None, seed: int = 0, device="cuda", **config_overrides):
+                        cache_dir=None, synthetic: Optional[bool] = None, allow_synthetic_aux: bool = False,
+                        seed: int = 0, device="cuda", **config_overrides):
         """run.py:65-70.  Offline there are no checkpoints: ``synthetic=True`` (or ``ALG_SYNTHETIC=1``) builds the true
         CogVideoX-5b-I2V architecture with seeded random weights directly on ``device``."""
         import os
 
         if synthetic is None:
             synthetic = os.environ.get("ALG_SYNTHETIC", "0") == "1" or str(pretrained_model_name_or_path).startswith("synthetic")
+        scheduler = None
         if not synthetic:
-            raise NotImplementedError(
-                f"loading real checkpoints ({pretrained_model_name_or_path!r}) needs the diffusers-safetensors weight "
-                "mapper, which is the next scope item (SURVEY 8(f).2); pass synthetic=True or set ALG_SYNTHETIC=1")
+            from alg_b200 import checkpoint
+
+            snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir)
+            if snap is None:
+                raise FileNotFoundError(
+                    f"no local diffusers snapshot for {pretrained_model_name_or_path!r}: there is no network, so pass a "
+                    "directory (or a hub id already present under cache_dir), or synthetic=True / ALG_SYNTHETIC=1")
+            if transformer is None:
+                transformer, scheduler = checkpoint.build_from_snapshot(CogVideoXTransformer3DModel, CogVideoXDDIMScheduler, snap, device)
+            else:
+                scheduler = CogVideoXDDIMScheduler.from_config(checkpoint.scheduler_config(snap))
+            if vae is None and not allow_synthetic_aux:
+                raise NotImplementedError(checkpoint.AUX_MESSAGE)
         if transformer is None:
             transformer = CogVideoXTransformer3DModel.from_synthetic(seed=seed, device=device, **config_overrides)
         if vae is None:
             vae = SyntheticVideoVAE(z_dim=transformer.config.in_channels // 2, scaling_factor=0.7, dtype=torch_dtype)
         return cls(tokenizer=None, text_encoder=SyntheticTextEncoder(transformer.config.text_embed_dim, torch_dtype), vae=vae,
-                   transformer=transformer, scheduler=CogVideoXDDIMScheduler())
+                   transformer=transformer, scheduler=scheduler or CogVideoXDDIMScheduler())
 
     # ------------------------------------------------------------------------------------------------
     # once-per-video conditioning (cog:228-350).  The real T5 is out of scope; a synthetic encoder stands in.

@@ -61,18 +61,30 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
     # ------------------------------------------------------------------------------------------------
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, vae=None, image_encoder=None, transformer=None,
-                        torch_dtype=torch.bfloat16, cache_dir=None, synthetic: Optional[bool] = None, seed: int = 0,
-                        device="cuda", **config_overrides):
-        """run.py:56-61.  Offline there are no checkpoints: ``synthetic=True`` (or ``ALG_SYNTHETIC=1``) builds the
-        true Wan2.1-I2V-14B architecture with seeded random weights directly on ``device``."""
+                        torch_dtype=torch.bfloat16, cache_dir=None, synthetic: Optional[bool] = None,
+                        allow_synthetic_aux: bool = False, seed: int = 0, device="cuda", **config_overrides):
+        """run.py:56-61.  A local diffusers snapshot (directory, or hub id found under ``cache_dir``) loads the real DiT
+        weights and scheduler config (alg_b200/checkpoint.py); ``synthetic=True`` (or ``ALG_SYNTHETIC=1``) builds the true
+        Wan2.1-I2V-14B architecture with seeded random weights directly on ``device`` (no checkpoints exist offline)."""
         import os
 
         if synthetic is None:
             synthetic = os.environ.get("ALG_SYNTHETIC", "0") == "1" or str(pretrained_model_name_or_path).startswith("synthetic")
+        scheduler = None
         if not synthetic:
-            raise NotImplementedError(
-                f"loading real checkpoints ({pretrained_model_name_or_path!r}) needs the diffusers-safetensors weight "
-                "mapper, which is the next scope item (SURVEY 8(f).2); pass synthetic=True or set ALG_SYNTHETIC=1")
+            from alg_b200 import checkpoint
+
+            snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir)
+            if snap is None:
+                raise FileNotFoundError(
+                    f"no local diffusers snapshot for {pretrained_model_name_or_path!r}: there is no network, so pass a "
+                    "directory (or a hub id already present under cache_dir), or synthetic=True / ALG_SYNTHETIC=1")
+            if transformer is None:
+                transformer, scheduler = checkpoint.build_from_snapshot(WanTransformer3DModel, UniPCMultistepScheduler, snap, device)
+            else:
+                scheduler = UniPCMultistepScheduler.from_config(checkpoint.scheduler_config(snap))
+            if vae is None and not allow_synthetic_aux:
+                raise NotImplementedError(checkpoint.AUX_MESSAGE)
         if transformer is None:
             transformer = WanTransformer3DModel.from_synthetic(seed=seed, device=device, **config_overrides)
         if vae is None:
@@ -81,7 +93,7 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
         image_dim = transformer.config.image_dim
         pipe = cls(tokenizer=None, text_encoder=SyntheticTextEncoder(text_dim, torch_dtype),
                    image_encoder=image_encoder or SyntheticImageEncoder(257, image_dim), image_processor=None,
-                   transformer=transformer, vae=vae, scheduler=UniPCMultistepScheduler(flow_shift=3.0))
+                   transformer=transformer, vae=vae, scheduler=scheduler or UniPCMultistepScheduler(flow_shift=3.0))
         return pipe
 
     # ------------------------------------------------------------------------------------------------

@@ -189,16 +189,29 @@ def test_config1_full_architecture_two_steps():
     def prepare_lp_ref(kind, sigma, k, f):
         return pipe.prepare_lp(kind, sigma, k, f, None, 9, True, True, img_lat, None)
 
-    per_step = []
-    Co.denoise_loop(lambda x, text, t: Co.forward(sd, ocfg, x, text, t.cuda(), rope), sched_oracle.CogDDIMOracle(), lat0, img_lat,
-                    pos, neg, steps, gs, alg, prepare_lp_ref, lowpass.get_lp_strength,
-                    on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
+    per_step, calls = [], []
+    sd32 = {k: v.float() for k, v in sd.items()}
+
+    def transformer(x, text, t):  # bf16 eager oracle; also evaluates the same input in fp32 (same bf16-rounded weights)
+        calls.append(Co.forward(sd32, ocfg, x.float(), text.float(), t.cuda(), rope))
+        return Co.forward(sd, ocfg, x, text, t.cuda(), rope)
+
+    Co.denoise_loop(transformer, sched_oracle.CogDDIMOracle(), lat0, img_lat, pos, neg, steps, gs, alg, prepare_lp_ref,
+                    lowpass.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
     xs = [lat0] + [p[0] for p in per_step]
     pipe.scheduler.set_timesteps(steps, device="cuda")
+    step32 = sched_oracle.CogDDIMOracle()
+    step32.set_timesteps(steps)
     shapes = []
     for i, t in enumerate(pipe.scheduler.timesteps.tolist()):
         x_next, npred = pipe.denoise_step(i, t, xs[i], img_lat, None, pos, neg, rope, None, 9, steps, alg, gs)
         shapes.append(npred.shape[0])
-        assert rel_l2(npred, per_step[i][1]) < 3e-2, (i, rel_l2(npred, per_step[i][1]))
-        assert rel_l2(x_next, xs[i + 1]) < 2 ** -7, (i, rel_l2(x_next, xs[i + 1]))
+        # with 2 steps the DDIM update multiplies the CFG-amplified bf16 noise of ANY implementation by a large factor, so
+        # the bar is the fp32 evaluation: the engine may not be further from it than eager PyTorch bf16 is (x1.5)
+        n32 = calls[i]
+        e_eng, e_torch = rel_l2(npred, n32), rel_l2(per_step[i][1], n32)
+        assert e_eng < max(1.5 * e_torch, 3e-3), (i, e_eng, e_torch)
+        x32 = step32.step(sched_oracle.cfg_combine(n32, gs, fp32=True), int(t), xs[i]).to(torch.bfloat16)
+        d_eng, d_torch = rel_l2(x_next, x32), rel_l2(xs[i + 1], x32)
+        assert d_eng < max(1.5 * d_torch, 2 ** -7), (i, d_eng, d_torch)
     assert shapes == [3, 2]

@@ -151,3 +151,30 @@ def test_pipeline_call_surface_and_callbacks():
 def test_smoke_entry():
     import __graft_entry__ as G
     G.smoke()
+
+
+def test_checkpoint_round_trip(tmp_path):
+    """A diffusers-layout snapshot of the tiny Wan model loads back through WanTransformer3DModel.from_pretrained and
+    WanImageToVideoPipeline.from_pretrained(local_dir) and produces the same forward (SURVEY 8(f).2 loader)."""
+    import json
+    import os
+    from alg_b200 import checkpoint, wan
+    from pipeline_wan_image2video_lowpass import WanImageToVideoPipeline
+    cfg, model, inp, _ = _problem(4)
+    snap = str(tmp_path / "snap")
+    full_cfg = dict(wan.WAN_I2V_14B, **cfg)
+    full_cfg["patch_size"] = list(full_cfg["patch_size"])
+    checkpoint.save_transformer(snap, full_cfg, model.state_dict(), "WanTransformer3DModel", max_shard_bytes=1 << 20)
+    os.makedirs(os.path.join(snap, "scheduler"))
+    json.dump({"_class_name": "UniPCMultistepScheduler", "flow_shift": 3.0, "prediction_type": "flow_prediction",
+               "use_flow_sigmas": True, "solver_order": 2, "num_train_timesteps": 1000},
+              open(os.path.join(snap, "scheduler", "scheduler_config.json"), "w"))
+    pipe = WanImageToVideoPipeline.from_pretrained(snap, allow_synthetic_aux=True)
+    assert pipe.scheduler.config.flow_shift == 3.0 and pipe.transformer.config.num_layers == cfg["num_layers"]
+    lat, c0 = inp["latents"][0], inp["condition"][0]
+    texts = [inp["negative_prompt_embeds"][0], inp["prompt_embeds"][0]]
+    a = model.forward_passes([lat, lat], [c0, c0], texts, inp["image_embeds"][0], 500)
+    b = pipe.transformer.forward_passes([lat, lat], [c0, c0], texts, inp["image_embeds"][0], 500)
+    assert torch.equal(a, b)
+    with pytest.raises(NotImplementedError, match="VAE"):
+        WanImageToVideoPipeline.from_pretrained(snap)
