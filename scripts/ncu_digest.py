@@ -31,7 +31,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(src.splitlines()))
 h = rows[1]
 ix = {n: i for i, n in enumerate(h)}
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) >= len(h) and r[ix["# Samples"]].strip().isdigit()]
 tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
 print("total samples", tot)
 keys = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
