@@ -31,6 +31,14 @@ class UniPCStep(C.Structure):
     ]
 
 
+class DpmStep(C.Structure):
+    _fields_ = [
+        ("n_pass", C.c_int32), ("second_order", C.c_int32), ("guidance", C.c_float), ("sqrt_alpha_t", C.c_float),
+        ("sqrt_beta_t", C.c_float), ("m0", C.c_float), ("m1", C.c_float), ("m2", C.c_float), ("m3", C.c_float),
+        ("m_noise", C.c_float),
+    ]
+
+
 class Gemm(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("B", C.c_void_p), ("D", C.c_void_p), ("bias", C.c_void_p), ("R", C.c_void_p),
@@ -97,6 +105,7 @@ SIGNATURES = {
     "alg_gaussian_kernel1d": (C.c_int, [C.c_int, C.c_double, C.c_int, C.POINTER(C.c_float)]),
     "alg_cfg_unipc_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(UniPCStep), C.c_void_p]),
     "alg_cfg_ddim_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "alg_cfg_dpm_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(DpmStep), C.c_void_p]),
     "alg_cfg_euler_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "alg_gemm_bf16": (C.c_int, [C.POINTER(Gemm), C.c_void_p]),
     "alg_attention_bf16": (C.c_int, [C.POINTER(Attention), C.c_void_p]),

@@ -3,6 +3,7 @@
 //   alg_cfg_unipc_step  wan:919-927   (CFG in bf16 with three roundings + UniPCMultistepScheduler.step)
 //   alg_cfg_ddim_step   cog:1091-1123 (fp32 CFG + CogVideoXDDIMScheduler.step + cast back)
 //   alg_cfg_euler_step  hy:1254-1270  (true CFG + FlowMatchEulerDiscreteScheduler.step on frames 1.. + re-prepend)
+//   alg_cfg_dpm_step    cog:1091-1123 (fp32 CFG + CogVideoXDPMScheduler.step: SDE DPM-Solver++ 2M, two noise draws)
 //
 // Every intermediate that PyTorch materialises as a tensor is rounded here at the same point
 // (__fmul_rn/__fadd_rn keep ptxas from contracting mul+add into FMA), so that given identical
@@ -73,6 +74,30 @@ __global__ void __launch_bounds__(256) ddim_kernel(const void* __restrict__ nois
     const float pred = __fsub_rn(Elem<SDT>::round(__fmul_rn(sa, xs)), __fmul_rn(sb, v));
     // prev = a * sample [sample dtype] + b * pred [fp32]; then .to(sample dtype) (cog:1123)
     const float prev = __fadd_rn(Elem<SDT>::round(__fmul_rn(a, xs)), __fmul_rn(b, pred));
+    Elem<SDT>::store(x_out, i, prev);
+  }
+}
+
+// CogVideoXDPMScheduler.step (v-prediction).  Tensors and their dtypes as eager PyTorch materialises them:
+//   pred_x0  = sa * sample [S] - sb * v [f32]                                   -> f32, returned (next step's old_pred)
+//   prev     = m0 * sample [S] - m1 * pred_x0 [f32] + mn * noise1 [S]           -> f32
+//   second-order (old_pred given, not the last step):
+//   d        = m2 * pred_x0 - m3 * old_pred                                     -> f32
+//   prev     = m0 * sample [S] - m1 * d + mn * noise2 [S]                       -> f32;  then .to(S) (cog:1123)
+template <int NDT, int SDT>
+__global__ void __launch_bounds__(256) dpm_kernel(const void* __restrict__ noise, const void* __restrict__ x,
+                                                  void* __restrict__ x_out, const float* __restrict__ old_pred,
+                                                  float* __restrict__ pred_out, const void* __restrict__ rnd, int64_t E,
+                                                  alg_dpm_step_t p) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = cfg_combine<NDT>(noise, i, E, p.n_pass, p.guidance, true);  // noise_pred.float() first (cog:1091)
+    const float xs = Elem<SDT>::load(x, i);
+    const float pred = __fsub_rn(Elem<SDT>::round(__fmul_rn(p.sqrt_alpha_t, xs)), __fmul_rn(p.sqrt_beta_t, v));
+    const float mx = Elem<SDT>::round(__fmul_rn(p.m0, xs));
+    const float nz = Elem<SDT>::round(__fmul_rn(p.m_noise, Elem<SDT>::load(rnd, i)));
+    const float den = p.second_order ? __fsub_rn(__fmul_rn(p.m2, pred), __fmul_rn(p.m3, old_pred[i])) : pred;
+    const float prev = __fadd_rn(__fsub_rn(mx, __fmul_rn(p.m1, den)), nz);
+    pred_out[i] = pred;
     Elem<SDT>::store(x_out, i, prev);
   }
 }
@@ -159,6 +184,26 @@ extern "C" int alg_cfg_euler_step(const void* noise, int noise_dtype, const floa
     euler_kernel<ALG_F16><<<ew_grid(E), 256, 0, st>>>(noise, x, x_out, first_frame, C, T, HW, n_pass, guidance, dt);
   else
     ALG_REQUIRE(false, "euler_step: unsupported noise dtype");
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_cfg_dpm_step(const void* noise, int noise_dtype, const void* x, void* x_out, int sample_dtype,
+                                const float* old_pred, float* pred_out, const void* rnd, int64_t E,
+                                const alg_dpm_step_t* p, void* stream) {
+  using namespace alg;
+  ALG_REQUIRE(noise && x && x_out && pred_out && rnd && p, "dpm_step: null pointer");
+  ALG_REQUIRE(p->n_pass >= 1 && p->n_pass <= 3, "dpm_step: n_pass must be 1, 2 or 3");
+  ALG_REQUIRE(!p->second_order || old_pred, "dpm_step: the second-order update needs old_pred");
+  if (E == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define ALG_DPM(N, S) dpm_kernel<N, S><<<ew_grid(E), 256, 0, st>>>(noise, x, x_out, old_pred, pred_out, rnd, E, *p)
+  if (noise_dtype == ALG_BF16 && sample_dtype == ALG_BF16) ALG_DPM(ALG_BF16, ALG_BF16);
+  else if (noise_dtype == ALG_F32 && sample_dtype == ALG_F32) ALG_DPM(ALG_F32, ALG_F32);
+  else if (noise_dtype == ALG_BF16 && sample_dtype == ALG_F32) ALG_DPM(ALG_BF16, ALG_F32);
+  else if (noise_dtype == ALG_F32 && sample_dtype == ALG_BF16) ALG_DPM(ALG_F32, ALG_BF16);
+  else ALG_REQUIRE(false, "dpm_step: unsupported dtype combination");
+#undef ALG_DPM
   ALG_LAUNCH_OK();
   return 0;
 }

@@ -260,6 +260,66 @@ class CogVideoXDDIMScheduler(_ConfigMixin):
 
 
 # =====================================================================================================
+class CogVideoXDPMScheduler(CogVideoXDDIMScheduler):
+    """CogVideoX SDE DPM-Solver++ (2M) scheduler, v-prediction (cog:1113-1122).  Same betas / timesteps as the DDIM variant;
+    ``step`` returns ``(prev_sample, pred_original_sample)`` and draws N(0, 1) noise on ``generator`` like the reference:
+    once for the first-order update and once more when the second-order update replaces it (RNG stream position kept)."""
+
+    def _dpm_coeffs(self, t: int, t_back: Optional[int]):
+        prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
+        a_back = self.alphas_cumprod[t_back] if t_back is not None else None
+        lamb = ((a_t / (1 - a_t)) ** 0.5).log()
+        lamb_next = ((a_prev / (1 - a_prev)) ** 0.5).log()
+        h = lamb_next - lamb
+        m0 = ((1 - a_prev) / (1 - a_t)) ** 0.5 * (-h).exp()
+        m1 = (-2 * h).expm1() * a_prev ** 0.5
+        m_noise = (1 - a_prev) ** 0.5 * (1 - (-2 * h).exp()) ** 0.5
+        m2 = m3 = 0.0
+        if a_back is not None:
+            r = (lamb - ((a_back / (1 - a_back)) ** 0.5).log()) / h
+            m2, m3 = 1 + 1 / (2 * r), 1 / (2 * r)
+        return dict(sa=float(a_t ** 0.5), sb=float((1 - a_t) ** 0.5), m0=float(m0), m1=float(m1), m2=float(m2), m3=float(m3),
+                    mn=float(m_noise), prev_t=prev_t)
+
+    def step_cfg(self, noise_pred, guidance_scale: float, old_pred_original_sample, timestep, timestep_back, sample,
+                 generator=None, out=None):
+        """fp32 CFG over the stacked passes + one DPM step; returns (prev_sample [sample dtype], pred_original_sample fp32)."""
+        from .pipeline_utils import randn_tensor
+
+        _lib.require_cuda(noise_pred, sample, old_pred_original_sample)
+        E = sample.numel()
+        n_pass = _as_passes(noise_pred, E)
+        k = self._dpm_coeffs(int(timestep), None if timestep_back is None else int(timestep_back))
+        second = old_pred_original_sample is not None and k["prev_t"] >= 0
+        rnd = randn_tensor(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
+        if second:  # the reference discards the first-order sample and draws again (cog scheduler `step`)
+            rnd = randn_tensor(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
+        p = _lib.DpmStep()
+        p.n_pass, p.second_order, p.guidance = n_pass, int(second), float(guidance_scale)
+        p.sqrt_alpha_t, p.sqrt_beta_t = k["sa"], k["sb"]
+        p.m0, p.m1, p.m2, p.m3, p.m_noise = k["m0"], k["m1"], k["m2"], k["m3"], k["mn"]
+        noise_pred, sample = noise_pred.contiguous(), sample.contiguous()
+        if out is None:
+            out = torch.empty_like(sample)
+        pred = torch.empty(sample.shape, device=sample.device, dtype=torch.float32)
+        old = old_pred_original_sample.contiguous() if second else None
+        if old is not None and old.dtype != torch.float32:
+            raise TypeError("old_pred_original_sample is the fp32 tensor a previous step returned")
+        with torch.cuda.device(sample.device):
+            _lib.check(_lib.lib().alg_cfg_dpm_step(
+                noise_pred.data_ptr(), _lib.dtype_code(noise_pred.dtype), sample.data_ptr(), out.data_ptr(),
+                _lib.dtype_code(sample.dtype), None if old is None else old.data_ptr(), pred.data_ptr(), rnd.data_ptr(), E,
+                C.byref(p), _lib.stream_ptr(sample.device)))
+        return out, pred
+
+    def step(self, model_output, old_pred_original_sample, timestep, timestep_back, sample, eta: float = 0.0,
+             use_clipped_model_output: bool = False, generator=None, variance_noise=None, return_dict: bool = False):
+        return self.step_cfg(model_output, 1.0, old_pred_original_sample, timestep, timestep_back, sample, generator)
+
+
+# =====================================================================================================
 class FlowMatchEulerDiscreteScheduler(_ConfigMixin):
     """Flow-match Euler as configured for HunyuanVideo-I2V (run.py:82-86).  SURVEY Appendix B.3."""
 

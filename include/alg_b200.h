@@ -99,6 +99,26 @@ int alg_cfg_ddim_step(const void* noise, int noise_dtype, const void* x, void* x
                       int64_t E, int n_pass, float guidance, float sqrt_alpha_t, float sqrt_beta_t,
                       float a, float b, void* stream);
 
+/* Host-computed scalars of one CogVideoXDPMScheduler step (fp64 in the scheduler, handed to the kernel as fp32 the way
+ * ATen hands 0-dim CPU tensors to CUDA kernels). */
+typedef struct {
+  int32_t n_pass;        /* 1: no CFG; 2: u + w (t - u); 3: u0 + w (t - u), in fp32 (cog:1091-1102)      */
+  int32_t second_order;  /* old_pred_original_sample given and prev_timestep >= 0                       */
+  float guidance;
+  float sqrt_alpha_t, sqrt_beta_t; /* pred_x0 = sqrt(a_t) x - sqrt(1 - a_t) v                             */
+  float m0, m1, m2, m3;  /* get_mult(): sqrt((1-a_prev)/(1-a_t)) e^-h ; expm1(-2h) sqrt(a_prev) ; 1 + 1/(2r) ; 1/(2r) */
+  float m_noise;         /* sqrt(1 - a_prev) sqrt(1 - e^-2h)                                            */
+} alg_dpm_step_t;
+
+/* cog:1113-1123 -- fp32 CFG + CogVideoXDPMScheduler.step (SDE DPM-Solver++, v-prediction) + cast back.
+ *   noise [n_pass, E] noise_dtype; x, x_out, rnd [E] sample_dtype (rnd = the N(0,1) draw THIS branch of the step uses:
+ *   the reference draws once for the first-order update and once more for the second-order one -- the caller makes both
+ *   draws on its torch.Generator, in that order, and passes the one that survives);
+ *   old_pred [E] fp32 = previous step's pred_original_sample (NULL on the first step); pred_out [E] fp32 (may alias old_pred). */
+int alg_cfg_dpm_step(const void* noise, int noise_dtype, const void* x, void* x_out, int sample_dtype,
+                     const float* old_pred, float* pred_out, const void* rnd, int64_t E, const alg_dpm_step_t* p,
+                     void* stream);
+
 /* hy:1254-1270 -- (true-)CFG + FlowMatchEulerDiscreteScheduler.step on frames 1.. + re-prepend
  * of the conditioning frame.  Layout [C, T, HW]; noise holds all T frames (frame 0 ignored).
  *   x_out[c, 0] = first_frame[c, 0];  x_out[c, f>0] = fp32(noise_dtype(x + noise_dtype(dt * v)))  */

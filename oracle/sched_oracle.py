@@ -215,6 +215,36 @@ class CogDDIMOracle:
         return _smul(a, sample) + _smul(b, pred_x0)
 
 
+class CogDPMOracle(CogDDIMOracle):
+    """``CogVideoXDPMScheduler.step`` (scheduling_dpm_cogvideox.py, v-prediction), restated op by op.  ``randn`` is the
+    callable that draws the N(0, 1) tensors (the caller owns the generator): one draw for the first-order update and a
+    second one when the second-order update replaces it."""
+
+    def dpm_coeffs(self, t: int, t_back):
+        prev_t = t - self.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
+        a_back = self.alphas_cumprod[t_back] if t_back is not None else None
+        lamb = ((a_t / (1 - a_t)) ** 0.5).log()
+        lamb_next = ((a_prev / (1 - a_prev)) ** 0.5).log()
+        h = lamb_next - lamb
+        mult = [((1 - a_prev) / (1 - a_t)) ** 0.5 * (-h).exp(), (-2 * h).expm1() * a_prev ** 0.5]
+        if a_back is not None:
+            r = (lamb - ((a_back / (1 - a_back)) ** 0.5).log()) / h
+            mult += [1 + 1 / (2 * r), 1 / (2 * r)]
+        mult_noise = (1 - a_prev) ** 0.5 * (1 - (-2 * h).exp()) ** 0.5
+        return a_t, prev_t, mult, mult_noise
+
+    def step(self, model_output, old_pred, t: int, t_back, sample, randn):
+        a_t, prev_t, mult, mult_noise = self.dpm_coeffs(int(t), None if t_back is None else int(t_back))
+        pred = _smul(a_t ** 0.5, sample) - _smul((1 - a_t) ** 0.5, model_output)
+        prev = _smul(mult[0], sample) - _smul(mult[1], pred) + _smul(mult_noise, randn())
+        if old_pred is None or prev_t < 0:
+            return prev, pred
+        d = _smul(mult[2], pred) - _smul(mult[3], old_pred)
+        return _smul(mult[0], sample) - _smul(mult[1], d) + _smul(mult_noise, randn()), pred
+
+
 # ----------------------------------------------------------------------------
 # FlowMatchEuler as configured for HunyuanVideo
 # ----------------------------------------------------------------------------

@@ -27,7 +27,7 @@ from alg_b200.embeddings import get_3d_rotary_pos_embed, get_resize_crop_region_
 from alg_b200.pipeline_utils import (CogVideoXPipelineOutput, DiffusionPipelineBase, MultiPipelineCallbacks,
                                      PipelineCallback, SyntheticTextEncoder, SyntheticVideoVAE, VideoProcessor,
                                      randn_tensor)
-from alg_b200.schedulers import CogVideoXDDIMScheduler
+from alg_b200.schedulers import CogVideoXDDIMScheduler, CogVideoXDPMScheduler
 
 PipelineImageInput = Union[PIL.Image.Image, torch.Tensor, List[PIL.Image.Image]]
 
@@ -299,7 +299,7 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
     # ------------------------------------------------------------------------------------------------
     def denoise_step(self, i, t, latents, image_latents, image_tensor, prompt_embeds, negative_prompt_embeds, rope,
                      generator, num_frames, num_inference_steps, alg: Dict[str, Any], guidance_scale: float,
-                     use_dynamic_cfg: bool = False):
+                     use_dynamic_cfg: bool = False, t_back: Optional[int] = None):
         """One iteration of cog:1005-1123 for a single sample: returns (new latents, bf16 noise prediction of all passes).
 
         ``t`` is the host integer timestep.  Branches and pass order follow the reference exactly."""
@@ -339,7 +339,12 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
         if do_cfg and not use_lp and use_dynamic_cfg:  # cog:1105-1108
             w = 1 + guidance_scale * ((1 - math.cos(math.pi * ((num_inference_steps - int(t)) / num_inference_steps) ** 5.0)) / 2)
             self._guidance_scale = w
-        latents = self.scheduler.step_cfg(noise_pred, w if do_cfg else 1.0, int(t), latents)
+        if isinstance(self.scheduler, CogVideoXDPMScheduler):  # cog:1113-1122: carries old_pred_original_sample
+            latents, self._old_pred_original_sample = self.scheduler.step_cfg(
+                noise_pred, w if do_cfg else 1.0, getattr(self, "_old_pred_original_sample", None), int(t), t_back, latents,
+                generator)
+        else:
+            latents = self.scheduler.step_cfg(noise_pred, w if do_cfg else 1.0, int(t), latents)
         return latents, noise_pred
 
     @torch.no_grad()
@@ -429,8 +434,9 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
         latents, image_latents = self.prepare_latents(image_tensor, batch_size * num_videos_per_prompt, latent_channels,
                                                       num_frames, height, width, prompt_embeds.dtype, device, generator, latents)
         extra_step_kwargs = self.prepare_extra_step_kwargs(generator, eta)
-        if extra_step_kwargs.get("eta", 0.0) != 0.0:
+        if extra_step_kwargs.get("eta", 0.0) != 0.0 and not isinstance(self.scheduler, CogVideoXDPMScheduler):
             raise NotImplementedError("eta > 0 (stochastic DDIM) is outside the hot path built here")
+        self._old_pred_original_sample = None
         image_rotary_emb = (self._prepare_rotary_positional_embeddings(height, width, latents.size(1), device)
                             if cfg.use_rotary_positional_embeddings else None)
 
@@ -453,7 +459,8 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
                 self._current_timestep = t
                 latents, _ = self.denoise_step(i, t_host, latents, image_latents, image_tensor, prompt_embeds,
                                                negative_prompt_embeds, image_rotary_emb, generator, num_frames,
-                                               num_inference_steps, alg, guidance_scale, use_dynamic_cfg)
+                                               num_inference_steps, alg, guidance_scale, use_dynamic_cfg,
+                                               timesteps_host[i - 1] if i > 0 else None)
                 latents = latents.to(prompt_embeds.dtype)
                 if callback_on_step_end is not None:
                     scope = dict(latents=latents, prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds)

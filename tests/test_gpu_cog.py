@@ -215,3 +215,20 @@ def test_config1_full_architecture_two_steps():
         d_eng, d_torch = rel_l2(x_next, x32), rel_l2(xs[i + 1], x32)
         assert d_eng < max(1.5 * d_torch, 2 ** -7), (i, d_eng, d_torch)
     assert shapes == [3, 2]
+
+
+def test_pipeline_with_dpm_scheduler():
+    """cog:1113-1122: swapping in CogVideoXDPMScheduler routes the loop through alg_cfg_dpm_step (state carried across
+    steps, RNG drawn on the caller's generator) and reproduces itself for the same seed."""
+    from alg_b200.schedulers import CogVideoXDPMScheduler
+    from PIL import Image
+    cfg, model = _model(5)
+    pipe = _pipe(model)
+    pipe.scheduler = CogVideoXDPMScheduler.from_config(pipe.scheduler.config)
+    img = Image.new("RGB", (96, 64), (90, 20, 200))
+    kw = dict(image=img, prompt="a boat", num_frames=9, num_inference_steps=4, max_sequence_length=16, output_type="latent")
+    a = pipe(**kw, generator=torch.Generator("cuda").manual_seed(1), **ALG).frames
+    b = pipe(**kw, generator=torch.Generator("cuda").manual_seed(1), **ALG).frames
+    c = pipe(**kw, generator=torch.Generator("cuda").manual_seed(2), **ALG).frames
+    assert a.shape == (1, 3, 16, 8, 12) and torch.isfinite(a.float()).all()
+    assert torch.equal(a, b) and not torch.equal(a, c)

@@ -88,3 +88,33 @@ def test_full_size_property_constant_velocity():
     for _ in range(50):
         x = s.step_cfg((eps - x0).unsqueeze(0).reshape(1, -1), 1.0, x)
     assert float((x - x0).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("n_pass", [1, 2, 3])
+def test_cog_dpm_step_matches_oracle(n_pass):
+    """cog:1113-1123: fp32 CFG + CogVideoXDPMScheduler.step (first step first-order, then second-order with the carried
+    pred_original_sample, last step onto alpha = 1) against the oracle; both sides draw their noise from CUDA generators
+    with the same seed, in the reference's order (one draw, plus a second one for the second-order update)."""
+    from alg_b200 import schedulers as S
+    from oracle import sched_oracle as O
+    torch.manual_seed(3)
+    steps, shape = 8, (1, 3, 16, 12, 20)
+    e, oe = S.CogVideoXDPMScheduler(), O.CogDPMOracle()
+    e.set_timesteps(steps, device="cuda")
+    oe.set_timesteps(steps)
+    g_e, g_o = (torch.Generator(device="cuda").manual_seed(9) for _ in range(2))
+    x = torch.randn(shape, device="cuda").bfloat16()
+    xo, old_e, old_o = x.clone(), None, None
+    ts = e.timesteps.tolist()
+    assert ts == oe.timesteps.tolist()
+    for i, t in enumerate(ts):
+        npred = torch.randn((n_pass,) + shape[1:], device="cuda").bfloat16()
+        t_back = ts[i - 1] if i > 0 else None
+        noise = O.cfg_combine(npred, 6.0, fp32=True) if n_pass > 1 else npred.float()
+        xo, old_o = oe.step(noise, old_o, t, t_back, xo,
+                            lambda: torch.randn(shape, generator=g_o, device="cuda", dtype=torch.bfloat16))
+        xo = xo.to(torch.bfloat16)
+        x, old_e = e.step_cfg(npred, 6.0, old_e, t, t_back, x, generator=g_e)
+        assert old_e.dtype == torch.float32 and torch.equal(old_e, old_o), i
+        assert x.dtype == torch.bfloat16 and torch.equal(x, xo), i
+    assert torch.isfinite(x.float()).all()

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header(tmp_path):
 
     from alg_b200 import _lib
 
-    pairs = {"alg_unipc_step_t": _lib.UniPCStep, "alg_gemm_t": _lib.Gemm, "alg_attention_t": _lib.Attention,
+    pairs = {"alg_unipc_step_t": _lib.UniPCStep, "alg_dpm_step_t": _lib.DpmStep, "alg_gemm_t": _lib.Gemm, "alg_attention_t": _lib.Attention,
              "alg_wan_config_t": _lib.WanConfig, "alg_layer_norm_t": _lib.LayerNorm,
              "alg_head_norm_rope_t": _lib.HeadNormRope, "alg_patch_src_t": _lib.PatchSrc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "alg_b200.h"', 'int main(void) {']
@@ -158,3 +158,25 @@ def test_scheduler_host_scalars_match_oracle():
     # run.py:82 passes flow_shift= to a scheduler whose parameter is named shift: ignored like in diffusers
     e2 = S.FlowMatchEulerDiscreteScheduler.from_config(e.config, flow_shift=17.0, invert_sigmas=False)
     assert e2.config.shift == 7.0 and e2.ignored_config_keys == ["flow_shift"]
+
+
+def test_dpm_host_scalars_match_oracle():
+    """CogVideoXDPMScheduler coefficients (host fp64 -> fp32) against the oracle's, including the zero-terminal-SNR first
+    step (alpha = 0: h = inf, mult finite) and the final step onto alpha = 1."""
+    from alg_b200 import schedulers as S
+    from oracle import sched_oracle as O
+    e, o = S.CogVideoXDPMScheduler(), O.CogDPMOracle()
+    for n in (2, 10, 50):
+        e.set_timesteps(n)
+        o.set_timesteps(n)
+        ts = o.timesteps.tolist()
+        assert e.timesteps.tolist() == ts
+        for i, t in enumerate(ts):
+            tb = ts[i - 1] if i > 0 else None
+            k = e._dpm_coeffs(t, tb)
+            a_t, prev_t, mult, mn = o.dpm_coeffs(t, tb)
+            got = [k["m0"], k["m1"]] + ([k["m2"], k["m3"]] if tb is not None else [])
+            used = got[:2] if (tb is None or prev_t < 0) else got  # mult[2:] feed the second-order update only
+            assert k["prev_t"] == prev_t and all(np.isfinite(used)) and np.isfinite(k["mn"])
+            np.testing.assert_array_equal(got, [float(m) for m in mult])  # NaN == NaN here (unused last-step r = 0)
+            assert k["mn"] == float(mn) and k["sa"] == float(a_t ** 0.5)
