@@ -178,3 +178,49 @@ def test_checkpoint_round_trip(tmp_path):
     assert torch.equal(a, b)
     with pytest.raises(NotImplementedError, match="VAE"):
         WanImageToVideoPipeline.from_pretrained(snap)
+
+
+@pytest.mark.parametrize("mode", ["pixel_gaussian_exponential", "latent_down_up_linear"])
+def test_loop_non_interval_schedules_and_pixel_space(mode):
+    """wan:863-880 with strength schedules that change the filter EVERY step (operator tables / taps rebuilt per step, quirk
+    q8: `k * s` stays a float fraction of H) and the pixel-space branch (wan:493-540: filter the RGB frame, VAE-encode +
+    `sample(generator)` every step, rebuild the 4-channel mask), teacher-forced against the oracle loop."""
+    import __graft_entry__ as G
+    from alg_b200 import lowpass
+    from alg_b200.schedulers import UniPCMultistepScheduler
+    from oracle import sched_oracle, wan_oracle as W
+    from pipeline_wan_image2video_lowpass import WanImageToVideoPipeline
+    cfg, model, inp, alg = _problem(6)
+    steps, gs = 8, 5.0
+    if mode == "pixel_gaussian_exponential":
+        alg = dict(alg, lp_filter_type="gaussian_blur", lp_filter_in_latent=False, lp_blur_sigma=4.0, lp_blur_kernel_size=0.11,
+                   lp_strength_schedule_type="exponential", schedule_exp_decay_rate=3.0, schedule_blur_kernel_size=True)
+    else:
+        alg = dict(alg, lp_strength_schedule_type="linear", schedule_linear_start_weight=1.0, schedule_linear_end_weight=0.2,
+                   schedule_linear_end_time=0.6, lp_resize_factor=0.3)
+    pipe = WanImageToVideoPipeline.from_pretrained("synthetic", transformer=model, synthetic=True)
+    pipe.scheduler = UniPCMultistepScheduler.from_config(pipe.scheduler.config, flow_shift=5.0)
+    pipe.to("cuda")
+    pipe._guidance_scale = gs
+    g = torch.Generator(device="cuda").manual_seed(5)
+    image = torch.rand(1, 3, 128, 192, generator=g, device="cuda") * 2 - 1
+    cond = inp["condition"]
+    g_ref, g_mine = (torch.Generator(device="cuda").manual_seed(21) for _ in range(2))
+    ocfg = W.WanConfig(**cfg)
+    sd = model.state_dict()
+
+    def lp_filter_ref(c, kind, sigma, k, f):  # the reference's prepare_lp around the real (CUDA) filter and the VAE stub
+        return pipe.prepare_lp(kind, sigma, k, f, g_ref, 9, True, alg["lp_filter_in_latent"], c, image)
+
+    per_step = []
+    W.denoise_loop(lambda x, t, text, img: W.forward(sd, ocfg, x, t.to(x.device), text, img), sched_oracle.UniPCOracle(flow_shift=5.0),
+                   inp["latents"], cond, inp["prompt_embeds"], inp["negative_prompt_embeds"], inp["image_embeds"], steps, gs,
+                   alg, lp_filter_ref, lowpass.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
+    xs = [inp["latents"]] + [p[0] for p in per_step]
+    sched = pipe.scheduler
+    sched.set_timesteps(steps, device="cuda")
+    for i, t in enumerate(sched.timesteps.tolist()):
+        x_next, npred = pipe.denoise_step(i, t, xs[i], cond, image, inp["prompt_embeds"], inp["negative_prompt_embeds"],
+                                          inp["image_embeds"], g_mine, 9, steps, alg)
+        assert npred.shape == per_step[i][1].shape and npred.shape[0] == 3  # strength > 0 on every step: three passes
+        assert rel_l2(x_next, xs[i + 1]) < 4e-3, (i, rel_l2(x_next, xs[i + 1]))  # 8-step schedule: large |d sigma| per step
