@@ -246,9 +246,11 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if FAST:
             torch.cuda.cudart().cudaProfilerStart()  # ncu --profile-from-start off: capture the timed region only
+        marks = [torch.cuda.Event(enable_timing=True) for _ in idxs]
         e0.record()
-        for idx in idxs:
+        for k, idx in enumerate(idxs):
             lat = step(idx, lat0)
+            marks[k].record()
         e1.record()
         barrier()
         if FAST:
@@ -256,6 +258,7 @@ def run_ours(args):
         sampler.stop_flag = True
         launches = _lib.launch_count() - launches0
         ms_total = e0.elapsed_time(e1)
+        step_ms = [(e0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]) for k in range(len(idxs))]
         prof = transformer.profile_read()
         transformer.profile(False)
         # ---------------- end-to-end region: host buffers in, host result out, every step ----------------
@@ -289,6 +292,7 @@ def run_ours(args):
         passes = sum(n_pass_of(i) for i in idxs)
         # one self-attention launch covers all passes of a step x 40 heads: flops = 4 * B * heads * N^2 * d_head
         flops_launch = {p: 4 * p * n_tok * n_tok * 5120 for p in (2, 3)}
+        kernel_name = f"attention_kernel<128> (DiT self-attention, N={n_tok}, 40 heads x 128)"
         flops_total = sum(40 * flops_launch[n_pass_of(i)] for i in idxs)
         achieved = flops_total / (sa["ms"] / 1e3) / 1e12 if sa["ms"] > 0 else None
         total_flops = passes * forward_flops(n_tok)[0]
@@ -296,8 +300,8 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "r01_attention_traffic.json")
         if os.path.exists(tpath) and sa["launches"]:
             heads_per_launch = 40 * passes / (sa["launches"] / 40)  # 40 layers -> launches / 40 steps-worth of launches
-            traffic = json.load(open(tpath))["dram_bytes_per_head"] * heads_per_launch
-        roofline = {"kernel": "attention_kernel<128> (DiT self-attention, N=32760, 40 heads x 128)", "bound": "tensor",
+            traffic = json.load(open(tpath))["dram_bytes_per_head"] * heads_per_launch * n_tok / 32760  # linear in tokens
+        roofline = {"kernel": kernel_name, "bound": "tensor",
                     "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s",
                     "frac": achieved / tf_sust if achieved else None, "peak_kind": f"bf16_tflops_sustained ({src}); kernel timed inside a long step",
                     "frac_of_burst_peak": achieved / tf_burst if achieved else None, "traffic": traffic,
@@ -305,7 +309,10 @@ def run_ours(args):
                     "launches": sa["launches"], "avg_launch_ms": sa["ms"] / max(sa["launches"], 1),
                     "share_of_step": sa["ms"] / ms_total,
                     "per_class_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
-                    "whole_step_tflops": total_flops / (ms_total / 1e3) / 1e12}
+                    "whole_step_tflops": total_flops / (ms_total / 1e3) / 1e12,
+                    "ms_per_step_by_passes": {str(p): round(sum(m for m, i in zip(step_ms, idxs) if n_pass_of(i) == p) /
+                                                            max(1, sum(1 for i in idxs if n_pass_of(i) == p)), 3)
+                                              for p in (3, 2) if any(n_pass_of(i) == p for i in idxs)}}
         cpu = None
         if not FAST:
             try:
@@ -314,11 +321,13 @@ def run_ours(args):
             except Exception as ex:  # pragma: no cover
                 cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
         line = {
-            "metric": "video frames/sec (Wan-I2V-14B 480p, 81 frames, 50 steps, ALG down_up)", "value": fps,
+            "metric": f"video frames/sec (Wan-I2V-14B {HEIGHT}p, 81 frames, 50 steps, ALG down_up)", "value": fps,
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Wan-I2V-14B 480x832, 81 frames, 50 steps, ALG down_up f=0.4 interval[0,0.2], gs 5, UniPC "
-                                   "flow_shift 5.0 (BASELINE.json configs[1]); one sample per GPU",
+            "config": {"workload": f"Wan-I2V-14B {HEIGHT}x{WIDTH}, 81 frames, 50 steps, ALG down_up f=0.4 interval[0,0.2], gs 5, UniPC "
+                                   "flow_shift 5.0 (BASELINE.json configs[1]); one sample per GPU" if HEIGHT == 480 else
+                                   f"Wan-I2V-14B {HEIGHT}x{WIDTH} (720p variant of BASELINE.json configs[1]), 81 frames, 50 steps, "
+                                   "ALG down_up f=0.4 interval[0,0.2], gs 5, UniPC flow_shift 5.0; one sample per GPU",
                        "step_sampling": f"schedule indices {idxs} ({passes} sample-forwards in {args.steps} steps; full video = 110 in 50)",
                        "weights": "seeded random init at the true 16.4 B-parameter architecture (no checkpoints offline)",
                        "l2": "inputs_exceed_l2 (32.8 GB of weights stream through the 126 MB L2 every step)",
@@ -338,7 +347,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--resolution", default="480p", choices=["480p", "720p"],
+                    help="480p = BASELINE.json configs[1] (the headline workload); 720p = the same loop on 720x1280 latents "
+                         "(75 600 tokens; north_star asks for both to be reported)")
     args = ap.parse_args()
+    if args.resolution == "720p":
+        global HEIGHT, WIDTH, H_LAT, W_LAT
+        HEIGHT, WIDTH, H_LAT, W_LAT = 720, 1280, 90, 160
     if args.impl == "reference":
         run_reference(args)
     else:
