@@ -33,10 +33,13 @@ using namespace tc;
 
 constexpr int BQ = 128;  // query rows per tile (two tiles per CTA)
 constexpr int BKV = 64;  // keys per pipeline step
-constexpr int kStages = 4;
+constexpr int kStages = 4;  // barrier-array stride (the SHORT variant uses only the first two stages)
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef ALG_ATTN_POLY_DEFAULT
 #define ALG_ATTN_POLY_DEFAULT 8
+#endif
+#ifndef ALG_ATTN_SHORT_MAX_DEFAULT
+#define ALG_ATTN_SHORT_MAX_DEFAULT 1024
 #endif
 #ifndef ALG_ATTN_SPLIT_DEFAULT
 #define ALG_ATTN_SPLIT_DEFAULT 0
@@ -48,7 +51,9 @@ struct Cfg {
   static constexpr int kBytesK = BKV * D * 2;  // one K stage  [64 keys][D]
   static constexpr int kBytesV = D * BKV * 2;  // one V^T stage [D][64 keys]
   static constexpr int kXchBytes = 2 * 2 * 2 * BQ * 4;  // SPLIT: [tile][step parity][half][row] partial row maxima
-  static constexpr int kSmemBytes = 2 * kBytesQ + kStages * (kBytesK + kBytesV) + 1024 + 512 + kXchBytes;
+  static constexpr int smem_bytes(int tiles, int stages) {
+    return tiles * kBytesQ + stages * (kBytesK + kBytesV) + 1024 + 512 + kXchBytes;
+  }
   static constexpr int kSubQ = BQ * 128;   // bytes of one [128 rows][64 elem] swizzle sub-tile of Q
   static constexpr int kSubK = BKV * 128;  // bytes of one [64 keys][64 elem] sub-tile of K
 };
@@ -97,12 +102,13 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 // step is unrolled over j % 4 so stage, S-buffer, barrier offsets and barrier parities are compile-time, and every
 // operand descriptor is (base low word) + (compile-time offset).
 struct MmaCtx {
-  uint32_t tmem, bar, q_lo, k_lo, v_lo;
+  uint32_t tmem, tmem_o, bar, q_lo, k_lo, v_lo;  // tmem_o = first O column (behind the S buffers of all tiles)
   int n_steps;
 };
 constexpr int kBarKFull = 1, kBarKEmpty = 1 + kStages, kBarVFull = 1 + 2 * kStages, kBarVEmpty = 1 + 3 * kStages,
               kBarSFull = 1 + 4 * kStages, kBarPFull = kBarSFull + 4, kBarODone = kBarPFull + 4, kBarOFull = kBarODone + 2;
-static_assert(kStages == 4, "the issuer's compile-time parities assume four K/V stages");
+static_assert(kStages == 4, "the issuer's compile-time parities assume a four-step unroll");
+// MmaCtx::tiles = query tiles of the CTA: O accumulators start behind the S buffers of all tiles
 
 // NOTE on the S shape: with 64-key (N = 64) S MMAs both operands stream from shared memory at 6 KB per MMA; the tensor
 // core fetches 128 B/clk, so a 128x64x16 SS MMA takes 48 cycles instead of its 32-cycle floor (measured:
@@ -126,7 +132,7 @@ template <int D, int I, int BUF, int ST>
 __device__ __forceinline__ void issue_pv(const MmaCtx& c, uint32_t acc_first) {  // O_I (+)= P_I (buffer BUF) V (stage ST)
   using C = Cfg<D>;
   constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D);
-  const uint32_t d = c.tmem + 256 + I * 128, a = c.tmem + I * 128 + BUF * 64;
+  const uint32_t d = c.tmem_o + I * 128, a = c.tmem + I * 128 + BUF * 64;
 #pragma unroll
   for (int ks = 0; ks < BKV / 16; ++ks)
     mma_ts_lo(d, a + ks * 8, c.v_lo + ((ST * C::kBytesV + ks * 32) >> 4), idesc_o, ks == 0 ? acc_first : 1u);
@@ -135,11 +141,15 @@ __device__ __forceinline__ void issue_pv(const MmaCtx& c, uint32_t acc_first) { 
 // step j = 4 m + JJ of query tile I; ph = m & 1 (parity of the K/V stage ring at this step).  Each tile has its OWN issuer
 // warp: one thread issuing for both tiles still needed ~230 instructions (~1 000+ cycles) per step; two threads halve that,
 // and the tiles' MMA streams are independent (disjoint TMEM), sharing only the K/V stage barriers (two arrivals each).
-template <int D, int I, int JJ>
-__device__ __forceinline__ void mma_tile_step(const MmaCtx& c, const int j, const uint32_t ph) {
-  constexpr int BUF = JJ & 1, ST = JJ % kStages, STN = (JJ + 2) % kStages;
+template <int D, int I, int JJ, int STAGES>
+__device__ __forceinline__ void mma_tile_step(const MmaCtx& c, const int j, uint32_t ph) {
+  constexpr int BUF = JJ & 1, ST = JJ % STAGES, STN = (JJ + 2) % STAGES;
   constexpr uint32_t p_par = (JJ >> 1) & 1;                      // ((4 m + JJ) >> 1) & 1
-  const uint32_t phn = (JJ + 2 >= kStages) ? (ph ^ 1u) : ph;     // parity of (j + 2) / kStages
+  uint32_t phn = (JJ + 2 >= kStages) ? (ph ^ 1u) : ph;           // parity of (j + 2) / STAGES (four stages)
+  if constexpr (STAGES == 2) {                                   // two stages: (4 m + JJ) / 2 = 2 m + JJ / 2 -> compile-time
+    ph = (JJ >> 1) & 1;
+    phn = ((JJ + 2) >> 1) & 1;
+  }
   const bool has_next = j + 2 < c.n_steps, last = j == c.n_steps - 1;
   mbar_wait_a(c.bar + 8 * (kBarPFull + I * 2 + BUF), p_par);
   mbar_wait_a(c.bar + 8 * (kBarVFull + ST), ph);
@@ -154,7 +164,7 @@ __device__ __forceinline__ void mma_tile_step(const MmaCtx& c, const int j, cons
     tc_commit_a(c.bar + 8 * (kBarKEmpty + STN));
   }
 }
-template <int D, int I>
+template <int D, int I, int STAGES>
 __device__ __forceinline__ void mma_tile_loop(const MmaCtx& c) {
   mbar_wait_a(c.bar, 0);  // q_full
   mbar_wait_a(c.bar + 8 * (kBarKFull + 0), 0);
@@ -170,10 +180,10 @@ __device__ __forceinline__ void mma_tile_loop(const MmaCtx& c) {
   uint32_t ph = 0;
 #pragma unroll 1
   for (int j0 = 0; j0 < c.n_steps; j0 += 4, ph ^= 1u) {
-    mma_tile_step<D, I, 0>(c, j0, ph);
-    if (j0 + 1 < c.n_steps) mma_tile_step<D, I, 1>(c, j0 + 1, ph);
-    if (j0 + 2 < c.n_steps) mma_tile_step<D, I, 2>(c, j0 + 2, ph);
-    if (j0 + 3 < c.n_steps) mma_tile_step<D, I, 3>(c, j0 + 3, ph);
+    mma_tile_step<D, I, 0, STAGES>(c, j0, ph);
+    if (j0 + 1 < c.n_steps) mma_tile_step<D, I, 1, STAGES>(c, j0 + 1, ph);
+    if (j0 + 2 < c.n_steps) mma_tile_step<D, I, 2, STAGES>(c, j0 + 2, ph);
+    if (j0 + 3 < c.n_steps) mma_tile_step<D, I, 3, STAGES>(c, j0 + 3, ph);
   }
 }
 
@@ -188,20 +198,26 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 //            the MUFU / FMA latencies the 2-warp version exposed: 0.44 IPC, profiles/r01_attention.md).  The halves
 //            exchange their partial row maxima through shared memory behind one 256-thread named barrier per step,
 //            keep partial row sums, and each rescales / writes half of the O columns.
-template <int D, int POLY, int SPLIT>
-__global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
+// TILES = 2, STAGES = 4: the long-sequence layout described above (one CTA per SM).
+// TILES = 1, STAGES = 2: SHORT variant for a few hundred keys (Wan cross-attention: 257 image / 512 text keys; the Hunyuan
+//            token refiner): one query tile, two K/V stages, ~100 KB of shared memory and 256 TMEM columns, so TWO CTAs
+//            share an SM and one CTA's prologue (TMEM alloc, Q load) and epilogue overlap the other's steps -- with 5-8
+//            steps per CTA those fixed costs were more than half of the long layout's time per CTA.
+template <int D, int POLY, int SPLIT, int TILES, int STAGES>
+__global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TILES == 1 ? 2 : 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Params p) {
   using C = Cfg<D>;
-  constexpr int kSoftmaxWarps = SPLIT ? 16 : 8;
+  constexpr int kSoftmaxWarps = (SPLIT ? 8 : 4) * TILES;
   constexpr int kTmaWarp = kSoftmaxWarps, kMmaWarp = kSoftmaxWarps + 1;  // MMA issuers: kMmaWarp (tile 0), kMmaWarp + 1 (tile 1)
-  constexpr int kWarpsPerTile = kSoftmaxWarps / 2;
+  constexpr int kWarpsPerTile = kSoftmaxWarps / TILES;
+  constexpr uint32_t kTmemCols = 256 * TILES;  // per tile: two 64-column S buffers + 128 O columns
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                          // [2][BQ x D]
-  uint8_t* sK = sQ + 2 * C::kBytesQ;           // [stages][BKV x D]
-  uint8_t* sV = sK + kStages * C::kBytesK;     // [stages][D x BKV]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * C::kBytesV);
+  uint8_t* sK = sQ + TILES * C::kBytesQ;       // [STAGES][BKV x D]
+  uint8_t* sV = sK + STAGES * C::kBytesK;      // [STAGES][D x BKV]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * C::kBytesV);
   uint64_t* q_full = bars;                     // 1
   uint64_t* k_full = bars + 1;                 // kStages
   uint64_t* k_empty = k_full + kStages;        // kStages
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, batch = blockIdx.z;
-  const int q0 = blockIdx.x * 2 * BQ;
+  const int q0 = blockIdx.x * TILES * BQ;
   const int n_steps = (p.n_kv + BKV - 1) / BKV;
 
   if (warp == kTmaWarp && lane == 0) {
@@ -227,9 +243,9 @@ __global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
     mbar_init(q_full, 1);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 2);  // one commit per issuer warp
+      mbar_init(&k_empty[i], TILES);  // one commit per issuer warp
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 2);
+      mbar_init(&v_empty[i], TILES);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -242,7 +258,7 @@ __global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -252,20 +268,20 @@ __global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
 
   if (warp == kTmaWarp) {
     if (elect_one()) {  // ===== TMA producer: Q0 Q1 | K0 K1 | V0 K2 | V1 K3 | ... (the order the MMA warp consumes) =====
-      mbar_arrive_expect_tx(q_full, 2 * C::kBytesQ);
-      for (int i = 0; i < 2; ++i)
+      mbar_arrive_expect_tx(q_full, TILES * C::kBytesQ);
+      for (int i = 0; i < TILES; ++i)
         for (int s = 0; s < D / 64; ++s)
           tma_load_3d(sQ + i * C::kBytesQ + s * C::kSubQ, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
       auto load_k = [&](int j) {
-        const int st = j % kStages;
-        mbar_wait(&k_empty[st], ((j / kStages) & 1) ^ 1);
+        const int st = j % STAGES;
+        mbar_wait(&k_empty[st], ((j / STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], C::kBytesK);
         for (int s = 0; s < D / 64; ++s)
           tma_load_3d(sK + st * C::kBytesK + s * C::kSubK, &tmK, &k_full[st], head * D + s * 64, j * BKV, batch);
       };
       auto load_v = [&](int j) {
-        const int st = j % kStages;
-        mbar_wait(&v_empty[st], ((j / kStages) & 1) ^ 1);
+        const int st = j % STAGES;
+        mbar_wait(&v_empty[st], ((j / STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[st], C::kBytesV);
         tma_load_3d(sV + st * C::kBytesV, &tmV, &v_full[st], j * BKV, head * D, batch);
       };
@@ -276,18 +292,19 @@ __global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
         if (j + 2 < n_steps) load_k(j + 2);
       }
     }
-  } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
+  } else if (warp >= kMmaWarp) {
     if (elect_one()) {  // ===== MMA issuers.  elect.sync (not `lane == 0`) tells ptxas that a single lane runs this region, so
                         // the descriptors stay in uniform registers; otherwise every UTCHMMA is wrapped in an ELECT / R2UR loop =====
       MmaCtx c;
       c.tmem = tmem_base;
+      c.tmem_o = tmem_base + TILES * 128;
       c.bar = smem_u32(bars);
       c.q_lo = smem_desc_lo_sw128(smem_u32(sQ));
       c.k_lo = smem_desc_lo_sw128(smem_u32(sK));
       c.v_lo = smem_desc_lo_sw128(smem_u32(sV));
       c.n_steps = n_steps;
-      if (warp == kMmaWarp) mma_tile_loop<D, 0>(c);
-      else mma_tile_loop<D, 1>(c);
+      if (warp == kMmaWarp) mma_tile_loop<D, 0, STAGES>(c);
+      else if constexpr (TILES == 2) mma_tile_loop<D, 1, STAGES>(c);
     }
   } else {  // ===== softmax warps =====
     constexpr int W = SPLIT ? BKV / 2 : BKV;      // key columns of a step owned by this thread
@@ -297,7 +314,7 @@ __global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t t_s = tmem_base + lane_base + i * 128;
-    const uint32_t t_o = tmem_base + lane_base + 256 + i * 128 + hh * OC;
+    const uint32_t t_o = tmem_base + lane_base + TILES * 128 + i * 128 + hh * OC;
     const int row_in_tile = quad * 32 + lane;
     const int row = q0 + i * BQ + row_in_tile;
     float m_used = -INFINITY, l = 0.f;
@@ -455,17 +472,18 @@ __global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-template <int D, int POLY, int SPLIT>
+template <int D, int POLY, int SPLIT, int TILES, int STAGES>
 static int launch(const alg_attention_t* a, cudaStream_t st) {
   using C = Cfg<D>;
-  constexpr int kThreads = (SPLIT ? 19 : 11) * 32;
+  constexpr int kThreads = ((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32;
+  constexpr int kSmem = C::smem_bytes(TILES, STAGES);
   static bool attr_done = false;
   if (!attr_done) {
-    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT, TILES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_done = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -494,8 +512,8 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   p.heads = a->heads;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
-  dim3 grid((unsigned)((a->n_q + 2 * BQ - 1) / (2 * BQ)), (unsigned)a->heads, (unsigned)a->batch);
-  attention_kernel<D, POLY, SPLIT><<<grid, kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  dim3 grid((unsigned)((a->n_q + TILES * BQ - 1) / (TILES * BQ)), (unsigned)a->heads, (unsigned)a->batch);
+  attention_kernel<D, POLY, SPLIT, TILES, STAGES><<<grid, kThreads, kSmem, st>>>(tmQ, tmK, tmV, p);
   ALG_LAUNCH_OK();
   return 0;
 }
@@ -516,28 +534,30 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   ALG_REQUIRE((reinterpret_cast<uintptr_t>(a->O) & 15) == 0, "attention: O must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static int poly = -1, split = -1;  // tuning knobs; defaults from profiling
+  static int poly = -1, split = -1, short_max = -1;  // tuning knobs; defaults from profiling
   if (poly < 0) {
     const char* e = getenv("ALG_ATTN_POLY");
     poly = e ? atoi(e) : ALG_ATTN_POLY_DEFAULT;
     e = getenv("ALG_ATTN_SPLIT");
     split = e ? atoi(e) : ALG_ATTN_SPLIT_DEFAULT;
+    e = getenv("ALG_ATTN_SHORT_MAX");  // key counts up to this use the SHORT (one tile, two CTAs per SM) variant; 0 = never
+    short_max = e ? atoi(e) : ALG_ATTN_SHORT_MAX_DEFAULT;
   }
-#define ALG_ATTN_DISPATCH(DD)                                                       \
-  if (split) {                                                                      \
-    switch (poly) {                                                                 \
-      case 0: return attn::launch<DD, 0, 1>(a, st);                                 \
-      case 2: return attn::launch<DD, 2, 1>(a, st);                                 \
-      case 4: return attn::launch<DD, 4, 1>(a, st);                                 \
-      default: return attn::launch<DD, 8, 1>(a, st);                                \
-    }                                                                               \
-  } else {                                                                          \
-    switch (poly) {                                                                 \
-      case 0: return attn::launch<DD, 0, 0>(a, st);                                 \
-      case 2: return attn::launch<DD, 2, 0>(a, st);                                 \
-      case 4: return attn::launch<DD, 4, 0>(a, st);                                 \
-      default: return attn::launch<DD, 8, 0>(a, st);                                \
-    }                                                                               \
+  const bool use_short = a->n_kv <= short_max;
+#define ALG_ATTN_DISPATCH(DD)                                                        \
+  if (use_short) return attn::launch<DD, 8, 0, 1, 2>(a, st);                         \
+  if (split) {                                                                       \
+    switch (poly) {                                                                  \
+      case 0: return attn::launch<DD, 0, 1, 2, 4>(a, st);                            \
+      case 4: return attn::launch<DD, 4, 1, 2, 4>(a, st);                            \
+      default: return attn::launch<DD, 8, 1, 2, 4>(a, st);                           \
+    }                                                                                \
+  } else {                                                                           \
+    switch (poly) {                                                                  \
+      case 0: return attn::launch<DD, 0, 0, 2, 4>(a, st);                            \
+      case 4: return attn::launch<DD, 4, 0, 2, 4>(a, st);                            \
+      default: return attn::launch<DD, 8, 0, 2, 4>(a, st);                           \
+    }                                                                                \
   }
   if (a->head_dim == 128) {
     ALG_ATTN_DISPATCH(128)

@@ -10,8 +10,13 @@ from alg_b200 import ops
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 var = f"poly={os.environ.get('ALG_ATTN_POLY', 'default')} split={os.environ.get('ALG_ATTN_SPLIT', 'default')}"
-for name, B, H, D, N in (("wan", 1, 40, 128, 32760), ("cog", 2, 48, 64, 17776), ("hunyuan", 1, 24, 128, 118980)):
-    q = torch.randn(B, N, H, D, device="cuda").bfloat16()
+SHAPES = (("wan", 1, 40, 128, 32760, 32760), ("cog", 2, 48, 64, 17776, 17776), ("hunyuan", 1, 24, 128, 118980, 118980),
+          ("wan_cross_text", 3, 40, 128, 32760, 512), ("wan_cross_image", 3, 40, 128, 32760, 257))
+only = os.environ.get("SHAPES")
+for name, B, H, D, Nq, N in SHAPES:
+    if only and name not in only.split(","):
+        continue
+    q = torch.randn(B, Nq, H, D, device="cuda").bfloat16()
     k = torch.randn(B, N, H, D, device="cuda").bfloat16()
     vt = torch.randn(B, H, D, (N + 7) // 8 * 8, device="cuda").bfloat16()
     o = torch.empty_like(q)
@@ -25,5 +30,5 @@ for name, B, H, D, N in (("wan", 1, 40, 128, 32760), ("cog", 2, 48, 64, 17776), 
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / r
-    print(f"{var} {name}: B={B} H={H} D={D} N={N}: {ms:.2f} ms {4 * B * H * N * N * D / ms / 1e9:.1f} TFLOP/s", flush=True)
+    print(f"{var} {name}: B={B} H={H} D={D} Nq={Nq} Nkv={N}: {ms:.3f} ms {4 * B * H * Nq * N * D / ms / 1e9:.1f} TFLOP/s", flush=True)
     del q, k, vt, o
