@@ -481,10 +481,12 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   using C = Cfg<D>;
   constexpr int kThreads = ((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32;
   constexpr int kSmem = C::smem_bytes(TILES, STAGES);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0};  // per-device bit: the attribute is device state
+  int dev = 0;
+  ALG_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 64 || !(attr_done.load(std::memory_order_relaxed) >> dev & 1)) {
     ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT, TILES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_done = true;
+    if (dev < 64) attr_done.fetch_or(uint64_t(1) << dev, std::memory_order_relaxed);
   }
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t hd = (uint64_t)a->heads * D;

@@ -395,10 +395,12 @@ static int num_sms() {
 template <int BN, int CL>
 static int launch(const alg_gemm_t* g, cudaStream_t st) {
   using C = Cfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0};  // per-device bit: the attribute is device state
+  int dev = 0;
+  ALG_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 64 || !(attr_done.load(std::memory_order_relaxed) >> dev & 1)) {
     ALG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_done = true;
+    if (dev < 64) attr_done.fetch_or(uint64_t(1) << dev, std::memory_order_relaxed);
   }
   CUtensorMap tmA, tmB;
   {

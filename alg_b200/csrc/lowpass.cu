@@ -315,11 +315,8 @@ static int down_up_dispatch(const void* in, void* out, int64_t planes, int H, in
   const int64_t b_elems = std::max<int64_t>((int64_t)H * w1, (int64_t)h1 * W);
   const size_t smem = (size_t)(a_elems + b_elems + t.n_weights + t.n_ints) * sizeof(float);
   if (smem > 200 * 1024) return down_up_generic<DT>(in, out, planes, H, W, h1, w1, t, st);
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[DT]) {
-    ALG_CUDA_OK(cudaFuncSetAttribute(down_up_fused_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set[DT] = true;
-  }
+  // once per denoise step: set every time (the attribute is per-device state; no per-process cache to go stale)
+  ALG_CUDA_OK(cudaFuncSetAttribute(down_up_fused_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
   const int grid = (int)std::min<int64_t>(planes, (int64_t)148 * ctas_per_sm);
   DownUpGeom g;
@@ -419,11 +416,7 @@ static int gaussian_dispatch(const void* in, void* out, int64_t planes, int H, i
   memset(&taps, 0, sizeof(taps));
   gaussian_taps(k, sigma, DT, taps.w);
   const size_t smem = ((size_t)(GT_W + k - 1) * (GT_H + k - 1) + (size_t)k * k) * sizeof(float);
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[DT]) {
-    ALG_CUDA_OK(cudaFuncSetAttribute(gaussian_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set[DT] = true;
-  }
+  ALG_CUDA_OK(cudaFuncSetAttribute(gaussian_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   for (int64_t p0 = 0; p0 < planes; p0 += 65535) {
     const int64_t np = std::min<int64_t>(65535, planes - p0);
     dim3 grid((W + GT_W - 1) / GT_W, (H + GT_H - 1) / GT_H, (unsigned)np);
