@@ -7,6 +7,7 @@
 // kernel is one read + one write of its activation with 16-byte accesses; modulation / affine vectors are read as
 // vectors too (scalar fp32 loads of scale/shift made the first Wan LayerNorm LSU-bound at 1.7 TB/s).
 #include <algorithm>
+#include <cstdlib>
 
 #include "dit_kernels.cuh"
 
@@ -60,9 +61,29 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm
 // ------------------------------------------------------------------------------------------------
-template <bool CHAIN>
-__global__ void __launch_bounds__(kRowThreads) layer_norm_kernel(const alg_layer_norm_t p) {
-  __shared__ float red[kRowThreads / 32];
+// One row per block, held in registers.  TH threads x CH chunks of 8 elements cover the row; CH is a template parameter so
+// the register file is sized for the actual width (d = 5120: 84 registers at 128 x 5, 6 blocks per SM, against 64 registers
+// x 256 threads = 4 blocks for the first version): 3.47 -> 3.94 TB/s.  A cp.async row-streaming variant (persistent blocks,
+// 4-stage shared-memory ring, 120 KB in flight per SM) was slower (3.2 TB/s): the per-row block reductions, not the bytes in
+// flight, pace this kernel.
+template <int TH>
+__device__ __forceinline__ float block_sum_t(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // protect `red` from the previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < TH / 32; ++i) t += red[i];
+  return t;
+}
+
+template <bool CHAIN, int TH, int CH>
+__global__ void __launch_bounds__(TH) layer_norm_kernel(const alg_layer_norm_t p) {
+  constexpr int kRowThreads = TH, kMaxChunks = CH;
+  __shared__ float red[TH / 32];
   const int64_t row = blockIdx.x;
   const int d = p.d;
   const uint4* xr = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * d);
@@ -88,7 +109,7 @@ __global__ void __launch_bounds__(kRowThreads) layer_norm_kernel(const alg_layer
     scale = reinterpret_cast<const char*>(alt ? p.scale_alt : p.scale) + b * p.mod_batch_stride * esz;
     shift = reinterpret_cast<const char*>(alt ? p.shift_alt : p.shift) + b * p.mod_batch_stride * esz;
   }
-  const float mean = block_sum(sum, red) / (float)d;
+  const float mean = block_sum_t<TH>(sum, red) / (float)d;
   float sq = 0.f;
 #pragma unroll
   for (int c = 0; c < kMaxChunks; ++c) {
@@ -101,7 +122,7 @@ __global__ void __launch_bounds__(kRowThreads) layer_norm_kernel(const alg_layer
       }
     }
   }
-  const float rstd = rsqrtf(block_sum(sq, red) / (float)d + p.eps);
+  const float rstd = rsqrtf(block_sum_t<TH>(sq, red) / (float)d + p.eps);
 #pragma unroll
   for (int c = 0; c < kMaxChunks; ++c) {
     const int ci = threadIdx.x + c * kRowThreads;
@@ -135,125 +156,92 @@ __global__ void __launch_bounds__(kRowThreads) layer_norm_kernel(const alg_layer
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-head norm + RoPE: one warp per (row, head); HD / 32 elements per lane (adjacent rotary pairs stay in one lane)
+// per-head norm + RoPE: one block per row; a thread owns 16-byte chunks (8 elements = 4 rotary pairs), HD / 8 consecutive
+// threads share a head and reduce with shuffles.  The chunk column inside the head is the same for every chunk of a thread
+// (TH % (HD / 8) == 0), so its norm weights and cos / sin values are loaded once per row.  The first version (one warp
+// per (row, head), 4-8 bytes per lane) reached 1.8 TB/s; 16-byte accesses and whole rows in flight fix that.
 // ------------------------------------------------------------------------------------------------
-template <int HD>
-__global__ void __launch_bounds__(256) head_norm_rope_kernel(const alg_head_norm_rope_t p) {
-  constexpr int E = HD / 32;  // 2 or 4
-  const int lane = threadIdx.x & 31;
-  const int64_t total = p.rows * p.heads;
-  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  constexpr int kItems = 4;  // independent (row, head) items per warp: memory-level parallelism
-  float w[E], bsv[E];
+template <int HD, int TH, int CH>
+__global__ void __launch_bounds__(TH) head_norm_rope_kernel(const alg_head_norm_rope_t p) {
+  constexpr int LPH = HD / 8;  // threads per head
+  const int64_t row = blockIdx.x;
+  const int chunks = p.heads * LPH;
+  uint4* xr = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.x) + row * p.ld);
+  const int sub = threadIdx.x % LPH;  // 8-element column block inside the head
+  float v[CH][8];
 #pragma unroll
-  for (int e = 0; e < E; ++e) {
+  for (int c = 0; c < CH; ++c) {
+    const int ci = threadIdx.x + c * TH;
+    if (ci < chunks) unpack8(xr[ci], v[c]);
+  }
+  float w[8], bs[8], cs[8], sn[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
     w[e] = 1.f;
-    bsv[e] = 0.f;
+    bs[e] = 0.f;
   }
   if (p.norm_kind != ALG_NORM_NONE) {
-    const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(p.weight) + lane * E;
-#pragma unroll
-    for (int e = 0; e < E; ++e) w[e] = __bfloat162float(wp[e]);
-    if (p.norm_kind == ALG_NORM_LAYER && p.bias) {
-      const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(p.bias) + lane * E;
-#pragma unroll
-      for (int e = 0; e < E; ++e) bsv[e] = __bfloat162float(bp[e]);
-    }
+    load_vec8(p.weight, ALG_BF16, sub, w);
+    if (p.norm_kind == ALG_NORM_LAYER && p.bias) load_vec8(p.bias, ALG_BF16, sub, bs);
   }
-  float x[kItems][E];
-  __nv_bfloat16* ptr[kItems];
-  int64_t rin[kItems];
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    const int64_t item = warp_global * kItems + k;
-    ptr[k] = nullptr;
-    if (item < total) {
-      const int64_t row = item / p.heads;
-      const int head = (int)(item - row * p.heads);
-      ptr[k] = reinterpret_cast<__nv_bfloat16*>(p.x) + row * p.ld + (int64_t)head * HD + lane * E;
-      rin[k] = row % p.rows_per_batch;
-      if (E == 2) {
-        const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ptr[k]));
-        x[k][0] = t.x;
-        x[k][1] = t.y;
-      } else {
-        const uint2 u = *reinterpret_cast<const uint2*>(ptr[k]);
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-        x[k][0] = a.x;
-        x[k][1] = a.y;
-        x[k][E - 2] = b.x;
-        x[k][E - 1] = b.y;
-      }
-    }
+  const int64_t rr = row % p.rows_per_batch - p.rope_row0;
+  const bool rope = p.cos && rr >= 0 && rr < p.rope_rows;
+  if (rope) {
+    load_vec8(p.cos + rr * HD, ALG_F32, sub, cs);
+    load_vec8(p.sin + rr * HD, ALG_F32, sub, sn);
   }
 #pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    if (!ptr[k]) continue;  // warp-uniform
-    float y[E];
+  for (int c = 0; c < CH; ++c) {
+    const int ci = threadIdx.x + c * TH;
+    const bool live = ci < chunks;  // uniform within a head's LPH threads (chunks % LPH == 0)
+    float y[8];
     if (p.norm_kind == ALG_NORM_RMS) {
       float sq = 0.f;
+      if (live)
 #pragma unroll
-      for (int e = 0; e < E; ++e) sq += x[k][e] * x[k][e];
+        for (int e = 0; e < 8; ++e) sq += v[c][e] * v[c][e];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      for (int o = LPH / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
       const float rstd = rsqrtf(sq / (float)HD + p.eps);
 #pragma unroll
-      for (int e = 0; e < E; ++e) y[e] = bf16_round(__fmul_rn(bf16_round(__fmul_rn(x[k][e], rstd)), w[e]));
+      for (int e = 0; e < 8; ++e) y[e] = bf16_round(__fmul_rn(bf16_round(__fmul_rn(v[c][e], rstd)), w[e]));
     } else if (p.norm_kind == ALG_NORM_LAYER) {
-      float s = 0.f;
+      float sm = 0.f;
+      if (live)
 #pragma unroll
-      for (int e = 0; e < E; ++e) s += x[k][e];
+        for (int e = 0; e < 8; ++e) sm += v[c][e];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float mean = s / (float)HD;
+      for (int o = LPH / 2; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      const float mean = sm / (float)HD;
       float sq = 0.f;
+      if (live)
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const float t = x[k][e] - mean;
-        sq += t * t;
-      }
+        for (int e = 0; e < 8; ++e) {
+          const float t = v[c][e] - mean;
+          sq += t * t;
+        }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      for (int o = LPH / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
       const float rstd = rsqrtf(sq / (float)HD + p.eps);
 #pragma unroll
-      for (int e = 0; e < E; ++e)
-        y[e] = bf16_round(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x[k][e], mean), rstd), w[e]), bsv[e]));
+      for (int e = 0; e < 8; ++e)
+        y[e] = bf16_round(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[c][e], mean), rstd), w[e]), bs[e]));
     } else {
 #pragma unroll
-      for (int e = 0; e < E; ++e) y[e] = x[k][e];
+      for (int e = 0; e < 8; ++e) y[e] = v[c][e];
     }
-    const int64_t rr = rin[k] - p.rope_row0;
-    if (p.cos && rr >= 0 && rr < p.rope_rows) {
-      const float* cp = p.cos + rr * HD + lane * E;
-      const float* sp = p.sin + rr * HD + lane * E;
-      float c[E], s[E];
-      if (E == 2) {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(cp)), b = __ldg(reinterpret_cast<const float2*>(sp));
-        c[0] = a.x; c[1] = a.y; s[0] = b.x; s[1] = b.y;
-      } else {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(cp)), b = __ldg(reinterpret_cast<const float4*>(sp));
-        c[0] = a.x; c[1] = a.y; c[E - 2] = a.z; c[E - 1] = a.w;
-        s[0] = b.x; s[1] = b.y; s[E - 2] = b.z; s[E - 1] = b.w;
-      }
-      float o[E];
+    if (rope) {
+      float o[8];
 #pragma unroll
-      for (int q = 0; q < E / 2; ++q) {  // x_rot = (-x_imag, x_real); out = x * cos + x_rot * sin, fp32 op by op
+      for (int q = 0; q < 4; ++q) {  // x_rot = (-x_imag, x_real); out = x * cos + x_rot * sin, fp32 op by op
         const float re = y[2 * q], im = y[2 * q + 1];
-        o[2 * q] = __fadd_rn(__fmul_rn(re, c[2 * q]), __fmul_rn(-im, s[2 * q]));
-        o[2 * q + 1] = __fadd_rn(__fmul_rn(im, c[2 * q + 1]), __fmul_rn(re, s[2 * q + 1]));
+        o[2 * q] = __fadd_rn(__fmul_rn(re, cs[2 * q]), __fmul_rn(-im, sn[2 * q]));
+        o[2 * q + 1] = __fadd_rn(__fmul_rn(im, cs[2 * q + 1]), __fmul_rn(re, sn[2 * q + 1]));
       }
 #pragma unroll
-      for (int e = 0; e < E; ++e) y[e] = o[e];
+      for (int e = 0; e < 8; ++e) y[e] = o[e];
     }
-    if (E == 2) {
-      *reinterpret_cast<__nv_bfloat162*>(ptr[k]) = __floats2bfloat162_rn(y[0], y[1]);
-    } else {
-      uint2 u;
-      *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(y[0], y[1]);
-      *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(y[E - 2], y[E - 1]);
-      *reinterpret_cast<uint2*>(ptr[k]) = u;
-    }
+    if (live) xr[ci] = pack8(y);
   }
 }
 
@@ -420,10 +408,27 @@ extern "C" int alg_layer_norm(const alg_layer_norm_t* p, void* stream) {
   if (int rc = alg_check_device()) return rc;
   if (p->rows == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p->chain_bf16)
-    ops::layer_norm_kernel<true><<<(unsigned)p->rows, ops::kRowThreads, 0, st>>>(*p);
-  else
-    ops::layer_norm_kernel<false><<<(unsigned)p->rows, ops::kRowThreads, 0, st>>>(*p);
+  static int th_knob = -1;
+  if (th_knob < 0) {
+    const char* e = getenv("ALG_LN_THREADS");
+    th_knob = e ? atoi(e) : 128;
+  }
+#define ALG_LN(TH, CH)                                                                         \
+  do {                                                                                         \
+    if (p->chain_bf16) ops::layer_norm_kernel<true, TH, CH><<<(unsigned)p->rows, TH, 0, st>>>(*p);  \
+    else ops::layer_norm_kernel<false, TH, CH><<<(unsigned)p->rows, TH, 0, st>>>(*p);           \
+  } while (0)
+  const int chunks = p->d / 8;
+  if (th_knob == 256) {
+    if (chunks <= 256 * 2) ALG_LN(256, 2);
+    else if (chunks <= 256 * 3) ALG_LN(256, 3);
+    else ALG_LN(256, 4);
+  } else {
+    if (chunks <= 128 * 3) ALG_LN(128, 3);
+    else if (chunks <= 128 * 5) ALG_LN(128, 5);
+    else ALG_LN(128, 8);
+  }
+#undef ALG_LN
   ALG_LAUNCH_OK();
   return 0;
 }
@@ -431,12 +436,14 @@ extern "C" int alg_layer_norm(const alg_layer_norm_t* p, void* stream) {
 extern "C" int alg_head_norm_rope(const alg_head_norm_rope_t* p, void* stream) {
   ALG_REQUIRE(p && p->x, "head_norm_rope: null pointer");
   ALG_REQUIRE(p->head_dim == 64 || p->head_dim == 128, "head_norm_rope: head_dim must be 64 or 128");
-  ALG_REQUIRE(p->heads > 0 && p->rows >= 0 && p->ld >= (int64_t)p->heads * p->head_dim && p->ld % 4 == 0,
-              "head_norm_rope: bad shape");
+  ALG_REQUIRE(p->heads > 0 && p->rows >= 0 && p->ld >= (int64_t)p->heads * p->head_dim && p->ld % 8 == 0,
+              "head_norm_rope: bad shape (row stride must keep rows 16-byte aligned)");
+  ALG_REQUIRE((int64_t)p->heads * p->head_dim <= 8192 && p->rows <= 0x7fffffff, "head_norm_rope: heads * head_dim <= 8192");
   ALG_REQUIRE(p->norm_kind >= ALG_NORM_NONE && p->norm_kind <= ALG_NORM_LAYER, "head_norm_rope: unknown norm kind");
   ALG_REQUIRE(p->norm_kind == ALG_NORM_NONE || p->weight, "head_norm_rope: the norm needs a weight");
   ALG_REQUIRE((p->cos == nullptr) == (p->sin == nullptr), "head_norm_rope: cos and sin come together");
-  ALG_REQUIRE((reinterpret_cast<uintptr_t>(p->x) & 7) == 0 && (reinterpret_cast<uintptr_t>(p->cos) & 15) == 0 &&
+  ALG_REQUIRE((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->weight) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->cos) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(p->sin) & 15) == 0,
               "head_norm_rope: misaligned pointer");
   if (int rc = alg_check_device()) return rc;
@@ -444,10 +451,18 @@ extern "C" int alg_head_norm_rope(const alg_head_norm_rope_t* p, void* stream) {
   alg_head_norm_rope_t q = *p;
   if (q.rows_per_batch <= 0) q.rows_per_batch = q.rows;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int64_t warps = (q.rows * q.heads + 3) / 4;
-  const unsigned grid = (unsigned)((warps + 7) / 8);
-  if (q.head_dim == 64) ops::head_norm_rope_kernel<64><<<grid, 256, 0, st>>>(q);
-  else ops::head_norm_rope_kernel<128><<<grid, 256, 0, st>>>(q);
+  const int chunks = q.heads * q.head_dim / 8;
+#define ALG_HNR(HD, CH) ops::head_norm_rope_kernel<HD, 128, CH><<<(unsigned)q.rows, 128, 0, st>>>(q)
+  if (q.head_dim == 64) {
+    if (chunks <= 128 * 3) ALG_HNR(64, 3);
+    else if (chunks <= 128 * 5) ALG_HNR(64, 5);
+    else ALG_HNR(64, 8);
+  } else {
+    if (chunks <= 128 * 3) ALG_HNR(128, 3);
+    else if (chunks <= 128 * 5) ALG_HNR(128, 5);
+    else ALG_HNR(128, 8);
+  }
+#undef ALG_HNR
   ALG_LAUNCH_OK();
   return 0;
 }
