@@ -50,6 +50,9 @@ template <> struct Elem<ALG_F32> {
   __device__ static float load(const void* p, size_t i) { return reinterpret_cast<const float*>(p)[i]; }
   __device__ static void store(void* p, size_t i, float v) { reinterpret_cast<float*>(p)[i] = v; }
   __device__ static float round(float v) { return v; }
+  __device__ static void store4(void* p, size_t i, const float* v) {  // i % 4 == 0, p 16-byte aligned
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = make_float4(v[0], v[1], v[2], v[3]);
+  }
 };
 template <> struct Elem<ALG_BF16> {
   using type = __nv_bfloat16;
@@ -60,12 +63,24 @@ template <> struct Elem<ALG_BF16> {
     reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
   }
   __device__ static float round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+  __device__ static void store4(void* p, size_t i, const float* v) {
+    uint2 u;
+    *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(v[0], v[1]);
+    *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = u;
+  }
 };
 template <> struct Elem<ALG_F16> {
   using type = __half;
   __device__ static float load(const void* p, size_t i) { return __half2float(reinterpret_cast<const __half*>(p)[i]); }
   __device__ static void store(void* p, size_t i, float v) { reinterpret_cast<__half*>(p)[i] = __float2half_rn(v); }
   __device__ static float round(float v) { return __half2float(__float2half_rn(v)); }
+  __device__ static void store4(void* p, size_t i, const float* v) {
+    uint2 u;
+    *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v[0], v[1]);
+    *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p) + i) = u;
+  }
 };
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }

@@ -80,7 +80,7 @@ struct DownUpTables {
   float* weights = nullptr;
   int n_ints = 0, n_weights = 0;
   // element offsets into ints / weights, and the per-operator weight row stride
-  int s_off[4], c_off[4], w_off[4], stride[4];
+  int s_off[4], c_off[4], w_off[4], stride[4], max_cnt[4];
 };
 
 static std::mutex g_tab_mu;
@@ -116,6 +116,8 @@ static int get_tables(int H, int W, int h1, int w1, int dt, DownUpTables* out) {
     ints.insert(ints.end(), bands[i].cnt.begin(), bands[i].cnt.end());
     t.w_off[i] = (int)ws.size();
     t.stride[i] = bands[i].stride;
+    t.max_cnt[i] = 1;
+    for (int c : bands[i].cnt) t.max_cnt[i] = std::max(t.max_cnt[i], c);
     ws.insert(ws.end(), bands[i].w.begin(), bands[i].w.end());
   }
   t.n_ints = (int)ints.size();
@@ -136,8 +138,6 @@ struct BandPtr {
   int stride;
 };
 
-constexpr int kRegTaps = 8;  // taps cached in registers; longer bands read the rest from the table
-
 // One tap of interpolate_aa_single_dim (UpSample.cuh:349-365): taps and samples are widened to fp32 and summed with
 // `output += t * wts` (an FMA chain under nvcc's default contraction), for every tensor dtype.
 template <int DT>
@@ -145,48 +145,56 @@ __device__ __forceinline__ float tap(float acc, float w, float x, bool first) {
   return first ? w * x : fmaf(w, x, acc);
 }
 
+// The passes are instruction-issue bound (ncu, profiles/r01_lowpass.md), so the number of tap slots NT that a pass unrolls
+// is a template parameter chosen from the operator's longest band: up-sampling bands hold 2-3 taps, down-sampling ones
+// ceil(2 * scale) + 1; bands longer than 8 read the remaining taps from the shared-memory table.
+
 // dst[r][j] = sum_k w * src[r][start_j + k]      (resample along the contiguous axis)
 // thread (tx, ty): columns j = tx + 32 m with that column's taps in registers, rows r = ty + 8 m'.
-template <int DT>
+template <int DT, int NT>
 __device__ __forceinline__ void pass_w(const float* __restrict__ src, float* __restrict__ dst, int rows, int in_w,
-                                       int out_w, BandPtr b) {
+                                       int out_w, int dst_ld, BandPtr b) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
   for (int j = tx; j < out_w; j += 32) {
     const int s = b.start[j], n = b.cnt[j];
     const float* wt = b.w + j * b.stride;
-    float w[kRegTaps];
+    float w[NT];
 #pragma unroll
-    for (int k = 0; k < kRegTaps; ++k) w[k] = k < n ? wt[k] : 0.f;
+    for (int k = 0; k < NT; ++k) w[k] = k < n ? wt[k] : 0.f;
+#pragma unroll 2
     for (int r = ty; r < rows; r += ny) {
       const float* p = src + r * in_w + s;
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < kRegTaps; ++k)
+      for (int k = 0; k < NT; ++k)
         if (k < n) acc = tap<DT>(acc, w[k], p[k], k == 0);
-      for (int k = kRegTaps; k < n; ++k) acc = tap<DT>(acc, wt[k], p[k], false);
-      dst[r * out_w + j] = Elem<DT>::round(acc);  // ATen keeps the row-pass result in a scalar_t buffer
+      if (NT == 8)
+        for (int k = NT; k < n; ++k) acc = tap<DT>(acc, wt[k], p[k], false);
+      dst[r * dst_ld + j] = Elem<DT>::round(acc);  // ATen keeps the row-pass result in a scalar_t buffer
     }
   }
 }
 // dst[i][c] = sum_k w * src[start_i + k][c]       (resample along the strided axis)
 // thread (tx, ty): output rows i = ty + 8 m (taps warp-uniform, in registers), columns c = tx + 32 m'.
-template <int DT, bool ROUND, bool TO_GLOBAL>
+template <int DT, int NT, bool ROUND, bool TO_GLOBAL>
 __device__ __forceinline__ void pass_h(const float* __restrict__ src, void* __restrict__ dst, int cols, int out_h,
                                        BandPtr b) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
   for (int i = ty; i < out_h; i += ny) {
     const int s = b.start[i], n = b.cnt[i];
     const float* wt = b.w + i * b.stride;
-    float w[kRegTaps];
+    float w[NT];
 #pragma unroll
-    for (int k = 0; k < kRegTaps; ++k) w[k] = k < n ? wt[k] : 0.f;
+    for (int k = 0; k < NT; ++k) w[k] = k < n ? wt[k] : 0.f;
+#pragma unroll 2
     for (int c = tx; c < cols; c += 32) {
       const float* p = src + s * cols + c;
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < kRegTaps; ++k)
+      for (int k = 0; k < NT; ++k)
         if (k < n) acc = tap<DT>(acc, w[k], p[k * cols], k == 0);
-      for (int k = kRegTaps; k < n; ++k) acc = tap<DT>(acc, wt[k], p[k * cols], false);
+      if (NT == 8)
+        for (int k = NT; k < n; ++k) acc = tap<DT>(acc, wt[k], p[k * cols], false);
       if (TO_GLOBAL) {
         Elem<DT>::store(dst, (size_t)i * cols + c, acc);
       } else {
@@ -196,8 +204,77 @@ __device__ __forceinline__ void pass_h(const float* __restrict__ src, void* __re
   }
 }
 
+// The same pass, four columns per thread: rows of `src` / `dst` are `ld` floats apart (a multiple of 4, 16-byte aligned),
+// so one LDS.128 feeds four FMAs and the result leaves as one 16-byte (fp32) / 8-byte (16-bit) store.  Work items
+// (row, column group) are flattened over the CTA so narrow buffers still fill every lane.
+template <int DT, int NT, bool ROUND, bool TO_GLOBAL>
+__device__ __forceinline__ void pass_h4(const float* __restrict__ src, void* __restrict__ dst, int ld, int dst_ld,
+                                        int out_h, BandPtr b) {
+  const int c4n = ld >> 2, total = out_h * c4n;
+  const float inv = 1.0f / (float)c4n;
+#pragma unroll 2
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int i = (int)(((float)idx + 0.5f) * inv);  // exact: total < 2^16
+    const int c = (idx - i * c4n) * 4;
+    const int s = b.start[i], n = b.cnt[i];
+    const float* wt = b.w + i * b.stride;
+    const float* p = src + s * ld + c;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < NT; ++k)
+      if (k < n) {
+        const float w = wt[k];
+        const float4 x = *reinterpret_cast<const float4*>(p + k * ld);
+        acc[0] = tap<DT>(acc[0], w, x.x, k == 0);
+        acc[1] = tap<DT>(acc[1], w, x.y, k == 0);
+        acc[2] = tap<DT>(acc[2], w, x.z, k == 0);
+        acc[3] = tap<DT>(acc[3], w, x.w, k == 0);
+      }
+    if (NT == 8)
+      for (int k = NT; k < n; ++k) {
+        const float w = wt[k];
+        const float4 x = *reinterpret_cast<const float4*>(p + k * ld);
+        acc[0] = fmaf(w, x.x, acc[0]);
+        acc[1] = fmaf(w, x.y, acc[1]);
+        acc[2] = fmaf(w, x.z, acc[2]);
+        acc[3] = fmaf(w, x.w, acc[3]);
+      }
+    if (TO_GLOBAL) {
+      Elem<DT>::store4(dst, (size_t)i * dst_ld + c, acc);
+    } else {
+      float4 o;
+      o.x = ROUND ? Elem<DT>::round(acc[0]) : acc[0];
+      o.y = ROUND ? Elem<DT>::round(acc[1]) : acc[1];
+      o.z = ROUND ? Elem<DT>::round(acc[2]) : acc[2];
+      o.w = ROUND ? Elem<DT>::round(acc[3]) : acc[3];
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + i * dst_ld + c) = o;
+    }
+  }
+}
+
+// NT from the longest band of the operator (block-uniform)
+#define ALG_BAND_SWITCH(maxn, CALL) \
+  do {                              \
+    if ((maxn) <= 2) {              \
+      constexpr int NT = 2;         \
+      CALL;                         \
+    } else if ((maxn) <= 3) {       \
+      constexpr int NT = 3;         \
+      CALL;                         \
+    } else if ((maxn) <= 4) {       \
+      constexpr int NT = 4;         \
+      CALL;                         \
+    } else if ((maxn) <= 6) {       \
+      constexpr int NT = 6;         \
+      CALL;                         \
+    } else {                        \
+      constexpr int NT = 8;         \
+      CALL;                         \
+    }                               \
+  } while (0)
+
 struct DownUpGeom {
-  int s_off[4], c_off[4], w_off[4], stride[4];
+  int s_off[4], c_off[4], w_off[4], stride[4], max_cnt[4];
   int n_ints, n_weights;
 };
 
@@ -206,7 +283,7 @@ __global__ void __launch_bounds__(256) down_up_fused_kernel(const void* __restri
                                                             int64_t planes, int H, int W, int h1, int w1,
                                                             const int* __restrict__ ints,
                                                             const float* __restrict__ weights, DownUpGeom g,
-                                                            int bufA_elems, int bufB_elems) {
+                                                            int bufA_elems, int bufB_elems, int vec) {
   extern __shared__ __align__(16) float smem[];
   float* A = smem;                           // in [H, W]      -> small [h1, w1]
   float* B = smem + bufA_elems;              // t1 [H, w1]     -> t2 [h1, W]
@@ -241,13 +318,25 @@ __global__ void __launch_bounds__(256) down_up_fused_kernel(const void* __restri
       for (int i = threadIdx.x; i < HW; i += blockDim.x) A[i] = (float)src[i];
     }
     __syncthreads();
-    pass_w<DT>(A, B, H, W, w1, bw_down);  // t1 [H, w1]
-    __syncthreads();
-    pass_h<DT, true, false>(B, A, w1, h1, bh_down);  // small [h1, w1], rounded to dtype (reference materialises it)
-    __syncthreads();
-    pass_w<DT>(A, B, h1, w1, W, bw_up);  // t2 [h1, W]
-    __syncthreads();
-    pass_h<DT, false, true>(B, dst, W, H, bh_up);  // out [H, W]
+    if (vec) {  // W % 4 == 0 and 16-byte aligned planes: H-passes run four columns per thread on padded strides
+      const int w1p = (w1 + 3) & ~3;
+      ALG_BAND_SWITCH(g.max_cnt[0], (pass_w<DT, NT>(A, B, H, W, w1, w1p, bw_down)));  // t1 [H, w1p]
+      __syncthreads();
+      // small [h1, w1p], rounded to dtype (reference materialises it)
+      ALG_BAND_SWITCH(g.max_cnt[1], (pass_h4<DT, NT, true, false>(B, A, w1p, w1p, h1, bh_down)));
+      __syncthreads();
+      ALG_BAND_SWITCH(g.max_cnt[2], (pass_w<DT, NT>(A, B, h1, w1p, W, W, bw_up)));  // t2 [h1, W]
+      __syncthreads();
+      ALG_BAND_SWITCH(g.max_cnt[3], (pass_h4<DT, NT, false, true>(B, dst, W, W, H, bh_up)));  // out [H, W]
+    } else {
+      ALG_BAND_SWITCH(g.max_cnt[0], (pass_w<DT, NT>(A, B, H, W, w1, w1, bw_down)));  // t1 [H, w1]
+      __syncthreads();
+      ALG_BAND_SWITCH(g.max_cnt[1], (pass_h<DT, NT, true, false>(B, A, w1, h1, bh_down)));
+      __syncthreads();
+      ALG_BAND_SWITCH(g.max_cnt[2], (pass_w<DT, NT>(A, B, h1, w1, W, W, bw_up)));  // t2 [h1, W]
+      __syncthreads();
+      ALG_BAND_SWITCH(g.max_cnt[3], (pass_h<DT, NT, false, true>(B, dst, W, H, bh_up)));  // out [H, W]
+    }
     __syncthreads();
   }
 }
@@ -311,8 +400,10 @@ static int down_up_dispatch(const void* in, void* out, int64_t planes, int H, in
                             cudaStream_t st) {
   DownUpTables t;
   if (int rc = get_tables(H, W, h1, w1, DT, &t)) return rc;
-  const int64_t a_elems = std::max<int64_t>((int64_t)H * W, (int64_t)h1 * w1);
-  const int64_t b_elems = std::max<int64_t>((int64_t)H * w1, (int64_t)h1 * W);
+  const int vec = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const int w1p = vec ? (w1 + 3) & ~3 : w1;
+  const int64_t a_elems = (std::max<int64_t>((int64_t)H * W, (int64_t)h1 * w1p) + 3) & ~(int64_t)3;
+  const int64_t b_elems = (std::max<int64_t>((int64_t)H * w1p, (int64_t)h1 * W) + 3) & ~(int64_t)3;
   const size_t smem = (size_t)(a_elems + b_elems + t.n_weights + t.n_ints) * sizeof(float);
   if (smem > 200 * 1024) return down_up_generic<DT>(in, out, planes, H, W, h1, w1, t, st);
   // once per denoise step: set every time (the attribute is per-device state; no per-process cache to go stale)
@@ -325,11 +416,12 @@ static int down_up_dispatch(const void* in, void* out, int64_t planes, int H, in
     g.c_off[i] = t.c_off[i];
     g.w_off[i] = t.w_off[i];
     g.stride[i] = t.stride[i];
+    g.max_cnt[i] = t.max_cnt[i];
   }
   g.n_ints = t.n_ints;
   g.n_weights = t.n_weights;
   down_up_fused_kernel<DT><<<grid, 256, smem, st>>>(in, out, planes, H, W, h1, w1, t.ints, t.weights, g, (int)a_elems,
-                                                    (int)b_elems);
+                                                    (int)b_elems, vec);
   ALG_LAUNCH_OK();
   return 0;
 }
@@ -366,46 +458,102 @@ static void gaussian_taps(int k, double sigma, int dt, float* out) {
   for (int i = 0; i < k; ++i) out[i] = host_round(pdf[i] / total, dt);
 }
 
-constexpr int GT_W = 32, GT_H = 32;  // output tile per CTA
+// Dense k x k taps (torchvision multiplies the two 1-D kernels into a [k, k] matrix in the tensor dtype and runs a
+// depthwise conv2d), so the kernel is FMA-bound: k * k FMAs per output against 2 elements of HBM traffic.  Each thread owns
+// 8 consecutive outputs of one row and slides a 12-float register window along the tile row: one 16-byte shared-memory
+// load feeds 32 FMAs, and the four taps of a group arrive in one broadcast 16-byte load.  (The first version, one output
+// column per thread with one LDS per FMA, was shared-memory-issue bound at 0.16 TB/s -- profiles/r01_lowpass.md.)
+constexpr int GT_W = 64, GT_H = 32;  // output tile per CTA: 256 threads x 8 outputs
+
+// The 8 threads of a quarter warp read 16-byte chunks 32 bytes apart: flipping the low chunk bit of every other group of
+// eight chunks makes those reads bank-conflict free.
+__device__ __forceinline__ int gswz(int x) { return x ^ (((x >> 5) & 1) << 2); }
+
+__device__ __forceinline__ void lds128(float* v, uint32_t addr) {
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+
+__host__ __device__ inline int gauss_tile_w(int k) { return (GT_W + 4 * (k >> 2) + 8 + 7) & ~7; }
 
 template <int DT>
 __global__ void __launch_bounds__(256) gaussian_kernel(const void* __restrict__ in, void* __restrict__ out, int H,
                                                        int W, int k, Taps taps) {
   extern __shared__ __align__(16) float smem[];
   const int r = k / 2;
-  const int tw = GT_W + k - 1, th = GT_H + k - 1;
-  float* tile = smem;          // [th][tw]
-  float* w2 = smem + th * tw;  // [k][k], each product rounded to dtype (torch.mm in the tensor dtype)
+  const int tw = gauss_tile_w(k), th = GT_H + k - 1;
+  const int kp = (k + 3) & ~3;
+  float* tile = smem;          // [th][tw], columns swizzled by gswz
+  float* w2 = smem + th * tw;  // [k][kp], each product rounded to dtype (torch.mm in the tensor dtype), zero padded
   const int64_t plane = blockIdx.z;
   const int x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
   const size_t base = (size_t)plane * H * W;
-  for (int i = threadIdx.x; i < k * k; i += blockDim.x) w2[i] = Elem<DT>::round(taps.w[i / k] * taps.w[i % k]);
-  for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
-    int ty = i / tw, tx = i - ty * tw;
-    int y = y0 + ty - r, x = x0 + tx - r;
-    // reflect (no edge repeat): -1 -> 1, H -> H-2.  Tiles may overhang the image: clamp after reflecting.
-    if (y < 0) y = -y;
-    if (y >= H) y = 2 * H - 2 - y;
-    if (x < 0) x = -x;
-    if (x >= W) x = 2 * W - 2 - x;
-    y = min(max(y, 0), H - 1);
-    x = min(max(x, 0), W - 1);
-    tile[i] = Elem<DT>::load(in, base + (size_t)y * W + x);
+  for (int i = threadIdx.x; i < k * kp; i += blockDim.x) {
+    const int dy = i / kp, dx = i - dy * kp;
+    w2[i] = dx < k ? Elem<DT>::round(taps.w[dy] * taps.w[dx]) : 0.f;
   }
-  __syncthreads();
-  const int tx = threadIdx.x & 31, ty0 = threadIdx.x >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int dy = 0; dy < k; ++dy) {
-    for (int dx = 0; dx < k; ++dx) {
-      const float w = w2[dy * k + dx];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = fmaf(w, tile[(ty0 + 8 * q + dy) * tw + tx + dx], acc[q]);
+  // tile fill, one warp per tile row: reflect (no edge repeat): -1 -> 1, H -> H-2.  Tiles may overhang the image:
+  // clamp after reflecting.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int ty = warp; ty < th; ty += 8) {
+    int y = y0 + ty - r;
+    y = y < 0 ? -y : y;
+    y = y >= H ? 2 * H - 2 - y : y;
+    y = min(max(y, 0), H - 1);
+    const size_t rbase = base + (size_t)y * W;
+    float* trow = tile + ty * tw;
+    for (int tx = lane; tx < tw; tx += 32) {
+      int x = x0 + tx - r;
+      x = x < 0 ? -x : x;
+      x = x >= W ? 2 * W - 2 - x : x;
+      x = min(max(x, 0), W - 1);
+      trow[gswz(tx)] = Elem<DT>::load(in, rbase + x);
     }
   }
+  __syncthreads();
+  const int xt = (threadIdx.x & 7) * 8, yy = threadIdx.x >> 3;
+  const int kg = k >> 2, rem = k & 3;
+  float acc[8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    int y = y0 + ty0 + 8 * q, x = x0 + tx;
-    if (y < H && x < W) Elem<DT>::store(out, base + (size_t)y * W + x, acc[q]);
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  // shared-window byte addresses, advanced incrementally (the compiler otherwise rebuilds them every tile row)
+  uint32_t row_s = (uint32_t)__cvta_generic_to_shared(tile + yy * tw);
+  uint32_t w_s = (uint32_t)__cvta_generic_to_shared(w2);
+  const uint32_t off0 = gswz(xt) * 4, off1 = gswz(xt + 4) * 4;
+  for (int dy = 0; dy < k; ++dy, row_s += tw * 4, w_s += kp * 4) {
+    float a[12];
+    lds128(a, row_s + off0);
+    lds128(a + 4, row_s + off1);
+    int xw = xt + 8;
+#pragma unroll 3
+    for (int g = 0; g < kg; ++g, xw += 4) {
+      lds128(a + 8, row_s + gswz(xw) * 4);
+      float wq[4];
+      lds128(wq, w_s + g * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)  // taps in ascending dx, like the one-output-per-thread chain
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wq[q], a[i + q], acc[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = a[i + 4];
+    }
+    {
+      lds128(a + 8, row_s + gswz(xw) * 4);
+      float wq[4];
+      lds128(wq, w_s + kg * 16);
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (q < rem)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(wq[q], a[i + q], acc[i]);
+    }
+  }
+  const int y = y0 + yy;
+  if (y < H) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int x = x0 + xt + i;
+      if (x < W) Elem<DT>::store(out, base + (size_t)y * W + x, acc[i]);
+    }
   }
 }
 
@@ -415,8 +563,8 @@ static int gaussian_dispatch(const void* in, void* out, int64_t planes, int H, i
   Taps taps;
   memset(&taps, 0, sizeof(taps));
   gaussian_taps(k, sigma, DT, taps.w);
-  const size_t smem = ((size_t)(GT_W + k - 1) * (GT_H + k - 1) + (size_t)k * k) * sizeof(float);
-  ALG_CUDA_OK(cudaFuncSetAttribute(gaussian_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  const size_t smem = ((size_t)gauss_tile_w(k) * (GT_H + k - 1) + (size_t)k * ((k + 3) & ~3)) * sizeof(float);
+  ALG_CUDA_OK(cudaFuncSetAttribute(gaussian_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   for (int64_t p0 = 0; p0 < planes; p0 += 65535) {
     const int64_t np = std::min<int64_t>(65535, planes - p0);
     dim3 grid((W + GT_W - 1) / GT_W, (H + GT_H - 1) / GT_H, (unsigned)np);
