@@ -150,27 +150,39 @@ __device__ __forceinline__ float tap(float acc, float w, float x, bool first) {
 // ceil(2 * scale) + 1; bands longer than 8 read the remaining taps from the shared-memory table.
 
 // dst[r][j] = sum_k w * src[r][start_j + k]      (resample along the contiguous axis)
-// thread (tx, ty): columns j = tx + 32 m with that column's taps in registers, rows r = ty + 8 m'.
+// A thread owns one output column j (its taps stay in registers) and every ng-th row: the CTA's threads are laid out
+// as ng = blockDim / out_w row groups x out_w columns, so narrow outputs (42 columns) still occupy 252 of 256 lanes
+// and the per-column set-up is paid once.
 template <int DT, int NT>
 __device__ __forceinline__ void pass_w(const float* __restrict__ src, float* __restrict__ dst, int rows, int in_w,
                                        int out_w, int dst_ld, BandPtr b) {
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
-  for (int j = tx; j < out_w; j += 32) {
+  const int nt = blockDim.x;
+  int ng = 1, rg = 0, j = threadIdx.x, jstep = nt;
+  if (out_w <= nt) {
+    ng = nt / out_w;
+    rg = threadIdx.x / out_w;
+    j = threadIdx.x - rg * out_w;
+    jstep = out_w;  // one sweep
+    if (rg >= ng) return;
+  }
+  for (; j < out_w; j += jstep) {
     const int s = b.start[j], n = b.cnt[j];
     const float* wt = b.w + j * b.stride;
     float w[NT];
 #pragma unroll
     for (int k = 0; k < NT; ++k) w[k] = k < n ? wt[k] : 0.f;
-#pragma unroll 2
-    for (int r = ty; r < rows; r += ny) {
-      const float* p = src + r * in_w + s;
+    const float* p = src + rg * in_w + s;
+    float* q = dst + rg * dst_ld + j;
+    const int pstep = ng * in_w, qstep = ng * dst_ld;
+#pragma unroll 4
+    for (int r = rg; r < rows; r += ng, p += pstep, q += qstep) {
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < NT; ++k)
         if (k < n) acc = tap<DT>(acc, w[k], p[k], k == 0);
       if (NT == 8)
         for (int k = NT; k < n; ++k) acc = tap<DT>(acc, wt[k], p[k], false);
-      dst[r * dst_ld + j] = Elem<DT>::round(acc);  // ATen keeps the row-pass result in a scalar_t buffer
+      *q = Elem<DT>::round(acc);  // ATen keeps the row-pass result in a scalar_t buffer
     }
   }
 }
