@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libalg_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ALG_F32, ALG_BF16, ALG_F16 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 NORM_NONE, NORM_RMS, NORM_LAYER = 0, 1, 2
 EW_ADD, EW_SILU, EW_COPY, EW_GELU_TANH = 0, 1, 2, 3
 EPI_NONE, EPI_GELU_TANH, EPI_GATE_RESIDUAL, EPI_RESIDUAL, EPI_GELU_ERF, EPI_SILU = range(6)
@@ -36,6 +36,22 @@ class DpmStep(C.Structure):
         ("n_pass", C.c_int32), ("second_order", C.c_int32), ("guidance", C.c_float), ("sqrt_alpha_t", C.c_float),
         ("sqrt_beta_t", C.c_float), ("m0", C.c_float), ("m1", C.c_float), ("m2", C.c_float), ("m3", C.c_float),
         ("m_noise", C.c_float),
+    ]
+
+
+class Im2col(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("cols", C.c_void_p), ("T", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
+        ("pad_t", C.c_int32), ("pad_top", C.c_int32), ("pad_left", C.c_int32), ("To", C.c_int32), ("Ho", C.c_int32),
+        ("Wo", C.c_int32), ("ld", C.c_int64),
+    ]
+
+
+class GroupNorm(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("stats", C.c_void_p),
+        ("rows", C.c_int64), ("C", C.c_int32), ("groups", C.c_int32), ("eps", C.c_float), ("silu", C.c_int32),
     ]
 
 
@@ -110,6 +126,8 @@ SIGNATURES = {
     "alg_gemm_bf16": (C.c_int, [C.POINTER(Gemm), C.c_void_p]),
     "alg_attention_bf16": (C.c_int, [C.POINTER(Attention), C.c_void_p]),
     "alg_layer_norm": (C.c_int, [C.POINTER(LayerNorm), C.c_void_p]),
+    "alg_im2col_bf16": (C.c_int, [C.POINTER(Im2col), C.c_void_p]),
+    "alg_group_norm_bf16": (C.c_int, [C.POINTER(GroupNorm), C.c_void_p]),
     "alg_head_norm_rope": (C.c_int, [C.POINTER(HeadNormRope), C.c_void_p]),
     "alg_patch_gather": (C.c_int, [C.POINTER(PatchSrc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "alg_unpatchify": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),

@@ -66,6 +66,28 @@ def load_transformer(snapshot: str, device="cuda") -> Tuple[dict, Dict[str, torc
     return read_config(folder), load_safetensors_dir(folder, device)
 
 
+def load_component(snapshot: str, subfolder: str, device="cuda", key_prefix: Optional[str] = None
+                   ) -> Tuple[dict, Dict[str, torch.Tensor]]:
+    """(config, state dict) of one component folder of a snapshot (e.g. ``vae``); ``key_prefix`` keeps only the tensors
+    whose name starts with it (the native VAE loads ``encoder.*`` and ignores the decoder)."""
+    from safetensors import safe_open
+
+    folder = os.path.join(snapshot, subfolder)
+    cfg = read_config(folder)
+    if key_prefix is None:
+        return cfg, load_safetensors_dir(folder, device)
+    files = sorted(f for f in os.listdir(folder) if f.endswith(".safetensors"))
+    if not files:
+        raise FileNotFoundError(f"no .safetensors weights under {folder}")
+    sd: Dict[str, torch.Tensor] = {}
+    for name in files:
+        with safe_open(os.path.join(folder, name), framework="pt", device=str(device)) as f:
+            for k in f.keys():
+                if k.startswith(key_prefix):
+                    sd[k] = f.get_tensor(k)
+    return cfg, sd
+
+
 def scheduler_config(snapshot: str) -> dict:
     folder = os.path.join(snapshot, "scheduler")
     return read_config(folder, "scheduler_config.json") if os.path.isdir(folder) else {}

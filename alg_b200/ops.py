@@ -235,3 +235,55 @@ def copy_rows(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     _launch(_lib.lib().alg_copy_rows_bf16, src.device, src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0),
             src.shape[0], src.shape[1])
     return dst
+
+
+def im2col(x: torch.Tensor, T: int, H: int, W: int, *, kernel, stride=(1, 1, 1), pad_t: int = 0, pad_top: int = 0,
+           pad_left: int = 0, out_hw=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Patch gather for a (causal 3-D / strided 2-D) convolution on channels-last x [T*H*W, C] bf16.  See alg_im2col_bf16.
+
+    Returns cols [To*Ho*Wo, kt*kh*kw*C] (column order (it, ih, iw, c)); ``out_hw`` = (Ho, Wo), default: same size.
+    ``out`` may be a larger flat bf16 workspace: the result is a view of its head."""
+    _lib.require_cuda(x, out)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous() and x.shape[0] == T * H * W
+    Cc = x.shape[1]
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    Ho, Wo = out_hw if out_hw is not None else (H, W)
+    To = (T + pad_t - kt) // st + 1
+    K = kt * kh * kw * Cc
+    M = To * Ho * Wo
+    if out is None:
+        cols = torch.empty(M, K, device=x.device, dtype=torch.bfloat16)
+    else:
+        assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.numel() >= M * K
+        cols = out.view(-1)[: M * K].view(M, K)
+    p = _lib.Im2col()
+    p.x, p.cols = x.data_ptr(), cols.data_ptr()
+    p.T, p.H, p.W, p.C = T, H, W, Cc
+    p.kt, p.kh, p.kw, p.st, p.sh, p.sw = kt, kh, kw, st, sh, sw
+    p.pad_t, p.pad_top, p.pad_left = pad_t, pad_top, pad_left
+    p.To, p.Ho, p.Wo, p.ld = To, Ho, Wo, K
+    _launch(_lib.lib().alg_im2col_bf16, x.device, C.byref(p))
+    return cols
+
+
+def group_norm(x: torch.Tensor, groups: int, weight=None, bias=None, *, eps: float = 1e-6, silu: bool = False,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.GroupNorm (+ SiLU) over channels-last x [rows, C] bf16 (one sample).  See alg_group_norm_bf16."""
+    _lib.require_cuda(x, weight, bias, out)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.shape == x.shape and out.dtype == torch.bfloat16 and out.is_contiguous()
+    stats = torch.empty(2 * groups, device=x.device, dtype=torch.float64)
+    p = _lib.GroupNorm()
+    p.x, p.y, p.stats = x.data_ptr(), out.data_ptr(), stats.data_ptr()
+    if weight is not None:
+        assert weight.dtype == torch.bfloat16 and weight.numel() == x.shape[1] and weight.is_contiguous()
+        p.weight = weight.data_ptr()
+    if bias is not None:
+        assert bias.dtype == torch.bfloat16 and bias.numel() == x.shape[1] and bias.is_contiguous()
+        p.bias = bias.data_ptr()
+    p.rows, p.C, p.groups, p.eps, p.silu = x.shape[0], x.shape[1], groups, eps, int(silu)
+    _launch(_lib.lib().alg_group_norm_bf16, x.device, C.byref(p))
+    return out

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ALG_B200_ABI_VERSION 2
+#define ALG_B200_ABI_VERSION 3
 
 typedef enum { ALG_F32 = 0, ALG_BF16 = 1, ALG_F16 = 2 } alg_dtype_t;
 
@@ -322,6 +322,44 @@ int alg_wan_set_debug_buffer(alg_wan_engine_t* e, void* buf, size_t bytes);
  * then read: the read synchronises on the recorded events, returns summed milliseconds + launch counts and resets. */
 int alg_wan_profile(alg_wan_engine_t* e, int enable);
 int alg_wan_profile_read(alg_wan_engine_t* e, float* ms_per_class, int32_t* launches_per_class, int n_classes);
+
+/* ------------------------------------------------------------------------- */
+/* CogVideoX VAE encoder blocks (ABI 3).  cog:257 (`self.vae.encode(image_lp)` EVERY step when the filter runs in    */
+/* pixel space, BASELINE configs[2]) and cog:166 (conditioning image): AutoencoderKLCogVideoX.encode on ONE frame.    */
+/* Activations are channels-last [T*H*W, C] bf16; every (causal 3-D / strided 2-D) convolution is                    */
+/* alg_im2col_bf16 + ONE alg_gemm_bf16 (bias / residual in its epilogue).                                            */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+  const void* x;  /* [T, H, W, C] bf16 channels-last, C % 8 == 0                                                  */
+  void* cols;     /* [To*Ho*Wo, ld] bf16; column order (it, ih, iw, c) -- conv weight [Co, Ci, kt, kh, kw]
+                     permuted to [Co, kt, kh, kw, Ci] is the matching GEMM B operand; columns >= kt*kh*kw*C are zero  */
+  int32_t T, H, W, C;
+  int32_t kt, kh, kw;
+  int32_t st, sh, sw;        /* strides                                                                           */
+  int32_t pad_t;             /* causal padding: source frame = max(to*st + it - pad_t, 0), i.e. frames before t = 0
+                                replicate frame 0 (CogVideoXCausalConv3d.fake_context_parallel_forward, no cache)   */
+  int32_t pad_top, pad_left; /* zero padding; bottom / right padding is implied by Ho, Wo                          */
+  int32_t To, Ho, Wo;
+  int64_t ld;                /* >= kt*kh*kw*C, multiple of 8                                                        */
+} alg_im2col_t;
+int alg_im2col_bf16(const alg_im2col_t* p, void* stream);
+
+/* nn.GroupNorm over [rows, C] channels-last (one sample; rows = T*H*W) followed by an optional SiLU:
+ *   y = bf16(a*x + b), a = rstd_g * weight_c, b = bias_c - a * mean_g, statistics in fp32/fp64; silu != 0:
+ *   y = bf16(y / (1 + exp(-y))).  `stats` is a caller-provided scratch of 2*groups doubles (zeroed by the call). */
+typedef struct {
+  const void* x;
+  void* y;            /* may alias x */
+  const void* weight; /* bf16 [C] or NULL */
+  const void* bias;   /* bf16 [C] or NULL */
+  double* stats;
+  int64_t rows;
+  int32_t C, groups;
+  float eps;
+  int32_t silu;
+} alg_group_norm_t;
+int alg_group_norm_bf16(const alg_group_norm_t* p, void* stream);
 
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 int64_t alg_launch_count(void);

@@ -181,3 +181,49 @@ def mean_rows(x):
 def copy_rows(src, dst):
     dst.copy_(src)
     return dst
+
+
+def im2col(x, T, H, W, *, kernel, stride=(1, 1, 1), pad_t=0, pad_top=0, pad_left=0, out_hw=None, out=None):
+    """alg_im2col_bf16: columns ordered (it, ih, iw, c); frames before 0 replicate frame 0; zero spatial padding."""
+    Cc = x.shape[1]
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    Ho, Wo = out_hw if out_hw is not None else (H, W)
+    To = (T + pad_t - kt) // st + 1
+    v = x.view(T, H, W, Cc)
+    need_h, need_w = (Ho - 1) * sh + kh, (Wo - 1) * sw + kw
+    vp = torch.zeros(T, need_h, need_w, Cc, dtype=x.dtype, device=x.device)
+    hh, ww = min(H, need_h - pad_top), min(W, need_w - pad_left)
+    vp[:, pad_top:pad_top + hh, pad_left:pad_left + ww] = v[:, :hh, :ww]
+    taps = []
+    for it in range(kt):
+        tidx = torch.clamp(torch.arange(To) * st + it - pad_t, min=0)
+        for ih in range(kh):
+            for iw in range(kw):
+                taps.append(vp[tidx][:, ih:ih + (Ho - 1) * sh + 1:sh, iw:iw + (Wo - 1) * sw + 1:sw])
+    cols = torch.stack(taps, dim=3).reshape(To * Ho * Wo, kt * kh * kw * Cc)
+    if out is not None:
+        out.view(-1)[: cols.numel()].view_as(cols).copy_(cols)
+        return out.view(-1)[: cols.numel()].view_as(cols)
+    return cols.contiguous()
+
+
+def group_norm(x, groups, weight=None, bias=None, *, eps=1e-6, silu=False, out=None):
+    """alg_group_norm_bf16: fp32 statistics over (rows, C/groups); y = bf16(a*x + b); optional SiLU rounded again."""
+    rows, Cc = x.shape
+    xf = x.float().view(rows, groups, Cc // groups)
+    mean = xf.double().mean(dim=(0, 2))
+    var = (xf.double() ** 2).mean(dim=(0, 2)) - mean ** 2
+    rstd = torch.rsqrt(var.clamp_min(0).float() + eps)
+    ga = weight.float() if weight is not None else torch.ones(Cc, device=x.device)
+    be = bias.float() if bias is not None else torch.zeros(Cc, device=x.device)
+    a = rstd.repeat_interleave(Cc // groups) * ga
+    b = be - a * mean.float().repeat_interleave(Cc // groups)
+    y = _r(x.float() * a[None, :] + b[None, :])
+    if silu:
+        y = _r(y / (1.0 + torch.exp(-y)))
+    y = y.to(torch.bfloat16)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y

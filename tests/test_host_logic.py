@@ -33,7 +33,8 @@ def test_struct_layouts_match_header(tmp_path):
 
     pairs = {"alg_unipc_step_t": _lib.UniPCStep, "alg_dpm_step_t": _lib.DpmStep, "alg_gemm_t": _lib.Gemm, "alg_attention_t": _lib.Attention,
              "alg_wan_config_t": _lib.WanConfig, "alg_layer_norm_t": _lib.LayerNorm,
-             "alg_head_norm_rope_t": _lib.HeadNormRope, "alg_patch_src_t": _lib.PatchSrc}
+             "alg_head_norm_rope_t": _lib.HeadNormRope, "alg_patch_src_t": _lib.PatchSrc,
+             "alg_im2col_t": _lib.Im2col, "alg_group_norm_t": _lib.GroupNorm}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "alg_b200.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
