@@ -62,6 +62,7 @@ class Gemm(C.Structure):
         ("ldb", C.c_int64), ("ldd", C.c_int64), ("rows_per_batch", C.c_int64), ("gate_ld", C.c_int64),
         ("epilogue", C.c_int32), ("bias_per_row", C.c_int32), ("out_f32", C.c_int32),
         ("gate_dtype", C.c_int32), ("gate_round", C.c_int32), ("gate_split_row", C.c_int64), ("gate_alt", C.c_void_p),
+        ("a_k_period", C.c_int64),
     ]
 
 

@@ -86,6 +86,7 @@ struct Params {
   int64_t M, N, K, ldd, rows_per_batch, gate_ld, gate_split_row;
   int epilogue, bias_per_row, out_f32, gate_bf16, gate_round;
   int m_tiles, n_tiles, k_blocks;
+  int a_k_period;  // 0, or the A operand repeats along K with this period (multiple of BK)
 };
 
 __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], C::kBytesA + C::kBytesB);
-          tma_load_2d(sA + stage * C::kBytesA, &tmA, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sA + stage * C::kBytesA, &tmA, &full[stage], p.a_k_period ? (kb * BK) % p.a_k_period : kb * BK,
+                      m_blk * BM);
           if (CL > 1)  // this CTA's half of the B tile, multicast to the pair
             tma_load_2d_mc(sB + stage * C::kBytesB + crank * (C::kBytesB / CL), &tmB, &full[stage], kb * BK,
                            n_blk * BN + (int)crank * (BN / CL), (uint16_t)((1u << CL) - 1));
@@ -404,7 +406,7 @@ static int launch(const alg_gemm_t* g, cudaStream_t st) {
   }
   CUtensorMap tmA, tmB;
   {
-    uint64_t dims[2] = {(uint64_t)g->K, (uint64_t)g->M}, strides[2] = {1, (uint64_t)g->lda};
+    uint64_t dims[2] = {(uint64_t)(g->a_k_period ? g->a_k_period : g->K), (uint64_t)g->M}, strides[2] = {1, (uint64_t)g->lda};
     uint32_t box[2] = {BK, BM};
     if (int rc = make_tmap_bf16(&tmA, g->A, 2, dims, strides, box)) return rc;
   }
@@ -434,6 +436,7 @@ static int launch(const alg_gemm_t* g, cudaStream_t st) {
   p.m_tiles = (int)((g->M + BM - 1) / BM);
   p.n_tiles = (int)((g->N + BN - 1) / BN);
   p.k_blocks = (int)((g->K + BK - 1) / BK);
+  p.a_k_period = (int)g->a_k_period;
   const int units = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
   if (CL == 1) {
     const int grid = std::min(units, num_sms());
@@ -465,7 +468,11 @@ extern "C" int alg_gemm_bf16(const alg_gemm_t* g, void* stream) {
   ALG_REQUIRE(g && g->A && g->B && g->D, "gemm: null pointer");
   ALG_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "gemm: empty problem");
   ALG_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
-  ALG_REQUIRE(g->lda >= g->K && g->ldb >= g->K && g->ldd >= g->N, "gemm: leading dimension too small");
+  ALG_REQUIRE(g->a_k_period >= 0 && g->a_k_period < (int64_t(1) << 30) &&
+                  (g->a_k_period == 0 || (g->a_k_period % 64 == 0 && g->K % g->a_k_period == 0)),
+              "gemm: a_k_period must be a multiple of 64 that divides K");
+  ALG_REQUIRE(g->lda >= (g->a_k_period ? g->a_k_period : g->K) && g->ldb >= g->K && g->ldd >= g->N,
+              "gemm: leading dimension too small");
   ALG_REQUIRE(g->ldd % (g->out_f32 ? 4 : 8) == 0, "gemm: ldd must keep rows 16-byte aligned");
   ALG_REQUIRE((reinterpret_cast<uintptr_t>(g->D) & 15) == 0, "gemm: D must be 16-byte aligned");
   ALG_REQUIRE(g->epilogue >= ALG_EPI_NONE && g->epilogue <= ALG_EPI_SILU, "gemm: unknown epilogue");

@@ -17,15 +17,18 @@ from . import _lib
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = _lib.EPI_NONE,
          residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
          bias_per_row: bool = False, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
-         gate_alt: Optional[torch.Tensor] = None, gate_split_row: int = 0, gate_round: bool = False) -> torch.Tensor:
+         gate_alt: Optional[torch.Tensor] = None, gate_split_row: int = 0, gate_round: bool = False,
+         a_k_period: int = 0) -> torch.Tensor:
     """``epilogue(a @ w.T + bias)``: a [M, K] bf16, w [N, K] bf16 (nn.Linear layout).  See alg_gemm_bf16.
+
+    ``a_k_period``: a is [M, period] and repeats along K (``a.repeat(1, K // period)`` without materialising it).
 
     ``gate`` fp32 or bf16, [N] or [batches, N]; ``gate_alt`` replaces it for rows whose index inside their sample is
     below ``gate_split_row``; ``gate_round`` rounds ``gate * y`` to bf16 before the residual add (eager bf16 chain)."""
     _lib.require_cuda(a, w, bias, residual, gate, out, gate_alt)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
-    assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
-    M, K = a.shape
+    assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == (a_k_period or w.shape[1])
+    M, K = a.shape[0], w.shape[1]
     N = w.shape[0]
     if out is None:
         ldd = (N + 7) // 8 * 8
@@ -44,6 +47,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     g.epilogue = epilogue
     g.bias_per_row = int(bias_per_row)
     g.out_f32 = int(out.dtype == torch.float32)
+    g.a_k_period = int(a_k_period)
     if gate is not None:
         assert gate.dtype in (torch.float32, torch.bfloat16) and gate.stride(-1) == 1
         g.gate_dtype = _lib.dtype_code(gate.dtype)

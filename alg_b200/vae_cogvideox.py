@@ -12,8 +12,10 @@ video frames happens once per video and is out of scope, SURVEY 8(f).1 -- pass `
 
 This module only SEQUENCES C-ABI calls (``alg_b200.ops``); activations are channels-last ``[H*W, C]`` bf16:
 
-    CogVideoXCausalConv3d (3x3x3)        alg_im2col_bf16 (frames before t=0 replicate frame 0: the three temporal taps
-                                         all read the one frame) + ONE alg_gemm_bf16 with K = 27*C, bias in the epilogue
+    CogVideoXCausalConv3d (3x3x3)        alg_im2col_bf16 + ONE alg_gemm_bf16 with K = 27*C, bias in the epilogue.  Frames
+                                         before t=0 replicate frame 0, so on one frame the three temporal taps read the
+                                         same [3, 3, C] patch: it is gathered once and the GEMM's A operand repeats along
+                                         K (``a_k_period``) against the three temporal weight slices
     ResnetBlock3D ``hidden + inputs``    the residual epilogue of conv2's GEMM
     1x1x1 conv_shortcut                  alg_gemm_bf16
     CogVideoXDownsample3D                compress_time is the identity on one frame; pad (0,1,0,1) + Conv2d stride 2 =
@@ -189,11 +191,19 @@ class AutoencoderKLCogVideoX:
     def _conv3(self, x, H, W, name, residual=None):
         """CogVideoXCausalConv3d(k=3) on one frame: [H*W, Ci] -> [H*W, Co]."""
         wt, b = self._w[name + ".conv.weight"], self._w[name + ".conv.bias"]
-        cols = ops.im2col(x, 1, H, W, kernel=(3, 3, 3), pad_t=2, pad_top=1, pad_left=1,
-                          out=self._workspace(H * W * wt.shape[1], x.device))
+        Cc = x.shape[1]
+        if (9 * Cc) % 64 == 0:
+            # one frame: the three temporal taps read the same [3, 3, C] patch, so it is gathered once and the GEMM walks
+            # it three times along K (a_k_period) against the three temporal weight slices
+            cols = ops.im2col(x, 1, H, W, kernel=(1, 3, 3), pad_top=1, pad_left=1, out=self._workspace(H * W * 9 * Cc, x.device))
+            kw = dict(a_k_period=9 * Cc)
+        else:  # conv_in (3 -> 8 padded channels): K = 216, materialised in full
+            cols = ops.im2col(x, 1, H, W, kernel=(3, 3, 3), pad_t=2, pad_top=1, pad_left=1,
+                              out=self._workspace(H * W * wt.shape[1], x.device))
+            kw = {}
         if residual is not None:
-            return ops.gemm(cols, wt, b, epilogue=_lib.EPI_RESIDUAL, residual=residual)
-        return ops.gemm(cols, wt, b)
+            return ops.gemm(cols, wt, b, epilogue=_lib.EPI_RESIDUAL, residual=residual, **kw)
+        return ops.gemm(cols, wt, b, **kw)
 
     def _resnet(self, x, H, W, name):
         g, eps = self._cfg["norm_num_groups"], self._cfg["norm_eps"]

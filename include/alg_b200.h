@@ -160,6 +160,11 @@ typedef struct {
   int64_t gate_split_row;    /* rows with (row % rows_per_batch) < gate_split_row use gate_alt (0 = unused)       */
   const void* gate_alt;      /* Cog: text rows use enc_gate (cog DiT block); Hy: first-frame rows use the
                                 token-replace gate (hy DiT block, image_condition_type token_replace)            */
+  /* --- ABI 3 --- */
+  int64_t a_k_period;        /* 0, or A holds only a_k_period columns that repeat along K: A[m, k] = A[m, k % period]
+                                (multiple of 64 dividing K; lda >= period).  A causal 3-D convolution on ONE frame reads
+                                the same [kh, kw, C] patch for each of its kt temporal taps, so the patch matrix is
+                                gathered once and only the weights differ along K                                  */
 } alg_gemm_t;
 
 /* D = epilogue(A * B^T + bias): every nn.Linear of the DiT (SURVEY kernel K6). */

@@ -27,7 +27,9 @@ def _r(x):  # round to bf16, keep fp32 container
 
 
 def gemm(a, w, bias=None, *, epilogue=EPI_NONE, residual=None, gate=None, rows_per_batch=0, bias_per_row=False, out=None,
-         out_dtype=torch.bfloat16, gate_alt=None, gate_split_row=0, gate_round=False):
+         out_dtype=torch.bfloat16, gate_alt=None, gate_split_row=0, gate_round=False, a_k_period=0):
+    if a_k_period:
+        a = a.repeat(1, w.shape[1] // a_k_period)
     M, N = a.shape[0], w.shape[0]
     acc = a.float() @ w.float().t()
     if bias is not None:

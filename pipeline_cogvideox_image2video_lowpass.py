@@ -28,6 +28,7 @@ from alg_b200.pipeline_utils import (CogVideoXPipelineOutput, DiffusionPipelineB
                                      PipelineCallback, SyntheticTextEncoder, SyntheticVideoVAE, VideoProcessor,
                                      randn_tensor)
 from alg_b200.schedulers import CogVideoXDDIMScheduler, CogVideoXDPMScheduler
+from alg_b200.vae_cogvideox import AutoencoderKLCogVideoX
 
 PipelineImageInput = Union[PIL.Image.Image, torch.Tensor, List[PIL.Image.Image]]
 
@@ -86,9 +87,13 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, transformer=None, vae=None, torch_dtype=torch.bfloat16,
                         cache_dir=None, synthetic: Optional[bool] = None, allow_synthetic_aux: bool = False,
-                        seed: int = 0, device="cuda", **config_overrides):
+                        seed: int = 0, device="cuda", native_vae_encoder: bool = True, **config_overrides):
         """run.py:65-70.  Offline there are no checkpoints: ``synthetic=True`` (or ``ALG_SYNTHETIC=1``) builds the true
-        CogVideoX-5b-I2V architecture with seeded random weights directly on ``device``."""
+        CogVideoX-5b-I2V architecture with seeded random weights directly on ``device``.
+
+        VAE: ``encode`` -- called every step by pixel-space ALG (cog:645) -- runs on the native encoder
+        (``alg_b200.vae_cogvideox``): its weights come from the snapshot's ``vae/`` folder (or are synthetic); ``vae=``,
+        when given, serves ``decode`` (once per video, not built) -- or everything if ``native_vae_encoder=False``."""
         import os
 
         if synthetic is None:
@@ -108,10 +113,16 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
                 scheduler = CogVideoXDDIMScheduler.from_config(checkpoint.scheduler_config(snap))
             if vae is None and not allow_synthetic_aux:
                 raise NotImplementedError(checkpoint.AUX_MESSAGE)
+            if native_vae_encoder and os.path.isdir(os.path.join(snap, "vae")):
+                decoder = vae if vae is not None else SyntheticVideoVAE(z_dim=16, scaling_factor=0.7, dtype=torch_dtype)
+                vae = AutoencoderKLCogVideoX.from_pretrained(snap, device=device, decoder=decoder)
         if transformer is None:
             transformer = CogVideoXTransformer3DModel.from_synthetic(seed=seed, device=device, **config_overrides)
         if vae is None:
             vae = SyntheticVideoVAE(z_dim=transformer.config.in_channels // 2, scaling_factor=0.7, dtype=torch_dtype)
+            if native_vae_encoder and synthetic:
+                vae = AutoencoderKLCogVideoX.from_synthetic(seed=seed, device=device, decoder=vae,
+                                                            latent_channels=transformer.config.in_channels // 2)
         return cls(tokenizer=None, text_encoder=SyntheticTextEncoder(transformer.config.text_embed_dim, torch_dtype), vae=vae,
                    transformer=transformer, scheduler=scheduler or CogVideoXDDIMScheduler())
 

@@ -79,7 +79,33 @@ def hunyuan(reps):
                       "model_tflops": fwd / (ms1 / 1e3) / 1e12, "tokens": T * (H // 2) * (W // 2) + 180}), flush=True)
 
 
+def vae(reps):
+    """The per-step VAE call of pixel-space ALG (cog:645): AutoencoderKLCogVideoX.encode of one 480x720 frame."""
+    from alg_b200 import _lib, vae_cogvideox as V
+    m = V.AutoencoderKLCogVideoX.from_synthetic(seed=0)
+    x = torch.randn(1, 3, 1, 480, 720, device="cuda").clamp(-1, 1).bfloat16()
+    n0 = _lib.lib().alg_launch_count()
+    m.encode(x)
+    launches = _lib.lib().alg_launch_count() - n0
+    ms = timed(lambda: m.encode(x), reps)
+    flop = 0
+    H, W = 480, 720
+    for name, shape in V.encoder_parameter_shapes(m._cfg).items():
+        if name.endswith(".weight") and len(shape) >= 4:
+            lvl = int(name.split("down_blocks.")[1][0]) if "down_blocks" in name else 3
+            px = (H >> lvl) * (W >> lvl)
+            if "downsamplers" in name:
+                px //= 4
+            k = 1
+            for d in shape[1:]:
+                k *= d
+            flop += 2 * px * shape[0] * k
+    print(json.dumps({"model": "AutoencoderKLCogVideoX.encode, one 480x720 frame (cog:645, every step of pixel-space ALG)",
+                      "ms_per_encode": ms, "launches": int(launches), "conv_tflop": flop / 1e12,
+                      "conv_tflops_rate": flop / ms / 1e9}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "cog"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-    {"cog": cog, "hunyuan": hunyuan}[which](reps)
+    {"cog": cog, "hunyuan": hunyuan, "vae": vae}[which](reps)

@@ -99,3 +99,18 @@ def test_encoder_full_architecture_480x720():
     g = torch.Generator(device="cuda").manual_seed(0)
     z = post.sample(g)
     assert z.shape == (1, 16, 1, 60, 90) and torch.isfinite(z).all()
+
+
+def test_gemm_a_k_period_equals_repeated_operand():
+    """alg_gemm_t.a_k_period: A [M, period] walked K / period times == the GEMM on A.repeat(1, K / period), bit for bit."""
+    from alg_b200 import _lib, ops
+    M, N, period, reps = 1000, 96, 192, 3
+    a = torch.randn(M, period, device="cuda").bfloat16()
+    w = (torch.randn(N, period * reps, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda").bfloat16()
+    r = torch.randn(M, N, device="cuda").bfloat16()
+    got = ops.gemm(a, w, b, epilogue=_lib.EPI_RESIDUAL, residual=r, a_k_period=period)
+    ref = ops.gemm(a.repeat(1, reps).contiguous(), w, b, epilogue=_lib.EPI_RESIDUAL, residual=r)
+    assert torch.equal(got, ref)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a[:, :100].contiguous(), w, a_k_period=100)  # not a multiple of 64
