@@ -187,11 +187,20 @@ __global__ void __launch_bounds__(TH) head_norm_rope_kernel(const alg_head_norm_
   const int chunks = p.heads * LPH;
   uint4* xr = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.x) + row * p.ld);
   const int sub = threadIdx.x % LPH;  // 8-element column block inside the head
-  float v[CH][8];
+  // packed fp32x2 arithmetic throughout (IEEE rn per lane: same rounding chain as the scalar ops, half the issue slots)
+  float2 v[CH][4];
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     const int ci = threadIdx.x + c * TH;
-    if (ci < chunks) unpack8(xr[ci], v[c]);
+    if (ci < chunks) {
+      const uint4 u = xr[ci];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[c][e] = __bfloat1622float2(h[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[c][e] = make_float2(0.f, 0.f);
+    }
   }
   float w[8], bs[8], cs[8], sn[8];
 #pragma unroll
@@ -203,64 +212,78 @@ __global__ void __launch_bounds__(TH) head_norm_rope_kernel(const alg_head_norm_
     load_vec8(p.weight, ALG_BF16, sub, w);
     if (p.norm_kind == ALG_NORM_LAYER && p.bias) load_vec8(p.bias, ALG_BF16, sub, bs);
   }
-  const int64_t rr = row % p.rows_per_batch - p.rope_row0;
+  const uint32_t rpb = (uint32_t)min(p.rows_per_batch, (int64_t)0x7fffffff);  // rows <= 2^31 - 1 (grid size)
+  const int64_t rr = (int64_t)((uint32_t)row % rpb) - p.rope_row0;
   const bool rope = p.cos && rr >= 0 && rr < p.rope_rows;
   if (rope) {
     load_vec8(p.cos + rr * HD, ALG_F32, sub, cs);
     load_vec8(p.sin + rr * HD, ALG_F32, sub, sn);
   }
+  float2 w2[4], bs2[4], cs2[4], sn2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    w2[e] = make_float2(w[2 * e], w[2 * e + 1]);
+    bs2[e] = make_float2(bs[2 * e], bs[2 * e + 1]);
+    cs2[e] = make_float2(cs[2 * e], cs[2 * e + 1]);
+    sn2[e] = make_float2(sn[2 * e], sn[2 * e + 1]);
+  }
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     const int ci = threadIdx.x + c * TH;
-    const bool live = ci < chunks;  // uniform within a head's LPH threads (chunks % LPH == 0)
-    float y[8];
+    const bool live = ci < chunks;  // uniform within a head's LPH threads (chunks % LPH == 0); dead chunks hold zeros
+    float2 y[4];
     if (p.norm_kind == ALG_NORM_RMS) {
-      float sq = 0.f;
-      if (live)
+      float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sq += v[c][e] * v[c][e];
+      for (int e = 0; e < 4; ++e) sq2 = __ffma2_rn(v[c][e], v[c][e], sq2);
+      float sq = sq2.x + sq2.y;
 #pragma unroll
       for (int o = LPH / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
       const float rstd = rsqrtf(sq / (float)HD + p.eps);
+      const float2 rstd2 = make_float2(rstd, rstd);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = bf16_round(__fmul_rn(bf16_round(__fmul_rn(v[c][e], rstd)), w[e]));
+      for (int e = 0; e < 4; ++e) y[e] = bf16x2_round(__fmul2_rn(bf16x2_round(__fmul2_rn(v[c][e], rstd2)), w2[e]));
     } else if (p.norm_kind == ALG_NORM_LAYER) {
-      float sm = 0.f;
-      if (live)
+      float2 sm2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sm += v[c][e];
+      for (int e = 0; e < 4; ++e) sm2 = __fadd2_rn(sm2, v[c][e]);
+      float sm = sm2.x + sm2.y;
 #pragma unroll
       for (int o = LPH / 2; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
       const float mean = sm / (float)HD;
-      float sq = 0.f;
-      if (live)
+      const float2 nmean2 = make_float2(-mean, -mean);
+      float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float t = v[c][e] - mean;
-          sq += t * t;
-        }
+      for (int e = 0; e < 4; ++e) {
+        v[c][e] = __fadd2_rn(v[c][e], nmean2);  // x - mean, reused below
+        sq2 = __ffma2_rn(v[c][e], v[c][e], sq2);
+      }
+      float sq = live ? sq2.x + sq2.y : 0.f;
 #pragma unroll
       for (int o = LPH / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
       const float rstd = rsqrtf(sq / (float)HD + p.eps);
+      const float2 rstd2 = make_float2(rstd, rstd);
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        y[e] = bf16_round(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[c][e], mean), rstd), w[e]), bs[e]));
+      for (int e = 0; e < 4; ++e)
+        y[e] = bf16x2_round(__fadd2_rn(__fmul2_rn(__fmul2_rn(v[c][e], rstd2), w2[e]), bs2[e]));
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = v[c][e];
+      for (int e = 0; e < 4; ++e) y[e] = v[c][e];
     }
     if (rope) {
-      float o[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {  // x_rot = (-x_imag, x_real); out = x * cos + x_rot * sin, fp32 op by op
-        const float re = y[2 * q], im = y[2 * q + 1];
-        o[2 * q] = __fadd_rn(__fmul_rn(re, cs[2 * q]), __fmul_rn(-im, sn[2 * q]));
-        o[2 * q + 1] = __fadd_rn(__fmul_rn(im, cs[2 * q + 1]), __fmul_rn(re, sn[2 * q + 1]));
+        const float2 rot = make_float2(-y[q].y, y[q].x);
+        y[q] = __fadd2_rn(__fmul2_rn(y[q], cs2[q]), __fmul2_rn(rot, sn2[q]));
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = o[e];
     }
-    if (live) xr[ci] = pack8(y);
+    if (live) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __float22bfloat162_rn(y[e]);
+      xr[ci] = u;
+    }
   }
 }
 
