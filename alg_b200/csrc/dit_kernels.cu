@@ -6,39 +6,6 @@
 namespace alg {
 namespace dit {
 
-constexpr int kRowThreads = 256;
-constexpr int kMaxChunks = 4;  // 8 bf16 per chunk per thread -> d <= 8192
-
-__device__ __forceinline__ float block_sum(float v, float* red) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();  // protect `red` from the previous reduction
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  float t = 0.f;
-#pragma unroll
-  for (int i = 0; i < kRowThreads / 32; ++i) t += red[i];
-  return t;
-}
-
-__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float2 t = __bfloat1622float2(h[e]);
-    f[2 * e] = t.x;
-    f[2 * e + 1] = t.y;
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-  return u;
-}
-
 // ------------------------------------------------------------------------------------------------
 __global__ void patch_gather_kernel(const CondPtrs cond, int n_pass, int lat_ch, int cond_ch, int T, int H, int W, __nv_bfloat16* __restrict__ A) {
   const int ph = H / 2, pw = W / 2;
@@ -71,28 +38,70 @@ int patch_gather(CondPtrs cond_dev, int n_pass, int lat_ch, int cond_ch, int T, 
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowThreads)
+// RMSNorm across heads (+ RoPE).  One row per block, the row in registers, packed fp32x2 arithmetic (IEEE rn per lane).
+//
+// RoPE: diffusers multiplies in complex128 (`view_as_complex(x.to(float64)) * freqs`) and casts back to bf16.  The first
+// version did exactly that in fp64 and was bound by the f32 <-> f64 conversions on the XU pipe (16 lanes/clk, 67 % busy:
+// 0.82 ms per launch against 0.41 ms without RoPE, profiles/r01_lowpass_norm_ncu.txt).  Now each of re*cos - im*sin and
+// re*sin + im*cos is evaluated in double-float arithmetic: cos / sin are split into fp32 (hi, lo) pairs when the row's
+// table entries are staged in shared memory, the two leading products carry their exact FMA residuals, their sum goes
+// through TwoSum, and all the low-order terms are added before the single final fp32 rounding.  That is ~2^-44 relative
+// accuracy: after the cast to bf16 the result equals the fp64 one (0 differences in 4e7 random outputs on the host model
+// of this sequence, tests/test_host_logic.py; a plain fp32 FMA evaluation differs in 2e-5 of the outputs).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 bf16x2_round(float2 x) { return __bfloat1622float2(__float22bfloat162_rn(x)); }
+
+// a * x + b * y per lane with x = xh + xl, y = yh + yl (double-float), one final rounding to fp32
+__device__ __forceinline__ float2 dd_dot2(float2 a, float2 xh, float2 xl, float2 b, float2 yh, float2 yl) {
+  const float2 p1 = __fmul2_rn(a, xh), e1 = __ffma2_rn(a, xh, neg2(p1));  // a*xh = p1 + e1 exactly
+  const float2 p2 = __fmul2_rn(b, yh), e2 = __ffma2_rn(b, yh, neg2(p2));
+  const float2 s = __fadd2_rn(p1, p2), bb = __fadd2_rn(s, neg2(p1));      // TwoSum(p1, p2) = s + err exactly
+  const float2 err = __fadd2_rn(__fadd2_rn(p1, neg2(__fadd2_rn(s, neg2(bb)))), __fadd2_rn(p2, neg2(bb)));
+  const float2 low = __fadd2_rn(__fadd2_rn(__fadd2_rn(e1, e2), err), __ffma2_rn(a, xl, __fmul2_rn(b, yl)));
+  return __fadd2_rn(s, low);
+}
+
+template <int TH, int CH>
+__device__ __forceinline__ float block_sum_t(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < TH / 32; ++i) t += red[i];
+  return t;
+}
+
+template <int TH, int CH>
+__global__ void __launch_bounds__(TH)
     rms_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int d, int head_dim, float eps,
                          const __nv_bfloat16* __restrict__ w, RopeTables rope, int use_rope) {
-  __shared__ float red[kRowThreads / 32];
+  __shared__ float red[TH / 32];
+  __shared__ float4 cs_row[64];  // (cos_hi, cos_lo, sin_hi, sin_lo) of the row's head_dim / 2 rotary pairs
   const int64_t row = blockIdx.x;
   uint4* xr = reinterpret_cast<uint4*>(x + row * d);
   const uint4* wr = reinterpret_cast<const uint4*>(w);
   const int chunks = d / 8;
-  float v[kMaxChunks][8];
-  float sq = 0.f;
+  float2 v[CH][4];
+  float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int ci = threadIdx.x + c * kRowThreads;
+  for (int c = 0; c < CH; ++c) {
+    const int ci = threadIdx.x + c * TH;
     if (ci < chunks) {
-      unpack8(xr[ci], v[c]);
+      const uint4 u = xr[ci];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sq += v[c][e] * v[c][e];
+      for (int e = 0; e < 4; ++e) {
+        v[c][e] = __bfloat1622float2(h[e]);
+        sq2 = __ffma2_rn(v[c][e], v[c][e], sq2);
+      }
     }
   }
   // the row's head_dim / 2 (cos, sin) pairs are the same for every head: stage them once per block in shared memory
-  // instead of re-reading the fp64 tables for each of the 40 heads (the table reads were 4x the activation bytes)
-  __shared__ double2 cs_row[64];
+  // (the fp64 table reads were 4x the activation bytes when every head re-read them), split into fp32 hi + lo
   if (use_rope) {
     const int64_t N = (int64_t)rope.ppf * rope.pph * rope.ppw;
     const int n = (int)(row % N);
@@ -105,45 +114,56 @@ __global__ void __launch_bounds__(kRowThreads)
       if (pi < rope.n_t) cs = rope.t + ((int64_t)t * rope.n_t + pi) * 2;
       else if (pi < rope.n_t + rope.n_h) cs = rope.h + ((int64_t)y * rope.n_h + (pi - rope.n_t)) * 2;
       else cs = rope.w + ((int64_t)xx * rope.n_w + (pi - rope.n_t - rope.n_h)) * 2;
-      cs_row[pi] = make_double2(cs[0], cs[1]);
+      const double c = cs[0], s = cs[1];
+      const float ch = (float)c, sh = (float)s;
+      cs_row[pi] = make_float4(ch, (float)(c - (double)ch), sh, (float)(s - (double)sh));
     }
   }
-  const float rstd = rsqrtf(block_sum(sq, red) / (float)d + eps);  // its __syncthreads also publish cs_row
+  const float rstd = rsqrtf(block_sum_t<TH, CH>(sq2.x + sq2.y, red) / (float)d + eps);  // its __syncthreads also publishes cs_row
+  const float2 rstd2 = make_float2(rstd, rstd);
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int ci = threadIdx.x + c * kRowThreads;
+  for (int c = 0; c < CH; ++c) {
+    const int ci = threadIdx.x + c * TH;
     if (ci < chunks) {
-      float wv[8], o[8];
-      unpack8(wr[ci], wv);
+      const uint4 wu = __ldg(wr + ci);
+      const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wu);
+      float2 o[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float h = bf16_round(__fmul_rn(v[c][e], rstd));  // hidden_states.to(weight.dtype)
-        o[e] = bf16_round(__fmul_rn(h, wv[e]));                  // * weight (bf16 tensor op)
+      for (int e = 0; e < 4; ++e) {
+        const float2 h = bf16x2_round(__fmul2_rn(v[c][e], rstd2));            // hidden_states.to(weight.dtype)
+        o[e] = bf16x2_round(__fmul2_rn(h, __bfloat1622float2(wh[e])));         // * weight (bf16 tensor op)
       }
       if (use_rope) {
         const int pair0 = ((ci * 8) % head_dim) >> 1;  // 4 complex pairs per chunk, never straddling a head
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const double2 cs = cs_row[pair0 + q];
-          const double cr = cs.x, si = cs.y;
-          const double re = (double)o[2 * q], im = (double)o[2 * q + 1];
-          o[2 * q] = (float)(re * cr - im * si);  // complex128 multiply, then .type_as(bf16) in pack8
-          o[2 * q + 1] = (float)(re * si + im * cr);
+          const float4 t = cs_row[pair0 + q];
+          const float re = o[q].x, im = o[q].y;
+          // lane 0: re*cos - im*sin, lane 1: re*sin + im*cos; rounded to bf16 (.type_as) by the pack below
+          o[q] = dd_dot2(make_float2(re, re), make_float2(t.x, t.z), make_float2(t.y, t.w), make_float2(-im, im),
+                         make_float2(t.z, t.x), make_float2(t.w, t.y));
         }
       }
-      xr[ci] = pack8(o);
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __float22bfloat162_rn(o[e]);
+      xr[ci] = u;
     }
   }
 }
 
 int rms_norm_rope(__nv_bfloat16* x, int64_t rows, int d, int head_dim, float eps, const __nv_bfloat16* w,
                   const RopeTables* rope, cudaStream_t st) {
-  ALG_REQUIRE(d % 8 == 0 && d <= kRowThreads * 8 * kMaxChunks && head_dim % 8 == 0, "rms_norm: unsupported width");
+  ALG_REQUIRE(d % 8 == 0 && d <= 128 * 8 * 8 && head_dim % 8 == 0 && head_dim <= 128, "rms_norm: unsupported width");
   ALG_REQUIRE(rows <= 0x7fffffff, "rms_norm: too many rows");
   if (rows == 0) return 0;
   RopeTables r{};
   if (rope) r = *rope;
-  rms_norm_rope_kernel<<<(unsigned)rows, kRowThreads, 0, st>>>(x, d, head_dim, eps, w, r, rope != nullptr);
+  const int chunks = d / 8;
+  if (chunks <= 128 * 3) rms_norm_rope_kernel<128, 3><<<(unsigned)rows, 128, 0, st>>>(x, d, head_dim, eps, w, r, rope != nullptr);
+  else if (chunks <= 128 * 5) rms_norm_rope_kernel<128, 5><<<(unsigned)rows, 128, 0, st>>>(x, d, head_dim, eps, w, r, rope != nullptr);
+  else rms_norm_rope_kernel<128, 8><<<(unsigned)rows, 128, 0, st>>>(x, d, head_dim, eps, w, r, rope != nullptr);
   ALG_LAUNCH_OK();
   return 0;
 }

@@ -181,3 +181,48 @@ def test_dpm_host_scalars_match_oracle():
             assert k["prev_t"] == prev_t and all(np.isfinite(used)) and np.isfinite(k["mn"])
             np.testing.assert_array_equal(got, [float(m) for m in mult])  # NaN == NaN here (unused last-step r = 0)
             assert k["mn"] == float(mn) and k["sa"] == float(a_t ** 0.5)
+
+
+def test_double_float_rope_equals_complex128_after_bf16_rounding():
+    """Host model of dd_dot2 (alg_b200/csrc/dit_kernels.cu): re*cos - im*sin evaluated with fp32 (hi, lo) tables, exact FMA
+    residuals and TwoSum, one final fp32 rounding -- after the cast to bf16 it equals the complex128 product diffusers
+    computes (wan DiT RoPE), where a plain fp32 FMA evaluation does not."""
+    import torch
+    rng = np.random.default_rng(0)
+    n = 2_000_000
+    f32, f64 = np.float32, np.float64
+
+    def bf16(x):
+        return torch.from_numpy(x).to(torch.bfloat16).float().numpy()
+
+    def to_bf16_bits(x):
+        return torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy()
+
+    def fma(a, b, c):  # fp32 FMA: the product of two fp32 is exact in fp64
+        return (a.astype(f64) * b.astype(f64) + c.astype(f64)).astype(f32)
+
+    re, im = bf16((rng.standard_normal(n) * 2).astype(f32)), bf16((rng.standard_normal(n) * 2).astype(f32))
+    ang = rng.uniform(0, 1000, n)
+    c, s = np.cos(ang), np.sin(ang)
+    ref_re = (re.astype(f64) * c - im.astype(f64) * s).astype(f32)
+    ref_im = (re.astype(f64) * s + im.astype(f64) * c).astype(f32)
+    ch, sh = c.astype(f32), s.astype(f32)
+    cl, sl = (c - ch.astype(f64)).astype(f32), (s - sh.astype(f64)).astype(f32)
+
+    def dd(a, xh, xl, b, yh, yl):
+        p1 = (a * xh).astype(f32)
+        e1 = fma(a, xh, -p1)
+        p2 = (b * yh).astype(f32)
+        e2 = fma(b, yh, -p2)
+        ss = (p1 + p2).astype(f32)
+        bb = (ss - p1).astype(f32)
+        err = ((p1 - (ss - bb).astype(f32)).astype(f32) + (p2 - bb).astype(f32)).astype(f32)
+        low = (((e1 + e2).astype(f32) + err).astype(f32) + fma(a, xl, (b * yl).astype(f32))).astype(f32)
+        return (ss + low).astype(f32)
+
+    got_re, got_im = dd(re, ch, cl, -im, sh, sl), dd(re, sh, sl, im, ch, cl)
+    assert np.array_equal(to_bf16_bits(got_re), to_bf16_bits(ref_re))
+    assert np.array_equal(to_bf16_bits(got_im), to_bf16_bits(ref_im))
+    assert (got_re != ref_re).mean() < 1e-5  # even the fp32 values agree almost everywhere
+    plain = fma(re, ch, -(im * sh).astype(f32))
+    assert (to_bf16_bits(plain) != to_bf16_bits(ref_re)).sum() > 0
