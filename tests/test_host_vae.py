@@ -78,3 +78,40 @@ def test_vae_surface_and_errors():
         t.decode(torch.zeros(1, 16, 1, 2, 2))
     with pytest.raises(RuntimeError):  # the product path has no CPU mode
         t.encode(torch.zeros(1, 3, 1, 16, 16))
+
+
+def test_patch_gather_and_group_norm_properties():
+    """Seeded sweep over random geometries (CPU): the patch-gather + matmul formulation IS conv3d / strided conv2d with
+    CogVideoX's padding rules, and the GroupNorm emulation IS torch's group_norm (then one bf16 rounding)."""
+    import random
+
+    import torch.nn.functional as F
+    from oracle import ops_emulation as emu
+    rnd = random.Random(7)
+    g = torch.Generator().manual_seed(7)
+    for _ in range(12):
+        T, H, W = rnd.randint(1, 4), rnd.randint(3, 9), rnd.randint(3, 11)
+        Ci, Co = 8 * rnd.randint(1, 3), rnd.randint(1, 6)
+        x = torch.randn(T * H * W, Ci, generator=g)
+        w = torch.randn(Co, Ci, 3, 3, 3, generator=g)
+        cols = emu.im2col(x, T, H, W, kernel=(3, 3, 3), pad_t=2, pad_top=1, pad_left=1)
+        xc = x.view(T, H, W, Ci).permute(3, 0, 1, 2)[None]
+        ref = F.conv3d(torch.cat([xc[:, :, :1]] * 2 + [xc], dim=2), w, padding=(0, 1, 1))[0].permute(1, 2, 3, 0)
+        assert torch.allclose(cols @ w.movedim(1, -1).reshape(Co, -1).t(), ref.reshape(-1, Co), atol=2e-4)
+        # CogVideoXDownsample3D: F.pad (0, 1, 0, 1) then Conv2d(3, stride 2, padding 0), frame by frame
+        w2 = torch.randn(Co, Ci, 3, 3, generator=g)
+        Ho, Wo = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1
+        cols2 = emu.im2col(x, T, H, W, kernel=(1, 3, 3), stride=(1, 2, 2), out_hw=(Ho, Wo))
+        x2 = x.view(T, H, W, Ci).permute(0, 3, 1, 2)
+        ref2 = F.conv2d(F.pad(x2, (0, 1, 0, 1)), w2, stride=2).permute(0, 2, 3, 1).reshape(-1, Co)
+        assert torch.allclose(cols2 @ w2.movedim(1, -1).reshape(Co, -1).t(), ref2, atol=2e-4)
+    for _ in range(8):
+        rows, groups = rnd.randint(5, 300), rnd.choice([1, 2, 4, 8])
+        Cc = groups * rnd.choice([1, 2, 4, 8, 16])
+        if Cc % 8:
+            Cc *= 8
+        x = (torch.randn(rows, Cc, generator=g) * 3 + 1).bfloat16()
+        w, b = (1 + 0.2 * torch.randn(Cc, generator=g)).bfloat16(), (0.3 * torch.randn(Cc, generator=g)).bfloat16()
+        got = emu.group_norm(x, groups, w, b, eps=1e-6, silu=False).float()
+        ref = F.group_norm(x.float().t()[None], groups, w.float(), b.float(), eps=1e-6)[0].t()
+        assert (got - ref).abs().max() <= 2 ** -7 * max(1.0, ref.abs().max().item())
