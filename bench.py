@@ -43,6 +43,19 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line, on the process's ORIGINAL stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def step_indices(k):
     return [int(i * STEPS_PER_VIDEO / k) for i in range(k)]
 
@@ -161,7 +174,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ======================================================================================================
@@ -337,7 +350,7 @@ def run_ours(args):
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -355,6 +368,12 @@ def main():
     if args.resolution == "720p":
         global HEIGHT, WIDTH, H_LAT, W_LAT
         HEIGHT, WIDTH, H_LAT, W_LAT = 720, 1280, 90, 160
+    # stdout carries exactly ONE line, the JSON: everything a library prints there while the run is in flight (NCCL's
+    # "NCCL version ..." banner at init, for one) is routed to stderr, and the result goes to the saved descriptor.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
