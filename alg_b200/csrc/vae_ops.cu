@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256) group_norm_stats_kernel(const uint4* __re
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+#pragma unroll 4
   for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + rr; r < rows; r += (int64_t)gridDim.x * rows_per_iter) {
     float f[8];
     unpack8(__ldg(x + r * c8 + cc), f);
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(256) group_norm_apply_kernel(const uint4* __re
     a[e] = rstd * ga;
     b[e] = be - a[e] * (float)mean;
   }
+#pragma unroll 4
   for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + rr; r < rows; r += (int64_t)gridDim.x * rows_per_iter) {
     float f[8];
     unpack8(__ldg(x + r * c8 + cc), f);

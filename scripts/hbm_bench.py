@@ -77,3 +77,15 @@ ang = torch.rand(32760, 64, device=dev) * 6.28
 cos, sin = ang.cos().repeat_interleave(2, dim=1).contiguous(), ang.sin().repeat_interleave(2, dim=1).contiguous()
 report("head RMSNorm + RoPE 98280 x (40 x 128) bf16", 2 * x.numel() * 2,
        timed(lambda: ops.head_norm_rope(x, 40, 128, norm_kind=1, weight=w, cos=cos, sin=sin, rows_per_batch=32760)))
+del x, out
+# ---- CogVideoX VAE encoder blocks at its 128-channel level (480x720 frame)
+H, W, Cc = 480, 720, 128
+a = torch.randn(H * W, Cc, device=dev).bfloat16()
+gw, gb = torch.randn(Cc, device=dev).bfloat16(), torch.randn(Cc, device=dev).bfloat16()
+go = torch.empty_like(a)
+# GroupNorm reads the activation twice (statistics, then apply) and writes it once
+report("group_norm(32) + SiLU 345600x128 bf16 (2 reads + 1 write)", 3 * a.numel() * 2,
+       timed(lambda: ops.group_norm(a, 32, gw, gb, eps=1e-6, silu=True, out=go)))
+ws = torch.empty(H * W * 9 * Cc, device=dev, dtype=torch.bfloat16)
+report("im2col 3x3 patches 345600 x (9 x 128) bf16 (1 read + 9 writes)", 10 * a.numel() * 2,
+       timed(lambda: ops.im2col(a, 1, H, W, kernel=(1, 3, 3), pad_top=1, pad_left=1, out=ws)))
