@@ -128,6 +128,8 @@ SIGNATURES = {
     "alg_attention_bf16": (C.c_int, [C.POINTER(Attention), C.c_void_p]),
     "alg_layer_norm": (C.c_int, [C.POINTER(LayerNorm), C.c_void_p]),
     "alg_im2col_bf16": (C.c_int, [C.POINTER(Im2col), C.c_void_p]),
+    "alg_wan_rms_norm_rope": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "alg_group_norm_bf16": (C.c_int, [C.POINTER(GroupNorm), C.c_void_p]),
     "alg_head_norm_rope": (C.c_int, [C.POINTER(HeadNormRope), C.c_void_p]),
     "alg_patch_gather": (C.c_int, [C.POINTER(PatchSrc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -298,3 +298,21 @@ int copy_rows(const __nv_bfloat16* src, int64_t src_ld, __nv_bfloat16* dst, int6
 
 }  // namespace dit
 }  // namespace alg
+
+extern "C" int alg_wan_rms_norm_rope(void* x, int64_t rows, int d, int head_dim, float eps, const void* weight,
+                                     const double* rope_t, const double* rope_h, const double* rope_w, int n_t, int n_h,
+                                     int n_w, int ppf, int pph, int ppw, void* stream) {
+  using namespace alg;
+  ALG_REQUIRE(x && weight && rows >= 0, "wan_rms_norm_rope: null pointer");
+  ALG_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight)) & 15) == 0, "wan_rms_norm_rope: misaligned pointer");
+  if (int rc = alg_check_device()) return rc;
+  dit::RopeTables r{rope_t, rope_h, rope_w, n_t, n_h, n_w, ppf, pph, ppw};
+  if (rope_t) {
+    ALG_REQUIRE(rope_h && rope_w && n_t + n_h + n_w == head_dim / 2 && ppf > 0 && pph > 0 && ppw > 0,
+                "wan_rms_norm_rope: the three axis tables must cover head_dim / 2 rotary pairs");
+  }
+  return dit::rms_norm_rope(reinterpret_cast<__nv_bfloat16*>(x), rows, d, head_dim, eps,
+                            reinterpret_cast<const __nv_bfloat16*>(weight), rope_t ? &r : nullptr,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+

@@ -317,6 +317,14 @@ int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents, const floa
                     const void* image, int n_img_tokens, int n_pass, int T, int H, int W, int64_t timestep,
                     void* noise_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Parity hook for the Wan q/k norm (WanAttnProcessor: norm_q / norm_k = RMSNorm across heads, then rotary embedding in
+ * complex128): in place on x [rows, d] bf16.  rope_t / rope_h / rope_w are the fp64 tables [pos][n_*][2] = (cos, sin) of
+ * the frame / height / width axes (n_t + n_h + n_w = head_dim / 2 rotary pairs per head; token row -> (t, y, x) over the
+ * ppf x pph x ppw patch grid); rope_t == NULL skips the rotation (cross-attention q / k).  The engine calls the same kernel. */
+int alg_wan_rms_norm_rope(void* x, int64_t rows, int d, int head_dim, float eps, const void* weight,
+                          const double* rope_t, const double* rope_h, const double* rope_w, int n_t, int n_h, int n_w,
+                          int ppf, int pph, int ppw, void* stream);
+
 /* Debug / parity hook: when a device buffer is set, every forward appends to it (while space lasts), in order:
  * the patch embedding [n_pass*N, d] bf16, temb [d] bf16, timestep_proj [6d] bf16, then the residual stream
  * [n_pass*N, d] bf16 after each block.  Pass NULL to switch it off. */

@@ -224,3 +224,49 @@ def test_loop_non_interval_schedules_and_pixel_space(mode):
                                           inp["image_embeds"], g_mine, 9, steps, alg)
         assert npred.shape == per_step[i][1].shape and npred.shape[0] == 3  # strength > 0 on every step: three passes
         assert rel_l2(x_next, xs[i + 1]) < 4e-3, (i, rel_l2(x_next, xs[i + 1]))  # 8-step schedule: large |d sigma| per step
+
+
+def test_rope_double_float_equals_complex128_on_gpu():
+    """alg_wan_rms_norm_rope: the double-float rotation in the kernel gives, after the bf16 cast, exactly what diffusers'
+    complex128 multiply gives (apply_rotary_emb of WanAttnProcessor) on the kernel's own normalised values."""
+    import ctypes as C
+
+    from alg_b200 import _lib
+    L = _lib.lib()
+    heads, hd = 5, 128
+    d = heads * hd
+    n_t, n_h, n_w = 22, 21, 21
+    ppf, pph, ppw = 3, 10, 13
+    N, B = ppf * pph * ppw, 2
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = (torch.randn(B * N, d, generator=g, device="cuda") * 3).bfloat16()
+    w = (1 + 0.2 * torch.randn(d, generator=g, device="cuda")).bfloat16()
+
+    def table(n):  # [pos][n][2] = (cos, sin) in fp64, like the engine's tables
+        ang = torch.rand(64, n, generator=g, device="cuda", dtype=torch.float64) * 200.0
+        return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+
+    tt, th, tw = table(n_t), table(n_h), table(n_w)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run(rope):
+        y = x.clone()
+        ptrs = [C.c_void_p(t.data_ptr()) for t in (tt, th, tw)] if rope else [None, None, None]
+        rc = L.alg_wan_rms_norm_rope(C.c_void_p(y.data_ptr()), B * N, d, hd, C.c_float(1e-6), C.c_void_p(w.data_ptr()), *ptrs,
+                                     n_t, n_h, n_w, ppf, pph, ppw, st)
+        assert rc == 0, L.alg_last_error()
+        return y
+
+    normed, rotated = run(False), run(True)
+    # RMSNorm itself: fp32 statistics, bf16(x * rstd), bf16(. * weight)
+    xf = x.float()
+    ref_n = ((xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).bfloat16() * w).float()
+    assert (normed.float() - ref_n).abs().max() <= 2 ** -7 * ref_n.abs().max()
+    # rotation in complex128 on the kernel's normalised values
+    n = torch.arange(N, device="cuda")
+    f, yy, xx = n // (pph * ppw), (n // ppw) % pph, n % ppw
+    cs = torch.cat([tt[f], th[yy], tw[xx]], dim=1)                      # [N, hd/2, 2]
+    freqs = torch.complex(cs[..., 0], cs[..., 1])[None, :, None, :]     # [1, N, 1, hd/2]
+    z = torch.view_as_complex(normed.view(B, N, heads, hd // 2, 2).to(torch.float64))
+    ref = torch.view_as_real(z * freqs).flatten(3, 4).to(torch.bfloat16).view(B * N, d)
+    assert torch.equal(rotated, ref), (rotated.float() - ref.float()).abs().max()
