@@ -67,3 +67,44 @@ def test_hunyuan_snapshot_round_trip(tmp_path):
     model = hunyuan.HunyuanVideoTransformer3DModel.from_pretrained(snap, device="cpu")
     assert model.config.rope_axes_dim == (16, 56, 56)  # JSON lists come back as tuples
     assert all(torch.equal(model.state_dict()[k], sd[k]) for k in sd)
+
+
+def test_cog_vae_encoder_snapshot(tmp_path):
+    """A snapshot with a ``vae/`` folder: the pipeline builds the native single-frame encoder from its ``encoder.*`` tensors
+    (decoder tensors are ignored) and hands ``decode`` to the object passed as ``vae=`` (or the synthetic stand-in)."""
+    from safetensors.torch import save_file
+
+    from alg_b200 import checkpoint, cogvideox, vae_cogvideox as V
+    from alg_b200.pipeline_utils import SyntheticVideoVAE
+    from oracle import cog_oracle as Co
+    from pipeline_cogvideox_image2video_lowpass import CogVideoXImageToVideoPipeline
+    snap = str(tmp_path / "snap")
+    checkpoint.save_transformer(snap, dict(cogvideox.COGVIDEOX_5B_I2V, **COG_TINY),
+                                Co.make_weights(Co.tiny_config(), dtype=torch.bfloat16, seed=6), "CogVideoXTransformer3DModel")
+    _write_scheduler(snap, dict(snr_shift_scale=1.0))
+    vcfg = dict(V.COGVIDEOX_5B_VAE, block_out_channels=[32, 64, 64, 64], layers_per_block=1, latent_channels=16)
+    vsd = V.synthetic_state_dict(dict(vcfg, block_out_channels=tuple(vcfg["block_out_channels"])), seed=9, device="cpu")
+    os.makedirs(os.path.join(snap, "vae"))
+    with open(os.path.join(snap, "vae", "config.json"), "w") as f:
+        json.dump(dict(vcfg, _class_name="AutoencoderKLCogVideoX", _diffusers_version="0.34.0.dev0", some_future_key=3), f)
+    save_file(dict(vsd, **{"decoder.conv_in.conv.weight": torch.zeros(4, 4)}), os.path.join(snap, "vae", checkpoint.WEIGHTS_NAME))
+
+    enc = V.AutoencoderKLCogVideoX.from_pretrained(snap, device="cpu")
+    assert enc.config.block_out_channels == (32, 64, 64, 64) and enc.config.layers_per_block == 1
+    w = vsd["encoder.down_blocks.1.resnets.0.conv1.conv.weight"]  # [64, 32, 3, 3, 3] -> GEMM operand [64, (kt, kh, kw, ci)]
+    assert torch.equal(enc._w["encoder.down_blocks.1.resnets.0.conv1.conv.weight"], w.movedim(1, -1).reshape(64, -1))
+    w_in = enc._w["encoder.conv_in.conv.weight"].view(32, 27, 8)  # 3 input channels zero-padded to 8
+    assert torch.equal(w_in[..., :3], vsd["encoder.conv_in.conv.weight"].movedim(1, -1).reshape(32, 27, 3))
+    assert not w_in[..., 3:].any()
+    assert not any(k.startswith("decoder.") for k in enc._w)
+
+    pipe = CogVideoXImageToVideoPipeline.from_pretrained(snap, device="cpu", allow_synthetic_aux=True)
+    assert isinstance(pipe.vae, V.AutoencoderKLCogVideoX) and isinstance(pipe.vae.decoder, SyntheticVideoVAE)
+    assert pipe.vae_scale_factor_spatial == 8 and pipe.vae_scaling_factor_image == 0.7
+    mine = SyntheticVideoVAE(z_dim=16)
+    pipe2 = CogVideoXImageToVideoPipeline.from_pretrained(snap, device="cpu", vae=mine)
+    assert pipe2.vae.decoder is mine
+    pipe3 = CogVideoXImageToVideoPipeline.from_pretrained(snap, device="cpu", vae=mine, native_vae_encoder=False)
+    assert pipe3.vae is mine
+    with pytest.raises(KeyError, match="missing encoder weights"):
+        V.AutoencoderKLCogVideoX(**dict(vcfg, layers_per_block=2)).load_state_dict(vsd)
