@@ -145,6 +145,56 @@ __device__ __forceinline__ float tap(float acc, float w, float x, bool first) {
   return first ? w * x : fmaf(w, x, acc);
 }
 
+// Shared-memory storage of the staged plane and of the pass results: fp32 for fp32 tensors; for 16-bit tensors the TENSOR
+// dtype itself -- the input is 16-bit and ATen rounds every pass result to scalar_t, so nothing is lost, the staging
+// buffers halve (twice the CTAs per SM) and one 16-byte shared-memory access carries 8 columns instead of 4.
+template <int DT> struct Stage { using type = typename Elem<DT>::type; };
+template <> struct Stage<ALG_F32> { using type = float; };
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(v); }
+// one 16-byte vector = VW columns
+__device__ __forceinline__ void ldv(const float* p, float* f) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+__device__ __forceinline__ void ldv(const __nv_bfloat16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __bfloat1622float2(h[e]);
+    f[2 * e] = t.x; f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void ldv(const __half* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __half22float2(h[e]);
+    f[2 * e] = t.x; f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void stv(float* p, const float* f) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+__device__ __forceinline__ void stv(__nv_bfloat16* p, const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void stv(__half* p, const float* f) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
 // The passes are instruction-issue bound (ncu, profiles/r01_lowpass.md), so the number of tap slots NT that a pass unrolls
 // is a template parameter chosen from the operator's longest band: up-sampling bands hold 2-3 taps, down-sampling ones
 // ceil(2 * scale) + 1; bands longer than 8 read the remaining taps from the shared-memory table.
@@ -154,8 +204,10 @@ __device__ __forceinline__ float tap(float acc, float w, float x, bool first) {
 // as ng = blockDim / out_w row groups x out_w columns, so narrow outputs (42 columns) still occupy 252 of 256 lanes
 // and the per-column set-up is paid once.
 template <int DT, int NT>
-__device__ __forceinline__ void pass_w(const float* __restrict__ src, float* __restrict__ dst, int rows, int in_w,
-                                       int out_w, int dst_ld, BandPtr b) {
+__device__ __forceinline__ void pass_w(const typename Stage<DT>::type* __restrict__ src,
+                                       typename Stage<DT>::type* __restrict__ dst, int rows, int in_w, int out_w,
+                                       int dst_ld, BandPtr b) {
+  using S = typename Stage<DT>::type;
   const int nt = blockDim.x;
   int ng = 1, rg = 0, j = threadIdx.x, jstep = nt;
   if (out_w <= nt) {
@@ -171,26 +223,27 @@ __device__ __forceinline__ void pass_w(const float* __restrict__ src, float* __r
     float w[NT];
 #pragma unroll
     for (int k = 0; k < NT; ++k) w[k] = k < n ? wt[k] : 0.f;
-    const float* p = src + rg * in_w + s;
-    float* q = dst + rg * dst_ld + j;
+    const S* p = src + rg * in_w + s;
+    S* q = dst + rg * dst_ld + j;
     const int pstep = ng * in_w, qstep = ng * dst_ld;
 #pragma unroll 4
     for (int r = rg; r < rows; r += ng, p += pstep, q += qstep) {
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < NT; ++k)
-        if (k < n) acc = tap<DT>(acc, w[k], p[k], k == 0);
+        if (k < n) acc = tap<DT>(acc, w[k], ldf(p + k), k == 0);
       if (NT == 8)
-        for (int k = NT; k < n; ++k) acc = tap<DT>(acc, wt[k], p[k], false);
-      *q = Elem<DT>::round(acc);  // ATen keeps the row-pass result in a scalar_t buffer
+        for (int k = NT; k < n; ++k) acc = tap<DT>(acc, wt[k], ldf(p + k), false);
+      stf(q, acc);  // ATen keeps the row-pass result in a scalar_t buffer (16-bit storage rounds, fp32 keeps)
     }
   }
 }
 // dst[i][c] = sum_k w * src[start_i + k][c]       (resample along the strided axis)
 // thread (tx, ty): output rows i = ty + 8 m (taps warp-uniform, in registers), columns c = tx + 32 m'.
 template <int DT, int NT, bool ROUND, bool TO_GLOBAL>
-__device__ __forceinline__ void pass_h(const float* __restrict__ src, void* __restrict__ dst, int cols, int out_h,
-                                       BandPtr b) {
+__device__ __forceinline__ void pass_h(const typename Stage<DT>::type* __restrict__ src, void* __restrict__ dst, int cols,
+                                       int out_h, BandPtr b) {
+  using S = typename Stage<DT>::type;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
   for (int i = ty; i < out_h; i += ny) {
     const int s = b.start[i], n = b.cnt[i];
@@ -200,66 +253,63 @@ __device__ __forceinline__ void pass_h(const float* __restrict__ src, void* __re
     for (int k = 0; k < NT; ++k) w[k] = k < n ? wt[k] : 0.f;
 #pragma unroll 2
     for (int c = tx; c < cols; c += 32) {
-      const float* p = src + s * cols + c;
+      const S* p = src + s * cols + c;
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < NT; ++k)
-        if (k < n) acc = tap<DT>(acc, w[k], p[k * cols], k == 0);
+        if (k < n) acc = tap<DT>(acc, w[k], ldf(p + k * cols), k == 0);
       if (NT == 8)
-        for (int k = NT; k < n; ++k) acc = tap<DT>(acc, wt[k], p[k * cols], false);
+        for (int k = NT; k < n; ++k) acc = tap<DT>(acc, wt[k], ldf(p + k * cols), false);
       if (TO_GLOBAL) {
         Elem<DT>::store(dst, (size_t)i * cols + c, acc);
       } else {
-        reinterpret_cast<float*>(dst)[i * cols + c] = ROUND ? Elem<DT>::round(acc) : acc;
+        stf(reinterpret_cast<S*>(dst) + i * cols + c, acc);  // shared-memory results are always dtype-rounded (ROUND)
       }
     }
   }
 }
 
-// The same pass, four columns per thread: rows of `src` / `dst` are `ld` floats apart (a multiple of 4, 16-byte aligned),
-// so one LDS.128 feeds four FMAs and the result leaves as one 16-byte (fp32) / 8-byte (16-bit) store.  Work items
-// (row, column group) are flattened over the CTA so narrow buffers still fill every lane.
+// The same pass, one 16-byte vector of columns per thread (VW = 4 fp32 / 8 16-bit columns): rows of `src` / `dst` are `ld`
+// elements apart (a multiple of VW, 16-byte aligned), so one LDS.128 feeds VW FMAs and the result leaves as one 16-byte
+// store.  Work items (row, column group) are flattened over the CTA so narrow buffers still fill every lane.
 template <int DT, int NT, bool ROUND, bool TO_GLOBAL>
-__device__ __forceinline__ void pass_h4(const float* __restrict__ src, void* __restrict__ dst, int ld, int dst_ld,
-                                        int out_h, BandPtr b) {
-  const int c4n = ld >> 2, total = out_h * c4n;
-  const float inv = 1.0f / (float)c4n;
+__device__ __forceinline__ void pass_h4(const typename Stage<DT>::type* __restrict__ src, void* __restrict__ dst, int ld,
+                                        int dst_ld, int out_h, BandPtr b) {
+  using S = typename Stage<DT>::type;
+  constexpr int VW = 16 / (int)sizeof(S);
+  const int cvn = ld / VW, total = out_h * cvn;
+  const float inv = 1.0f / (float)cvn;
 #pragma unroll 2
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int i = (int)(((float)idx + 0.5f) * inv);  // exact: total < 2^16
-    const int c = (idx - i * c4n) * 4;
+    const int c = (idx - i * cvn) * VW;
     const int s = b.start[i], n = b.cnt[i];
     const float* wt = b.w + i * b.stride;
-    const float* p = src + s * ld + c;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const S* p = src + s * ld + c;
+    float acc[VW];
+#pragma unroll
+    for (int e = 0; e < VW; ++e) acc[e] = 0.f;
 #pragma unroll
     for (int k = 0; k < NT; ++k)
       if (k < n) {
         const float w = wt[k];
-        const float4 x = *reinterpret_cast<const float4*>(p + k * ld);
-        acc[0] = tap<DT>(acc[0], w, x.x, k == 0);
-        acc[1] = tap<DT>(acc[1], w, x.y, k == 0);
-        acc[2] = tap<DT>(acc[2], w, x.z, k == 0);
-        acc[3] = tap<DT>(acc[3], w, x.w, k == 0);
+        float x[VW];
+        ldv(p + k * ld, x);
+#pragma unroll
+        for (int e = 0; e < VW; ++e) acc[e] = tap<DT>(acc[e], w, x[e], k == 0);
       }
     if (NT == 8)
       for (int k = NT; k < n; ++k) {
         const float w = wt[k];
-        const float4 x = *reinterpret_cast<const float4*>(p + k * ld);
-        acc[0] = fmaf(w, x.x, acc[0]);
-        acc[1] = fmaf(w, x.y, acc[1]);
-        acc[2] = fmaf(w, x.z, acc[2]);
-        acc[3] = fmaf(w, x.w, acc[3]);
+        float x[VW];
+        ldv(p + k * ld, x);
+#pragma unroll
+        for (int e = 0; e < VW; ++e) acc[e] = fmaf(w, x[e], acc[e]);
       }
     if (TO_GLOBAL) {
-      Elem<DT>::store4(dst, (size_t)i * dst_ld + c, acc);
+      stv(reinterpret_cast<typename Elem<DT>::type*>(dst) + (size_t)i * dst_ld + c, acc);  // global tensor dtype == S for 16-bit
     } else {
-      float4 o;
-      o.x = ROUND ? Elem<DT>::round(acc[0]) : acc[0];
-      o.y = ROUND ? Elem<DT>::round(acc[1]) : acc[1];
-      o.z = ROUND ? Elem<DT>::round(acc[2]) : acc[2];
-      o.w = ROUND ? Elem<DT>::round(acc[3]) : acc[3];
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + i * dst_ld + c) = o;
+      stv(reinterpret_cast<S*>(dst) + i * dst_ld + c, acc);
     }
   }
 }
@@ -296,42 +346,35 @@ __global__ void __launch_bounds__(256) down_up_fused_kernel(const void* __restri
                                                             const int* __restrict__ ints,
                                                             const float* __restrict__ weights, DownUpGeom g,
                                                             int bufA_elems, int bufB_elems, int vec) {
-  extern __shared__ __align__(16) float smem[];
-  float* A = smem;                           // in [H, W]      -> small [h1, w1]
-  float* B = smem + bufA_elems;              // t1 [H, w1]     -> t2 [h1, W]
-  float* sw = B + bufB_elems;                // operator taps
-  int* si = reinterpret_cast<int*>(sw + g.n_weights);  // operator starts / counts
+  using T = typename Elem<DT>::type;
+  using S = typename Stage<DT>::type;
+  constexpr int VW = 16 / (int)sizeof(S);  // columns per 16-byte shared-memory vector
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S* A = reinterpret_cast<S*>(smem_raw);     // in [H, W]      -> small [h1, w1]
+  S* B = A + bufA_elems;                     // t1 [H, w1]     -> t2 [h1, W]     (bufA_elems, bufB_elems: multiples of 8)
+  float* sw = reinterpret_cast<float*>(B + bufB_elems);  // operator taps
+  int* si = reinterpret_cast<int*>(sw + g.n_weights);    // operator starts / counts
   for (int i = threadIdx.x; i < g.n_weights; i += blockDim.x) sw[i] = weights[i];
   for (int i = threadIdx.x; i < g.n_ints; i += blockDim.x) si[i] = ints[i];
   BandPtr bw_down{si + g.s_off[0], si + g.c_off[0], sw + g.w_off[0], g.stride[0]};
   BandPtr bh_down{si + g.s_off[1], si + g.c_off[1], sw + g.w_off[1], g.stride[1]};
   BandPtr bw_up{si + g.s_off[2], si + g.c_off[2], sw + g.w_off[2], g.stride[2]};
   BandPtr bh_up{si + g.s_off[3], si + g.c_off[3], sw + g.w_off[3], g.stride[3]};
-  using T = typename Elem<DT>::type;
   const int HW = H * W;
   for (int64_t plane = blockIdx.x; plane < planes; plane += gridDim.x) {
     const T* src = reinterpret_cast<const T*>(in) + plane * HW;
     T* dst = reinterpret_cast<T*>(out) + plane * HW;
-    // ---- stage the plane: 16-byte vector loads when the plane start is aligned -------------
-    constexpr int VEC = 16 / sizeof(T);
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (HW % VEC) == 0) {
+    // ---- stage the plane: 16-byte vector loads when the plane start is aligned (S == T: a plain copy) -------------
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (HW % VW) == 0) {
       const uint4* s4 = reinterpret_cast<const uint4*>(src);
-      for (int i = threadIdx.x; i < HW / VEC; i += blockDim.x) {
-        uint4 v = __ldg(s4 + i);
-        const T* e = reinterpret_cast<const T*>(&v);
-        if (VEC == 4) {
-          *reinterpret_cast<float4*>(A + i * 4) = make_float4((float)e[0], (float)e[1], (float)e[2], (float)e[3]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) A[i * VEC + k] = (float)e[k];
-        }
-      }
+      uint4* a4 = reinterpret_cast<uint4*>(A);
+      for (int i = threadIdx.x; i < HW / VW; i += blockDim.x) a4[i] = __ldg(s4 + i);
     } else {
-      for (int i = threadIdx.x; i < HW; i += blockDim.x) A[i] = (float)src[i];
+      for (int i = threadIdx.x; i < HW; i += blockDim.x) A[i] = src[i];
     }
     __syncthreads();
-    if (vec) {  // W % 4 == 0 and 16-byte aligned planes: H-passes run four columns per thread on padded strides
-      const int w1p = (w1 + 3) & ~3;
+    if (vec) {  // W % VW == 0 and 16-byte aligned planes: H-passes run one 16-byte vector of columns per thread
+      const int w1p = (w1 + VW - 1) / VW * VW;
       ALG_BAND_SWITCH(g.max_cnt[0], (pass_w<DT, NT>(A, B, H, W, w1, w1p, bw_down)));  // t1 [H, w1p]
       __syncthreads();
       // small [h1, w1p], rounded to dtype (reference materialises it)
@@ -412,11 +455,13 @@ static int down_up_dispatch(const void* in, void* out, int64_t planes, int H, in
                             cudaStream_t st) {
   DownUpTables t;
   if (int rc = get_tables(H, W, h1, w1, DT, &t)) return rc;
-  const int vec = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-  const int w1p = vec ? (w1 + 3) & ~3 : w1;
-  const int64_t a_elems = (std::max<int64_t>((int64_t)H * W, (int64_t)h1 * w1p) + 3) & ~(int64_t)3;
-  const int64_t b_elems = (std::max<int64_t>((int64_t)H * w1p, (int64_t)h1 * W) + 3) & ~(int64_t)3;
-  const size_t smem = (size_t)(a_elems + b_elems + t.n_weights + t.n_ints) * sizeof(float);
+  constexpr int kStageBytes = DT == ALG_F32 ? 4 : 2;  // sizeof(Stage<DT>::type)
+  constexpr int VW = 16 / kStageBytes;                // columns per 16-byte shared-memory vector
+  const int vec = (W % VW == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const int w1p = vec ? (w1 + VW - 1) / VW * VW : w1;
+  const int64_t a_elems = (std::max<int64_t>((int64_t)H * W, (int64_t)h1 * w1p) + 7) & ~(int64_t)7;
+  const int64_t b_elems = (std::max<int64_t>((int64_t)H * w1p, (int64_t)h1 * W) + 7) & ~(int64_t)7;
+  const size_t smem = (size_t)(a_elems + b_elems) * kStageBytes + (size_t)(t.n_weights + t.n_ints) * sizeof(float);
   if (smem > 200 * 1024) return down_up_generic<DT>(in, out, planes, H, W, h1, w1, t, st);
   // once per denoise step: set every time (the attribute is per-device state; no per-process cache to go stale)
   ALG_CUDA_OK(cudaFuncSetAttribute(down_up_fused_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
