@@ -49,17 +49,22 @@ int patch_gather(CondPtrs cond_dev, int n_pass, int lat_ch, int cond_ch, int T, 
 // accuracy: after the cast to bf16 the result equals the fp64 one (0 differences in 4e7 random outputs on the host model
 // of this sequence, tests/test_host_logic.py; a plain fp32 FMA evaluation differs in 2e-5 of the outputs).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 bf16x2_round(float2 x) { return __bfloat1622float2(__float22bfloat162_rn(x)); }
 
-// a * x + b * y per lane with x = xh + xl, y = yh + yl (double-float), one final rounding to fp32
-__device__ __forceinline__ float2 dd_dot2(float2 a, float2 xh, float2 xl, float2 b, float2 yh, float2 yl) {
-  const float2 p1 = __fmul2_rn(a, xh), e1 = __ffma2_rn(a, xh, neg2(p1));  // a*xh = p1 + e1 exactly
-  const float2 p2 = __fmul2_rn(b, yh), e2 = __ffma2_rn(b, yh, neg2(p2));
-  const float2 s = __fadd2_rn(p1, p2), bb = __fadd2_rn(s, neg2(p1));      // TwoSum(p1, p2) = s + err exactly
-  const float2 err = __fadd2_rn(__fadd2_rn(p1, neg2(__fadd2_rn(s, neg2(bb)))), __fadd2_rn(p2, neg2(bb)));
-  const float2 low = __fadd2_rn(__fadd2_rn(__fadd2_rn(e1, e2), err), __ffma2_rn(a, xl, __fmul2_rn(b, yl)));
-  return __fadd2_rn(s, low);
+// a * x + b * y per lane with x = xh + xl, y = yh + yl (double-float), one final rounding to fp32.  `na`, `nb` are -a, -b:
+// every subtraction is an FFMA2 with the constant pair (-1, -1) or a product formed with the negated multiplicand, so no
+// packed negation (two scalar instructions each) is ever materialised -- the first form of this function made the kernel
+// instruction-issue bound (549 M warp instructions per launch, ncu norm_r41).
+__device__ __forceinline__ float2 dd_dot2(float2 a, float2 na, float2 xh, float2 xl, float2 b, float2 nb, float2 yh,
+                                          float2 yl) {
+  const float2 m1 = make_float2(-1.f, -1.f);
+  const float2 p1n = __fmul2_rn(na, xh), e1 = __ffma2_rn(a, xh, p1n);  // a*xh = -p1n + e1 exactly
+  const float2 p2n = __fmul2_rn(nb, yh), e2 = __ffma2_rn(b, yh, p2n);
+  const float2 sn = __fadd2_rn(p1n, p2n);                               // TwoSum(p1n, p2n) = sn + errn exactly
+  const float2 bbn = __ffma2_rn(p1n, m1, sn);
+  const float2 errn = __fadd2_rn(__ffma2_rn(__ffma2_rn(bbn, m1, sn), m1, p1n), __ffma2_rn(bbn, m1, p2n));
+  const float2 low = __fadd2_rn(__ffma2_rn(errn, m1, __fadd2_rn(e1, e2)), __ffma2_rn(a, xl, __fmul2_rn(b, yl)));
+  return __ffma2_rn(sn, m1, low);                                       // -(sn + errn) + e1 + e2 + a*xl + b*yl
 }
 
 template <int TH, int CH>
@@ -80,7 +85,10 @@ __global__ void __launch_bounds__(TH)
     rms_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int d, int head_dim, float eps,
                          const __nv_bfloat16* __restrict__ w, RopeTables rope, int use_rope) {
   __shared__ float red[TH / 32];
-  __shared__ float4 cs_row[64];  // (cos_hi, cos_lo, sin_hi, sin_lo) of the row's head_dim / 2 rotary pairs
+  // per rotary pair p: (cos_hi, cos_hi, cos_lo, cos_lo) and (sin_hi, sin_hi, sin_lo, sin_lo), the packed operands as stored,
+  // at slot p + (p >> 3): consecutive threads read pairs 4 apart, and the one-in-eight padding spreads a quarter warp's
+  // eight 16-byte reads over all 32 banks (a dense [pair] layout is 4-way conflicted, an interleaved one 8-way)
+  __shared__ float4 cs_c[72], cs_s[72];
   const int64_t row = blockIdx.x;
   uint4* xr = reinterpret_cast<uint4*>(x + row * d);
   const uint4* wr = reinterpret_cast<const uint4*>(w);
@@ -116,10 +124,12 @@ __global__ void __launch_bounds__(TH)
       else cs = rope.w + ((int64_t)xx * rope.n_w + (pi - rope.n_t - rope.n_h)) * 2;
       const double c = cs[0], s = cs[1];
       const float ch = (float)c, sh = (float)s;
-      cs_row[pi] = make_float4(ch, (float)(c - (double)ch), sh, (float)(s - (double)sh));
+      const float cl = (float)(c - (double)ch), sl = (float)(s - (double)sh);
+      cs_c[pi + (pi >> 3)] = make_float4(ch, ch, cl, cl);
+      cs_s[pi + (pi >> 3)] = make_float4(sh, sh, sl, sl);
     }
   }
-  const float rstd = rsqrtf(block_sum_t<TH, CH>(sq2.x + sq2.y, red) / (float)d + eps);  // its __syncthreads also publishes cs_row
+  const float rstd = rsqrtf(block_sum_t<TH, CH>(sq2.x + sq2.y, red) / (float)d + eps);  // its __syncthreads also publishes cs_c / cs_s
   const float2 rstd2 = make_float2(rstd, rstd);
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
@@ -137,11 +147,13 @@ __global__ void __launch_bounds__(TH)
         const int pair0 = ((ci * 8) % head_dim) >> 1;  // 4 complex pairs per chunk, never straddling a head
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 t = cs_row[pair0 + q];
+          const int slot = pair0 + q + ((pair0 + q) >> 3);
+          const float4 tc = cs_c[slot], ts = cs_s[slot];
           const float re = o[q].x, im = o[q].y;
-          // lane 0: re*cos - im*sin, lane 1: re*sin + im*cos; rounded to bf16 (.type_as) by the pack below
-          o[q] = dd_dot2(make_float2(re, re), make_float2(t.x, t.z), make_float2(t.y, t.w), make_float2(-im, im),
-                         make_float2(t.z, t.x), make_float2(t.w, t.y));
+          // (re, im) * (cos, cos) + (-im, re) * (sin, sin): lane 0 = re*cos - im*sin, lane 1 = im*cos + re*sin; rounded to
+          // bf16 (.type_as) by the pack below
+          o[q] = dd_dot2(o[q], make_float2(-re, -im), make_float2(tc.x, tc.y), make_float2(tc.z, tc.w), make_float2(-im, re),
+                         make_float2(im, -re), make_float2(ts.x, ts.y), make_float2(ts.z, ts.w));
         }
       }
       uint4 u;
