@@ -68,11 +68,11 @@ constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int kThreads = 192;
 constexpr int kGroupM = 16;
 
-template <int BN>
+template <int BN, int CL = 1>
 struct Cfg {
   static constexpr int kBytesA = BM * BK * 2;
-  static constexpr int kBytesB = BN * BK * 2;
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kBytesB = (BN / CL) * BK * 2;  // CL = 2: each CTA of the pair holds half of the B tile
+  static constexpr int kStages = CL == 2 ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32)
   static constexpr int kSmemBytes = kStages * (kBytesA + kBytesB) + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -106,14 +106,19 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return 0.5f * x * (1.0f + t);
 }
 
-// CL = 2: the kernel runs as 2-CTA clusters; the CTAs of a pair work on two M tiles of the SAME N tile, each loads half of
-// the B tile and TMA-multicasts it into both CTAs' shared memory, so a k-block costs a CTA 16 KB (A) + 16 KB (half of B)
-// of L2 -> SM traffic instead of 48 KB.  MMA / TMEM / epilogue stay per-CTA (cta_group::1); a stage is released to the
-// producers by BOTH CTAs' commits (multicast arrive), because each producer writes into both CTAs' shared memory.
+// CL = 2: CTA pairs (2-CTA clusters on one TPC) with cta_group::2 MMAs.  A pair works on a 256 x BN output tile: each CTA
+// loads its own 128 rows of A and HALF of the B tile (BN / 2 rows), the leader CTA (cluster rank 0) issues ONE
+// tcgen05.mma.cta_group::2 of shape 256 x BN x 16 per k-step that reads A and its B half from BOTH CTAs' shared memory
+// (the B halves are broadcast to both tensor cores) and accumulates each CTA's 128 rows in that CTA's own TMEM.  Per
+// k-block a CTA moves 32 KB L2 -> SM instead of 48 KB and its shared memory serves 32 KB of operand reads instead of
+// 48 KB: less data movement per FLOP, which is what the power-capped clock responds to.
+//   full[stage]      lives in the leader: one arrive.expect_tx for both CTAs' bytes; the peer's TMA completes on it too
+//   empty[stage]     in each CTA, released by the leader's multicast commit
+//   tmem_full[acc]   in each CTA (multicast commit); tmem_empty[acc] in the leader, 4 epilogue warps x 2 CTAs arrive
 template <int BN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CL>;
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   const int cluster_id = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
   const int num_clusters = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
@@ -137,21 +142,26 @@ __global__ void __launch_bounds__(kThreads, 1)
     prefetch_tmap(&tmB);
     for (int i = 0; i < C::kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], CL);
+      mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 4 * CL);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
-    tmem_relinquish();
+    if (CL > 1) {
+      tmem_alloc_pair(tmem_slot, C::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything lands in its shared memory
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything completes / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -165,14 +175,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         m_blk = m_blk * CL + (int)crank;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], C::kBytesA + C::kBytesB);
-          tma_load_2d(sA + stage * C::kBytesA, &tmA, &full[stage], p.a_k_period ? (kb * BK) % p.a_k_period : kb * BK,
-                      m_blk * BM);
-          if (CL > 1)  // this CTA's half of the B tile, multicast to the pair
-            tma_load_2d_mc(sB + stage * C::kBytesB + crank * (C::kBytesB / CL), &tmB, &full[stage], kb * BK,
-                           n_blk * BN + (int)crank * (BN / CL), (uint16_t)((1u << CL) - 1));
-          else
+          const int ka = p.a_k_period ? (kb * BK) % p.a_k_period : kb * BK;
+          if (CL > 1) {  // own A rows + own half of the B tile; the bytes of both CTAs complete on the leader's barrier
+            if (crank == 0) mbar_arrive_expect_tx(&full[stage], CL * (C::kBytesA + C::kBytesB));
+            tma_load_2d_pair(sA + stage * C::kBytesA, &tmA, &full[stage], ka, m_blk * BM);
+            tma_load_2d_pair(sB + stage * C::kBytesB, &tmB, &full[stage], kb * BK, n_blk * BN + (int)crank * (BN / CL));
+          } else {
+            mbar_arrive_expect_tx(&full[stage], C::kBytesA + C::kBytesB);
+            tma_load_2d(sA + stage * C::kBytesA, &tmA, &full[stage], ka, m_blk * BM);
             tma_load_2d(sB + stage * C::kBytesB, &tmB, &full[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -181,9 +193,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {  // ===== MMA issuer: elect.sync tells ptxas a single lane runs this region, so descriptors stay in
+    if (crank == 0 && elect_one()) {  // ===== MMA issuer (the leader CTA of a pair): elect.sync tells ptxas a single lane runs this region, so descriptors stay in
                         // uniform registers (a plain lane == 0 test wraps every UTCHMMA in an ELECT / R2UR loop) =====
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CL, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -200,17 +212,22 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t b_addr = smem_u32(sB + stage * C::kBytesB);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            mma_ss(d_tmem, make_smem_desc_sw128(a_addr + k * UMMA_K * 2), make_smem_desc_sw128(b_addr + k * UMMA_K * 2),
-                   idesc, (kb | k) != 0);
+            if (CL > 1)
+              mma_ss_lo_pair(d_tmem, smem_desc_lo_sw128(a_addr + k * UMMA_K * 2), smem_desc_lo_sw128(b_addr + k * UMMA_K * 2),
+                             idesc, (kb | k) != 0);
+            else
+              mma_ss(d_tmem, make_smem_desc_sw128(a_addr + k * UMMA_K * 2), make_smem_desc_sw128(b_addr + k * UMMA_K * 2),
+                     idesc, (kb | k) != 0);
           }
-          if (CL > 1) tc_commit_mc(&empty[stage], (uint16_t)((1u << CL) - 1));  // both producers write this slot
-          else tc_commit(&empty[stage]);  // slot is free once these MMAs have read it
+          if (CL > 1) tc_commit_pair(&empty[stage]);  // the slot is free in BOTH CTAs once these MMAs have read it
+          else tc_commit(&empty[stage]);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (CL > 1) tc_commit_pair(&tmem_full[acc]);  // accumulator complete -> both CTAs' epilogues
+        else tc_commit(&tmem_full[acc]);
       }
     }
   } else {  // ===== epilogue warps 2..5 =====
@@ -370,16 +387,20 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CL > 1) mbar_arrive_remote(&tmem_empty[acc], 0);  // the leader's issuer waits for both CTAs' epilogues
+        else mbar_arrive(&tmem_empty[acc]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while the pair's MMAs / commits / remote arrives may still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if (CL > 1) tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -396,7 +417,7 @@ static int num_sms() {
 
 template <int BN, int CL>
 static int launch(const alg_gemm_t* g, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CL>;
   static std::atomic<uint64_t> attr_done{0};  // per-device bit: the attribute is device state
   int dev = 0;
   ALG_CUDA_OK(cudaGetDevice(&dev));
@@ -493,17 +514,20 @@ extern "C" int alg_gemm_bf16(const alg_gemm_t* g, void* stream) {
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static int force_bn = -1, cluster = -1;  // experiment knobs
+  static int64_t pair_min_m = 128;
   if (force_bn < 0) {
     const char* e = getenv("ALG_GEMM_BN");
     force_bn = e ? atoi(e) : 0;
     e = getenv("ALG_GEMM_CLUSTER");
     cluster = e ? atoi(e) : ALG_GEMM_CLUSTER_DEFAULT;
+    e = getenv("ALG_GEMM_PAIR_MIN_M");
+    if (e) pair_min_m = atoll(e);
   }
   if (force_bn == 128) return gemm::launch<128, 1>(g, st);
   if (force_bn == 64) return gemm::launch<64, 1>(g, st);
   if (g->N % 256 == 0 || g->N > 512) {
-    // CTA pairs with the B tile multicast pay off once there are enough M tiles to fill the machine with pairs
-    if (cluster == 2 && g->M >= 4 * gemm::BM * 74) return gemm::launch<256, 2>(g, st);
+    // CTA pairs (cta_group::2 MMAs on 256 x 256 tiles)
+    if (cluster == 2 && g->M > pair_min_m) return gemm::launch<256, 2>(g, st);
     return gemm::launch<256, 1>(g, st);
   }
   if (g->N % 128 == 0 || g->N > 128) return gemm::launch<128, 1>(g, st);
