@@ -58,7 +58,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }  // namespace tc
 
 #ifndef ALG_GEMM_CLUSTER_DEFAULT
-#define ALG_GEMM_CLUSTER_DEFAULT 1
+#define ALG_GEMM_CLUSTER_DEFAULT 2
 #endif
 
 namespace gemm {
