@@ -44,18 +44,24 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef ALG_ATTN_SPLIT_DEFAULT
 #define ALG_ATTN_SPLIT_DEFAULT 0
 #endif
+#ifndef ALG_ATTN_PAIR_DEFAULT
+#define ALG_ATTN_PAIR_DEFAULT 0
+#endif
 
-template <int D>
+// PAIR = 1: the CTA is one half of a CTA pair (cta_group::2 MMAs, see attention_kernel): a K stage holds this CTA's 32 of
+// the step's 64 keys and a V^T stage this CTA's half of the head_dim rows.
+template <int D, int PAIR = 0>
 struct Cfg {
+  static constexpr int kCtas = PAIR ? 2 : 1;
   static constexpr int kBytesQ = BQ * D * 2;   // one query tile
-  static constexpr int kBytesK = BKV * D * 2;  // one K stage  [64 keys][D]
-  static constexpr int kBytesV = D * BKV * 2;  // one V^T stage [D][64 keys]
+  static constexpr int kBytesK = BKV * D * 2 / kCtas;  // one K stage  [64 (32) keys][D]
+  static constexpr int kBytesV = D * BKV * 2 / kCtas;  // one V^T stage [D (D / 2)][64 keys]
   static constexpr int kXchBytes = 2 * 2 * 2 * BQ * 4;  // SPLIT: [tile][step parity][half][row] partial row maxima
   static constexpr int smem_bytes(int tiles, int stages) {
     return tiles * kBytesQ + stages * (kBytesK + kBytesV) + 1024 + 512 + kXchBytes;
   }
   static constexpr int kSubQ = BQ * 128;   // bytes of one [128 rows][64 elem] swizzle sub-tile of Q
-  static constexpr int kSubK = BKV * 128;  // bytes of one [64 keys][64 elem] sub-tile of K
+  static constexpr int kSubK = BKV * 128 / kCtas;  // bytes of one [64 (32) keys][64 elem] sub-tile of K
 };
 
 struct Params {
@@ -115,33 +121,41 @@ static_assert(kStages == 4, "the issuer's compile-time parities assume a four-st
 // scripts/microbench/mma_rate.cu; TS and N >= 128 run at the floor).  A paired 128-key S MMA runs at the floor but needs
 // both S buffers of the tile at once, which serialises S -> softmax -> softmax -> PV per tile; measured slower
 // (1 120 vs 1 270 TFLOP/s, profiles/r01_attention.md) because the softmax warps, not the tensor pipe, pace the kernel.
-template <int D, int I, int BUF, int ST>
+template <int PAIR>
+__device__ __forceinline__ void commit(uint32_t bar_addr) {  // PAIR: the arrive lands in both CTAs of the pair
+  if constexpr (PAIR) tc_commit_pair_a(bar_addr, 3);
+  else tc_commit_a(bar_addr);
+}
+template <int D, int I, int BUF, int ST, int PAIR>
 __device__ __forceinline__ void issue_s(const MmaCtx& c) {  // S_I = Q_I K^T (stage ST) into S buffer BUF
-  using C = Cfg<D>;
-  constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
+  using C = Cfg<D, PAIR>;
+  constexpr uint32_t idesc_s = make_idesc_bf16(BQ * C::kCtas, BKV);
   const uint32_t d = c.tmem + I * 128 + BUF * 64;
 #pragma unroll
   for (int ks = 0; ks < D / 16; ++ks) {
     const uint32_t qoff = (I * C::kBytesQ + (ks >> 2) * C::kSubQ + (ks & 3) * 32) >> 4;
     const uint32_t koff = (ST * C::kBytesK + (ks >> 2) * C::kSubK + (ks & 3) * 32) >> 4;
-    mma_ss_lo(d, c.q_lo + qoff, c.k_lo + koff, idesc_s, ks != 0);
+    if constexpr (PAIR) mma_ss_lo_pair(d, c.q_lo + qoff, c.k_lo + koff, idesc_s, ks != 0);
+    else mma_ss_lo(d, c.q_lo + qoff, c.k_lo + koff, idesc_s, ks != 0);
   }
-  tc_commit_a(c.bar + 8 * (kBarSFull + I * 2 + BUF));
+  commit<PAIR>(c.bar + 8 * (kBarSFull + I * 2 + BUF));
 }
-template <int D, int I, int BUF, int ST>
+template <int D, int I, int BUF, int ST, int PAIR>
 __device__ __forceinline__ void issue_pv(const MmaCtx& c, uint32_t acc_first) {  // O_I (+)= P_I (buffer BUF) V (stage ST)
-  using C = Cfg<D>;
-  constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D);
+  using C = Cfg<D, PAIR>;
+  constexpr uint32_t idesc_o = make_idesc_bf16(BQ * C::kCtas, D);
   const uint32_t d = c.tmem_o + I * 128, a = c.tmem + I * 128 + BUF * 64;
 #pragma unroll
-  for (int ks = 0; ks < BKV / 16; ++ks)
-    mma_ts_lo(d, a + ks * 8, c.v_lo + ((ST * C::kBytesV + ks * 32) >> 4), idesc_o, ks == 0 ? acc_first : 1u);
-  tc_commit_a(c.bar + 8 * (kBarODone + I));
+  for (int ks = 0; ks < BKV / 16; ++ks) {
+    if constexpr (PAIR) mma_ts_lo_pair(d, a + ks * 8, c.v_lo + ((ST * C::kBytesV + ks * 32) >> 4), idesc_o, ks == 0 ? acc_first : 1u);
+    else mma_ts_lo(d, a + ks * 8, c.v_lo + ((ST * C::kBytesV + ks * 32) >> 4), idesc_o, ks == 0 ? acc_first : 1u);
+  }
+  commit<PAIR>(c.bar + 8 * (kBarODone + I));
 }
 // step j = 4 m + JJ of query tile I; ph = m & 1 (parity of the K/V stage ring at this step).  Each tile has its OWN issuer
 // warp: one thread issuing for both tiles still needed ~230 instructions (~1 000+ cycles) per step; two threads halve that,
 // and the tiles' MMA streams are independent (disjoint TMEM), sharing only the K/V stage barriers (two arrivals each).
-template <int D, int I, int JJ, int STAGES>
+template <int D, int I, int JJ, int STAGES, int PAIR>
 __device__ __forceinline__ void mma_tile_step(const MmaCtx& c, const int j, uint32_t ph) {
   constexpr int BUF = JJ & 1, ST = JJ % STAGES, STN = (JJ + 2) % STAGES;
   constexpr uint32_t p_par = (JJ >> 1) & 1;                      // ((4 m + JJ) >> 1) & 1
@@ -154,36 +168,36 @@ __device__ __forceinline__ void mma_tile_step(const MmaCtx& c, const int j, uint
   mbar_wait_a(c.bar + 8 * (kBarPFull + I * 2 + BUF), p_par);
   mbar_wait_a(c.bar + 8 * (kBarVFull + ST), ph);
   tc_fence_after();
-  issue_pv<D, I, BUF, ST>(c, j > 0);
-  tc_commit_a(c.bar + 8 * (kBarVEmpty + ST));
-  if (last) tc_commit_a(c.bar + 8 * (kBarOFull + I));
+  issue_pv<D, I, BUF, ST, PAIR>(c, j > 0);
+  commit<PAIR>(c.bar + 8 * (kBarVEmpty + ST));
+  if (last) commit<PAIR>(c.bar + 8 * (kBarOFull + I));
   if (has_next) {
     mbar_wait_a(c.bar + 8 * (kBarKFull + STN), phn);
     tc_fence_after();
-    issue_s<D, I, BUF, STN>(c);  // reuses the S buffer whose P was consumed by the PV just issued (in-order tensor pipe)
-    tc_commit_a(c.bar + 8 * (kBarKEmpty + STN));
+    issue_s<D, I, BUF, STN, PAIR>(c);  // reuses the S buffer whose P was consumed by the PV just issued (in-order tensor pipe)
+    commit<PAIR>(c.bar + 8 * (kBarKEmpty + STN));
   }
 }
-template <int D, int I, int STAGES>
+template <int D, int I, int STAGES, int PAIR>
 __device__ __forceinline__ void mma_tile_loop(const MmaCtx& c) {
   mbar_wait_a(c.bar, 0);  // q_full
   mbar_wait_a(c.bar + 8 * (kBarKFull + 0), 0);
   tc_fence_after();
-  issue_s<D, I, 0, 0>(c);
-  tc_commit_a(c.bar + 8 * (kBarKEmpty + 0));
+  issue_s<D, I, 0, 0, PAIR>(c);
+  commit<PAIR>(c.bar + 8 * (kBarKEmpty + 0));
   if (c.n_steps > 1) {
     mbar_wait_a(c.bar + 8 * (kBarKFull + 1), 0);
     tc_fence_after();
-    issue_s<D, I, 1, 1>(c);
-    tc_commit_a(c.bar + 8 * (kBarKEmpty + 1));
+    issue_s<D, I, 1, 1, PAIR>(c);
+    commit<PAIR>(c.bar + 8 * (kBarKEmpty + 1));
   }
   uint32_t ph = 0;
 #pragma unroll 1
   for (int j0 = 0; j0 < c.n_steps; j0 += 4, ph ^= 1u) {
-    mma_tile_step<D, I, 0, STAGES>(c, j0, ph);
-    if (j0 + 1 < c.n_steps) mma_tile_step<D, I, 1, STAGES>(c, j0 + 1, ph);
-    if (j0 + 2 < c.n_steps) mma_tile_step<D, I, 2, STAGES>(c, j0 + 2, ph);
-    if (j0 + 3 < c.n_steps) mma_tile_step<D, I, 3, STAGES>(c, j0 + 3, ph);
+    mma_tile_step<D, I, 0, STAGES, PAIR>(c, j0, ph);
+    if (j0 + 1 < c.n_steps) mma_tile_step<D, I, 1, STAGES, PAIR>(c, j0 + 1, ph);
+    if (j0 + 2 < c.n_steps) mma_tile_step<D, I, 2, STAGES, PAIR>(c, j0 + 2, ph);
+    if (j0 + 3 < c.n_steps) mma_tile_step<D, I, 3, STAGES, PAIR>(c, j0 + 3, ph);
   }
 }
 
@@ -203,11 +217,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 //            token refiner): one query tile, two K/V stages, ~100 KB of shared memory and 256 TMEM columns, so TWO CTAs
 //            share an SM and one CTA's prologue (TMEM alloc, Q load) and epilogue overlap the other's steps -- with 5-8
 //            steps per CTA those fixed costs were more than half of the long layout's time per CTA.
-template <int D, int POLY, int SPLIT, int TILES, int STAGES>
+// PAIR = 1: the kernel runs as 2-CTA clusters (one TPC) and every MMA is a cta_group::2 instruction issued by the leader CTA
+//            (cluster rank 0): M = 256 = query tile i of BOTH CTAs; the K tile of a step is split by keys and the V^T tile by
+//            head_dim rows between the two CTAs' shared memories and broadcast to both tensor cores, so a CTA fetches and
+//            stores HALF of every K / V tile (L2 -> SM traffic and shared-memory reads of the B operands halve; the
+//            128 x 64 x 16 S MMA, which at 6 KB of operands per 32 cycles out-runs the 128 B/clk shared-memory port, drops to
+//            5 KB).  K/V "full" barriers live in the leader (both CTAs' TMA bytes complete there), "P ready" collects the
+//            softmax warps of both CTAs by remote arrives, everything the issuer signals is a multicast commit.
+template <int D, int POLY, int SPLIT, int TILES, int STAGES, int PAIR>
 __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TILES == 1 ? 2 : 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Params p) {
-  using C = Cfg<D>;
+  using C = Cfg<D, PAIR>;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   constexpr int kSoftmaxWarps = (SPLIT ? 8 : 4) * TILES;
   constexpr int kTmaWarp = kSoftmaxWarps, kMmaWarp = kSoftmaxWarps + 1;  // MMA issuers: kMmaWarp (tile 0), kMmaWarp + 1 (tile 1)
   constexpr int kWarpsPerTile = kSoftmaxWarps / TILES;
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], kWarpsPerTile);  // one arrival per softmax warp of the tile
+      mbar_init(&p_full[i], kWarpsPerTile * C::kCtas);  // one arrival per softmax warp of the tile (of both CTAs of a pair)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&o_done[i], 1);
@@ -258,32 +280,45 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers exist before anything completes / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kTmaWarp) {
     if (elect_one()) {  // ===== TMA producer: Q0 Q1 | K0 K1 | V0 K2 | V1 K3 | ... (the order the MMA warp consumes) =====
-      mbar_arrive_expect_tx(q_full, TILES * C::kBytesQ);
+      // PAIR: the bytes of both CTAs complete on the LEADER's barriers (one expect_tx there covers the pair); each CTA
+      // loads its own query tiles, its 32 keys of the K tile and its half of the V^T rows
+      auto load = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+        if constexpr (PAIR) tma_load_3d_pair(dst, m, bar, c0, c1, c2);
+        else tma_load_3d(dst, m, bar, c0, c1, c2);
+      };
+      if (crank == 0) mbar_arrive_expect_tx(q_full, C::kCtas * TILES * C::kBytesQ);
       for (int i = 0; i < TILES; ++i)
         for (int s = 0; s < D / 64; ++s)
-          tma_load_3d(sQ + i * C::kBytesQ + s * C::kSubQ, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
+          load(sQ + i * C::kBytesQ + s * C::kSubQ, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
       auto load_k = [&](int j) {
         const int st = j % STAGES;
         mbar_wait(&k_empty[st], ((j / STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], C::kBytesK);
+        if (crank == 0) mbar_arrive_expect_tx(&k_full[st], C::kCtas * C::kBytesK);
         for (int s = 0; s < D / 64; ++s)
-          tma_load_3d(sK + st * C::kBytesK + s * C::kSubK, &tmK, &k_full[st], head * D + s * 64, j * BKV, batch);
+          load(sK + st * C::kBytesK + s * C::kSubK, &tmK, &k_full[st], head * D + s * 64,
+               j * BKV + (int)crank * (BKV / C::kCtas), batch);
       };
       auto load_v = [&](int j) {
         const int st = j % STAGES;
         mbar_wait(&v_empty[st], ((j / STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], C::kBytesV);
-        tma_load_3d(sV + st * C::kBytesV, &tmV, &v_full[st], j * BKV, head * D, batch);
+        if (crank == 0) mbar_arrive_expect_tx(&v_full[st], C::kCtas * C::kBytesV);
+        load(sV + st * C::kBytesV, &tmV, &v_full[st], j * BKV, head * D + (int)crank * (D / C::kCtas), batch);
       };
       load_k(0);
       if (n_steps > 1) load_k(1);
@@ -293,7 +328,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       }
     }
   } else if (warp >= kMmaWarp) {
-    if (elect_one()) {  // ===== MMA issuers.  elect.sync (not `lane == 0`) tells ptxas that a single lane runs this region, so
+    if (crank == 0 && elect_one()) {  // ===== MMA issuers (of the leader CTA when PAIR).  elect.sync (not `lane == 0`) tells ptxas that a single lane runs this region, so
                         // the descriptors stay in uniform registers; otherwise every UTCHMMA is wrapped in an ELECT / R2UR loop =====
       MmaCtx c;
       c.tmem = tmem_base;
@@ -303,8 +338,8 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       c.k_lo = smem_desc_lo_sw128(smem_u32(sK));
       c.v_lo = smem_desc_lo_sw128(smem_u32(sV));
       c.n_steps = n_steps;
-      if (warp == kMmaWarp) mma_tile_loop<D, 0, STAGES>(c);
-      else if constexpr (TILES == 2) mma_tile_loop<D, 1, STAGES>(c);
+      if (warp == kMmaWarp) mma_tile_loop<D, 0, STAGES, PAIR>(c);
+      else if constexpr (TILES == 2) mma_tile_loop<D, 1, STAGES, PAIR>(c);
     }
   } else {  // ===== softmax warps =====
     constexpr int W = SPLIT ? BKV / 2 : BKV;      // key columns of a step owned by this thread
@@ -410,7 +445,10 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(bar_p0 + 8 * BUF);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_remote_a(bar_p0 + 8 * BUF, 0);  // the leader's issuer waits for both CTAs' P
+        else mbar_arrive_a(bar_p0 + 8 * BUF);
+      }
     };
     const int n_full = p.n_kv / BKV;
     using B0 = std::integral_constant<int, 0>;
@@ -470,22 +508,24 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // no CTA leaves while the pair's MMAs / commits / remote arrives may touch it
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-template <int D, int POLY, int SPLIT, int TILES, int STAGES>
+template <int D, int POLY, int SPLIT, int TILES, int STAGES, int PAIR = 0>
 static int launch(const alg_attention_t* a, cudaStream_t st) {
-  using C = Cfg<D>;
+  using C = Cfg<D, PAIR>;
   constexpr int kThreads = ((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32;
   constexpr int kSmem = C::smem_bytes(TILES, STAGES);
   static std::atomic<uint64_t> attr_done{0};  // per-device bit: the attribute is device state
   int dev = 0;
   ALG_CUDA_OK(cudaGetDevice(&dev));
   if (dev >= 64 || !(attr_done.load(std::memory_order_relaxed) >> dev & 1)) {
-    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT, TILES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     if (dev < 64) attr_done.fetch_or(uint64_t(1) << dev, std::memory_order_relaxed);
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -497,12 +537,12 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   }
   {
     uint64_t dims[3] = {hd, (uint64_t)a->n_kv, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->k_rs, (uint64_t)a->k_bs};
-    uint32_t box[3] = {64, BKV, 1};
+    uint32_t box[3] = {64, BKV / C::kCtas, 1};
     if (int rc = make_tmap_bf16(&tmK, a->K, 3, dims, strides, box)) return rc;
   }
   {
     uint64_t dims[3] = {(uint64_t)a->n_kv, hd, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->v_rs, (uint64_t)a->v_bs};
-    uint32_t box[3] = {BKV, (uint32_t)D, 1};
+    uint32_t box[3] = {BKV, (uint32_t)D / C::kCtas, 1};
     if (int rc = make_tmap_bf16(&tmV, a->Vt, 3, dims, strides, box)) return rc;
   }
   Params p;
@@ -515,7 +555,24 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
   dim3 grid((unsigned)((a->n_q + TILES * BQ - 1) / (TILES * BQ)), (unsigned)a->heads, (unsigned)a->batch);
-  attention_kernel<D, POLY, SPLIT, TILES, STAGES><<<grid, kThreads, kSmem, st>>>(tmQ, tmK, tmV, p);
+  if constexpr (PAIR) {
+    grid.x = (grid.x + 1) / 2 * 2;  // whole pairs: a CTA past the last query rows loads zero-filled tiles and stores nothing
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ALG_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR>, tmQ, tmK, tmV, p));
+  } else {
+    attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR><<<grid, kThreads, kSmem, st>>>(tmQ, tmK, tmV, p);
+  }
   ALG_LAUNCH_OK();
   return 0;
 }
@@ -536,7 +593,7 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   ALG_REQUIRE((reinterpret_cast<uintptr_t>(a->O) & 15) == 0, "attention: O must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static int poly = -1, split = -1, short_max = -1;  // tuning knobs; defaults from profiling
+  static int poly = -1, split = -1, short_max = -1, pair = 0;  // tuning knobs; defaults from profiling
   if (poly < 0) {
     const char* e = getenv("ALG_ATTN_POLY");
     poly = e ? atoi(e) : ALG_ATTN_POLY_DEFAULT;
@@ -544,10 +601,19 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
     split = e ? atoi(e) : ALG_ATTN_SPLIT_DEFAULT;
     e = getenv("ALG_ATTN_SHORT_MAX");  // key counts up to this use the SHORT (one tile, two CTAs per SM) variant; 0 = never
     short_max = e ? atoi(e) : ALG_ATTN_SHORT_MAX_DEFAULT;
+    e = getenv("ALG_ATTN_PAIR");  // CTA pairs (cta_group::2 MMAs) for the long variant
+    pair = e ? atoi(e) : ALG_ATTN_PAIR_DEFAULT;
   }
   const bool use_short = a->n_kv <= short_max;
 #define ALG_ATTN_DISPATCH(DD)                                                        \
   if (use_short) return attn::launch<DD, 8, 0, 1, 2>(a, st);                         \
+  if (pair && !split) {                                                              \
+    switch (poly) {                                                                  \
+      case 0: return attn::launch<DD, 0, 0, 2, 4, 1>(a, st);                         \
+      case 4: return attn::launch<DD, 4, 0, 2, 4, 1>(a, st);                         \
+      default: return attn::launch<DD, 8, 0, 2, 4, 1>(a, st);                        \
+    }                                                                                \
+  }                                                                                  \
   if (split) {                                                                       \
     switch (poly) {                                                                  \
       case 0: return attn::launch<DD, 0, 1, 2, 4>(a, st);                            \
@@ -557,6 +623,8 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   } else {                                                                           \
     switch (poly) {                                                                  \
       case 0: return attn::launch<DD, 0, 0, 2, 4>(a, st);                            \
+      case 2: return attn::launch<DD, 2, 0, 2, 4>(a, st);                            \
+      case 3: return attn::launch<DD, 3, 0, 2, 4>(a, st);                            \
       case 4: return attn::launch<DD, 4, 0, 2, 4>(a, st);                            \
       default: return attn::launch<DD, 8, 0, 2, 4>(a, st);                           \
     }                                                                                \
