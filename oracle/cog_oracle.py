@@ -290,7 +290,8 @@ def forward(sd, cfg: CogConfig, hidden, text, timestep, rope=None, return_interm
 # the ALG denoise loop, cog:1005-1140 (DDIM scheduler branch)
 # ----------------------------------------------------------------------------
 def denoise_loop(transformer, scheduler, latents, image_latents, prompt_embeds, negative_prompt_embeds,
-                 num_inference_steps, guidance_scale, alg, prepare_lp, get_lp_strength, on_step=None, teacher=None):
+                 num_inference_steps, guidance_scale, alg, prepare_lp, get_lp_strength, on_step=None, teacher=None,
+                 use_dynamic_cfg=False, dpm_randn=None):
     """``transformer(x [B, F, 32, H, W], text [B, L, D], timestep [B]) -> noise``; ``prepare_lp(type, sigma, k, f)``
     returns the low-passed image latents [1, F, 16, H, W] (cog:586-703, in latent or pixel space)."""
     do_cfg = guidance_scale > 1.0
@@ -333,10 +334,20 @@ def denoise_loop(transformer, scheduler, latents, image_latents, prompt_embeds, 
             noise = u0 + guidance_scale * (tx - u)
         elif do_cfg:
             u, tx = noise_pred.chunk(2)
-            noise = u + guidance_scale * (tx - u)
+            w = guidance_scale
+            if use_dynamic_cfg and not use_lp:  # cog:1103-1108 (only the non-ALG branch has it)
+                w = 1 + guidance_scale * ((1 - math.cos(math.pi * ((num_inference_steps - t.item()) / num_inference_steps) ** 5.0)) / 2)
+            noise = u + w * (tx - u)
         else:
             noise = noise_pred
-        latents = scheduler.step(noise, int(t), latents).to(prompt_embeds.dtype)
+        if dpm_randn is not None:  # CogVideoXDPMScheduler: carries pred_original_sample (cog:1113-1122)
+            if i == 0:
+                old_pred = None
+            latents, old_pred = scheduler.step(noise, old_pred, int(t), int(scheduler.timesteps[i - 1]) if i > 0 else None,
+                                               latents, dpm_randn)
+            latents = latents.to(prompt_embeds.dtype)
+        else:
+            latents = scheduler.step(noise, int(t), latents).to(prompt_embeds.dtype)
         if on_step is not None:
             on_step(i, t, latents, noise_pred)
     return latents

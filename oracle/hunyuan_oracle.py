@@ -323,7 +323,8 @@ def denoise_loop(transformer, scheduler, latents, image_latents, pos, neg, num_i
     use_lp = alg.get("use_low_pass_guidance", False)
     sigmas = torch.linspace(1.0, 0.0, num_inference_steps + 1, dtype=torch.float64)[:-1].numpy()
     scheduler.set_timesteps(num_inference_steps, sigmas=sigmas)
-    guidance = (torch.tensor([guidance_scale], dtype=dtype, device=latents.device) * 1000.0)
+    # hy:1115-1119: one entry per LATENT (not per pass): a [1] tensor that the embedder broadcasts over the 2-3 passes
+    guidance = (torch.tensor([guidance_scale] * latents.shape[0], dtype=dtype, device=latents.device) * 1000.0)
 
     def strength(i):
         s = get_lp_strength(i, num_inference_steps, alg["lp_strength_schedule_type"], alg["schedule_interval_start_time"],
@@ -360,7 +361,7 @@ def denoise_loop(transformer, scheduler, latents, image_latents, pos, neg, num_i
             x = torch.cat([lp, rest], dim=2).to(dtype)
             ctx = list(pos)
         timestep = t.expand(x.shape[0]).to(dtype).to(x.device)
-        noise_pred = transformer(x, timestep, ctx[0], ctx[2], ctx[1], guidance.expand(x.shape[0]))
+        noise_pred = transformer(x, timestep, ctx[0], ctx[2], ctx[1], guidance)
         if noise_pred.shape[0] == 3:
             u0, u, tx = noise_pred.chunk(3)
             noise = u0 + true_cfg_scale * (tx - u)

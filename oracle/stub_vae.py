@@ -89,3 +89,71 @@ class ArithVAE:
         if not return_dict:
             return (rgb,)
         return SimpleNamespace(sample=rgb)
+
+
+class _Batch(dict):
+    def to(self, *a, **k):
+        return self
+
+
+class StubImageProcessor:
+    """``CLIPImageProcessor`` call surface (wan:232): ``processor(images=..., return_tensors="pt").to(device)``."""
+
+    def __call__(self, images=None, return_tensors="pt"):
+        n = len(images) if isinstance(images, (list, tuple)) else (images.shape[0] if torch.is_tensor(images) and images.ndim == 4 else 1)
+        return _Batch(pixel_values=torch.zeros(n, 3, 2, 2))
+
+
+class StubImageEncoder:
+    """``CLIPVisionModel`` call surface (wan:233-234): ``hidden_states[-2]`` of image k is ``table[k]`` ([n, tokens, dim])."""
+
+    def __init__(self, table: torch.Tensor):
+        self.table = table
+        self.dtype = table.dtype
+
+    def to(self, *a, **k):
+        return self
+
+    def __call__(self, pixel_values=None, output_hidden_states=True, **kw):
+        h = self.table[: pixel_values.shape[0]]
+        return SimpleNamespace(hidden_states=[h * 0, h, h * 0])
+
+
+class StubTokenizer:
+    """HF tokenizer call surface (wan:200-209, cog:244-253): whitespace words -> ids in [2, vocab), one EOS (id 1), padded
+    with 0 to ``max_length``; returns ``input_ids`` / ``attention_mask``."""
+
+    def __init__(self, vocab=997):
+        self.vocab = vocab
+
+    def __call__(self, prompt, padding="max_length", max_length=32, truncation=True, add_special_tokens=True,
+                 return_attention_mask=True, return_tensors="pt"):
+        prompt = [prompt] if isinstance(prompt, str) else prompt
+        ids = torch.zeros(len(prompt), max_length, dtype=torch.int64)
+        mask = torch.zeros(len(prompt), max_length, dtype=torch.int64)
+        for b, text in enumerate(prompt):
+            toks = [2 + sum(ord(ch) * (i + 1) for i, ch in enumerate(w)) % (self.vocab - 2) for w in text.split()][: max_length - 1] + [1]
+            ids[b, : len(toks)] = torch.tensor(toks)
+            mask[b, : len(toks)] = 1
+        return SimpleNamespace(input_ids=ids, attention_mask=mask)
+
+
+class _EncoderOutput(SimpleNamespace):
+    def __getitem__(self, i):
+        return (self.last_hidden_state,)[i]
+
+
+class StubTextEncoder:
+    """HF encoder call surface (wan:212, cog:258): ``encoder(ids, mask).last_hidden_state`` (``encoder(ids)[0]`` for T5)."""
+
+    def __init__(self, dim=64, vocab=997, dtype=torch.bfloat16, seed=99):
+        g = torch.Generator().manual_seed(seed)
+        self.table = torch.randn(vocab, dim, generator=g).to(dtype)
+        self.dtype = dtype
+
+    def to(self, *a, **k):
+        return self
+
+    def __call__(self, input_ids, attention_mask=None, **kw):
+        h = self.table.to(input_ids.device)[input_ids]
+        return _EncoderOutput(last_hidden_state=h)

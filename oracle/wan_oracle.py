@@ -244,8 +244,10 @@ def forward(sd, cfg: WanConfig, hidden, timestep, text, image, return_intermedia
 # ----------------------------------------------------------------------------
 def denoise_loop(transformer, scheduler, latents, condition, prompt_embeds, negative_prompt_embeds, image_embeds,
                  num_inference_steps, guidance_scale, alg, lp_filter, get_lp_strength, dtype=torch.bfloat16,
-                 on_step=None, teacher=None):
-    """``transformer(x, t, text, img) -> noise``; ``lp_filter(cond, type, sigma, k, f) -> tensor``.
+                 on_step=None, teacher=None, prepare_lp=None):
+    """``transformer(x, t, text, img) -> noise``; ``lp_filter(cond, type, sigma, k, f) -> tensor`` (in-latent ALG), or
+    ``prepare_lp(type, sigma, k, f) -> lp condition`` for the full wan:451-559 (``oracle/prepare_lp_oracle.wan_prepare_lp``:
+    pixel-space filtering + VAE encode + mask rebuild).
 
     ``alg`` holds the 14 ALG kwargs (wan:612-633).  ``on_step(i, t, latents, noise_pred)`` observes every step.
     ``teacher[i]`` (optional) replaces ``latents`` before step i (teacher-forced parity).
@@ -262,7 +264,10 @@ def denoise_loop(transformer, scheduler, latents, condition, prompt_embeds, nega
             sigma = alg["lp_blur_sigma"] * s
             k = alg["lp_blur_kernel_size"] * s if alg["schedule_blur_kernel_size"] else alg["lp_blur_kernel_size"]
             f = 1.0 - (1.0 - alg["lp_resize_factor"]) * s
-            lp = lp_filter(condition, alg["lp_filter_type"], sigma, k, f).to(condition.dtype)
+            if prepare_lp is not None:
+                lp = prepare_lp(alg["lp_filter_type"], sigma, k, f)
+            else:
+                lp = lp_filter(condition, alg["lp_filter_type"], sigma, k, f).to(condition.dtype)
             if s == 0.0:
                 x = torch.cat([torch.cat([latents] * 2), torch.cat([condition, condition])], dim=1).to(dtype)
                 text = torch.cat([negative_prompt_embeds, prompt_embeds])
