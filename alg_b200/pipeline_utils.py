@@ -252,6 +252,62 @@ class SyntheticVideoVAE(torch.nn.Module):
         return SimpleNamespace(sample=x) if return_dict else (x,)
 
 
+class _Features(dict):
+    """transformers.BatchFeature-like: attribute access + ``.to(device)``."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def to(self, device=None, dtype=None):
+        return _Features({k: (v.to(device) if torch.is_tensor(v) else v) for k, v in self.items()})
+
+
+class SyntheticTokenizer:
+    """HF tokenizer call surface (wan:200-209, cog:244-253) without a vocabulary file: whitespace words -> CRC ids, one EOS
+    (id 1), zero padding to ``max_length``.  Stand-in for the UMT5 / T5 sentencepiece tokenizers (no tokenizer files offline)."""
+
+    def __init__(self, vocab_size: int = 256384):
+        self.vocab_size = vocab_size
+
+    def __call__(self, prompt, padding="max_length", max_length=512, truncation=True, add_special_tokens=True,
+                 return_attention_mask=True, return_tensors="pt", **kw):
+        import zlib
+
+        prompt = [prompt] if isinstance(prompt, str) else list(prompt)
+        ids = torch.zeros(len(prompt), max_length, dtype=torch.int64)
+        mask = torch.zeros(len(prompt), max_length, dtype=torch.int64)
+        for b, text in enumerate(prompt):
+            toks = [2 + zlib.crc32(w.encode()) % (self.vocab_size - 2) for w in text.split()][: max_length - 1] + [1]
+            ids[b, : len(toks)] = torch.tensor(toks)
+            mask[b, : len(toks)] = 1
+        return _Features(input_ids=ids, attention_mask=mask)
+
+
+class SyntheticImageProcessor:
+    """``CLIPImageProcessor`` call surface (wan:232): resize to 224 x 224 (bicubic), CLIP mean / std normalisation."""
+
+    MEAN, STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+
+    def __call__(self, images=None, return_tensors="pt", **kw):
+        from PIL import Image
+
+        images = images if isinstance(images, (list, tuple)) else [images]
+        out = []
+        for im in images:
+            if isinstance(im, Image.Image):
+                t = torch.from_numpy(np.asarray(im.convert("RGB").resize((224, 224), Image.BICUBIC), dtype=np.float32) / 255.0).permute(2, 0, 1)
+            else:
+                t = torch.as_tensor(im).float().cpu()
+                t = t[0] if t.ndim == 4 else t
+                t = (t + 1) / 2 if float(t.min()) < 0 else t
+                t = F.interpolate(t[None], size=(224, 224), mode="bicubic", align_corners=False)[0].clamp(0, 1)
+            out.append((t - torch.tensor(self.MEAN).view(3, 1, 1)) / torch.tensor(self.STD).view(3, 1, 1))
+        return _Features(pixel_values=torch.stack(out))
+
+
 class SyntheticTextEncoder:
     """Deterministic prompt -> [max_len, dim] embedding (hash-seeded); zero beyond the token count like Wan's
     zero-padding (wan:214-217).  NOT UMT5 / T5 / LLaVA."""
@@ -265,6 +321,14 @@ class SyntheticTextEncoder:
             self.device = torch.device(device)
         return self
 
+    def __call__(self, input_ids, attention_mask=None, **kw):
+        """HF encoder call surface (wan:212, cog:258): ``last_hidden_state`` [B, L, dim], one seeded vector per token id."""
+        ids = input_ids.cpu()
+        uniq, inv = torch.unique(ids, return_inverse=True)
+        table = torch.stack([torch.randn(self.dim, generator=torch.Generator().manual_seed(int(u) + 1)) for u in uniq])
+        h = table[inv].to(self.device, self.dtype)
+        return _EncOut(last_hidden_state=h)
+
     def embed(self, prompts: List[str], max_len: int, zero_pad=True) -> torch.Tensor:
         out = []
         for p in prompts:
@@ -277,6 +341,11 @@ class SyntheticTextEncoder:
                 e[n:] = 0
             out.append(e)
         return torch.stack(out).to(self.device, self.dtype)
+
+
+class _EncOut(SimpleNamespace):
+    def __getitem__(self, i):
+        return (self.last_hidden_state,)[i]
 
 
 class SyntheticImageEncoder:
@@ -295,3 +364,8 @@ class SyntheticImageEncoder:
         seed = int(abs(float(image_tensor.float().mean())) * 1e6) % (2 ** 31 - 1)
         g = torch.Generator().manual_seed(seed)
         return torch.randn(1, self.tokens, self.dim, generator=g).to(self.device, self.dtype)
+
+    def __call__(self, pixel_values=None, output_hidden_states=True, **kw):
+        """``CLIPVisionModel`` call surface (wan:233-234): the pipeline reads ``hidden_states[-2]``."""
+        h = torch.cat([self.embed(pv) for pv in pixel_values], dim=0)
+        return SimpleNamespace(hidden_states=[h, h, h], last_hidden_state=h)

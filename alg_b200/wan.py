@@ -212,6 +212,24 @@ class WanTransformer3DModel:
         n_pass = len(cond)
         _lib.require_cuda(*latents, *cond, *text, image)
         _, T, H, W = cond[0].shape[-4:]
+        # the engine reads fixed extents through raw pointers: refuse anything else instead of reading past a buffer
+        cfg = self._cfg
+        if not 1 <= n_pass <= 3 or len(latents) != n_pass or len(text) != n_pass:
+            raise ValueError(f"forward_passes: 1-3 passes with one latent / condition / text each, got {len(latents)}/{n_pass}/{len(text)}")
+        for p in range(n_pass):
+            lat_c, cond_c = latents[p].numel() // (T * H * W), cond[p].numel() // (T * H * W)
+            if lat_c != cfg["out_channels"] or latents[p].numel() != lat_c * T * H * W:
+                raise ValueError(f"latents[{p}]: expected {cfg['out_channels']} x {T} x {H} x {W}, got {tuple(latents[p].shape)}")
+            if cond_c != cfg["in_channels"] - cfg["out_channels"] or cond[p].numel() != cond_c * T * H * W:
+                raise ValueError(f"cond[{p}]: expected {cfg['in_channels'] - cfg['out_channels']} x {T} x {H} x {W}, got {tuple(cond[p].shape)}")
+            if tuple(text[p].reshape(-1, text[p].shape[-1]).shape) != (cfg["text_len"], cfg["text_dim"]):
+                raise ValueError(f"text[{p}]: the attention processor splits the context at text_len = {cfg['text_len']} rows of "
+                                 f"{cfg['text_dim']} (wan: max_sequence_length), got {tuple(text[p].shape)}")
+        if (image is None) != (not cfg.get("image_dim")) or (image is not None and image.shape[-1] != cfg["image_dim"]):
+            raise ValueError(f"image context: expected {'[n, %d]' % cfg['image_dim'] if cfg.get('image_dim') else 'None'}, got "
+                             f"{None if image is None else tuple(image.shape)}")
+        if H % cfg["patch_size"][1] or W % cfg["patch_size"][2] or T % cfg["patch_size"][0]:
+            raise ValueError(f"latent grid {T} x {H} x {W} is not a multiple of the patch size {cfg['patch_size']}")
         keep: List[torch.Tensor] = []
 
         def prep(t, dt):

@@ -20,8 +20,8 @@ import torch
 
 import lp_utils
 from alg_b200.pipeline_utils import (DiffusionPipelineBase, MultiPipelineCallbacks, PipelineCallback,
-                                     SyntheticImageEncoder, SyntheticTextEncoder, SyntheticVideoVAE, VideoProcessor,
-                                     WanPipelineOutput, randn_tensor)
+                                     SyntheticImageEncoder, SyntheticImageProcessor, SyntheticTextEncoder, SyntheticTokenizer,
+                                     SyntheticVideoVAE, VideoProcessor, WanPipelineOutput, randn_tensor)
 from alg_b200.schedulers import UniPCMultistepScheduler
 from alg_b200.wan import WAN_I2V_14B, WanTransformer3DModel
 
@@ -31,6 +31,21 @@ WAN_VAE_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5
                 -0.1922, -0.9497, 0.2503, -0.2921]
 WAN_VAE_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743, 3.2687, 2.1526, 2.8652, 1.5579, 1.6382,
                1.1253, 2.8251, 1.9160]
+
+
+def prompt_clean(text: str) -> str:
+    """wan:96-110: ftfy.fix_text (when ftfy is installed), double html.unescape, whitespace collapse."""
+    import html
+    import re
+
+    try:
+        import ftfy
+
+        text = ftfy.fix_text(text)
+    except ImportError:
+        pass
+    text = html.unescape(html.unescape(text)).strip()
+    return re.sub(r"\s+", " ", text).strip()
 
 
 def retrieve_latents(encoder_output, generator=None, sample_mode: str = "sample"):
@@ -53,7 +68,9 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
                  scheduler):
         self.register_modules(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, image_encoder=image_encoder,
                               transformer=transformer, scheduler=scheduler, image_processor=image_processor)
-        downs = getattr(getattr(vae, "config", None), "temperal_downsample", None)
+        downs = getattr(vae, "temperal_downsample", None)  # (sic) wan:180-181 reads the attribute off the VAE itself
+        if downs is None:
+            downs = getattr(getattr(vae, "config", None), "temperal_downsample", None)
         self.vae_scale_factor_temporal = 2 ** sum(downs) if downs is not None else 4
         self.vae_scale_factor_spatial = 2 ** len(downs) if downs is not None else 8
         self.video_processor = VideoProcessor(vae_scale_factor=self.vae_scale_factor_spatial)
@@ -62,18 +79,19 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, vae=None, image_encoder=None, transformer=None,
                         torch_dtype=torch.bfloat16, cache_dir=None, synthetic: Optional[bool] = None,
-                        allow_synthetic_aux: bool = False, seed: int = 0, device="cuda", **config_overrides):
+                        allow_synthetic_aux: bool = False, seed: int = 0, device="cuda", tokenizer=None, text_encoder=None,
+                        image_processor=None, **config_overrides):
         """run.py:56-61.  A local diffusers snapshot (directory, or hub id found under ``cache_dir``) loads the real DiT
         weights and scheduler config (alg_b200/checkpoint.py); ``synthetic=True`` (or ``ALG_SYNTHETIC=1``) builds the true
         Wan2.1-I2V-14B architecture with seeded random weights directly on ``device`` (no checkpoints exist offline)."""
         import os
 
+        from alg_b200 import checkpoint
+
         if synthetic is None:
             synthetic = os.environ.get("ALG_SYNTHETIC", "0") == "1" or str(pretrained_model_name_or_path).startswith("synthetic")
         scheduler = None
         if not synthetic:
-            from alg_b200 import checkpoint
-
             snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir)
             if snap is None:
                 raise FileNotFoundError(
@@ -91,23 +109,42 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
             vae = SyntheticVideoVAE(z_dim=16, latents_mean=WAN_VAE_MEAN, latents_std=WAN_VAE_STD, dtype=torch.float32)
         text_dim = transformer.config.text_dim
         image_dim = transformer.config.image_dim
-        pipe = cls(tokenizer=None, text_encoder=SyntheticTextEncoder(text_dim, torch_dtype),
-                   image_encoder=image_encoder or SyntheticImageEncoder(257, image_dim), image_processor=None,
-                   transformer=transformer, vae=vae, scheduler=scheduler or UniPCMultistepScheduler(flow_shift=3.0))
+        # conditioning encoders: real ones come in as objects with the transformers call surface (tokenizer / text_encoder /
+        # image_processor / image_encoder kwargs, e.g. alg_b200.encoders built from the snapshot); the synthetic stand-ins
+        # are only installed for synthetic weights or on explicit request -- never silently next to a real checkpoint
+        if (text_encoder is None or image_encoder is None) and not (synthetic or allow_synthetic_aux):
+            raise NotImplementedError(checkpoint.AUX_MESSAGE)
+        pipe = cls(tokenizer=tokenizer or SyntheticTokenizer(), text_encoder=text_encoder or SyntheticTextEncoder(text_dim, torch_dtype),
+                   image_encoder=image_encoder or SyntheticImageEncoder(257, image_dim),
+                   image_processor=image_processor or SyntheticImageProcessor(), transformer=transformer, vae=vae,
+                   scheduler=scheduler or UniPCMultistepScheduler(flow_shift=3.0))
         return pipe
 
     # ------------------------------------------------------------------------------------------------
-    # once-per-video conditioning (wan:185-316).  Real encoders are out of scope; synthetic ones stand in.
-    def _embed_text(self, prompt, num_videos_per_prompt, max_sequence_length, device, dtype):
+    # once-per-video conditioning (wan:185-316): tokenizer / text_encoder / image_processor / image_encoder are called
+    # through the transformers interfaces the reference uses, so real HF objects, the native encoders
+    # (alg_b200/encoders.py) and the synthetic stand-ins are interchangeable
+    def _get_t5_prompt_embeds(self, prompt=None, num_videos_per_prompt: int = 1, max_sequence_length: int = 512,
+                              device=None, dtype=None):
+        device = device or self._execution_device
+        dtype = dtype or self.text_encoder.dtype
         prompt = [prompt] if isinstance(prompt, str) else prompt
-        emb = self.text_encoder.embed(prompt, max_sequence_length).to(device=device, dtype=dtype or torch.bfloat16)
-        b, s, _ = emb.shape
-        return emb.repeat(1, num_videos_per_prompt, 1).view(b * num_videos_per_prompt, s, -1)
+        prompt = [prompt_clean(u) for u in prompt]
+        batch_size = len(prompt)
+        text_inputs = self.tokenizer(prompt, padding="max_length", max_length=max_sequence_length, truncation=True,
+                                     add_special_tokens=True, return_attention_mask=True, return_tensors="pt")
+        ids, mask = text_inputs.input_ids, text_inputs.attention_mask
+        seq_lens = mask.gt(0).sum(dim=1).long()
+        embeds = self.text_encoder(ids.to(device), mask.to(device)).last_hidden_state.to(dtype=dtype, device=device)
+        # zero beyond each prompt's own length, fixed [max_sequence_length] rows (wan:214-217; no mask downstream, q17)
+        embeds = torch.stack([torch.cat([u[:v], u.new_zeros(max_sequence_length - int(v), u.size(1))]) for u, v in zip(embeds, seq_lens)])
+        _, seq_len, _ = embeds.shape
+        return embeds.repeat(1, num_videos_per_prompt, 1).view(batch_size * num_videos_per_prompt, seq_len, -1)
 
     def encode_image(self, image, device=None):
         device = device or self._execution_device
-        t = image if torch.is_tensor(image) else self.video_processor.preprocess(image)
-        return self.image_encoder.embed(t).to(device)
+        feats = self.image_processor(images=image, return_tensors="pt").to(device)
+        return self.image_encoder(**feats, output_hidden_states=True).hidden_states[-2]
 
     def encode_prompt(self, prompt, negative_prompt=None, do_classifier_free_guidance: bool = True,
                       num_videos_per_prompt: int = 1, prompt_embeds=None, negative_prompt_embeds=None,
@@ -116,7 +153,7 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
         prompt = [prompt] if isinstance(prompt, str) else prompt
         batch_size = len(prompt) if prompt is not None else prompt_embeds.shape[0]
         if prompt_embeds is None:
-            prompt_embeds = self._embed_text(prompt, num_videos_per_prompt, max_sequence_length, device, dtype)
+            prompt_embeds = self._get_t5_prompt_embeds(prompt, num_videos_per_prompt, max_sequence_length, device, dtype)
         if do_classifier_free_guidance and negative_prompt_embeds is None:
             negative_prompt = negative_prompt or ""
             negative_prompt = batch_size * [negative_prompt] if isinstance(negative_prompt, str) else negative_prompt
@@ -127,7 +164,8 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
                 raise ValueError(f"`negative_prompt`: {negative_prompt} has batch size {len(negative_prompt)}, but `prompt`:"
                                  f" {prompt} has batch size {batch_size}. Please make sure that passed `negative_prompt` matches"
                                  " the batch size of `prompt`.")
-            negative_prompt_embeds = self._embed_text(negative_prompt, num_videos_per_prompt, max_sequence_length, device, dtype)
+            negative_prompt_embeds = self._get_t5_prompt_embeds(negative_prompt, num_videos_per_prompt, max_sequence_length,
+                                                                device, dtype)
         return prompt_embeds, negative_prompt_embeds
 
     # ------------------------------------------------------------------------------------------------
@@ -278,14 +316,27 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
                                          num_frames=num_frames, use_low_pass_guidance=True,
                                          lp_filter_in_latent=alg["lp_filter_in_latent"], orig_image_latents=condition,
                                          orig_image_tensor=image)
-        if alg["use_low_pass_guidance"] and strength != 0.0:  # three passes: uncond(orig), uncond(LP), text(LP)
-            conds = [condition[0], lp_latents[0], lp_latents[0]]
-            texts = [negative_prompt_embeds[0], negative_prompt_embeds[0], prompt_embeds[0]]
-        else:  # vanilla CFG
-            conds = [condition[0], condition[0]]
-            texts = [negative_prompt_embeds[0], prompt_embeds[0]]
-        noise_pred = self.transformer.forward_passes([latents[0]] * len(conds), conds, texts, image_embeds[0], int(t))
+        three = alg["use_low_pass_guidance"] and strength != 0.0
+        n_samples = latents.shape[0]
+        if three and n_samples > 1:
+            # the reference recognises a three-pass step by `noise_pred.shape[0] == 3` (wan:919): with B > 1 samples the 3B rows
+            # are chunked in two and scheduler.step fails on the shape (observed: tests/golden/loop_quirks.json)
+            raise RuntimeError(f"three-pass ALG steps support one sample per call (got {n_samples}): the reference's CFG combine "
+                               "(wan:919-924) breaks for num_videos_per_prompt > 1; shard samples across GPUs instead")
+        per_sample = []
+        for b in range(n_samples):  # independent samples: the reference batches them pass-major (wan:882-901)
+            if three:  # uncond(orig), uncond(LP), text(LP)
+                conds = [condition[b], lp_latents[b], lp_latents[b]]
+                texts = [negative_prompt_embeds[b], negative_prompt_embeds[b], prompt_embeds[b]]
+            else:  # vanilla CFG
+                conds = [condition[b], condition[b]]
+                texts = [negative_prompt_embeds[b], prompt_embeds[b]]
+            per_sample.append(self.transformer.forward_passes([latents[b]] * len(conds), conds, texts,
+                                                              image_embeds[b % image_embeds.shape[0]], int(t)))
+        noise_pred = per_sample[0] if n_samples == 1 else torch.stack(per_sample, dim=1).contiguous()  # [pass, sample, ...]
         latents = self.scheduler.step_cfg(noise_pred, guidance_scale, latents)
+        if n_samples > 1:
+            noise_pred = noise_pred.flatten(0, 1)  # the reference's row order: all samples of pass 0, then pass 1
         return latents, noise_pred
 
     @torch.no_grad()
@@ -349,8 +400,11 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
             batch_size = len(prompt)
         else:
             batch_size = prompt_embeds.shape[0]
-        if batch_size * num_videos_per_prompt != 1:
-            raise NotImplementedError("the native loop runs one sample per GPU (independent samples shard across GPUs)")
+        if batch_size != 1:
+            # wan:796-806 repeats image_embeds `batch_size` times and wan:905-908 again by the row count: the reference's own
+            # transformer call fails for a list of prompts (observed: tests/golden/loop_quirks.json, case two_prompts)
+            raise ValueError(f"a list of {batch_size} prompts is not supported (the reference's image_embeds batching, wan:905-908, "
+                             "fails for batch_size > 1); use num_videos_per_prompt or one call per prompt")
 
         prompt_embeds, negative_prompt_embeds = self.encode_prompt(
             prompt=prompt, negative_prompt=negative_prompt, do_classifier_free_guidance=self.do_classifier_free_guidance,
