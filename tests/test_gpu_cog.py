@@ -72,9 +72,10 @@ def test_forward_full_width_one_block():
     assert e_eng < max(1.5 * e_torch, 3e-3), (e_eng, e_torch)
 
 
-def _pipe(model):
+def _pipe(model, vae=None):
     from pipeline_cogvideox_image2video_lowpass import CogVideoXImageToVideoPipeline
-    pipe = CogVideoXImageToVideoPipeline.from_pretrained("synthetic", transformer=model, synthetic=True).to("cuda")
+    kw = {} if vae is None else dict(vae=vae, native_vae_encoder=False)
+    pipe = CogVideoXImageToVideoPipeline.from_pretrained("synthetic", transformer=model, synthetic=True, **kw).to("cuda")
     pipe.set_progress_bar_config(disable=True)
     return pipe
 
@@ -82,11 +83,12 @@ def _pipe(model):
 @pytest.mark.parametrize("mode", ["latent_down_up", "pixel_gaussian"])
 def test_loop_teacher_forced_per_step_latents(mode):
     """cog:1005-1140 against oracle/cog_oracle.denoise_loop, both sides consuming the oracle's x_i (teacher-forced)."""
-    from alg_b200 import lowpass
-    from oracle import cog_oracle as Co, sched_oracle
+    from oracle import cog_oracle as Co, lp_oracle, prepare_lp_oracle as P, sched_oracle
+    from oracle.stub_vae import ArithVAE
     cfg, model = _model(2)
     ocfg = _ocfg(cfg)
-    pipe = _pipe(model)
+    vae = ArithVAE("cog", dtype=torch.bfloat16)  # one VAE object for both sides (an input of prepare_lp; the native encoder
+    pipe = _pipe(model, vae)                      # has its own parity tests in test_gpu_vae.py)
     g = torch.Generator(device="cuda").manual_seed(7)
     Fr, H, W, steps, gs = 3, 8, 12, 10, 6.0
     lat0 = torch.randn(1, Fr, 16, H, W, generator=g, device="cuda").bfloat16()
@@ -99,13 +101,13 @@ def test_loop_teacher_forced_per_step_latents(mode):
     sd = model.state_dict()
     g_ref, g_mine = (torch.Generator(device="cuda").manual_seed(11) for _ in range(2))
 
-    def prepare_lp_ref(kind, sigma, k, f):  # the reference's prepare_lp with the real (CUDA) filter; VAE = the pipeline's stub
-        return pipe.prepare_lp(kind, sigma, k, f, g_ref, 9, True, alg["lp_filter_in_latent"], img_lat, image_rgb)
+    def prepare_lp_ref(kind, sigma, k, f):  # oracle/prepare_lp_oracle.py (pinned to the reference's cog:586-703): ATen filters
+        return P.cog_prepare_lp(vae, None, kind, sigma, k, f, g_ref, 9, True, alg["lp_filter_in_latent"], img_lat, image_rgb)
 
     per_step = []
     sched = sched_oracle.CogDDIMOracle()
     Co.denoise_loop(lambda x, text, t: Co.forward(sd, ocfg, x, text, t.cuda(), rope), sched, lat0, img_lat, pos, neg, steps, gs,
-                    alg, prepare_lp_ref, lowpass.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
+                    alg, prepare_lp_ref, lp_oracle.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
     xs = [lat0] + [p[0] for p in per_step]
     pipe.scheduler.set_timesteps(steps, device="cuda")
     n3 = 0
@@ -169,8 +171,8 @@ def test_config1_full_architecture_two_steps():
     """BASELINE.json configs[0] on the GPU: the TRUE CogVideoX-5b-I2V architecture (42 layers, 48 x 64, ff 12288, 226 text
     tokens), 9 frames / 2 steps / gs 6, ALG down_up f=0.25 in latent with the shipped interval [0, 0.04] -> step 0 runs
     three passes, step 1 two (SURVEY section 4 KAT), teacher-forced against the oracle loop (eager PyTorch bf16)."""
-    from alg_b200 import cogvideox, lowpass
-    from oracle import cog_oracle as Co, sched_oracle
+    from alg_b200 import cogvideox
+    from oracle import cog_oracle as Co, lp_oracle, prepare_lp_oracle as P, sched_oracle
     model = cogvideox.CogVideoXTransformer3DModel.from_synthetic(seed=11, device="cuda")
     ocfg = Co.CogConfig()
     pipe = _pipe(model)
@@ -187,7 +189,7 @@ def test_config1_full_architecture_two_steps():
     sd = model.state_dict()
 
     def prepare_lp_ref(kind, sigma, k, f):
-        return pipe.prepare_lp(kind, sigma, k, f, None, 9, True, True, img_lat, None)
+        return P.cog_prepare_lp(None, None, kind, sigma, k, f, None, 9, True, True, img_lat, None)
 
     per_step, calls = [], []
     sd32 = {k: v.float() for k, v in sd.items()}
@@ -197,7 +199,7 @@ def test_config1_full_architecture_two_steps():
         return Co.forward(sd, ocfg, x, text, t.cuda(), rope)
 
     Co.denoise_loop(transformer, sched_oracle.CogDDIMOracle(), lat0, img_lat, pos, neg, steps, gs, alg, prepare_lp_ref,
-                    lowpass.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
+                    lp_oracle.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
     xs = [lat0] + [p[0] for p in per_step]
     pipe.scheduler.set_timesteps(steps, device="cuda")
     step32 = sched_oracle.CogDDIMOracle()

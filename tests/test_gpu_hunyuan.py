@@ -89,9 +89,8 @@ def _pipe(model):
 def test_loop_teacher_forced_per_step_latents(true_cfg):
     """hy:1126-1270 against oracle/hunyuan_oracle.denoise_loop: single-pass ALG branch (the shipped yaml) and the
     true-CFG 3-pass / 2-pass branch, both sides consuming the oracle's x_i."""
-    from alg_b200 import lowpass
     from alg_b200.schedulers import FlowMatchEulerDiscreteScheduler
-    from oracle import hunyuan_oracle as Ho, sched_oracle
+    from oracle import hunyuan_oracle as Ho, lp_oracle, prepare_lp_oracle as P, sched_oracle
     cfg, model = _model(2)
     ocfg = _ocfg(cfg)
     pipe = _pipe(model)
@@ -108,12 +107,12 @@ def test_loop_teacher_forced_per_step_latents(true_cfg):
         return Ho.forward(sd, ocfg, xx, timestep, emb, m, pl, guidance)
 
     def lp_filter(img, kind, sigma, k, f):
-        return lowpass.apply_low_pass_filter(img, kind, sigma, k, f)
+        return P.hunyuan_prepare_lp(2, kind, sigma, k, f, True, True, img)  # pinned to hy:650-792 by the loop fixtures
 
     per_step = []
     sched = sched_oracle.FlowEulerOracle(shift=7.0)
     Ho.denoise_loop(transformer, sched, lat0, image_latents, pos, neg, steps, 6.0, true_cfg, ALG, lp_filter,
-                    lowpass.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
+                    lp_oracle.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
     xs = [lat0] + [p[0] for p in per_step]
     import numpy as np
     pipe.scheduler.set_timesteps(sigmas=np.linspace(1.0, 0.0, steps + 1)[:-1], device="cuda")

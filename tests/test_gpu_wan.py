@@ -186,9 +186,9 @@ def test_loop_non_interval_schedules_and_pixel_space(mode):
     q8: `k * s` stays a float fraction of H) and the pixel-space branch (wan:493-540: filter the RGB frame, VAE-encode +
     `sample(generator)` every step, rebuild the 4-channel mask), teacher-forced against the oracle loop."""
     import __graft_entry__ as G
-    from alg_b200 import lowpass
     from alg_b200.schedulers import UniPCMultistepScheduler
-    from oracle import sched_oracle, wan_oracle as W
+    from oracle import lp_oracle, prepare_lp_oracle as P, sched_oracle, wan_oracle as W
+    from oracle.stub_vae import ArithVAE
     from pipeline_wan_image2video_lowpass import WanImageToVideoPipeline
     cfg, model, inp, alg = _problem(6)
     steps, gs = 8, 5.0
@@ -198,7 +198,8 @@ def test_loop_non_interval_schedules_and_pixel_space(mode):
     else:
         alg = dict(alg, lp_strength_schedule_type="linear", schedule_linear_start_weight=1.0, schedule_linear_end_weight=0.2,
                    schedule_linear_end_time=0.6, lp_resize_factor=0.3)
-    pipe = WanImageToVideoPipeline.from_pretrained("synthetic", transformer=model, synthetic=True)
+    vae = ArithVAE("wan")  # the same arithmetic VAE object on both sides (it is an input of prepare_lp, not under test)
+    pipe = WanImageToVideoPipeline.from_pretrained("synthetic", transformer=model, synthetic=True, vae=vae)
     pipe.scheduler = UniPCMultistepScheduler.from_config(pipe.scheduler.config, flow_shift=5.0)
     pipe.to("cuda")
     pipe._guidance_scale = gs
@@ -209,13 +210,14 @@ def test_loop_non_interval_schedules_and_pixel_space(mode):
     ocfg = W.WanConfig(**cfg)
     sd = model.state_dict()
 
-    def lp_filter_ref(c, kind, sigma, k, f):  # the reference's prepare_lp around the real (CUDA) filter and the VAE stub
-        return pipe.prepare_lp(kind, sigma, k, f, g_ref, 9, True, alg["lp_filter_in_latent"], c, image)
+    def prepare_lp_ref(kind, sigma, k, f):  # oracle/prepare_lp_oracle.py (pinned to the reference's wan:451-559): ATen filters
+        return P.wan_prepare_lp(vae, 1, kind, sigma, k, f, g_ref, 9, True, alg["lp_filter_in_latent"], cond, image)
 
     per_step = []
     W.denoise_loop(lambda x, t, text, img: W.forward(sd, ocfg, x, t.to(x.device), text, img), sched_oracle.UniPCOracle(flow_shift=5.0),
                    inp["latents"], cond, inp["prompt_embeds"], inp["negative_prompt_embeds"], inp["image_embeds"], steps, gs,
-                   alg, lp_filter_ref, lowpass.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)))
+                   alg, None, lp_oracle.get_lp_strength, on_step=lambda i, t, lat, npred: per_step.append((lat, npred)),
+                   prepare_lp=prepare_lp_ref)
     xs = [inp["latents"]] + [p[0] for p in per_step]
     sched = pipe.scheduler
     sched.set_timesteps(steps, device="cuda")
