@@ -32,6 +32,39 @@ def broadcast_state_dict(sd: Dict[str, torch.Tensor], src: int = 0) -> Dict[str,
     return sd
 
 
+def arena_state_dict(shapes_dtypes: Dict[str, tuple], device, align: int = 256):
+    """One flat byte arena holding every tensor of a model (name -> (shape, dtype)); returns (views, arena).
+
+    The views are ordinary tensors (16-byte-aligned, as the TMA descriptors need) that ``load_state_dict`` borrows; the
+    arena is what crosses NVLink: ONE ``dist.broadcast`` instead of one per parameter (the Wan DiT has ~1 100)."""
+    offs, total = {}, 0
+    for name in sorted(shapes_dtypes):
+        shape, dtype = shapes_dtypes[name]
+        n = 1
+        for d in shape:
+            n *= int(d)
+        offs[name] = total
+        total += (n * torch.empty((), dtype=dtype).element_size() + align - 1) // align * align
+    arena = torch.empty(total, dtype=torch.uint8, device=device)
+    views = {}
+    for name, off in offs.items():
+        shape, dtype = shapes_dtypes[name]
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        views[name] = arena[off:off + nbytes].view(dtype).view(*shape)
+    return views, arena
+
+
+def broadcast_arena(arena: torch.Tensor, src: int = 0, chunk_bytes: int = 1 << 31) -> torch.Tensor:
+    """Broadcast a flat arena from ``src`` (in <= 2 GiB pieces: NCCL counts elements in 32-bit-friendly chunks)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        for o in range(0, arena.numel(), chunk_bytes):
+            dist.broadcast(arena[o:o + chunk_bytes], src=src)
+    return arena
+
+
 def max_over_ranks(values: Sequence[float], device) -> list:
     """Device-timed milliseconds -> the slowest rank's (what a multi-GPU throughput number must be computed from)."""
     t = torch.tensor(list(values), device=device, dtype=torch.float64)

@@ -14,6 +14,42 @@ import torch
 from . import _lib
 
 
+# ------------------------------------------------------------------------------------------------------
+# per-kernel-class device timing for the Python sequencers (CogVideoX / HunyuanVideo; the Wan engine times its own
+# classes in C++): CUDA events on the launching stream around every GEMM / attention launch while enabled
+# ------------------------------------------------------------------------------------------------------
+_PROFILE = None
+
+
+def profile_start():
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop():
+    """-> {class: {"ms", "launches", "flops"}} (synchronises the device)."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE or {}, None
+    torch.cuda.synchronize()
+    return {k: {"ms": sum(e0.elapsed_time(e1) for e0, e1, _ in v), "launches": len(v), "flops": sum(f for _, _, f in v)}
+            for k, v in rec.items()}
+
+
+class _Span:
+    def __init__(self, key, flops):
+        self.key, self.flops = key, flops
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _PROFILE is not None:
+            self.e1.record()
+            _PROFILE.setdefault(self.key, []).append((self.e0, self.e1, self.flops))
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = _lib.EPI_NONE,
          residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
          bias_per_row: bool = False, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
@@ -59,7 +95,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
             g.gate_split_row = int(gate_split_row)
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.stride(0) == out.stride(0)
-    with torch.cuda.device(a.device):
+    with torch.cuda.device(a.device), _Span("gemm", 2 * g.M * g.N * g.K):
         _lib.check(_lib.lib().alg_gemm_bf16(C.byref(g), _lib.stream_ptr(a.device)))
     return out
 
@@ -87,7 +123,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, n_kv: Optio
     a.o_bs, a.o_rs = out.stride(0), out.stride(1)
     a.scale = scale if scale is not None else 1.0 / math.sqrt(D)
     a.accumulate = int(accumulate)
-    with torch.cuda.device(q.device):
+    with torch.cuda.device(q.device), _Span("self_attention" if n_kv > 1024 else "short_attention", 4 * B * H * Nq * n_kv * D):
         _lib.check(_lib.lib().alg_attention_bf16(C.byref(a), _lib.stream_ptr(q.device)))
     return out
 

@@ -27,6 +27,17 @@ def _worker(rank, world, port, q):
         if rank != 0:  # non-root ranks start from garbage of the right shape, like bench.py's torch.empty
             sd = {k: torch.full_like(v, float("nan")) for k, v in sd.items()}
         D.broadcast_state_dict(sd)
+        # flat arena: one collective for the whole model, views stay aligned and typed
+        views, arena = D.arena_state_dict({"w": ((5, 3), torch.float32), "b": ((7,), torch.bfloat16), "s": ((1, 2, 4), torch.float32)}, "cpu")
+        if rank == 0:
+            for i, k in enumerate(sorted(views)):
+                views[k].copy_(torch.arange(views[k].numel(), dtype=torch.float32).view(views[k].shape) + 10 * i)
+        else:
+            arena.fill_(255)
+        D.broadcast_arena(arena, chunk_bytes=64)
+        assert all(v.data_ptr() % 16 == 0 for v in views.values())
+        assert [float(views[k].float().flatten()[1]) for k in sorted(views)] == [1.0, 11.0, 21.0]
+        assert views["w"].dtype == torch.float32 and views["b"].dtype == torch.bfloat16 and views["s"].shape == (1, 2, 4)
         ms = D.max_over_ranks([10.0 + rank, 5.0 - rank], "cpu")
         q.put((rank, D.sample_seed(rank), {k: v.float().sum().item() for k, v in sd.items()}, ms,
                D.aggregate_rate(81 / 50, world, ms[0])))
