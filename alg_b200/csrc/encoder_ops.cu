@@ -1,0 +1,366 @@
+// Kernels of the once-per-video conditioning encoders: UMT5 / T5 text encoder and CLIP vision / text
+// transformers (reference call sites wan:185-234, cog:228-268, hy:282-452; the networks themselves live in
+// transformers==4.48.1, requirements.txt).  The big linears run on the tcgen05 GEMM (gemm.cu); this file holds what is
+// left around them.  None of it is on the per-step path: a few hundred tokens, once per video -- plain CUDA-core kernels,
+// written for fidelity to the eager op chain (where each bf16 rounding happens), not for the tensor pipe.
+//
+//   t5_rms_norm_kernel       T5LayerNorm: h = bf16(x * rsqrt(mean(x^2) + eps)); y = bf16(w * h)
+//   gather_rows_kernel       nn.Embedding lookup
+//   small_attention_kernel   softmax(scale * q k^T + rel_bias[h, j - i] + mask) v for <= 768 keys, head_dim <= 128, bf16 or
+//                            fp32 (T5 attention has an additive relative-position bias and no scaling, CLIP-ViT-H has
+//                            head_dim 80 and runs in fp32, CLIP text is causal: none of it fits the flash kernel's shapes)
+//   layer_norm_f32_kernel, bias_act_f32_kernel, split3_kernel   the fp32 CLIP vision path: LayerNorm and bias / GELU /
+//                            residual in fp32, and the 3-term bf16 split [hi | hi | lo] x [hi | lo | hi] that lets the bf16
+//                            tensor-core GEMM (fp32 accumulation) reproduce an fp32 nn.Linear to ~1e-5
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace alg {
+namespace enc {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < THREADS / 32; ++i) t += red[i];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256) t5_rms_norm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                          int d, int64_t ld_x, int64_t ld_out, float eps,
+                                                          const __nv_bfloat16* __restrict__ w) {
+  __shared__ float red[8];
+  const __nv_bfloat16* xr = x + (int64_t)blockIdx.x * ld_x;
+  __nv_bfloat16* orow = out + (int64_t)blockIdx.x * ld_out;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < d; i += 256) {
+    const float v = __bfloat162float(xr[i]);
+    ss += v * v;
+  }
+  const float r = rsqrtf(block_sum<256>(ss, red) / (float)d + eps);
+  for (int i = threadIdx.x; i < d; i += 256) {
+    const float h = bf16_round(__bfloat162float(xr[i]) * r);  // hidden_states.to(weight.dtype)
+    orow[i] = __float2bfloat16_rn(__bfloat162float(w[i]) * h);
+  }
+}
+
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ table, const int64_t* __restrict__ ids,
+                                   __nv_bfloat16* __restrict__ out, int d, int64_t vocab) {
+  int64_t id = ids[blockIdx.x];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const uint4* src = reinterpret_cast<const uint4*>(table + id * d);
+  uint4* dst = reinterpret_cast<uint4*>(out + (int64_t)blockIdx.x * d);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+// ---- small attention ------------------------------------------------------------------------------------------------
+constexpr int kWarps = 4, kRowsPerWarp = 4, kRowsPerCta = kWarps * kRowsPerWarp * 2;  // two row groups per warp
+constexpr int kMaxKeysPerLane = 24;                                                  // <= 768 keys
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+struct SmallAttn {
+  const void *q, *k, *v;
+  void* out;
+  int64_t q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;  // element strides: batch, token row (head h starts at h * D)
+  int L_q, L_kv, D, Lp;                                    // Lp = keys padded to 32
+  float scale;
+  const float* rel_bias;  // [H, 2 * L_kv - 1]: added to the score of (query i, key j) at index j - i + L_kv - 1; or NULL
+  const int32_t* kv_valid;  // [B] keys >= kv_valid[b] are masked (right padding); or NULL
+  int causal;
+};
+
+template <typename T, int KPL>
+__global__ void __launch_bounds__(kWarps * 32) small_attention_kernel(const SmallAttn p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  T* sKt = reinterpret_cast<T*>(smem_raw);               // [D][Lp]
+  T* sV = sKt + (size_t)p.D * p.Lp;                      // [Lp][D]
+  float* sQ = reinterpret_cast<float*>(sV + (size_t)p.Lp * p.D);  // [kWarps][kRowsPerWarp][D]
+  float* sP = sQ + kWarps * kRowsPerWarp * p.D;          // [kWarps][kRowsPerWarp][Lp]
+  const int h = blockIdx.y, b = blockIdx.z, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = p.D, Lp = p.Lp;
+  const T* kb = reinterpret_cast<const T*>(p.k) + (int64_t)b * p.k_bs + (int64_t)h * D;
+  const T* vb = reinterpret_cast<const T*>(p.v) + (int64_t)b * p.v_bs + (int64_t)h * D;
+  for (int idx = threadIdx.x; idx < Lp * D; idx += blockDim.x) {
+    const int j = idx / D, d = idx - j * D;
+    const bool ok = j < p.L_kv;
+    sKt[(size_t)d * Lp + j] = ok ? kb[(int64_t)j * p.k_rs + d] : from_f<T>(0.f);
+    sV[idx] = ok ? vb[(int64_t)j * p.v_rs + d] : from_f<T>(0.f);
+  }
+  __syncthreads();
+  const int n_valid = p.kv_valid ? min(p.kv_valid[b], p.L_kv) : p.L_kv;
+  float* myQ = sQ + warp * kRowsPerWarp * D;
+  float* myP = sP + warp * kRowsPerWarp * Lp;
+  const T* qb = reinterpret_cast<const T*>(p.q) + (int64_t)b * p.q_bs + (int64_t)h * D;
+  T* ob = reinterpret_cast<T*>(p.out) + (int64_t)b * p.o_bs + (int64_t)h * D;
+  for (int grp = 0; grp < 2; ++grp) {
+    const int row0 = blockIdx.x * kRowsPerCta + (grp * kWarps + warp) * kRowsPerWarp;
+    if (row0 >= p.L_q) continue;  // warp-uniform
+    for (int idx = lane; idx < kRowsPerWarp * D; idx += 32) {
+      const int r = idx / D, d = idx - r * D;
+      myQ[idx] = row0 + r < p.L_q ? to_f<T>(qb[(int64_t)(row0 + r) * p.q_rs + d]) : 0.f;
+    }
+    __syncwarp();
+    float s[kRowsPerWarp][KPL];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r)
+#pragma unroll
+      for (int c = 0; c < KPL; ++c) s[r][c] = 0.f;
+    for (int d = 0; d < D; ++d) {
+      float kv[KPL];
+#pragma unroll
+      for (int c = 0; c < KPL; ++c) kv[c] = (c * 32 < Lp) ? to_f<T>(sKt[(size_t)d * Lp + c * 32 + lane]) : 0.f;
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        const float qv = myQ[r * D + d];
+#pragma unroll
+        for (int c = 0; c < KPL; ++c) s[r][c] = fmaf(qv, kv[c], s[r][c]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const int i = row0 + r;
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < KPL; ++c) {
+        const int j = c * 32 + lane;
+        float x = s[r][c];
+        if (sizeof(T) == 2) x = bf16_round(x);  // the q k^T matmul returns a bf16 tensor
+        x *= p.scale;
+        if (p.rel_bias && j < p.L_kv && i < p.L_q) {
+          x += p.rel_bias[(int64_t)h * (2 * p.L_kv - 1) + (j - i + p.L_kv - 1)];
+          if (sizeof(T) == 2) x = bf16_round(x);  // scores += position_bias, in the model dtype
+        }
+        if (j >= n_valid || (p.causal && j > i)) x = -INFINITY;
+        s[r][c] = x;
+        m = fmaxf(m, x);
+      }
+      m = warp_max(m);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < KPL; ++c) {
+        const float e = (s[r][c] == -INFINITY) ? 0.f : __expf(s[r][c] - m);
+        s[r][c] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+#pragma unroll
+      for (int c = 0; c < KPL; ++c)
+        if (c * 32 < Lp) myP[r * Lp + c * 32 + lane] = to_f<T>(from_f<T>(s[r][c] * inv));  // softmax(fp32).type_as(scores)
+    }
+    __syncwarp();
+    // O = P V: lanes own head_dim columns d = lane + 32 c
+    float o[kRowsPerWarp][4];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[r][c] = 0.f;
+    for (int j = 0; j < n_valid; ++j) {
+      float vv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) vv[c] = (c * 32 + lane < D) ? to_f<T>(sV[(size_t)j * D + c * 32 + lane]) : 0.f;
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        const float pv = myP[r * Lp + j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[r][c] = fmaf(pv, vv[c], o[r][c]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r)
+      if (row0 + r < p.L_q)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c * 32 + lane < D) ob[(int64_t)(row0 + r) * p.o_rs + c * 32 + lane] = from_f<T>(o[r][c]);
+    __syncwarp();
+  }
+}
+
+// ---- fp32 path of the CLIP vision tower ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layer_norm_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int d,
+                                                             float eps, const float* __restrict__ w,
+                                                             const float* __restrict__ b) {
+  __shared__ float red[8];
+  const float* xr = x + (int64_t)blockIdx.x * d;
+  float* orow = out + (int64_t)blockIdx.x * d;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < d; i += 256) s += xr[i];
+  const float mean = block_sum<256>(s, red) / (float)d;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < d; i += 256) {
+    const float c = xr[i] - mean;
+    ss += c * c;
+  }
+  const float r = rsqrtf(block_sum<256>(ss, red) / (float)d + eps);
+  for (int i = threadIdx.x; i < d; i += 256) orow[i] = (xr[i] - mean) * r * w[i] + b[i];
+}
+
+// x[r, c] = act(x[r, c] + bias[c]) (+ residual[r, c]);  act: 0 none, 1 GELU (erf), 2 quick-GELU
+__global__ void bias_act_f32_kernel(float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ res,
+                                    int64_t n, int cols, int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i] + (bias ? bias[i % cols] : 0.f);
+    if (act == 1) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    else if (act == 2) v = v / (1.0f + expf(-1.702f * v));
+    if (res) v += res[i];
+    x[i] = v;
+  }
+}
+
+// out[r, 0:K] = hi(x), out[r, K:2K] = order ? lo(x) : hi(x), out[r, 2K:3K] = order ? hi(x) : lo(x)   (bf16)
+// activations use order 0 -> [hi | hi | lo], weights order 1 -> [hi | lo | hi]: the K-concatenated product is
+// hi*hi + hi*lo + lo*hi, an fp32 product up to the dropped lo*lo term (2^-16 relative).
+__global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows, int K, int order) {
+  const int64_t n = rows * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / K;
+    const int c = (int)(i - r * K);
+    const float v = x[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + r * 3 * (int64_t)K;
+    o[c] = hi;
+    o[K + c] = order ? lo : hi;
+    o[2 * K + c] = order ? hi : lo;
+  }
+}
+
+__global__ void mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                __nv_bfloat16* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(__bfloat162float(a[i]) * __bfloat162float(b[i]));
+}
+
+static int grid_for(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 8); }
+
+template <typename T>
+static int launch_small_attention(const SmallAttn& p, int B, int H, cudaStream_t st) {
+  const size_t smem = 2 * (size_t)p.D * p.Lp * sizeof(T) + (size_t)kWarps * kRowsPerWarp * (p.D + p.Lp) * sizeof(float);
+  ALG_REQUIRE(smem <= 227 * 1024, "small_attention: keys x head_dim do not fit in shared memory (this kernel serves the "
+                                  "conditioning encoders: <= 768 keys)");
+  const int kpl = p.Lp / 32;
+  dim3 grid((unsigned)((p.L_q + kRowsPerCta - 1) / kRowsPerCta), (unsigned)H, (unsigned)B);
+#define ALG_SA_CASE(K)                                                                                             \
+  if (kpl <= K) {                                                                                                  \
+    ALG_CUDA_OK(cudaFuncSetAttribute(small_attention_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    small_attention_kernel<T, K><<<grid, kWarps * 32, smem, st>>>(p);                                              \
+    ALG_LAUNCH_OK();                                                                                               \
+    return 0;                                                                                                      \
+  }
+  ALG_SA_CASE(4)
+  ALG_SA_CASE(9)
+  ALG_SA_CASE(16)
+  ALG_SA_CASE(24)
+#undef ALG_SA_CASE
+  ALG_REQUIRE(false, "small_attention: more than 768 keys");
+}
+
+}  // namespace enc
+}  // namespace alg
+
+using namespace alg;
+
+extern "C" int alg_t5_rms_norm_bf16(const void* x, int64_t ld_x, void* out, int64_t ld_out, int64_t rows, int d, float eps,
+                                    const void* weight, void* stream) {
+  ALG_REQUIRE(x && out && weight && rows >= 0 && d > 0 && ld_x >= d && ld_out >= d, "t5_rms_norm: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  if (rows == 0) return 0;
+  enc::t5_rms_norm_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), d, ld_x, ld_out, eps,
+      reinterpret_cast<const __nv_bfloat16*>(weight));
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_gather_rows_bf16(const void* table, int64_t vocab, const int64_t* ids, void* out, int64_t rows, int d,
+                                    void* stream) {
+  ALG_REQUIRE(table && ids && out && rows >= 0 && d > 0 && d % 8 == 0 && vocab > 0, "gather_rows: bad arguments (d % 8 == 0)");
+  ALG_REQUIRE(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "gather_rows: 16-byte alignment");
+  if (int rc = alg_check_device()) return rc;
+  if (rows == 0) return 0;
+  enc::gather_rows_kernel<<<(unsigned)rows, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(table), ids, reinterpret_cast<__nv_bfloat16*>(out), d, vocab);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_small_attention(const alg_small_attention_t* a, void* stream) {
+  ALG_REQUIRE(a && a->q && a->k && a->v && a->out, "small_attention: null pointer");
+  ALG_REQUIRE(a->dtype == ALG_BF16 || a->dtype == ALG_F32, "small_attention: dtype must be bf16 or f32");
+  ALG_REQUIRE(a->batch > 0 && a->heads > 0 && a->n_q > 0 && a->n_kv > 0 && a->head_dim > 0 && a->head_dim <= 128,
+              "small_attention: empty problem or head_dim > 128");
+  ALG_REQUIRE(a->batch <= 65535 && a->heads <= 65535, "small_attention: batch / heads exceed the grid limits");
+  if (int rc = alg_check_device()) return rc;
+  enc::SmallAttn p;
+  p.q = a->q; p.k = a->k; p.v = a->v; p.out = a->out;
+  p.q_bs = a->q_bs; p.q_rs = a->q_rs; p.k_bs = a->k_bs; p.k_rs = a->k_rs;
+  p.v_bs = a->v_bs; p.v_rs = a->v_rs; p.o_bs = a->o_bs; p.o_rs = a->o_rs;
+  p.L_q = (int)a->n_q; p.L_kv = (int)a->n_kv; p.D = a->head_dim; p.Lp = ((int)a->n_kv + 31) / 32 * 32;
+  p.scale = a->scale; p.rel_bias = a->rel_bias; p.kv_valid = a->kv_valid; p.causal = a->causal;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->dtype == ALG_BF16) return enc::launch_small_attention<__nv_bfloat16>(p, a->batch, a->heads, st);
+  return enc::launch_small_attention<float>(p, a->batch, a->heads, st);
+}
+
+extern "C" int alg_layer_norm_f32(const float* x, float* out, int64_t rows, int d, float eps, const float* weight,
+                                  const float* bias, void* stream) {
+  ALG_REQUIRE(x && out && weight && bias && rows >= 0 && d > 0, "layer_norm_f32: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  if (rows == 0) return 0;
+  enc::layer_norm_f32_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, d, eps, weight, bias);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_bias_act_f32(float* x, const float* bias, const float* residual, int64_t rows, int cols, int act,
+                                void* stream) {
+  ALG_REQUIRE(x && rows >= 0 && cols > 0 && act >= 0 && act <= 2, "bias_act_f32: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  if (rows == 0) return 0;
+  enc::bias_act_f32_kernel<<<enc::grid_for(rows * cols), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, bias, residual, rows * cols, cols, act);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_split3_bf16(const float* x, void* out, int64_t rows, int K, int weight_order, void* stream) {
+  ALG_REQUIRE(x && out && rows >= 0 && K > 0, "split3: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  if (rows == 0) return 0;
+  enc::split3_kernel<<<enc::grid_for(rows * K), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), rows, K, weight_order);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_mul_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  ALG_REQUIRE(a && b && out && n >= 0, "mul_bf16: null pointer");
+  if (int rc = alg_check_device()) return rc;
+  if (n == 0) return 0;
+  enc::mul_bf16_kernel<<<enc::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b),
+      reinterpret_cast<__nv_bfloat16*>(out), n);
+  ALG_LAUNCH_OK();
+  return 0;
+}

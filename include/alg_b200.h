@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ALG_B200_ABI_VERSION 3
+#define ALG_B200_ABI_VERSION 4
 
 typedef enum { ALG_F32 = 0, ALG_BF16 = 1, ALG_F16 = 2 } alg_dtype_t;
 
@@ -275,6 +275,54 @@ int alg_mean_rows_bf16(const void* x, int64_t rows, int d, int64_t ld, void* out
 
 /* dst[r, 0:d] = src[r, 0:d] for rows rows, bf16, 16-byte vectorised (sequence concat). */
 int alg_copy_rows_bf16(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int d, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Once-per-video conditioning encoders: UMT5 / T5 text encoder  */
+/* and CLIP vision / text towers -- the networks `self.text_encoder(...)`,       */
+/* `self.image_encoder(...)` run at wan:212 / wan:233, cog:258, hy:333-452 (in   */
+/* transformers==4.48.1).  The linears are alg_gemm_bf16; these are the ops      */
+/* around them.  Host sequencing: alg_b200/encoders.py.                          */
+/* ------------------------------------------------------------------------- */
+
+/* T5LayerNorm: h = bf16(x * rsqrt(mean(x^2) + eps)) (fp32 statistics); out = bf16(weight * h).  bf16 rows of length d. */
+int alg_t5_rms_norm_bf16(const void* x, int64_t ld_x, void* out, int64_t ld_out, int64_t rows, int d, float eps,
+                         const void* weight, void* stream);
+
+/* nn.Embedding: out[r, :] = table[ids[r], :] (bf16 rows of d elements, d % 8 == 0; ids int64 on the device). */
+int alg_gather_rows_bf16(const void* table, int64_t vocab, const int64_t* ids, void* out, int64_t rows, int d, void* stream);
+
+/* softmax(scale * q k^T + rel_bias + mask) v for short sequences (<= 768 keys, head_dim <= 128), bf16 or fp32, with the
+ * eager op chain's roundings in bf16 mode (q k^T -> bf16, + bias -> bf16, softmax in fp32 -> bf16, P V -> bf16).
+ * q / k / v / out: element (b, token, h, d) at ptr + b * bs + token * rs + h * head_dim + d.
+ * rel_bias (optional) fp32 [heads, 2 * n_kv - 1]: the T5 relative-position bias of (query i, key j) sits at j - i + n_kv - 1.
+ * kv_valid (optional) int32 [batch]: keys >= kv_valid[b] are masked (right-padded prompts).  causal: keys j > i masked. */
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int32_t dtype; /* ALG_BF16 or ALG_F32 */
+  int32_t batch, heads, head_dim;
+  int64_t n_q, n_kv;
+  int64_t q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;
+  float scale;
+  const float* rel_bias;
+  const int32_t* kv_valid;
+  int32_t causal;
+} alg_small_attention_t;
+int alg_small_attention(const alg_small_attention_t* a, void* stream);
+
+/* fp32 path of the CLIP vision tower (run.py:48 loads image_encoder in float32): */
+/* out = LN(x) * weight + bias over fp32 rows of length d */
+int alg_layer_norm_f32(const float* x, float* out, int64_t rows, int d, float eps, const float* weight, const float* bias,
+                       void* stream);
+/* in place: x = act(x + bias[col]) (+ residual); act 0 none, 1 GELU (erf), 2 quick-GELU; bias / residual may be NULL */
+int alg_bias_act_f32(float* x, const float* bias, const float* residual, int64_t rows, int cols, int act, void* stream);
+/* fp32 [rows, K] -> bf16 [rows, 3K]: [hi | hi | lo] (weight_order 0, activations) or [hi | lo | hi] (1, weights); the
+ * K-concatenated bf16 GEMM with fp32 accumulation then equals the fp32 product up to the dropped lo * lo term (2^-16). */
+int alg_split3_bf16(const float* x, void* out, int64_t rows, int K, int weight_order, void* stream);
+/* out = bf16(a * b) elementwise (T5 gated-GELU feed-forward: gelu(wi_0 x) * wi_1 x) */
+int alg_mul_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Wan2.1 I2V DiT engine: WanTransformer3DModel.forward (call site wan:910-917) */
