@@ -24,9 +24,16 @@ def resolve_snapshot(path: str, cache_dir: Optional[str] = None) -> Optional[str
     if os.path.isdir(path) and os.path.isdir(os.path.join(path, "transformer")):
         return path
     if cache_dir:
-        root = os.path.join(cache_dir, "models--" + path.replace("/", "--"), "snapshots")
+        repo = os.path.join(cache_dir, "models--" + path.replace("/", "--"))
+        root = os.path.join(repo, "snapshots")
         if os.path.isdir(root):
-            for rev in sorted(os.listdir(root)):
+            revs = sorted(os.listdir(root))
+            ref = os.path.join(repo, "refs", "main")  # the revision the hub's `main` pointed at when it was cached
+            if os.path.isfile(ref):
+                main = open(ref).read().strip()
+                if main in revs:
+                    revs = [main] + [r for r in revs if r != main]
+            for rev in revs:
                 cand = os.path.join(root, rev)
                 if os.path.isdir(os.path.join(cand, "transformer")):
                     return cand
@@ -136,5 +143,43 @@ def build_from_snapshot(model_cls, scheduler_cls, snapshot: str, device="cuda"):
     return transformer, scheduler_cls.from_config(scheduler_config(snapshot))
 
 
-AUX_MESSAGE = ("the VAE and the text / image encoders are not built (SURVEY 8(f).1, 8(f).3): pass real `vae=` / encoder objects, "
-               "or allow_synthetic_aux=True for shape-only stand-ins (latent-space runs with your own prompt_embeds)")
+AUX_MESSAGE = ("this snapshot has no loadable VAE / text encoder / image encoder for the native loaders (the Wan / Hunyuan VAEs and "
+               "the LLaVA encoder are not built, SURVEY 8(f)): pass real `vae=` / `text_encoder=` / `image_encoder=` objects (anything "
+               "with the transformers / diffusers call surface), or allow_synthetic_aux=True for shape-only stand-ins "
+               "(latent-space runs with your own prompt_embeds / image_embeds)")
+
+
+def load_text_stack(snapshot: str, encoder_cls, device="cuda", tokenizer=None):
+    """(tokenizer, native text encoder) from ``<snapshot>/tokenizer`` + ``<snapshot>/text_encoder``; (tokenizer, None) when the
+    encoder folder is missing.  The tokenizer is transformers' own (host-side text processing) unless one is handed in."""
+    tdir, edir = os.path.join(snapshot, "tokenizer"), os.path.join(snapshot, "text_encoder")
+    if not os.path.isdir(edir) or (tokenizer is None and not os.path.isdir(tdir)):
+        return tokenizer, None
+    if tokenizer is None:
+        from transformers import AutoTokenizer
+
+        tokenizer = AutoTokenizer.from_pretrained(tdir)
+    return tokenizer, encoder_cls.from_pretrained(snapshot, device=device)
+
+
+def load_image_stack(snapshot: str, encoder_cls, device="cuda", image_processor=None):
+    """(image_processor, native CLIP vision tower) from ``<snapshot>/image_processor`` + ``<snapshot>/image_encoder``."""
+    pdir, edir = os.path.join(snapshot, "image_processor"), os.path.join(snapshot, "image_encoder")
+    if not os.path.isdir(edir) or (image_processor is None and not os.path.isdir(pdir)):
+        return image_processor, None
+    if image_processor is None:
+        from transformers import CLIPImageProcessor
+
+        image_processor = CLIPImageProcessor.from_pretrained(pdir)
+    return image_processor, encoder_cls.from_pretrained(snapshot, device=device)
+
+
+def save_component(snapshot: str, subfolder: str, config: dict, state_dict: Dict[str, torch.Tensor]) -> None:
+    """Write ``<snapshot>/<subfolder>/{config.json, model.safetensors}`` (transformers layout; used by the tests)."""
+    from safetensors.torch import save_file
+
+    folder = os.path.join(snapshot, subfolder)
+    os.makedirs(folder, exist_ok=True)
+    with open(os.path.join(folder, "config.json"), "w") as f:
+        json.dump(config, f, indent=2, default=list)
+    save_file({k: v.detach().cpu().contiguous() for k, v in state_dict.items()}, os.path.join(folder, "model.safetensors"))

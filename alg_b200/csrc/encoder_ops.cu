@@ -70,7 +70,6 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ table, cons
 
 // ---- small attention ------------------------------------------------------------------------------------------------
 constexpr int kWarps = 4, kRowsPerWarp = 4, kRowsPerCta = kWarps * kRowsPerWarp * 2;  // two row groups per warp
-constexpr int kMaxKeysPerLane = 24;                                                  // <= 768 keys
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
@@ -252,6 +251,36 @@ __global__ void mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
     out[i] = __float2bfloat16_rn(__bfloat162float(a[i]) * __bfloat162float(b[i]));
 }
 
+// CLIPVisionEmbeddings: the stride-P patch convolution as unfold + GEMM.  x [B, C, H, W] fp32 -> rows [B * gh * gw, ld]
+// fp32, row = the (c, i, j)-flattened patch (nn.Conv2d weight.view(out, -1) order), zero-padded from C*P*P to ld
+__global__ void patchify_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int H, int W, int P, int ld,
+                                    int64_t n) {
+  const int gh = H / P, gw = W / P;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % ld);
+    const int64_t row = i / ld;
+    float v = 0.f;
+    if (col < C * P * P) {
+      const int c = col / (P * P), ij = col - c * P * P, ii = ij / P, jj = ij - ii * P;
+      const int64_t b = row / (gh * gw);
+      const int pi = (int)(row - b * gh * gw), py = pi / gw, px = pi - py * gw;
+      v = x[((b * C + c) * H + py * P + ii) * (int64_t)W + px * P + jj];
+    }
+    out[i] = v;
+  }
+}
+// out[b, 0, :] = class_embedding + pos[0]; out[b, 1 + n, :] = patches[b * np + n, :] + pos[1 + n]
+__global__ void clip_embed_f32_kernel(const float* __restrict__ patches, const float* __restrict__ cls,
+                                      const float* __restrict__ pos, float* __restrict__ out, int np, int d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d);
+    const int64_t tok_all = i / d;
+    const int tok = (int)(tok_all % (np + 1));
+    const int64_t b = tok_all / (np + 1);
+    out[i] = (tok == 0 ? cls[c] : patches[(b * np + tok - 1) * (int64_t)d + c]) + pos[(int64_t)tok * d + c];
+  }
+}
+
 static int grid_for(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 8); }
 
 template <typename T>
@@ -361,6 +390,26 @@ extern "C" int alg_mul_bf16(const void* a, const void* b, void* out, int64_t n, 
   enc::mul_bf16_kernel<<<enc::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b),
       reinterpret_cast<__nv_bfloat16*>(out), n);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_patchify_f32(const float* x, float* out, int batch, int C, int H, int W, int P, int ld, void* stream) {
+  ALG_REQUIRE(x && out && batch > 0 && C > 0 && P > 0 && H % P == 0 && W % P == 0 && ld >= C * P * P, "patchify: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  const int64_t n = (int64_t)batch * (H / P) * (W / P) * ld;
+  enc::patchify_f32_kernel<<<enc::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, C, H, W, P, ld, n);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_clip_embed_f32(const float* patches, const float* class_embedding, const float* position_embedding, float* out,
+                                  int batch, int num_patches, int d, void* stream) {
+  ALG_REQUIRE(patches && class_embedding && position_embedding && out && batch > 0 && num_patches > 0 && d > 0, "clip_embed: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  const int64_t n = (int64_t)batch * (num_patches + 1) * d;
+  enc::clip_embed_f32_kernel<<<enc::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      patches, class_embedding, position_embedding, out, num_patches, d, n);
   ALG_LAUNCH_OK();
   return 0;
 }

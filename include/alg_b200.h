@@ -321,6 +321,12 @@ int alg_bias_act_f32(float* x, const float* bias, const float* residual, int64_t
 /* fp32 [rows, K] -> bf16 [rows, 3K]: [hi | hi | lo] (weight_order 0, activations) or [hi | lo | hi] (1, weights); the
  * K-concatenated bf16 GEMM with fp32 accumulation then equals the fp32 product up to the dropped lo * lo term (2^-16). */
 int alg_split3_bf16(const float* x, void* out, int64_t rows, int K, int weight_order, void* stream);
+/* CLIPVisionEmbeddings (fp32): the stride-P patch convolution as unfold + GEMM, then class token + position embeddings.
+ * x [batch, C, H, W] -> out [batch * (H/P) * (W/P), ld]: row = (c, i, j)-flattened patch, zero-padded from C*P*P to ld */
+int alg_patchify_f32(const float* x, float* out, int batch, int C, int H, int W, int P, int ld, void* stream);
+/* out [batch, num_patches + 1, d]: token 0 = class_embedding + pos[0]; token 1 + n = patches[b * num_patches + n] + pos[1 + n] */
+int alg_clip_embed_f32(const float* patches, const float* class_embedding, const float* position_embedding, float* out,
+                       int batch, int num_patches, int d, void* stream);
 /* out = bf16(a * b) elementwise (T5 gated-GELU feed-forward: gelu(wi_0 x) * wi_1 x) */
 int alg_mul_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 

@@ -25,7 +25,7 @@ import lp_utils
 from alg_b200.cogvideox import COGVIDEOX_5B_I2V, CogVideoXTransformer3DModel
 from alg_b200.embeddings import get_3d_rotary_pos_embed, get_resize_crop_region_for_grid
 from alg_b200.pipeline_utils import (CogVideoXPipelineOutput, DiffusionPipelineBase, MultiPipelineCallbacks,
-                                     PipelineCallback, SyntheticTextEncoder, SyntheticVideoVAE, VideoProcessor,
+                                     PipelineCallback, SyntheticTextEncoder, SyntheticTokenizer, SyntheticVideoVAE, VideoProcessor,
                                      randn_tensor)
 from alg_b200.schedulers import CogVideoXDDIMScheduler, CogVideoXDPMScheduler
 from alg_b200.vae_cogvideox import AutoencoderKLCogVideoX
@@ -87,7 +87,8 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, transformer=None, vae=None, torch_dtype=torch.bfloat16,
                         cache_dir=None, synthetic: Optional[bool] = None, allow_synthetic_aux: bool = False,
-                        seed: int = 0, device="cuda", native_vae_encoder: bool = True, **config_overrides):
+                        seed: int = 0, device="cuda", native_vae_encoder: bool = True, tokenizer=None, text_encoder=None,
+                        **config_overrides):
         """run.py:65-70.  Offline there are no checkpoints: ``synthetic=True`` (or ``ALG_SYNTHETIC=1``) builds the true
         CogVideoX-5b-I2V architecture with seeded random weights directly on ``device``.
 
@@ -123,18 +124,30 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
             if native_vae_encoder and synthetic:
                 vae = AutoencoderKLCogVideoX.from_synthetic(seed=seed, device=device, decoder=vae,
                                                             latent_channels=transformer.config.in_channels // 2)
-        return cls(tokenizer=None, text_encoder=SyntheticTextEncoder(transformer.config.text_embed_dim, torch_dtype), vae=vae,
+        if text_encoder is None and not synthetic:  # native T5 v1.1 + the snapshot's tokenizer (cog:228-268)
+            from alg_b200 import checkpoint, encoders
+
+            tokenizer, text_encoder = checkpoint.load_text_stack(snap, encoders.T5EncoderModel, device, tokenizer)
+            if text_encoder is None and not allow_synthetic_aux:
+                raise NotImplementedError(checkpoint.AUX_MESSAGE)
+        return cls(tokenizer=tokenizer or SyntheticTokenizer(vocab_size=32128),
+                   text_encoder=text_encoder or SyntheticTextEncoder(transformer.config.text_embed_dim, torch_dtype), vae=vae,
                    transformer=transformer, scheduler=scheduler or CogVideoXDDIMScheduler())
 
     # ------------------------------------------------------------------------------------------------
-    # once-per-video conditioning (cog:228-350).  The real T5 is out of scope; a synthetic encoder stands in.
+    # once-per-video conditioning (cog:228-350)
     def _get_t5_prompt_embeds(self, prompt=None, num_videos_per_prompt: int = 1, max_sequence_length: int = 226,
                               device=None, dtype=None):
         device = device or self._execution_device
         dtype = dtype or self.text_encoder.dtype
         prompt = [prompt] if isinstance(prompt, str) else prompt
         batch_size = len(prompt)
-        prompt_embeds = self.text_encoder.embed(prompt, max_sequence_length, zero_pad=False).to(dtype=dtype, device=device)
+        # cog:242-259: tokenizer -> text_encoder(ids)[0] through the transformers call surface (no attention mask: the padded
+        # positions take part in T5's self-attention, as in the reference); real HF objects, alg_b200.encoders.T5EncoderModel
+        # and the synthetic stand-ins are interchangeable
+        text_inputs = self.tokenizer(prompt, padding="max_length", max_length=max_sequence_length, truncation=True,
+                                     add_special_tokens=True, return_tensors="pt")
+        prompt_embeds = self.text_encoder(text_inputs.input_ids.to(device))[0].to(dtype=dtype, device=device)
         _, seq_len, _ = prompt_embeds.shape
         prompt_embeds = prompt_embeds.repeat(1, num_videos_per_prompt, 1)
         return prompt_embeds.view(batch_size * num_videos_per_prompt, seq_len, -1)

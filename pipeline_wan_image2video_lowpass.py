@@ -101,10 +101,22 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
                 transformer, scheduler = checkpoint.build_from_snapshot(WanTransformer3DModel, UniPCMultistepScheduler, snap, device)
             else:
                 scheduler = UniPCMultistepScheduler.from_config(checkpoint.scheduler_config(snap))
+            from alg_b200 import encoders
+
+            if text_encoder is None:  # native UMT5 + the snapshot's own tokenizer (wan:185-224)
+                tokenizer, text_encoder = checkpoint.load_text_stack(snap, encoders.UMT5EncoderModel, device, tokenizer)
+            if image_encoder is None:  # native CLIP-ViT-H in float32 (run.py:48) + the snapshot's CLIPImageProcessor
+                image_processor, image_encoder = checkpoint.load_image_stack(snap, encoders.CLIPVisionModel, device, image_processor)
             if vae is None and not allow_synthetic_aux:
                 raise NotImplementedError(checkpoint.AUX_MESSAGE)
         if transformer is None:
             transformer = WanTransformer3DModel.from_synthetic(seed=seed, device=device, **config_overrides)
+        if synthetic and os.environ.get("ALG_NATIVE_ENCODERS", "0") == "1":
+            # synthetic weights at the TRUE encoder architectures (UMT5-XXL 24 x 4096, CLIP-ViT-H/14) through the native kernels
+            from alg_b200 import encoders
+
+            text_encoder = text_encoder or encoders.UMT5EncoderModel.from_synthetic(seed=seed, device=device)
+            image_encoder = image_encoder or encoders.CLIPVisionModel.from_synthetic(seed=seed, device=device)
         if vae is None:
             vae = SyntheticVideoVAE(z_dim=16, latents_mean=WAN_VAE_MEAN, latents_std=WAN_VAE_STD, dtype=torch.float32)
         text_dim = transformer.config.text_dim

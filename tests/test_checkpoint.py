@@ -102,9 +102,9 @@ def test_cog_vae_encoder_snapshot(tmp_path):
     assert isinstance(pipe.vae, V.AutoencoderKLCogVideoX) and isinstance(pipe.vae.decoder, SyntheticVideoVAE)
     assert pipe.vae_scale_factor_spatial == 8 and pipe.vae_scaling_factor_image == 0.7
     mine = SyntheticVideoVAE(z_dim=16)
-    pipe2 = CogVideoXImageToVideoPipeline.from_pretrained(snap, device="cpu", vae=mine)
+    pipe2 = CogVideoXImageToVideoPipeline.from_pretrained(snap, device="cpu", vae=mine, allow_synthetic_aux=True)
     assert pipe2.vae.decoder is mine
-    pipe3 = CogVideoXImageToVideoPipeline.from_pretrained(snap, device="cpu", vae=mine, native_vae_encoder=False)
+    pipe3 = CogVideoXImageToVideoPipeline.from_pretrained(snap, device="cpu", vae=mine, native_vae_encoder=False, allow_synthetic_aux=True)
     assert pipe3.vae is mine
     with pytest.raises(KeyError, match="missing encoder weights"):
         V.AutoencoderKLCogVideoX(**dict(vcfg, layers_per_block=2)).load_state_dict(vsd)
