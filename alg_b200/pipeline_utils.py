@@ -10,6 +10,7 @@ checkpoints.  Nothing here is on the per-step path; the VAE and the conditioning
 from __future__ import annotations
 
 import contextlib
+import os
 import math
 from dataclasses import dataclass
 from types import SimpleNamespace
@@ -77,8 +78,25 @@ def write_video(path, frames, fps):
     if arr.dtype != np.uint8:
         arr = (np.clip(arr, 0, 1) * 255).round().astype(np.uint8)
     t, h, w, _ = arr.shape
-    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"mp4v"), float(fps), (w, h))
-    if not vw.isOpened():
+    # run.py:127-133 asks for h264 (crf 18).  This image's OpenCV / FFmpeg build has no software H.264 encoder (only the
+    # h264_v4l2m2m hardware wrapper, which needs a V4L2 device): try avc1 first, so a build that has libx264 / openh264 writes
+    # what the reference writes, and fall back to MPEG-4 part 2 (mp4v) here.
+    vw = None
+    prev = os.environ.get("OPENCV_LOG_LEVEL")
+    os.environ["OPENCV_LOG_LEVEL"] = "SILENT"
+    try:
+        for fourcc in ("avc1", "mp4v"):
+            cand = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*fourcc), float(fps), (w, h))
+            if cand.isOpened():
+                vw = cand
+                break
+            cand.release()
+    finally:
+        if prev is None:
+            os.environ.pop("OPENCV_LOG_LEVEL", None)
+        else:
+            os.environ["OPENCV_LOG_LEVEL"] = prev
+    if vw is None:
         raise RuntimeError(f"cannot open a video writer for {path}")
     for f in arr:
         vw.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
