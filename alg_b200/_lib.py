@@ -142,6 +142,9 @@ SIGNATURES = {
                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "alg_group_norm_bf16": (C.c_int, [C.POINTER(GroupNorm), C.c_void_p]),
     "alg_head_norm_rope": (C.c_int, [C.POINTER(HeadNormRope), C.c_void_p]),
+    "alg_upsample_nearest_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "alg_spatial_norm_apply_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, C.c_int, C.c_void_p]),
     "alg_patch_gather": (C.c_int, [C.POINTER(PatchSrc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "alg_unpatchify": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "alg_timestep_embedding": (C.c_int, [C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

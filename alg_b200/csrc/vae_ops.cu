@@ -150,6 +150,51 @@ __global__ void __launch_bounds__(256) group_norm_apply_kernel(const uint4* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Decoder pieces (AutoencoderKLCogVideoX.decode, cog:428-433): channels-last [T*H*W, C] bf16 like the encoder.
+//   upsample_nearest_kernel      F.interpolate(mode="nearest") on (T, H, W): src = floor(dst * in / out)
+//   spatial_norm_apply_kernel    CogVideoXSpatialNorm3D after the GroupNorm: out = bf16(bf16(norm_f * y) + b) (+ SiLU), with
+//                                (y | b) = [conv_y(zq) | conv_b(zq)] computed at LATENT resolution ([zt*zh*zw, 2C]) and gathered
+//                                at the nearest latent pixel -- a 1x1x1 convolution commutes with nearest resizing, so the
+//                                resized zq and the two full-resolution convolution outputs are never materialised
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample_nearest_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int c8,
+                                                               int Ti, int Hi, int Wi, int To, int Ho, int Wo, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8);
+    int64_t r = i / c8;
+    const int xo = (int)(r % Wo);
+    r /= Wo;
+    const int yo = (int)(r % Ho), to = (int)(r / Ho);
+    const int ti = (int)((int64_t)to * Ti / To), yi = (int)((int64_t)yo * Hi / Ho), xi = (int)((int64_t)xo * Wi / Wo);
+    out[i] = __ldg(x + (((int64_t)ti * Hi + yi) * Wi + xi) * c8 + c);
+  }
+}
+
+__global__ void __launch_bounds__(256) spatial_norm_apply_kernel(const uint4* __restrict__ fn, const uint4* __restrict__ yb,
+                                                                 uint4* __restrict__ out, int c8, int T, int H, int W, int zt,
+                                                                 int zh, int zw, int silu, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8);
+    int64_t r = i / c8;
+    const int xo = (int)(r % W);
+    r /= W;
+    const int yo = (int)(r % H), to = (int)(r / H);
+    const int64_t zr = ((int64_t)((int64_t)to * zt / T) * zh + (int64_t)yo * zh / H) * zw + (int64_t)xo * zw / W;
+    float f[8], y[8], b[8];
+    unpack8(__ldg(fn + i), f);
+    unpack8(__ldg(yb + zr * 2 * c8 + c), y);
+    unpack8(__ldg(yb + zr * 2 * c8 + c8 + c), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = bf16_round(bf16_round(f[e] * y[e]) + b[e]);
+      if (silu) v = v / (1.0f + __expf(-v));
+      f[e] = v;
+    }
+    out[i] = pack8(f);
+  }
+}
+
 }  // namespace vae
 }  // namespace alg
 
@@ -195,6 +240,34 @@ extern "C" int alg_group_norm_bf16(const alg_group_norm_t* p, void* stream) {
                                                      reinterpret_cast<const __nv_bfloat16*>(p->weight),
                                                      reinterpret_cast<const __nv_bfloat16*>(p->bias), p->rows, c8, cpg,
                                                      p->eps, p->silu, p->stats);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_upsample_nearest_bf16(const void* x, void* out, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo, void* stream) {
+  ALG_REQUIRE(x && out && C > 0 && C % 8 == 0 && Ti > 0 && Hi > 0 && Wi > 0 && To > 0 && Ho > 0 && Wo > 0, "upsample_nearest: bad arguments (C % 8 == 0)");
+  ALG_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "upsample_nearest: 16-byte alignment");
+  if (int rc = alg_check_device()) return rc;
+  const int64_t n = (int64_t)To * Ho * Wo * (C / 8);
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  alg::vae::upsample_nearest_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), C / 8, Ti, Hi, Wi, To, Ho, Wo, n);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_spatial_norm_apply_bf16(const void* f_norm, const void* yb, void* out, int C, int T, int H, int W, int zt, int zh,
+                                           int zw, int silu, void* stream) {
+  ALG_REQUIRE(f_norm && yb && out && C > 0 && C % 8 == 0 && T > 0 && H > 0 && W > 0 && zt > 0 && zh > 0 && zw > 0,
+              "spatial_norm_apply: bad arguments (C % 8 == 0)");
+  ALG_REQUIRE(((reinterpret_cast<uintptr_t>(f_norm) | reinterpret_cast<uintptr_t>(yb) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              "spatial_norm_apply: 16-byte alignment");
+  if (int rc = alg_check_device()) return rc;
+  const int64_t n = (int64_t)T * H * W * (C / 8);
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  alg::vae::spatial_norm_apply_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(f_norm), reinterpret_cast<const uint4*>(yb), reinterpret_cast<uint4*>(out), C / 8, T, H, W, zt,
+      zh, zw, silu, n);
   ALG_LAUNCH_OK();
   return 0;
 }

@@ -682,7 +682,7 @@ def run_ours(args):
         achieved = flops_total / (sa["ms"] / 1e3) / 1e12 if sa["ms"] > 0 else None
         total_flops = passes * wl.forward_flops()[0]
         traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of this kernel (per head x heads)
-        tpath = os.path.join(ROOT, "profiles", "r01_attention_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_attention_traffic.json")
         if wl.key == "wan" and os.path.exists(tpath) and sa["launches"]:
             heads_per_launch = 40 * passes / len(idxs)
             traffic = json.load(open(tpath))["dram_bytes_per_head"] * heads_per_launch * wl.n_tok / 32760  # linear in tokens

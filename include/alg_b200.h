@@ -428,6 +428,15 @@ typedef struct {
 } alg_group_norm_t;
 int alg_group_norm_bf16(const alg_group_norm_t* p, void* stream);
 
+/* AutoencoderKLCogVideoX.decode (cog:428-433), channels-last [T*H*W, C] bf16 like the encoder ops above. */
+/* F.interpolate(mode="nearest") over (T, H, W): out[to, yo, xo, :] = x[to*Ti/To, yo*Hi/Ho, xo*Wi/Wo, :]  (C % 8 == 0) */
+int alg_upsample_nearest_bf16(const void* x, void* out, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo, void* stream);
+/* CogVideoXSpatialNorm3D after its GroupNorm: out = bf16(bf16(f_norm * y) + b) (+ SiLU when silu != 0), where
+ * yb [zt*zh*zw, 2C] = [conv_y(zq) | conv_b(zq)] at latent resolution and (y, b) of pixel (t, yy, xx) are read at the nearest
+ * latent pixel (t*zt/T, yy*zh/H, xx*zw/W): conv(resize(zq)) == resize(conv(zq)) for 1x1x1 convolutions. */
+int alg_spatial_norm_apply_bf16(const void* f_norm, const void* yb, void* out, int C, int T, int H, int W, int zt, int zh,
+                                int zw, int silu, void* stream);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 int64_t alg_launch_count(void);
 
