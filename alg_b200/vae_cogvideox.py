@@ -1,4 +1,5 @@
-"""``AutoencoderKLCogVideoX.encode`` on the sm_100a kernels of ``libalg_b200.so`` (single-frame inputs).
+"""``AutoencoderKLCogVideoX`` on the sm_100a kernels of ``libalg_b200.so``: ``encode`` of single-frame inputs (the per-step call of
+pixel-space ALG) and the full video ``decode`` (cog:428-433, once per video: 13 latent frames -> 49 frames).
 
 Why it is here: with ``lp_filter_in_latent=False`` (BASELINE configs[2], ``configs/cogvideox_alg.yaml``) the reference
 low-pass-filters the IMAGE and runs ``self.vae.encode(image_lp.unsqueeze(2)).latent_dist.sample(generator)`` on EVERY
@@ -7,8 +8,10 @@ are one frame ``[1, 3, 1, H, W]``, so this module builds exactly that: the CogVi
 
 Mirrors the interface the pipeline uses on ``self.vae``: ``.config`` (``block_out_channels``,
 ``temporal_compression_ratio``, ``scaling_factor``, ``invert_scale_latents``), ``.dtype``, ``.encode(x)`` returning an
-object with ``.latent_dist.sample(generator)`` / ``.mode()``, and ``.decode`` (delegated: decoding 13 latent frames to 49
-video frames happens once per video and is out of scope, SURVEY 8(f).1 -- pass ``decoder=`` or the call raises).
+object with ``.latent_dist.sample(generator)`` / ``.mode()``, and ``.decode(z).sample`` -- native when the decoder weights are
+loaded (``CogVideoXDecoder3D``: latent frames in batches of two with every causal convolution's last two input frames carried
+to the next batch, ``CogVideoXSpatialNorm3D`` conditioning on the latent, nearest-neighbour ``CogVideoXUpsample3D``), otherwise
+delegated to ``decoder=``.
 
 This module only SEQUENCES C-ABI calls (``alg_b200.ops``); activations are channels-last ``[H*W, C]`` bf16:
 
@@ -75,6 +78,68 @@ def encoder_parameter_shapes(cfg: dict) -> Dict[str, tuple]:
     return s
 
 
+def decoder_parameter_shapes(cfg: dict) -> Dict[str, tuple]:
+    """name -> shape of every DECODER parameter (diffusers naming: CogVideoXDecoder3D)."""
+    s: Dict[str, tuple] = {}
+    boc = list(reversed(cfg["block_out_channels"]))
+    z = cfg["latent_channels"]
+
+    def conv3(name, o, i, k=3):
+        s[name + ".conv.weight"] = (o, i, k, k, k)
+        s[name + ".conv.bias"] = (o,)
+
+    def snorm(name, f):
+        s[name + ".norm_layer.weight"] = s[name + ".norm_layer.bias"] = (f,)
+        conv3(name + ".conv_y", f, z, 1)
+        conv3(name + ".conv_b", f, z, 1)
+
+    def resnet(name, i, o):
+        snorm(name + ".norm1", i)
+        conv3(name + ".conv1", o, i)
+        snorm(name + ".norm2", o)
+        conv3(name + ".conv2", o, o)
+        if i != o:
+            s[name + ".conv_shortcut.weight"] = (o, i, 1, 1, 1)
+            s[name + ".conv_shortcut.bias"] = (o,)
+
+    conv3("decoder.conv_in", boc[0], z)
+    for j in range(2):
+        resnet(f"decoder.mid_block.resnets.{j}", boc[0], boc[0])
+    ch = boc[0]
+    for b, out_ch in enumerate(boc):
+        for j in range(cfg["layers_per_block"] + 1):
+            resnet(f"decoder.up_blocks.{b}.resnets.{j}", ch if j == 0 else out_ch, out_ch)
+        if b != len(boc) - 1:
+            s[f"decoder.up_blocks.{b}.upsamplers.0.conv.weight"] = (out_ch, out_ch, 3, 3)
+            s[f"decoder.up_blocks.{b}.upsamplers.0.conv.bias"] = (out_ch,)
+        ch = out_ch
+    snorm("decoder.norm_out", ch)
+    conv3("decoder.conv_out", cfg["out_channels"], ch)
+    return s
+
+
+def synthetic_decoder_state_dict(cfg: dict, seed: int = 0, device="cuda") -> Dict[str, torch.Tensor]:
+    """Seeded decoder weights at the true shapes (fan-in scaled; the multiplicative conv_y branch is centred on 1)."""
+    sd = {}
+    for idx, (name, shape) in enumerate(decoder_parameter_shapes(cfg).items()):
+        g = torch.Generator(device=device).manual_seed(seed * 1_000_003 + 9_001 + idx)
+        if "norm_layer" in name and name.endswith(".weight"):
+            w = 1 + 0.1 * torch.randn(shape, generator=g, device=device)
+        elif name.endswith(".conv_y.conv.bias"):
+            w = 1 + 0.05 * torch.randn(shape, generator=g, device=device)
+        elif name.endswith(".bias"):
+            w = 0.05 * torch.randn(shape, generator=g, device=device)
+        elif ".conv_y." in name:
+            w = 0.1 * torch.randn(shape, generator=g, device=device)
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            w = torch.randn(shape, generator=g, device=device) * (1.0 / fan_in) ** 0.5
+        sd[name] = w.to(torch.bfloat16)
+    return sd
+
+
 def synthetic_state_dict(cfg: dict, seed: int = 0, device="cuda") -> Dict[str, torch.Tensor]:
     """Seeded random-init encoder weights at the true shapes (fan-in scaled so activations stay O(1) through 28 convs)."""
     sd = {}
@@ -127,23 +192,30 @@ class AutoencoderKLCogVideoX:
         self._cfg = cfg
         self._w: Dict[str, torch.Tensor] = {}
         self._cols: Optional[torch.Tensor] = None
+        self._cols_budget = 3 << 30  # bytes of patch matrix per im2col + GEMM call (whole frames)
+        self.num_latent_frames_batch_size = 2
         self.decoder = decoder
+        self.has_decoder = False
         self.dtype = torch.bfloat16
         self.device = torch.device("cpu")
 
     # ---- construction -------------------------------------------------------------------------------
     @classmethod
-    def from_synthetic(cls, seed: int = 0, device="cuda", decoder=None, **config):
+    def from_synthetic(cls, seed: int = 0, device="cuda", decoder=None, with_decoder: bool = False, **config):
         m = cls(decoder=decoder, **config)
-        return m.load_state_dict(synthetic_state_dict(m._cfg, seed=seed, device=device))
+        sd = synthetic_state_dict(m._cfg, seed=seed, device=device)
+        if with_decoder:
+            sd.update(synthetic_decoder_state_dict(m._cfg, seed=seed, device=device))
+        return m.load_state_dict(sd)
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, subfolder: str = "vae", torch_dtype=None, cache_dir=None,
                         device="cuda", decoder=None):
-        """Encoder weights from a LOCAL diffusers snapshot (``vae/config.json`` + safetensors); decoder keys are ignored."""
+        """Weights from a LOCAL diffusers snapshot (``vae/config.json`` + safetensors): encoder and decoder; with ``decoder=``
+        given only the encoder keys are read and ``decode`` is delegated."""
         from . import checkpoint
         root = checkpoint.resolve_snapshot(pretrained_model_name_or_path, cache_dir)
-        cfg, sd = checkpoint.load_component(root, subfolder, device=device, key_prefix="encoder.")
+        cfg, sd = checkpoint.load_component(root, subfolder, device=device, key_prefix=None if decoder is None else "encoder.")
         known = {k: v for k, v in cfg.items() if k in COGVIDEOX_5B_VAE}
         return cls(decoder=decoder, **known).load_state_dict(sd)
 
@@ -153,6 +225,13 @@ class AutoencoderKLCogVideoX:
         missing = [k for k in shapes if k not in sd]
         if strict and missing:
             raise KeyError(f"missing encoder weights: {missing[:4]}{'...' if len(missing) > 4 else ''}")
+        dshapes = decoder_parameter_shapes(self._cfg)
+        self.has_decoder = any(k.startswith("decoder.") for k in sd)
+        if self.has_decoder:
+            dmissing = [k for k in dshapes if k not in sd]
+            if strict and dmissing:
+                raise KeyError(f"missing decoder weights: {dmissing[:4]}{'...' if len(dmissing) > 4 else ''}")
+            shapes = dict(shapes, **dshapes)
         w: Dict[str, torch.Tensor] = {}
         for name, shape in shapes.items():
             t = sd[name]
@@ -167,6 +246,10 @@ class AutoencoderKLCogVideoX:
                 t = t.reshape(co, -1)
             w[name] = t.contiguous()
             self.device = t.device
+        if self.has_decoder:  # conv_y | conv_b of every spatial norm as ONE [2 f, z] projection of the latent
+            for name in [k[:-len(".conv_y.conv.weight")] for k in dshapes if k.endswith(".conv_y.conv.weight")]:
+                w[name + ".yb.weight"] = torch.cat([w.pop(name + ".conv_y.conv.weight"), w.pop(name + ".conv_b.conv.weight")]).contiguous()
+                w[name + ".yb.bias"] = torch.cat([w.pop(name + ".conv_y.conv.bias"), w.pop(name + ".conv_b.conv.bias")]).contiguous()
         self._w = w
         return self
 
@@ -261,8 +344,134 @@ class AutoencoderKLCogVideoX:
             return (posterior,)
         return SimpleNamespace(latent_dist=posterior)
 
+    # ---- decoder -------------------------------------------------------------------------------------
+    def _conv3_cached(self, x, T, H, W, name, cache, residual=None):
+        """CogVideoXCausalConv3d(k=3) on a chunk of T frames [T*H*W, Ci] -> [T*H*W, Co].  The two frames in front come from
+        the previous chunk (``conv_cache``) or replicate frame 0; the last two input frames are kept for the next chunk."""
+        wt, b = self._w[name + ".conv.weight"], self._w[name + ".conv.bias"]
+        Ci, HW = x.shape[1], H * W
+        xin = torch.empty((T + 2) * HW, Ci, device=x.device, dtype=torch.bfloat16)
+        prev = cache.get(name)
+        if prev is None:
+            ops.copy_rows(x[:HW], xin[:HW])
+            ops.copy_rows(x[:HW], xin[HW:2 * HW])
+        else:
+            ops.copy_rows(prev, xin[:2 * HW])
+        ops.copy_rows(x, xin[2 * HW:])
+        cache[name] = xin[T * HW:]  # the last two frames of the padded input (a view: xin stays alive through it)
+        K = wt.shape[1]
+        out = torch.empty(T * HW, wt.shape[0], device=x.device, dtype=torch.bfloat16) if wt.shape[0] % 8 == 0 else None
+        per_call = max(1, min(T, self._cols_budget // max(1, HW * K * 2)))
+        outs = []
+        for t0 in range(0, T, per_call):
+            n = min(per_call, T - t0)
+            cols = ops.im2col(xin[t0 * HW:(t0 + n + 2) * HW], n + 2, H, W, kernel=(3, 3, 3), pad_t=0, pad_top=1, pad_left=1,
+                              out=self._workspace(n * HW * K, x.device))
+            res = None if residual is None else residual[t0 * HW:(t0 + n) * HW]
+            kw = dict(epilogue=_lib.EPI_RESIDUAL, residual=res) if res is not None else {}
+            if out is not None:
+                ops.gemm(cols, wt, b, out=out[t0 * HW:(t0 + n) * HW], **kw)
+            else:
+                outs.append(ops.gemm(cols, wt, b, **kw))
+        return out if out is not None else torch.cat(outs)
+
+    def _spatial_norm(self, f, T, H, W, z, zt, zh, zw, name, silu=True):
+        """CogVideoXSpatialNorm3D: GroupNorm(f) * conv_y(zq') + conv_b(zq') (+ SiLU); f [T*H*W, C], z [zt*zh*zw, zc]."""
+        lib = _lib.lib()
+        fn = ops.group_norm(f, self._cfg["norm_num_groups"], self._w[name + ".norm_layer.weight"], self._w[name + ".norm_layer.bias"],
+                            eps=1e-6, silu=False)
+        yb = ops.gemm(z, self._w[name + ".yb.weight"], self._w[name + ".yb.bias"])  # [zrows, 2C] at latent resolution
+        out = torch.empty_like(f)
+        Cc, HW, zhw = f.shape[1], H * W, zh * zw
+
+        def apply(t0, t1, z0, z1):
+            with torch.cuda.device(f.device):
+                _lib.check(lib.alg_spatial_norm_apply_bf16(fn[t0 * HW:].data_ptr(), yb[z0 * zhw:].data_ptr(), out[t0 * HW:].data_ptr(), Cc,
+                                                           t1 - t0, H, W, z1 - z0, zh, zw, int(silu), _lib.stream_ptr(f.device)))
+        if T > 1 and T % 2 == 1:  # first frame <- first latent frame, the rest resized together
+            apply(0, 1, 0, 1)
+            apply(1, T, 1, zt)
+        else:
+            apply(0, T, 0, zt)
+        return out
+
+    def _dec_resnet(self, x, T, H, W, z, zdims, name, cache):
+        h = self._spatial_norm(x, T, H, W, z, *zdims, name + ".norm1")
+        h = self._conv3_cached(h, T, H, W, name + ".conv1", cache)
+        h = self._spatial_norm(h, T, H, W, z, *zdims, name + ".norm2")
+        if name + ".conv_shortcut.weight" in self._w:
+            x = ops.gemm(x, self._w[name + ".conv_shortcut.weight"], self._w[name + ".conv_shortcut.bias"])
+        return self._conv3_cached(h, T, H, W, name + ".conv2", cache, residual=x)
+
+    def _upsample(self, x, T, H, W, name, compress_time):
+        """CogVideoXUpsample3D: nearest x2 (space; time too when ``compress_time``, the first frame of an odd chunk kept single),
+        then a per-frame Conv2d(3, padding 1)."""
+        lib = _lib.lib()
+        Cc, HW = x.shape[1], H * W
+        if compress_time and T > 1 and T % 2 == 1:
+            To, parts = 1 + 2 * (T - 1), [(0, 1, 0, 1), (1, T, 1, 1 + 2 * (T - 1))]
+        elif compress_time and T > 1:
+            To, parts = 2 * T, [(0, T, 0, 2 * T)]
+        else:
+            To, parts = T, [(0, T, 0, T)]
+        up = torch.empty(To * 4 * HW, Cc, device=x.device, dtype=torch.bfloat16)
+        for (i0, i1, o0, o1) in parts:
+            with torch.cuda.device(x.device):
+                _lib.check(lib.alg_upsample_nearest_bf16(x[i0 * HW:].data_ptr(), up[o0 * 4 * HW:].data_ptr(), Cc, i1 - i0, H, W, o1 - o0,
+                                                         2 * H, 2 * W, _lib.stream_ptr(x.device)))
+        H, W, HW = 2 * H, 2 * W, 4 * HW
+        wt, b = self._w[name + ".conv.weight"], self._w[name + ".conv.bias"]
+        out = torch.empty(To * HW, wt.shape[0], device=x.device, dtype=torch.bfloat16)
+        per_call = max(1, min(To, self._cols_budget // max(1, HW * wt.shape[1] * 2)))
+        for t0 in range(0, To, per_call):
+            n = min(per_call, To - t0)
+            cols = ops.im2col(up[t0 * HW:(t0 + n) * HW], n, H, W, kernel=(1, 3, 3), pad_top=1, pad_left=1,
+                              out=self._workspace(n * HW * wt.shape[1], x.device))
+            ops.gemm(cols, wt, b, out=out[t0 * HW:(t0 + n) * HW])
+        return out, To, H, W
+
+    def _decode_chunk(self, zc: torch.Tensor, cache: dict) -> torch.Tensor:
+        """zc [zc, t, h, w] (one latent frame batch) -> [3, T, 8h, 8w] bf16."""
+        cfg = self._cfg
+        Cz, T, H, W = zc.shape
+        z = zc.to(torch.bfloat16).permute(1, 2, 3, 0).reshape(T * H * W, Cz).contiguous()  # channels-last
+        zdims = (T, H, W)
+        boc = list(reversed(cfg["block_out_channels"]))
+        n_compress = {1: 0, 2: 1, 4: 2, 8: 3}[cfg["temporal_compression_ratio"]]
+        x = self._conv3_cached(z, T, H, W, "decoder.conv_in", cache)
+        for j in range(2):
+            x = self._dec_resnet(x, T, H, W, z, zdims, f"decoder.mid_block.resnets.{j}", cache)
+        for bi in range(len(boc)):
+            for j in range(cfg["layers_per_block"] + 1):
+                x = self._dec_resnet(x, T, H, W, z, zdims, f"decoder.up_blocks.{bi}.resnets.{j}", cache)
+            if bi != len(boc) - 1:
+                x, T, H, W = self._upsample(x, T, H, W, f"decoder.up_blocks.{bi}.upsamplers.0", bi < n_compress)
+        x = self._spatial_norm(x, T, H, W, z, *zdims, "decoder.norm_out", silu=True)
+        x = self._conv3_cached(x, T, H, W, "decoder.conv_out", cache)
+        return x.reshape(T, H, W, -1).permute(3, 0, 1, 2)
+
     def decode(self, z: torch.Tensor, return_dict: bool = True):
-        if self.decoder is None:
-            raise NotImplementedError("AutoencoderKLCogVideoX.decode is not built (once per video, SURVEY 8(f).1): "
-                                      "pass decoder=<object with .decode(z)>")
-        return self.decoder.decode(z, return_dict=return_dict)
+        """z [B, zc, T, h, w] -> ``.sample`` [B, 3, 1 + 4 (T - 1), 8h, 8w] (cog:428-433; ``_decode``: latent frame batches of
+        ``num_latent_frames_batch_size`` = 2, the first batch also takes the remainder)."""
+        if not self.has_decoder:
+            if self.decoder is None:
+                raise NotImplementedError("AutoencoderKLCogVideoX.decode: no decoder weights loaded and no decoder= object given")
+            return self.decoder.decode(z, return_dict=return_dict)
+        if z.dim() != 5 or z.shape[1] != self._cfg["latent_channels"]:
+            raise ValueError(f"decode expects [B, {self._cfg['latent_channels']}, T, h, w], got {tuple(z.shape)}")
+        _lib.require_cuda(z)
+        fb, T = self.num_latent_frames_batch_size, z.shape[2]
+        n_batches, rem = max(T // fb, 1), T % fb
+        videos = []
+        for b in range(z.shape[0]):
+            cache: dict = {}
+            parts = []
+            for i in range(n_batches):
+                start = fb * i + (0 if i == 0 else rem)
+                parts.append(self._decode_chunk(z[b, :, start:fb * (i + 1) + rem], cache))
+            videos.append(torch.cat(parts, dim=1))
+        video = torch.stack(videos).to(z.dtype)
+        self._cols = None  # the patch-matrix workspace is large at 480 x 720: give it back once the video is decoded
+        if not return_dict:
+            return (video,)
+        return SimpleNamespace(sample=video)

@@ -112,17 +112,18 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
                 transformer, scheduler = checkpoint.build_from_snapshot(CogVideoXTransformer3DModel, CogVideoXDDIMScheduler, snap, device)
             else:
                 scheduler = CogVideoXDDIMScheduler.from_config(checkpoint.scheduler_config(snap))
+            if native_vae_encoder and os.path.isdir(os.path.join(snap, "vae")):
+                # the snapshot's own VAE on the native kernels: encoder (per-step path of pixel-space ALG) AND decoder; a `vae=`
+                # object, when given, keeps serving decode
+                vae = AutoencoderKLCogVideoX.from_pretrained(snap, device=device, decoder=vae)
             if vae is None and not allow_synthetic_aux:
                 raise NotImplementedError(checkpoint.AUX_MESSAGE)
-            if native_vae_encoder and os.path.isdir(os.path.join(snap, "vae")):
-                decoder = vae if vae is not None else SyntheticVideoVAE(z_dim=16, scaling_factor=0.7, dtype=torch_dtype)
-                vae = AutoencoderKLCogVideoX.from_pretrained(snap, device=device, decoder=decoder)
         if transformer is None:
             transformer = CogVideoXTransformer3DModel.from_synthetic(seed=seed, device=device, **config_overrides)
         if vae is None:
             vae = SyntheticVideoVAE(z_dim=transformer.config.in_channels // 2, scaling_factor=0.7, dtype=torch_dtype)
             if native_vae_encoder and synthetic:
-                vae = AutoencoderKLCogVideoX.from_synthetic(seed=seed, device=device, decoder=vae,
+                vae = AutoencoderKLCogVideoX.from_synthetic(seed=seed, device=device, decoder=None, with_decoder=True,
                                                             latent_channels=transformer.config.in_channels // 2)
         if text_encoder is None and not synthetic:  # native T5 v1.1 + the snapshot's tokenizer (cog:228-268)
             from alg_b200 import checkpoint, encoders

@@ -105,7 +105,35 @@ def vae(reps):
                       "conv_tflops_rate": flop / ms / 1e9}), flush=True)
 
 
+def vae_decode(reps):
+    """AutoencoderKLCogVideoX.decode of the full clip (cog:428-433): 13 latent frames of 60 x 90 -> 49 frames of 480 x 720."""
+    from alg_b200 import _lib, vae_cogvideox as V
+    m = V.AutoencoderKLCogVideoX.from_synthetic(seed=0, with_decoder=True)
+    z = torch.randn(1, 16, 13, 60, 90, device="cuda").bfloat16()
+    n0 = _lib.lib().alg_launch_count()
+    out = m.decode(z).sample
+    launches = _lib.lib().alg_launch_count() - n0
+    torch.cuda.synchronize()
+    ms = timed(lambda: m.decode(z), reps)
+    flop = 0
+    for name, shape in V.decoder_parameter_shapes(m._cfg).items():
+        if name.endswith(".weight") and len(shape) >= 4 and "conv_y" not in name and "conv_b" not in name:
+            lvl = int(name.split("up_blocks.")[1][0]) if "up_blocks" in name else (0 if "mid_block" in name or "conv_in" in name else 3)
+            if "upsamplers" in name:
+                lvl += 1
+            frames = {0: 13, 1: 25, 2: 49, 3: 49}[min(lvl, 3)]
+            px = frames * (60 << min(lvl, 3)) * (90 << min(lvl, 3))
+            k = 1
+            for d in shape[1:]:
+                k *= d
+            flop += 2 * px * shape[0] * k
+    print(json.dumps({"model": "AutoencoderKLCogVideoX.decode, 13 x 60 x 90 latents -> 49 frames of 480 x 720 (cog:428-433, once per video)",
+                      "ms_per_decode": ms, "launches": int(launches), "conv_tflop": flop / 1e12, "conv_tflops_rate": flop / ms / 1e9,
+                      "finite": bool(torch.isfinite(out).all()), "shape": list(out.shape),
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "cog"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-    {"cog": cog, "hunyuan": hunyuan, "vae": vae}[which](reps)
+    {"cog": cog, "hunyuan": hunyuan, "vae": vae, "vae_decode": vae_decode}[which](reps)

@@ -70,8 +70,8 @@ def test_hunyuan_snapshot_round_trip(tmp_path):
 
 
 def test_cog_vae_encoder_snapshot(tmp_path):
-    """A snapshot with a ``vae/`` folder: the pipeline builds the native single-frame encoder from its ``encoder.*`` tensors
-    (decoder tensors are ignored) and hands ``decode`` to the object passed as ``vae=`` (or the synthetic stand-in)."""
+    """A snapshot with a ``vae/`` folder: the pipeline builds the native VAE from it -- encoder (single-frame, the per-step
+    path) and decoder -- and hands ``decode`` to the object passed as ``vae=`` when there is one (then only ``encoder.*`` is read)."""
     from safetensors.torch import save_file
 
     from alg_b200 import checkpoint, cogvideox, vae_cogvideox as V
@@ -87,9 +87,16 @@ def test_cog_vae_encoder_snapshot(tmp_path):
     os.makedirs(os.path.join(snap, "vae"))
     with open(os.path.join(snap, "vae", "config.json"), "w") as f:
         json.dump(dict(vcfg, _class_name="AutoencoderKLCogVideoX", _diffusers_version="0.34.0.dev0", some_future_key=3), f)
-    save_file(dict(vsd, **{"decoder.conv_in.conv.weight": torch.zeros(4, 4)}), os.path.join(snap, "vae", checkpoint.WEIGHTS_NAME))
+    tcfg = dict(vcfg, block_out_channels=tuple(vcfg["block_out_channels"]))
+    dsd = V.synthetic_decoder_state_dict(tcfg, seed=9, device="cpu")
+    save_file(dict(vsd, **dsd), os.path.join(snap, "vae", checkpoint.WEIGHTS_NAME))
 
-    enc = V.AutoencoderKLCogVideoX.from_pretrained(snap, device="cpu")
+    full = V.AutoencoderKLCogVideoX.from_pretrained(snap, device="cpu")
+    assert full.has_decoder and "decoder.up_blocks.0.resnets.0.norm1.yb.weight" in full._w  # conv_y | conv_b fused: [2 f, z]
+    assert full._w["decoder.up_blocks.0.resnets.0.norm1.yb.weight"].shape == (128, 16)
+    with pytest.raises(KeyError, match="missing decoder weights"):
+        V.AutoencoderKLCogVideoX(**vcfg).load_state_dict(dict(vsd, **{"decoder.conv_in.conv.weight": dsd["decoder.conv_in.conv.weight"]}))
+    enc = V.AutoencoderKLCogVideoX.from_pretrained(snap, device="cpu", decoder=SyntheticVideoVAE(z_dim=16))
     assert enc.config.block_out_channels == (32, 64, 64, 64) and enc.config.layers_per_block == 1
     w = vsd["encoder.down_blocks.1.resnets.0.conv1.conv.weight"]  # [64, 32, 3, 3, 3] -> GEMM operand [64, (kt, kh, kw, ci)]
     assert torch.equal(enc._w["encoder.down_blocks.1.resnets.0.conv1.conv.weight"], w.movedim(1, -1).reshape(64, -1))
@@ -99,7 +106,7 @@ def test_cog_vae_encoder_snapshot(tmp_path):
     assert not any(k.startswith("decoder.") for k in enc._w)
 
     pipe = CogVideoXImageToVideoPipeline.from_pretrained(snap, device="cpu", allow_synthetic_aux=True)
-    assert isinstance(pipe.vae, V.AutoencoderKLCogVideoX) and isinstance(pipe.vae.decoder, SyntheticVideoVAE)
+    assert isinstance(pipe.vae, V.AutoencoderKLCogVideoX) and pipe.vae.has_decoder and pipe.vae.decoder is None
     assert pipe.vae_scale_factor_spatial == 8 and pipe.vae_scaling_factor_image == 0.7
     mine = SyntheticVideoVAE(z_dim=16)
     pipe2 = CogVideoXImageToVideoPipeline.from_pretrained(snap, device="cpu", vae=mine, allow_synthetic_aux=True)
