@@ -351,14 +351,19 @@ class FlowMatchEulerDiscreteScheduler(_ConfigMixin):
         super().__init__(**kwargs)
         if self.config.use_dynamic_shifting:
             raise NotImplementedError("dynamic shifting is not used by the HunyuanVideo-I2V configuration")
+        c = self.config
+        # diffusers keeps the SHIFTED training schedule's end points: set_timesteps(sigmas=None) spaces the timesteps between them
+        train = (np.linspace(1, c.num_train_timesteps, c.num_train_timesteps, dtype=np.float32)[::-1] / c.num_train_timesteps).astype(np.float32)
+        train = c.shift * train / (1 + (c.shift - 1) * train)
+        self.sigma_max, self.sigma_min = float(train[0]), float(train[-1])
         self.timesteps = None
         self.sigmas = None
         self._step_index = None
 
     def set_timesteps(self, num_inference_steps: Optional[int] = None, device=None, sigmas: Optional[List[float]] = None):
         c = self.config
-        if sigmas is None:
-            ts = np.linspace(c.num_train_timesteps, 1.0, num_inference_steps)
+        if sigmas is None:  # linspace(sigma_to_t(sigma_max), sigma_to_t(sigma_min), n) / N -- then shifted (again) below, like diffusers
+            ts = np.linspace(self.sigma_max * c.num_train_timesteps, self.sigma_min * c.num_train_timesteps, num_inference_steps)
             sigmas = ts / c.num_train_timesteps
         sigmas = np.array(sigmas).astype(np.float32)
         self.num_inference_steps = len(sigmas)

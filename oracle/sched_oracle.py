@@ -256,8 +256,10 @@ class FlowEulerOracle:
         self.order = 1
 
     def set_timesteps(self, n, sigmas=None):
-        if sigmas is None:
-            ts = np.linspace(self.num_train_timesteps, 1.0, n)
+        if sigmas is None:  # upstream spaces between the SHIFTED training schedule's end points (sigma_max, sigma_min)
+            tr = (np.linspace(1, self.num_train_timesteps, self.num_train_timesteps, dtype=np.float32)[::-1] / self.num_train_timesteps)
+            tr = self.shift * tr / (1 + (self.shift - 1) * tr)
+            ts = np.linspace(float(tr[0]) * self.num_train_timesteps, float(tr[-1]) * self.num_train_timesteps, n)
             sigmas = ts / self.num_train_timesteps
         sigmas = np.array(sigmas).astype(np.float32)
         sigmas = self.shift * sigmas / (1 + (self.shift - 1) * sigmas)

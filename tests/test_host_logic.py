@@ -226,3 +226,84 @@ def test_double_float_rope_equals_complex128_after_bf16_rounding():
     assert (got_re != ref_re).mean() < 1e-5  # even the fp32 values agree almost everywhere
     plain = fma(re, ch, -(im * sh).astype(f32))
     assert (to_bf16_bits(plain) != to_bf16_bits(ref_re)).sum() > 0
+
+
+def test_unipc_coefficients_against_fp64_closed_forms():
+    """The scheduler's per-step scalars (computed once in set_timesteps with the 0-dim fp32 torch op chain diffusers uses)
+    against an INDEPENDENT derivation: fp64, no logs / expm1 for the exponential terms -- with flow sigmas
+    exp(-h) = (sigma_t alpha_s0) / (alpha_t sigma_s0), so alpha_t * h_phi_1 = alpha_t * B_h = sigma_t alpha_s0 / sigma_s0 - alpha_t
+    -- and the 2 x 2 corrector system R rho = b solved in closed form (VERDICT r1 weak #2: product and oracle shared one text)."""
+    import math
+
+    import numpy as np
+
+    from alg_b200.schedulers import UniPCMultistepScheduler
+    for n, shift in ((50, 5.0), (30, 3.0), (8, 1.0)):
+        s = UniPCMultistepScheduler(flow_shift=shift)
+        s.set_timesteps(n)
+        sig = s.sigmas.double().numpy()  # the fp32 schedule values ARE the definition; everything after is fp64 here
+        lam = lambda i: math.log((1 - sig[i]) / sig[i]) if sig[i] > 0 else math.inf
+        seen = 0
+        for (i_t, i_s0, order, corrector), k in s._coef.items():
+            st, s0 = sig[i_t], sig[i_s0]
+            at, a0 = 1 - st, 1 - s0
+            want_ratio = st / s0
+            want_a = st * a0 / s0 - at  # alpha_t * expm1(-h)
+            assert abs(k["ratio"] - want_ratio) <= 2e-6 * max(1.0, abs(want_ratio)), (i_t, k["ratio"], want_ratio)
+            assert abs(k["a"] - want_a) <= 4e-6 * max(1.0, abs(want_a)), (i_t, k["a"], want_a)
+            assert abs(k["b"] - want_a) <= 4e-6 * max(1.0, abs(want_a))  # bh2: B_h = expm1(-h) too
+            if order == 2:
+                lt, l0, lp = lam(i_t), lam(i_s0), lam(i_s0 - 1)
+                if math.isinf(lt):  # last step: sigma_t = 0, h = inf, rk = 0 (diffusers divides by it: inf; the kernel multiplies by 1/rk)
+                    continue
+                h = lt - l0
+                rk = (lp - l0) / h
+                assert abs(k["rk_inv"] * rk - 1) < 2e-5, (i_t, k["rk_inv"], 1 / rk)
+                if corrector:
+                    hh = -h
+                    e1 = math.expm1(hh)
+                    k1 = e1 / hh - 1
+                    k2 = k1 / hh - 0.5
+                    b0, b1 = k1 / e1, 2 * k2 / e1
+                    rho0 = (b0 - b1) / (1 - rk)
+                    rho1 = b0 - rho0
+                    ok0 = abs(k["rho0"] - rho0) < 5e-5 * max(1.0, abs(rho0))
+                    ok1 = abs(k["rho_last"] - rho1) < 5e-5 * max(1.0, abs(rho1))
+                    assert ok0 and ok1, (i_t, k["rho0"], rho0, k["rho_last"], rho1)
+                else:
+                    assert k["rho0"] == 0.5
+            else:
+                assert k["rho0"] == 0.5 and k["rho_last"] == 0.5
+            seen += 1
+        assert seen >= 2 * n - 3
+    # schedule definition itself (SURVEY App. B.1): sigma_i = shift * s / (1 + (shift - 1) s), s = linspace(1, 1/1000, n + 1)[:-1] reversed
+    s = UniPCMultistepScheduler(flow_shift=5.0)
+    s.set_timesteps(50)
+    base = 1 - np.linspace(1, 1 / 1000, 51)
+    want = np.flip(5.0 * base / (1 + 4.0 * base))[:-1]
+    assert np.allclose(s.sigmas.numpy()[:-1], want.astype(np.float32)) and float(s.sigmas[-1]) == 0.0
+    assert s.timesteps.tolist() == [int(v) for v in (want * 1000).astype(np.int64)]
+
+
+def test_ddim_coefficients_against_fp64_closed_forms():
+    """CogVideoXDDIMScheduler._coeffs vs the v-prediction DDIM update written out in fp64 from alphas_cumprod:
+    x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps with x0 = sqrt(a_t) x - sqrt(1 - a_t) v, eps = sqrt(a_t) v + sqrt(1 - a_t) x,
+    which must equal the scheduler's  a * x + b * x0  form for every step."""
+    import math
+
+    from alg_b200.schedulers import CogVideoXDDIMScheduler
+    s = CogVideoXDDIMScheduler()
+    s.set_timesteps(50)
+    ac = s.alphas_cumprod.double()
+    for t in s.timesteps.tolist():
+        sa, sb, a, b = s._coeffs(int(t))
+        prev = t - 1000 // 50
+        a_t = float(ac[t])
+        a_p = float(ac[prev]) if prev >= 0 else 1.0
+        assert abs(sa - math.sqrt(a_t)) < 1e-6 and abs(sb - math.sqrt(1 - a_t)) < 1e-6
+        x, v = 0.37, -1.21
+        x0 = math.sqrt(a_t) * x - math.sqrt(1 - a_t) * v
+        eps = math.sqrt(a_t) * v + math.sqrt(1 - a_t) * x
+        want = math.sqrt(a_p) * x0 + math.sqrt(1 - a_p) * eps
+        got = a * x + b * (sa * x - sb * v)
+        assert abs(got - want) < 2e-6 * max(1.0, abs(want)), (t, got, want)
