@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libalg_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ALG_F32, ALG_BF16, ALG_F16 = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 NORM_NONE, NORM_RMS, NORM_LAYER = 0, 1, 2
 EW_ADD, EW_SILU, EW_COPY, EW_GELU_TANH = 0, 1, 2, 3
 EPI_NONE, EPI_GELU_TANH, EPI_GATE_RESIDUAL, EPI_RESIDUAL, EPI_GELU_ERF, EPI_SILU = range(6)
@@ -108,7 +108,7 @@ class SmallAttention(C.Structure):
         ("batch", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32), ("n_q", C.c_int64), ("n_kv", C.c_int64),
         ("q_bs", C.c_int64), ("q_rs", C.c_int64), ("k_bs", C.c_int64), ("k_rs", C.c_int64), ("v_bs", C.c_int64),
         ("v_rs", C.c_int64), ("o_bs", C.c_int64), ("o_rs", C.c_int64), ("scale", C.c_float), ("rel_bias", C.c_void_p),
-        ("kv_valid", C.c_void_p), ("causal", C.c_int32),
+        ("kv_valid", C.c_void_p), ("causal", C.c_int32), ("kv_group", C.c_int32), ("key_mask", C.c_void_p),
     ]
 
 
@@ -157,6 +157,9 @@ SIGNATURES = {
     "alg_layer_norm_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "alg_bias_act_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "alg_split3_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "alg_rms_norm_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "alg_rope_half_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "alg_swiglu_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "alg_mul_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "alg_patchify_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "alg_clip_embed_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

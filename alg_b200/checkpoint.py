@@ -143,23 +143,25 @@ def build_from_snapshot(model_cls, scheduler_cls, snapshot: str, device="cuda"):
     return transformer, scheduler_cls.from_config(scheduler_config(snapshot))
 
 
-AUX_MESSAGE = ("this snapshot has no loadable VAE / text encoder / image encoder for the native loaders (the Wan / Hunyuan VAEs and "
-               "the LLaVA encoder are not built, SURVEY 8(f)): pass real `vae=` / `text_encoder=` / `image_encoder=` objects (anything "
+AUX_MESSAGE = ("this snapshot has no loadable VAE / text encoder / image encoder for the native loaders (missing folder, or a "
+               "component that is not built natively, SURVEY 8(f)): pass real `vae=` / `text_encoder=` / `image_encoder=` objects (anything "
                "with the transformers / diffusers call surface), or allow_synthetic_aux=True for shape-only stand-ins "
                "(latent-space runs with your own prompt_embeds / image_embeds)")
 
 
-def load_text_stack(snapshot: str, encoder_cls, device="cuda", tokenizer=None):
-    """(tokenizer, native text encoder) from ``<snapshot>/tokenizer`` + ``<snapshot>/text_encoder``; (tokenizer, None) when the
-    encoder folder is missing.  The tokenizer is transformers' own (host-side text processing) unless one is handed in."""
-    tdir, edir = os.path.join(snapshot, "tokenizer"), os.path.join(snapshot, "text_encoder")
+def load_text_stack(snapshot: str, encoder_cls, device="cuda", tokenizer=None, tokenizer_dir: str = "tokenizer",
+                    encoder_dir: str = "text_encoder", **encoder_kwargs):
+    """(tokenizer, native text encoder) from ``<snapshot>/tokenizer`` + ``<snapshot>/text_encoder`` (or the ``_2`` folders of
+    HunyuanVideo); (tokenizer, None) when the encoder folder is missing.  The tokenizer is transformers' own (host-side text
+    processing) unless one is handed in."""
+    tdir, edir = os.path.join(snapshot, tokenizer_dir), os.path.join(snapshot, encoder_dir)
     if not os.path.isdir(edir) or (tokenizer is None and not os.path.isdir(tdir)):
         return tokenizer, None
     if tokenizer is None:
         from transformers import AutoTokenizer
 
         tokenizer = AutoTokenizer.from_pretrained(tdir)
-    return tokenizer, encoder_cls.from_pretrained(snapshot, device=device)
+    return tokenizer, encoder_cls.from_pretrained(snapshot, subfolder=encoder_dir, device=device, **encoder_kwargs)
 
 
 def load_image_stack(snapshot: str, encoder_cls, device="cuda", image_processor=None):

@@ -87,6 +87,8 @@ struct SmallAttn {
   const float* rel_bias;  // [H, 2 * L_kv - 1]: added to the score of (query i, key j) at index j - i + L_kv - 1; or NULL
   const int32_t* kv_valid;  // [B] keys >= kv_valid[b] are masked (right padding); or NULL
   int causal;
+  int kv_group;             // query heads per key / value head (grouped-query attention); 1 = one K/V head per query head
+  const uint8_t* key_mask;  // [B, L_kv] 0 = masked key (a padding mask that is not a prefix); or NULL
 };
 
 template <typename T, int KPL>
@@ -193,6 +195,160 @@ __global__ void __launch_bounds__(kWarps * 32) small_attention_kernel(const Smal
         for (int c = 0; c < 4; ++c)
           if (c * 32 + lane < D) ob[(int64_t)(row0 + r) * p.o_rs + c * 32 + lane] = from_f<T>(o[r][c]);
     __syncwarp();
+  }
+}
+
+// ---- tiled attention (LLaVA's Llama: ~900 tokens, causal + padding mask, 32 query heads on 8 K/V heads, fp32) --------
+// Same contract as small_attention_kernel without the 768-key limit and without rel_bias: keys stream through shared memory
+// 64 at a time with a running (max, sum) per query row.  A warp owns 8 query rows; a lane owns keys lane, lane + 32 of the
+// tile for the scores and head_dim columns lane + 32 c for the output.
+constexpr int kTK = 64, kTRows = 8;
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32) tiled_attention_kernel(const SmallAttn p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int D = p.D;
+  T* sKt = reinterpret_cast<T*>(smem_raw);                        // [D][kTK]
+  T* sV = sKt + (size_t)D * kTK;                                  // [kTK][D]
+  float* sQ = reinterpret_cast<float*>(sV + (size_t)kTK * D);     // [kWarps][kTRows][D]
+  float* sP = sQ + kWarps * kTRows * D;                           // [kWarps][kTRows][kTK]
+  const int h = blockIdx.y, b = blockIdx.z, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hk = h / p.kv_group;
+  const T* kb = reinterpret_cast<const T*>(p.k) + (int64_t)b * p.k_bs + (int64_t)hk * D;
+  const T* vb = reinterpret_cast<const T*>(p.v) + (int64_t)b * p.v_bs + (int64_t)hk * D;
+  const T* qb = reinterpret_cast<const T*>(p.q) + (int64_t)b * p.q_bs + (int64_t)h * D;
+  T* ob = reinterpret_cast<T*>(p.out) + (int64_t)b * p.o_bs + (int64_t)h * D;
+  const uint8_t* km = p.key_mask ? p.key_mask + (int64_t)b * p.L_kv : nullptr;
+  const int n_valid = p.kv_valid ? min(p.kv_valid[b], p.L_kv) : p.L_kv;
+  const int cta_row0 = blockIdx.x * (kWarps * kTRows), row0 = cta_row0 + warp * kTRows;
+  float* myQ = sQ + warp * kTRows * D;
+  float* myP = sP + warp * kTRows * kTK;
+  for (int idx = lane; idx < kTRows * D; idx += 32) {
+    const int r = idx / D, d = idx - r * D;
+    myQ[idx] = row0 + r < p.L_q ? to_f<T>(qb[(int64_t)(row0 + r) * p.q_rs + d]) : 0.f;
+  }
+  float m_run[kTRows], l_run[kTRows], o[kTRows][4];
+#pragma unroll
+  for (int r = 0; r < kTRows; ++r) {
+    m_run[r] = -INFINITY;
+    l_run[r] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[r][c] = 0.f;
+  }
+  // keys past the last query row of the CTA are never visible under the causal mask
+  const int key_end = p.causal ? min(n_valid, min(cta_row0 + kWarps * kTRows, p.L_q)) : n_valid;
+  for (int k0 = 0; k0 < key_end; k0 += kTK) {
+    __syncthreads();  // the previous tile is fully consumed
+    for (int idx = threadIdx.x; idx < kTK * D; idx += blockDim.x) {
+      const int j = idx / D, d = idx - j * D;
+      const bool ok = k0 + j < p.L_kv;
+      sKt[(size_t)d * kTK + j] = ok ? kb[(int64_t)(k0 + j) * p.k_rs + d] : from_f<T>(0.f);
+      sV[idx] = ok ? vb[(int64_t)(k0 + j) * p.v_rs + d] : from_f<T>(0.f);
+    }
+    __syncthreads();
+    float s[kTRows][2];
+#pragma unroll
+    for (int r = 0; r < kTRows; ++r) s[r][0] = s[r][1] = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float k_a = to_f<T>(sKt[(size_t)d * kTK + lane]), k_b = to_f<T>(sKt[(size_t)d * kTK + 32 + lane]);
+#pragma unroll
+      for (int r = 0; r < kTRows; ++r) {
+        const float qv = myQ[r * D + d];
+        s[r][0] = fmaf(qv, k_a, s[r][0]);
+        s[r][1] = fmaf(qv, k_b, s[r][1]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kTRows; ++r) {
+      const int i = row0 + r;
+      float mt = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int j = k0 + c * 32 + lane;
+        float x = s[r][c];
+        if (sizeof(T) == 2) x = bf16_round(x);
+        x *= p.scale;
+        if (j >= n_valid || (p.causal && j > i) || (km && j < p.L_kv && !km[j])) x = -INFINITY;
+        s[r][c] = x;
+        mt = fmaxf(mt, x);
+      }
+      mt = warp_max(mt);
+      const float m_new = fmaxf(m_run[r], mt);
+      const float f = (m_run[r] == -INFINITY) ? 0.f : __expf(m_run[r] - m_new);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float e = (s[r][c] == -INFINITY) ? 0.f : __expf(s[r][c] - m_new);
+        myP[r * kTK + c * 32 + lane] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      l_run[r] = l_run[r] * f + sum;
+      m_run[r] = m_new;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[r][c] *= f;
+    }
+    __syncwarp();
+    const int jn = min(kTK, key_end - k0);
+    for (int j = 0; j < jn; ++j) {
+      float vv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) vv[c] = (c * 32 + lane < D) ? to_f<T>(sV[(size_t)j * D + c * 32 + lane]) : 0.f;
+#pragma unroll
+      for (int r = 0; r < kTRows; ++r) {
+        const float pv = myP[r * kTK + j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[r][c] = fmaf(pv, vv[c], o[r][c]);
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int r = 0; r < kTRows; ++r) {
+    if (row0 + r >= p.L_q) continue;
+    const float inv = l_run[r] > 0.f ? 1.0f / l_run[r] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c * 32 + lane < D) ob[(int64_t)(row0 + r) * p.o_rs + c * 32 + lane] = from_f<T>(o[r][c] * inv);
+  }
+}
+
+// ---- fp32 pieces of the Llama decoder stack (LLaVA text encoder, hy:333-337) -----------------------------------------
+// LlamaRMSNorm: out = weight * (x * rsqrt(mean(x^2) + eps))
+__global__ void __launch_bounds__(256) rms_norm_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int d, float eps,
+                                                           const float* __restrict__ w) {
+  __shared__ float red[8];
+  const float* xr = x + (int64_t)blockIdx.x * d;
+  float* orow = out + (int64_t)blockIdx.x * d;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < d; i += 256) ss += xr[i] * xr[i];
+  const float r = rsqrtf(block_sum<256>(ss, red) / (float)d + eps);
+  for (int i = threadIdx.x; i < d; i += 256) orow[i] = w[i] * (xr[i] * r);
+}
+// apply_rotary_pos_emb, rotate-half convention, in place on `heads` heads of every row: x = x * cos + rotate_half(x) * sin
+// with cos / sin [rows, D] (the two halves of a table row are equal); products and sum rounded separately like the eager ops
+__global__ void rope_half_f32_kernel(float* __restrict__ x, int64_t ld, const float* __restrict__ cs, const float* __restrict__ sn,
+                                     int heads, int D, int64_t n) {
+  const int half = D / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % half);
+    const int64_t t = i / half;
+    const int h = (int)(t % heads);
+    const int64_t row = t / heads;
+    float* xp = x + row * ld + (int64_t)h * D;
+    const float a = xp[c], b2 = xp[c + half];
+    const float* cr = cs + row * D;
+    const float* sr = sn + row * D;
+    xp[c] = __fadd_rn(__fmul_rn(a, cr[c]), __fmul_rn(-b2, sr[c]));
+    xp[c + half] = __fadd_rn(__fmul_rn(b2, cr[c + half]), __fmul_rn(a, sr[c + half]));
+  }
+}
+// LlamaMLP gate: out[r, c] = silu(gu[r, c]) * gu[r, f + c] for the fused [gate | up] projection gu [rows, 2 f]
+__global__ void swiglu_f32_kernel(const float* __restrict__ gu, float* __restrict__ out, int f, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / f;
+    const int c = (int)(i - r * f);
+    const float g = gu[r * 2 * f + c], u = gu[r * 2 * f + f + c];
+    out[i] = (g / (1.0f + expf(-g))) * u;
   }
 }
 
@@ -305,6 +461,16 @@ static int launch_small_attention(const SmallAttn& p, int B, int H, cudaStream_t
   ALG_REQUIRE(false, "small_attention: more than 768 keys");
 }
 
+template <typename T>
+static int launch_tiled_attention(const SmallAttn& p, int B, int H, cudaStream_t st) {
+  const size_t smem = 2 * (size_t)p.D * kTK * sizeof(T) + (size_t)kWarps * kTRows * (p.D + kTK) * sizeof(float);
+  dim3 grid((unsigned)((p.L_q + kWarps * kTRows - 1) / (kWarps * kTRows)), (unsigned)H, (unsigned)B);
+  ALG_CUDA_OK(cudaFuncSetAttribute(tiled_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tiled_attention_kernel<T><<<grid, kWarps * 32, smem, st>>>(p);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace enc
 }  // namespace alg
 
@@ -347,7 +513,15 @@ extern "C" int alg_small_attention(const alg_small_attention_t* a, void* stream)
   p.v_bs = a->v_bs; p.v_rs = a->v_rs; p.o_bs = a->o_bs; p.o_rs = a->o_rs;
   p.L_q = (int)a->n_q; p.L_kv = (int)a->n_kv; p.D = a->head_dim; p.Lp = ((int)a->n_kv + 31) / 32 * 32;
   p.scale = a->scale; p.rel_bias = a->rel_bias; p.kv_valid = a->kv_valid; p.causal = a->causal;
+  p.kv_group = a->kv_group > 1 ? a->kv_group : 1;
+  p.key_mask = a->key_mask;
+  ALG_REQUIRE(a->heads % p.kv_group == 0, "small_attention: heads must be a multiple of kv_group");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p.kv_group > 1 || p.key_mask || a->n_kv > 768) {  // streamed-key variant: grouped K/V heads, general key mask, long prompts
+    ALG_REQUIRE(!a->rel_bias, "small_attention: rel_bias needs n_kv <= 768, kv_group 1 and no key_mask");
+    if (a->dtype == ALG_BF16) return enc::launch_tiled_attention<__nv_bfloat16>(p, a->batch, a->heads, st);
+    return enc::launch_tiled_attention<float>(p, a->batch, a->heads, st);
+  }
   if (a->dtype == ALG_BF16) return enc::launch_small_attention<__nv_bfloat16>(p, a->batch, a->heads, st);
   return enc::launch_small_attention<float>(p, a->batch, a->heads, st);
 }
@@ -410,6 +584,37 @@ extern "C" int alg_clip_embed_f32(const float* patches, const float* class_embed
   const int64_t n = (int64_t)batch * (num_patches + 1) * d;
   enc::clip_embed_f32_kernel<<<enc::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       patches, class_embedding, position_embedding, out, num_patches, d, n);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_rms_norm_f32(const float* x, float* out, int64_t rows, int d, float eps, const float* weight, void* stream) {
+  ALG_REQUIRE(x && out && weight && rows >= 0 && d > 0, "rms_norm_f32: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  if (rows == 0) return 0;
+  enc::rms_norm_f32_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, d, eps, weight);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_rope_half_f32(float* x, int64_t ld, const float* cos_table, const float* sin_table, int64_t rows, int heads,
+                                 int head_dim, void* stream) {
+  ALG_REQUIRE(x && cos_table && sin_table && rows >= 0 && heads > 0 && head_dim > 0 && head_dim % 2 == 0 &&
+                  ld >= (int64_t)heads * head_dim, "rope_half_f32: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  if (rows == 0) return 0;
+  const int64_t n = rows * heads * (head_dim / 2);
+  enc::rope_half_f32_kernel<<<enc::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ld, cos_table, sin_table,
+                                                                                                 heads, head_dim, n);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_swiglu_f32(const float* gate_up, float* out, int64_t rows, int f, void* stream) {
+  ALG_REQUIRE(gate_up && out && rows >= 0 && f > 0, "swiglu_f32: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  if (rows == 0) return 0;
+  enc::swiglu_f32_kernel<<<enc::grid_for(rows * f), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gate_up, out, f, rows * f);
   ALG_LAUNCH_OK();
   return 0;
 }

@@ -35,6 +35,8 @@ UMT5_XXL = dict(vocab_size=256384, d_model=4096, d_kv=64, d_ff=10240, num_layers
                 relative_attention_num_buckets=32, relative_attention_max_distance=128, layer_norm_epsilon=1e-6,
                 per_layer_relative_bias=True)   # google/umt5-xxl (Wan text_encoder)
 T5_V1_1_XXL = dict(UMT5_XXL, vocab_size=32128, per_layer_relative_bias=False)  # CogVideoX text_encoder: bias table in block 0 only
+CLIP_L_TEXT = dict(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+                   max_position_embeddings=77, hidden_act="quick_gelu", layer_norm_eps=1e-5, eos_token_id=2)  # HunyuanVideo text_encoder_2
 CLIP_VIT_H_14 = dict(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=16, image_size=224,
                      patch_size=14, num_channels=3, hidden_act="gelu", layer_norm_eps=1e-5)  # Wan image_encoder
 
@@ -44,9 +46,34 @@ def _launch(fn, device, *args):
         _lib.check(fn(*args, _lib.stream_ptr(device)))
 
 
+def split_weight(wt: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
+    """fp32 (or fp16) [N, K] -> bf16 [N, 3 K'] = [hi | lo | hi] (K zero-padded to K' so that rows stay 16-byte aligned)."""
+    wt = wt.float().reshape(wt.shape[0], -1).contiguous()
+    N, K = wt.shape
+    k_pad = k_pad or K
+    if k_pad != K:
+        wt = torch.cat([wt, wt.new_zeros(N, k_pad - K)], dim=1).contiguous()
+    out = torch.empty(N, 3 * k_pad, device=wt.device, dtype=torch.bfloat16)
+    _launch(_lib.lib().alg_split3_bf16, wt.device, wt.data_ptr(), out.data_ptr(), N, k_pad, 1)
+    return out
+
+
+def linear_f32(x: torch.Tensor, w3: torch.Tensor, bias, act: int = 0, residual=None) -> torch.Tensor:
+    """fp32 nn.Linear on the bf16 tensor cores: split the activations [hi | hi | lo], one K-tripled GEMM with fp32
+    accumulation and fp32 output, then bias / activation / residual in fp32."""
+    rows, K = x.shape
+    a3 = torch.empty(rows, 3 * K, device=x.device, dtype=torch.bfloat16)
+    _launch(_lib.lib().alg_split3_bf16, x.device, x.data_ptr(), a3.data_ptr(), rows, K, 0)
+    y = ops.gemm(a3, w3, None, out_dtype=torch.float32)
+    if bias is not None or act or residual is not None:
+        _launch(_lib.lib().alg_bias_act_f32, x.device, y.data_ptr(), None if bias is None else bias.data_ptr(),
+                None if residual is None else residual.data_ptr(), rows, y.shape[1], act)
+    return y
+
+
 def small_attention(q, k, v, out, *, batch, heads, head_dim, n_q, n_kv, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, scale,
-                    rel_bias=None, kv_valid=None, causal=False):
-    _lib.require_cuda(q, k, v, out, rel_bias, kv_valid)
+                    rel_bias=None, kv_valid=None, causal=False, kv_group=1, key_mask=None):
+    _lib.require_cuda(q, k, v, out, rel_bias, kv_valid, key_mask)
     a = _lib.SmallAttention()
     a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
     a.dtype, a.batch, a.heads, a.head_dim, a.n_q, a.n_kv = _lib.dtype_code(q.dtype), batch, heads, head_dim, n_q, n_kv
@@ -54,6 +81,8 @@ def small_attention(q, k, v, out, *, batch, heads, head_dim, n_q, n_kv, q_bs, q_
     a.scale, a.causal = float(scale), int(causal)
     a.rel_bias = None if rel_bias is None else rel_bias.data_ptr()
     a.kv_valid = None if kv_valid is None else kv_valid.data_ptr()
+    a.kv_group = int(kv_group)
+    a.key_mask = None if key_mask is None else key_mask.data_ptr()
     _launch(_lib.lib().alg_small_attention, q.device, C.byref(a))
     return out
 
@@ -323,15 +352,7 @@ class CLIPVisionModel:
         return m.load_state_dict(sd)
 
     def _split_weight(self, wt: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
-        """fp32 [N, K] -> bf16 [N, 3 K'] = [hi | lo | hi] (K zero-padded to K' so that rows stay 16-byte aligned)."""
-        wt = wt.float().reshape(wt.shape[0], -1).contiguous()
-        N, K = wt.shape
-        k_pad = k_pad or K
-        if k_pad != K:
-            wt = torch.cat([wt, wt.new_zeros(N, k_pad - K)], dim=1).contiguous()
-        out = torch.empty(N, 3 * k_pad, device=wt.device, dtype=torch.bfloat16)
-        _launch(_lib.lib().alg_split3_bf16, wt.device, wt.data_ptr(), out.data_ptr(), N, k_pad, 1)
-        return out
+        return split_weight(wt, k_pad)
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
         shapes = self.parameter_shapes()
@@ -347,14 +368,8 @@ class CLIPVisionModel:
         w = dict(self._sd)
         self._k_patch = (c["num_channels"] * c["patch_size"] ** 2 + 7) // 8 * 8
         w["patch.w3"] = self._split_weight(w["vision_model.embeddings.patch_embedding.weight"], self._k_patch)
-        for i in range(c["num_hidden_layers"]):
-            p = f"vision_model.encoder.layers.{i}."
-            qkv = torch.cat([w[p + f"self_attn.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")], dim=0)
-            w[p + "qkv.w3"] = self._split_weight(qkv)
-            w[p + "qkv.bias"] = torch.cat([w[p + f"self_attn.{n}.bias"] for n in ("q_proj", "k_proj", "v_proj")]).contiguous()
-            for n in ("self_attn.out_proj", "mlp.fc1", "mlp.fc2"):
-                w[p + n + ".w3"] = self._split_weight(w[p + n + ".weight"])
         self._w = w
+        self._prepare_layers(w, "vision_model.encoder.layers.")
         return self
 
     def state_dict(self):
@@ -369,15 +384,42 @@ class CLIPVisionModel:
         return self
 
     def _linear(self, x: torch.Tensor, w3: torch.Tensor, bias, act: int = 0, residual=None) -> torch.Tensor:
-        """fp32 nn.Linear on the bf16 tensor cores: split the activations [hi | hi | lo], one K-tripled GEMM with fp32
-        accumulation and fp32 output, then bias / activation / residual in fp32."""
-        rows, K = x.shape
-        a3 = torch.empty(rows, 3 * K, device=x.device, dtype=torch.bfloat16)
-        _launch(_lib.lib().alg_split3_bf16, x.device, x.data_ptr(), a3.data_ptr(), rows, K, 0)
-        y = ops.gemm(a3, w3, None, out_dtype=torch.float32)
-        _launch(_lib.lib().alg_bias_act_f32, x.device, y.data_ptr(), None if bias is None else bias.data_ptr(),
-                None if residual is None else residual.data_ptr(), rows, y.shape[1], act)
-        return y
+        return linear_f32(x, w3, bias, act, residual)
+
+    def _layers(self, x: torch.Tensor, B: int, L: int, prefix: str, causal: bool, kv_valid=None) -> List[torch.Tensor]:
+        """The pre-LN CLIP encoder stack on x [B*L, d] fp32; returns [input, after layer 0, after layer 1, ...] as [B, L, d] views."""
+        c, w, dev, lib = self._cfg, self._w, self.device, _lib.lib()
+        d, heads, eps, rows = c["hidden_size"], c["num_attention_heads"], c["layer_norm_eps"], x.shape[0]
+        hidden: List[torch.Tensor] = [x.view(B, L, d)]
+        act = 1 if c["hidden_act"] == "gelu" else 2
+        dh = d // heads
+        for i in range(c["num_hidden_layers"]):
+            p = f"{prefix}{i}."
+            h = torch.empty_like(x)
+            _launch(lib.alg_layer_norm_f32, dev, x.data_ptr(), h.data_ptr(), rows, d, eps, w[p + "layer_norm1.weight"].data_ptr(),
+                    w[p + "layer_norm1.bias"].data_ptr())
+            qkv = self._linear(h, w[p + "qkv.w3"], w[p + "qkv.bias"])
+            att = torch.empty(rows, d, device=dev, dtype=torch.float32)
+            small_attention(qkv, qkv[:, d:], qkv[:, 2 * d:], att, batch=B, heads=heads, head_dim=dh, n_q=L, n_kv=L,
+                            q_bs=L * 3 * d, q_rs=3 * d, k_bs=L * 3 * d, k_rs=3 * d, v_bs=L * 3 * d, v_rs=3 * d, o_bs=L * d, o_rs=d,
+                            scale=dh ** -0.5, causal=causal, kv_valid=kv_valid)
+            x = self._linear(att, w[p + "self_attn.out_proj.w3"], w[p + "self_attn.out_proj.bias"], residual=x)
+            h = torch.empty_like(x)
+            _launch(lib.alg_layer_norm_f32, dev, x.data_ptr(), h.data_ptr(), rows, d, eps, w[p + "layer_norm2.weight"].data_ptr(),
+                    w[p + "layer_norm2.bias"].data_ptr())
+            f = self._linear(h, w[p + "mlp.fc1.w3"], w[p + "mlp.fc1.bias"], act=act)
+            x = self._linear(f, w[p + "mlp.fc2.w3"], w[p + "mlp.fc2.bias"], residual=x)
+            hidden.append(x.view(B, L, d))
+        return hidden
+
+    def _prepare_layers(self, w: Dict[str, torch.Tensor], prefix: str) -> None:
+        for i in range(self._cfg["num_hidden_layers"]):
+            p = f"{prefix}{i}."
+            qkv = torch.cat([w[p + f"self_attn.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")], dim=0)
+            w[p + "qkv.w3"] = self._split_weight(qkv)
+            w[p + "qkv.bias"] = torch.cat([w[p + f"self_attn.{n}.bias"] for n in ("q_proj", "k_proj", "v_proj")]).contiguous()
+            for n in ("self_attn.out_proj", "mlp.fc1", "mlp.fc2"):
+                w[p + n + ".w3"] = self._split_weight(w[p + n + ".weight"])
 
     def __call__(self, pixel_values=None, output_hidden_states: bool = True, **kw):
         c, w, dev = self._cfg, self._w, self.device
@@ -402,25 +444,110 @@ class CLIPVisionModel:
         h = torch.empty_like(x)
         _launch(lib.alg_layer_norm_f32, dev, x.data_ptr(), h.data_ptr(), rows, d, eps, w["vision_model.pre_layrnorm.weight"].data_ptr(),
                 w["vision_model.pre_layrnorm.bias"].data_ptr())
-        x = h
-        hidden: List[torch.Tensor] = [x.view(B, L, d)]
-        act = 1 if c["hidden_act"] == "gelu" else 2
-        dh = d // heads
-        for i in range(c["num_hidden_layers"]):
-            p = f"vision_model.encoder.layers.{i}."
-            h = torch.empty_like(x)
-            _launch(lib.alg_layer_norm_f32, dev, x.data_ptr(), h.data_ptr(), rows, d, eps, w[p + "layer_norm1.weight"].data_ptr(),
-                    w[p + "layer_norm1.bias"].data_ptr())
-            qkv = self._linear(h, w[p + "qkv.w3"], w[p + "qkv.bias"])
-            att = torch.empty(rows, d, device=dev, dtype=torch.float32)
-            small_attention(qkv, qkv[:, d:], qkv[:, 2 * d:], att, batch=B, heads=heads, head_dim=dh, n_q=L, n_kv=L,
-                            q_bs=L * 3 * d, q_rs=3 * d, k_bs=L * 3 * d, k_rs=3 * d, v_bs=L * 3 * d, v_rs=3 * d, o_bs=L * d, o_rs=d,
-                            scale=dh ** -0.5)
-            x = self._linear(att, w[p + "self_attn.out_proj.w3"], w[p + "self_attn.out_proj.bias"], residual=x)
-            h = torch.empty_like(x)
-            _launch(lib.alg_layer_norm_f32, dev, x.data_ptr(), h.data_ptr(), rows, d, eps, w[p + "layer_norm2.weight"].data_ptr(),
-                    w[p + "layer_norm2.bias"].data_ptr())
-            f = self._linear(h, w[p + "mlp.fc1.w3"], w[p + "mlp.fc1.bias"], act=act)
-            x = self._linear(f, w[p + "mlp.fc2.w3"], w[p + "mlp.fc2.bias"], residual=x)
-            hidden.append(x.view(B, L, d))
+        hidden = self._layers(h, B, L, "vision_model.encoder.layers.", causal=False)
         return SimpleNamespace(hidden_states=tuple(hidden), last_hidden_state=hidden[-1])
+
+
+# ======================================================================================================
+# CLIP text tower (HunyuanVideo ``text_encoder_2``: the pooled prompt embedding, hy:421-452)
+# ======================================================================================================
+class CLIPTextModel(CLIPVisionModel):
+    """Native ``CLIPTextModel``: token + position embeddings, causal pre-LN encoder, final LayerNorm, EOS pooling.  Arithmetic
+    is float32 (the bf16x3 tensor-core linears of the vision tower), a superset of the fp16 the reference loads it in."""
+
+    HF_DEFAULTS = dict(vocab_size=49408, hidden_size=512, intermediate_size=2048, num_hidden_layers=12, num_attention_heads=8,
+                       max_position_embeddings=77, hidden_act="quick_gelu", layer_norm_eps=1e-5, eos_token_id=2)
+
+    def parameter_shapes(self) -> Dict[str, tuple]:
+        c = self._cfg
+        d, f = c["hidden_size"], c["intermediate_size"]
+        s = {"text_model.embeddings.token_embedding.weight": (c["vocab_size"], d),
+             "text_model.embeddings.position_embedding.weight": (c["max_position_embeddings"], d),
+             "text_model.final_layer_norm.weight": (d,), "text_model.final_layer_norm.bias": (d,)}
+        for i in range(c["num_hidden_layers"]):
+            p = f"text_model.encoder.layers.{i}."
+            for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                s[p + f"self_attn.{n}.weight"], s[p + f"self_attn.{n}.bias"] = (d, d), (d,)
+            for n in ("layer_norm1", "layer_norm2"):
+                s[p + n + ".weight"], s[p + n + ".bias"] = (d,), (d,)
+            s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"] = (f, d), (f,)
+            s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"] = (d, f), (d,)
+        return s
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: str = "text_encoder_2", torch_dtype=None, cache_dir=None,
+                        device="cuda"):
+        import os
+
+        from . import checkpoint
+        snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir)
+        if snap is None:
+            raise FileNotFoundError(f"no local snapshot for {pretrained_model_name_or_path!r} (there is no network)")
+        folder = os.path.join(snap, subfolder) if subfolder else snap
+        cfg = checkpoint.read_config(folder)
+        cfg = cfg.get("text_config", cfg)
+        return cls(**cfg).load_state_dict(checkpoint.load_safetensors_dir(folder, device))
+
+    @classmethod
+    def from_synthetic(cls, seed: int = 0, device="cuda", **config):
+        m = cls(**config)
+        sd = {}
+        for idx, (name, shape) in enumerate(m.parameter_shapes().items()):
+            g = torch.Generator(device=device).manual_seed(seed * 1_000_003 + 5_001 + idx)
+            if "norm" in name and name.endswith(".weight"):
+                w = 1 + 0.1 * torch.randn(shape, generator=g, device=device)
+            elif name.endswith(".bias"):
+                w = 0.02 * torch.randn(shape, generator=g, device=device)
+            elif "embedding" in name:
+                w = 0.5 * torch.randn(shape, generator=g, device=device)
+            else:
+                w = torch.randn(shape, generator=g, device=device) * (shape[1] ** -0.5)
+            sd[name] = w.float()
+        return m.load_state_dict(sd)
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        shapes = self.parameter_shapes()
+        missing = [k for k in shapes if k not in sd]
+        if missing:
+            raise KeyError(f"missing parameters: {missing[:4]}{'...' if len(missing) > 4 else ''}")
+        dev = sd["text_model.final_layer_norm.weight"].device
+        if dev.type != "cuda":
+            raise RuntimeError("encoder weights must live on a CUDA device (no CPU fallback)")
+        self.device = dev
+        self._sd = {k: sd[k].to(device=dev, dtype=torch.float32).contiguous() for k in shapes}
+        self._w = dict(self._sd)
+        self._prepare_layers(self._w, "text_model.encoder.layers.")
+        return self
+
+    def __call__(self, input_ids=None, attention_mask=None, output_hidden_states: bool = False, **kw):
+        c, w, dev, lib = self._cfg, self._w, self.device, _lib.lib()
+        if not w:
+            raise RuntimeError("CLIPTextModel has no weights loaded")
+        ids = input_ids.to(dev).to(torch.int64).contiguous()
+        B, L = ids.shape
+        d = c["hidden_size"]
+        if L > c["max_position_embeddings"]:
+            raise ValueError(f"sequence length {L} exceeds max_position_embeddings {c['max_position_embeddings']}")
+        x = torch.empty(B * L, d, device=dev, dtype=torch.float32)
+        tok = w["text_model.embeddings.token_embedding.weight"]
+        # fp32 rows moved as 2 d 16-bit lanes (the gather is a byte copy)
+        _launch(lib.alg_gather_rows_bf16, dev, tok.data_ptr(), c["vocab_size"], ids.data_ptr(), x.data_ptr(), B * L, 2 * d)
+        pos = w["text_model.embeddings.position_embedding.weight"]
+        for b in range(B):
+            _launch(lib.alg_bias_act_f32, dev, x[b * L:].data_ptr(), None, pos.data_ptr(), L, d, 0)
+        valid = None if attention_mask is None else attention_mask.to(dev).gt(0).sum(dim=1).to(torch.int32).contiguous()
+        hidden = self._layers(x, B, L, "text_model.encoder.layers.", causal=True, kv_valid=valid)
+        last = torch.empty(B * L, d, device=dev, dtype=torch.float32)
+        _launch(lib.alg_layer_norm_f32, dev, hidden[-1].data_ptr(), last.data_ptr(), B * L, d, c["layer_norm_eps"],
+                w["text_model.final_layer_norm.weight"].data_ptr(), w["text_model.final_layer_norm.bias"].data_ptr())
+        # pooled = the hidden state at the end-of-text token: argmax of the ids for the legacy eos id 2, else the first eos
+        host = ids.cpu()
+        if c["eos_token_id"] == 2:
+            eos = host.argmax(dim=-1)
+        else:
+            eos = (host == c["eos_token_id"]).int().argmax(dim=-1)
+        rows = (torch.arange(B) * L + eos).to(dev)
+        pooled = torch.empty(B, d, device=dev, dtype=torch.float32)
+        _launch(lib.alg_gather_rows_bf16, dev, last.data_ptr(), B * L, rows.data_ptr(), pooled.data_ptr(), B, 2 * d)
+        return SimpleNamespace(last_hidden_state=last.view(B, L, d), pooler_output=pooled,
+                               hidden_states=tuple(hidden) if output_hidden_states else None)

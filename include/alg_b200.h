@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ALG_B200_ABI_VERSION 4
+#define ALG_B200_ABI_VERSION 5
 
 typedef enum { ALG_F32 = 0, ALG_BF16 = 1, ALG_F16 = 2 } alg_dtype_t;
 
@@ -291,7 +291,8 @@ int alg_t5_rms_norm_bf16(const void* x, int64_t ld_x, void* out, int64_t ld_out,
 /* nn.Embedding: out[r, :] = table[ids[r], :] (bf16 rows of d elements, d % 8 == 0; ids int64 on the device). */
 int alg_gather_rows_bf16(const void* table, int64_t vocab, const int64_t* ids, void* out, int64_t rows, int d, void* stream);
 
-/* softmax(scale * q k^T + rel_bias + mask) v for short sequences (<= 768 keys, head_dim <= 128), bf16 or fp32, with the
+/* softmax(scale * q k^T + rel_bias + mask) v for short sequences (head_dim <= 128; <= 768 keys with rel_bias, any length
+ * streamed 64 keys at a time otherwise -- LLaVA's ~900-token Llama prompt, hy:333-337), bf16 or fp32, with the
  * eager op chain's roundings in bf16 mode (q k^T -> bf16, + bias -> bf16, softmax in fp32 -> bf16, P V -> bf16).
  * q / k / v / out: element (b, token, h, d) at ptr + b * bs + token * rs + h * head_dim + d.
  * rel_bias (optional) fp32 [heads, 2 * n_kv - 1]: the T5 relative-position bias of (query i, key j) sits at j - i + n_kv - 1.
@@ -309,6 +310,8 @@ typedef struct {
   const float* rel_bias;
   const int32_t* kv_valid;
   int32_t causal;
+  int32_t kv_group;        /* grouped-query attention: query head h reads K / V head h / kv_group (0 or 1 = one per head) */
+  const uint8_t* key_mask; /* optional [batch, n_kv]: 0 = masked key (padding that is not a suffix) */
 } alg_small_attention_t;
 int alg_small_attention(const alg_small_attention_t* a, void* stream);
 
@@ -327,6 +330,15 @@ int alg_patchify_f32(const float* x, float* out, int batch, int C, int H, int W,
 /* out [batch, num_patches + 1, d]: token 0 = class_embedding + pos[0]; token 1 + n = patches[b * num_patches + n] + pos[1 + n] */
 int alg_clip_embed_f32(const float* patches, const float* class_embedding, const float* position_embedding, float* out,
                        int batch, int num_patches, int d, void* stream);
+/* fp32 pieces of the Llama decoder inside LLaVA (HunyuanVideo text_encoder, hy:333-337; transformers modeling_llama.py): */
+/* LlamaRMSNorm: out = weight * (x * rsqrt(mean(x^2) + eps)) over fp32 rows of length d */
+int alg_rms_norm_f32(const float* x, float* out, int64_t rows, int d, float eps, const float* weight, void* stream);
+/* apply_rotary_pos_emb (rotate-half) in place on the first `heads` heads of every row of x [rows, ld]:
+ * x = x * cos + rotate_half(x) * sin, cos / sin fp32 [rows, head_dim] */
+int alg_rope_half_f32(float* x, int64_t ld, const float* cos_table, const float* sin_table, int64_t rows, int heads, int head_dim,
+                      void* stream);
+/* LlamaMLP: out[r, c] = silu(gate_up[r, c]) * gate_up[r, f + c] for the fused [gate | up] projection [rows, 2 f] */
+int alg_swiglu_f32(const float* gate_up, float* out, int64_t rows, int f, void* stream);
 /* out = bf16(a * b) elementwise (T5 gated-GELU feed-forward: gelu(wi_0 x) * wi_1 x) */
 int alg_mul_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 

@@ -85,6 +85,28 @@ def retrieve_latents(encoder_output, generator=None, sample_mode: str = "sample"
     raise AttributeError("Could not access latents of provided encoder_output")
 
 
+def _expand_input_ids_with_image_tokens(text_input_ids, prompt_attention_mask, max_sequence_length, image_token_index,
+                                        image_emb_len, image_emb_start, image_emb_end, pad_token_id):
+    """hy:107-149: every ``<image>`` token becomes ``image_emb_len`` slots; later tokens shift right; the attention mask is
+    rebuilt from "not the pad token" and ``position_ids`` count the attended tokens (masked slots get position 1)."""
+    is_image = text_input_ids == image_token_index
+    n_image = torch.sum(is_image, dim=-1)
+    rows, cols = torch.where(text_input_ids != image_token_index)
+    expanded_len = max_sequence_length + (n_image.max() * (image_emb_len - 1))
+    new_pos = torch.cumsum((is_image * (image_emb_len - 1) + 1), -1) - 1
+    expanded_ids = torch.full((text_input_ids.shape[0], expanded_len), pad_token_id, dtype=text_input_ids.dtype,
+                              device=text_input_ids.device)
+    expanded_ids[rows, new_pos[rows, cols]] = text_input_ids[rows, cols]
+    expanded_ids[rows, image_emb_start:image_emb_end] = image_token_index
+    expanded_mask = torch.zeros((text_input_ids.shape[0], expanded_len), dtype=prompt_attention_mask.dtype,
+                                device=prompt_attention_mask.device)
+    arows, acols = torch.where(expanded_ids != pad_token_id)
+    expanded_mask[arows, acols] = 1.0
+    expanded_mask = expanded_mask.to(prompt_attention_mask.dtype)
+    position_ids = (expanded_mask.cumsum(-1) - 1).masked_fill_((expanded_mask == 0), 1)
+    return {"input_ids": expanded_ids, "attention_mask": expanded_mask, "position_ids": position_ids}
+
+
 class HunyuanVideoImageToVideoPipeline(DiffusionPipelineBase):
     """Image-to-video generation with HunyuanVideo + ALG on the native sm_100a kernels (reference class: hy:224-280)."""
 
@@ -105,16 +127,19 @@ class HunyuanVideoImageToVideoPipeline(DiffusionPipelineBase):
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, transformer=None, vae=None, torch_dtype=torch.float16,
                         cache_dir=None, synthetic: Optional[bool] = None, allow_synthetic_aux: bool = False,
-                        seed: int = 0, device="cuda", **config_overrides):
-        """run.py:71-81.  Offline there are no checkpoints: ``synthetic=True`` (or ``ALG_SYNTHETIC=1``) builds the true
-        HunyuanVideo-I2V architecture with seeded random weights directly on ``device``."""
+                        seed: int = 0, device="cuda", tokenizer=None, text_encoder=None, tokenizer_2=None, text_encoder_2=None,
+                        image_processor=None, **config_overrides):
+        """run.py:71-81.  A local diffusers snapshot loads the real DiT weights and scheduler config plus the native LLaVA /
+        CLIP-L prompt encoders from its ``text_encoder`` / ``text_encoder_2`` folders; offline there are no checkpoints:
+        ``synthetic=True`` (or ``ALG_SYNTHETIC=1``) builds the true HunyuanVideo-I2V architecture with seeded random weights
+        directly on ``device``."""
         import os
 
         if synthetic is None:
             synthetic = os.environ.get("ALG_SYNTHETIC", "0") == "1" or str(pretrained_model_name_or_path).startswith("synthetic")
         scheduler = None
         if not synthetic:
-            from alg_b200 import checkpoint
+            from alg_b200 import checkpoint, encoders, llava
 
             snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir)
             if snap is None:
@@ -125,41 +150,125 @@ class HunyuanVideoImageToVideoPipeline(DiffusionPipelineBase):
                 transformer, scheduler = checkpoint.build_from_snapshot(HunyuanVideoTransformer3DModel, FlowMatchEulerDiscreteScheduler, snap, device)
             else:
                 scheduler = FlowMatchEulerDiscreteScheduler.from_config(checkpoint.scheduler_config(snap))
-            if vae is None and not allow_synthetic_aux:
+            if text_encoder is None:  # native LLaVA-Llama-3 (fp32 arithmetic, reported dtype = torch_dtype) + the snapshot's tokenizer
+                tokenizer, text_encoder = checkpoint.load_text_stack(snap, llava.LlavaForConditionalGeneration, device, tokenizer,
+                                                                     torch_dtype=torch_dtype)
+            if text_encoder_2 is None:  # native CLIP-L text tower
+                tokenizer_2, text_encoder_2 = checkpoint.load_text_stack(snap, encoders.CLIPTextModel, device, tokenizer_2,
+                                                                         tokenizer_dir="tokenizer_2", encoder_dir="text_encoder_2")
+            if image_processor is None and os.path.isdir(os.path.join(snap, "image_processor")):
+                from transformers import CLIPImageProcessor
+
+                image_processor = CLIPImageProcessor.from_pretrained(os.path.join(snap, "image_processor"))
+            if (vae is None or text_encoder is None or text_encoder_2 is None or image_processor is None) and not allow_synthetic_aux:
                 raise NotImplementedError(checkpoint.AUX_MESSAGE)
         if transformer is None:
             transformer = HunyuanVideoTransformer3DModel.from_synthetic(seed=seed, device=device, **config_overrides)
+        if synthetic and os.environ.get("ALG_NATIVE_ENCODERS", "0") == "1":
+            # synthetic weights at the TRUE encoder architectures (LLaVA-Llama-3-8B, CLIP-L) through the native kernels; the
+            # tokenizers have no offline vocabulary, so prompts still need tokenizer / tokenizer_2 objects from the caller
+            from alg_b200 import encoders, llava
+
+            text_encoder = text_encoder or llava.LlavaForConditionalGeneration.from_synthetic(seed=seed, device=device, torch_dtype=torch_dtype)
+            text_encoder_2 = text_encoder_2 or encoders.CLIPTextModel.from_synthetic(seed=seed, device=device, **encoders.CLIP_L_TEXT)
         if vae is None:
             vae = SyntheticVideoVAE(z_dim=transformer.config.in_channels, scaling_factor=0.476986, dtype=torch_dtype)
             vae.temporal_compression_ratio, vae.spatial_compression_ratio = 4, 8
-        return cls(text_encoder=SyntheticTextEncoder(transformer.config.text_embed_dim, torch_dtype), tokenizer=None,
+        return cls(text_encoder=text_encoder or SyntheticTextEncoder(transformer.config.text_embed_dim, torch_dtype), tokenizer=tokenizer,
                    transformer=transformer, vae=vae, scheduler=scheduler or FlowMatchEulerDiscreteScheduler(shift=7.0),
-                   text_encoder_2=SyntheticTextEncoder(transformer.config.pooled_projection_dim, torch_dtype),
-                   tokenizer_2=None, image_processor=None)
+                   text_encoder_2=text_encoder_2 or SyntheticTextEncoder(transformer.config.pooled_projection_dim, torch_dtype),
+                   tokenizer_2=tokenizer_2, image_processor=image_processor)
 
     # ------------------------------------------------------------------------------------------------
-    # once-per-video conditioning (hy:282-492).  LLaVA-Llama3 + CLIP-L are out of scope; synthetic encoders stand in and
-    # produce the same shapes: [B, L, 4096] tokens with a prefix attention mask, and a [B, 768] pooled vector.
+    # once-per-video conditioning (hy:282-492).  tokenizer / text_encoder (LLaVA-Llama-3) / image_processor and tokenizer_2 /
+    # text_encoder_2 (CLIP-L) are driven through the transformers call surface the reference uses, so real HF objects and the
+    # native encoders (alg_b200/llava.py, alg_b200/encoders.py::CLIPTextModel) are interchangeable; the hash-seeded
+    # SyntheticTextEncoder stand-ins (synthetic weights only) keep their own short path and produce the same shapes.
     def _get_llama_prompt_embeds(self, image, prompt, prompt_template, num_videos_per_prompt=1, device=None, dtype=None,
-                                 max_sequence_length: int = 256, image_embed_interleave: int = 2):
+                                 max_sequence_length: int = 256, num_hidden_layers_to_skip: int = 2,
+                                 image_embed_interleave: int = 2):
         device = device or self._execution_device
         dtype = dtype or self.text_encoder.dtype
         prompt = [prompt] if isinstance(prompt, str) else prompt
-        n_img = prompt_template.get("image_emb_len", 576) // max(image_embed_interleave, 1)
-        n_img = min(n_img, 16)  # the synthetic encoder keeps the image-token block short
-        total = n_img + max_sequence_length
-        embeds = self.text_encoder.embed(prompt, total, zero_pad=False).to(device=device, dtype=dtype)
-        mask = torch.zeros(len(prompt), total, device=device, dtype=torch.long)
-        for b, p in enumerate(prompt):
-            mask[b, : n_img + max(1, min(max_sequence_length, len(p.split()) + 2))] = 1
-        return embeds.repeat_interleave(num_videos_per_prompt, dim=0), mask.repeat_interleave(num_videos_per_prompt, dim=0)
+        if isinstance(self.text_encoder, SyntheticTextEncoder):
+            n_img = prompt_template.get("image_emb_len", 576) // max(image_embed_interleave, 1)
+            n_img = min(n_img, 16)  # the synthetic encoder keeps the image-token block short
+            total = n_img + max_sequence_length
+            embeds = self.text_encoder.embed(prompt, total, zero_pad=False).to(device=device, dtype=dtype)
+            mask = torch.zeros(len(prompt), total, device=device, dtype=torch.long)
+            for b, p in enumerate(prompt):
+                mask[b, : n_img + max(1, min(max_sequence_length, len(p.split()) + 2))] = 1
+            return embeds.repeat_interleave(num_videos_per_prompt, dim=0), mask.repeat_interleave(num_videos_per_prompt, dim=0)
+
+        # hy:297-337: template -> ids -> <image> expanded to image_emb_len slots -> LLaVA hidden state (skip + 1) from the end
+        prompt = [prompt_template["template"].format(p) for p in prompt]
+        crop_start = prompt_template.get("crop_start", None)
+        image_emb_len = prompt_template.get("image_emb_len", 576)
+        image_emb_start = prompt_template.get("image_emb_start", 5)
+        image_emb_end = prompt_template.get("image_emb_end", 581)
+        double_return_token_id = prompt_template.get("double_return_token_id", 271)
+        if crop_start is None:
+            template_ids = self.tokenizer(prompt_template["template"], padding="max_length", return_tensors="pt",
+                                          return_length=False, return_overflowing_tokens=False, return_attention_mask=False)
+            # minus <|start_header_id|>, <|end_header_id|>, assistant, <|eot_id|> and the {} placeholder (hy:308-310)
+            crop_start = template_ids["input_ids"].shape[-1] - 5
+        max_sequence_length += crop_start
+        text_inputs = self.tokenizer(prompt, max_length=max_sequence_length, padding="max_length", truncation=True,
+                                     return_tensors="pt", return_length=False, return_overflowing_tokens=False,
+                                     return_attention_mask=True)
+        text_input_ids = text_inputs.input_ids.to(device=device)
+        prompt_attention_mask = text_inputs.attention_mask.to(device=device)
+        pixel_values = self.image_processor(image, return_tensors="pt").pixel_values.to(device)
+        expanded = _expand_input_ids_with_image_tokens(
+            text_input_ids, prompt_attention_mask, max_sequence_length, self.text_encoder.config.image_token_index,
+            image_emb_len, image_emb_start, image_emb_end, self.text_encoder.config.pad_token_id)
+        prompt_embeds = self.text_encoder(**expanded, pixel_values=pixel_values,
+                                          output_hidden_states=True).hidden_states[-(num_hidden_layers_to_skip + 1)]
+        prompt_embeds = prompt_embeds.to(dtype=dtype)
+
+        if crop_start is not None and crop_start > 0:
+            # hy:342-399: drop the system template and the 4-token assistant header; image slots become their own block in front
+            text_crop_start = crop_start - 1 + image_emb_len
+            rows, cols = torch.where(text_input_ids == double_return_token_id)
+            if cols.shape[0] == 3:  # the prompt was truncated before the assistant header's "\n\n" (hy:346-351)
+                cols = torch.cat((cols, torch.tensor([text_input_ids.shape[-1]], device=cols.device)))
+                rows = torch.cat((rows, torch.tensor([0], device=rows.device)))
+            last_dr = cols.reshape(text_input_ids.shape[0], -1)[:, -1]
+            text_list, mask_list, image_list, image_mask_list = [], [], [], []
+            for i in range(text_input_ids.shape[0]):
+                dr = int(last_dr[i].item())
+                a0, a1 = dr - 1 + image_emb_len - 4, dr - 1 + image_emb_len  # the assistant header inside the expanded sequence
+                text_list.append(torch.cat([prompt_embeds[i, text_crop_start:a0], prompt_embeds[i, a1:]]))
+                mask_list.append(torch.cat([prompt_attention_mask[i, crop_start:dr - 4], prompt_attention_mask[i, dr:]]))
+                image_list.append(prompt_embeds[i, image_emb_start:image_emb_end])
+                image_mask_list.append(torch.ones(image_list[-1].shape[0]).to(prompt_embeds.device).to(prompt_attention_mask.dtype))
+            text_embeds, text_mask = torch.stack(text_list), torch.stack(mask_list)
+            image_embeds, image_mask = torch.stack(image_list), torch.stack(image_mask_list)
+            if 0 < image_embed_interleave < 6:
+                image_embeds = image_embeds[:, ::image_embed_interleave, :]
+                image_mask = image_mask[:, ::image_embed_interleave]
+            assert text_embeds.shape[0] == text_mask.shape[0] and image_embeds.shape[0] == image_mask.shape[0]
+            prompt_embeds = torch.cat([image_embeds, text_embeds], dim=1)
+            prompt_attention_mask = torch.cat([image_mask, text_mask], dim=1)
+        return prompt_embeds, prompt_attention_mask
 
     def _get_clip_prompt_embeds(self, prompt, num_videos_per_prompt=1, device=None, dtype=None, max_sequence_length: int = 77):
         device = device or self._execution_device
         dtype = dtype or self.text_encoder_2.dtype
         prompt = [prompt] if isinstance(prompt, str) else prompt
-        pooled = self.text_encoder_2.embed(prompt, 1, zero_pad=False)[:, 0].to(device=device, dtype=dtype)
-        return pooled.repeat_interleave(num_videos_per_prompt, dim=0)
+        if isinstance(self.text_encoder_2, SyntheticTextEncoder):
+            pooled = self.text_encoder_2.embed(prompt, 1, zero_pad=False)[:, 0].to(device=device, dtype=dtype)
+            return pooled.repeat_interleave(num_videos_per_prompt, dim=0)
+        # hy:421-452: ids only (no attention mask), pooled = the end-of-text token's final state; returned as the encoder made it
+        text_inputs = self.tokenizer_2(prompt, padding="max_length", max_length=max_sequence_length, truncation=True,
+                                       return_tensors="pt")
+        text_input_ids = text_inputs.input_ids
+        untruncated_ids = self.tokenizer_2(prompt, padding="longest", return_tensors="pt").input_ids
+        if untruncated_ids.shape[-1] >= text_input_ids.shape[-1] and not torch.equal(text_input_ids, untruncated_ids):
+            removed_text = self.tokenizer_2.batch_decode(untruncated_ids[:, max_sequence_length - 1: -1])
+            logger.warning("The following part of your input was truncated because CLIP can only handle sequences up to"
+                           f" {max_sequence_length} tokens: {removed_text}")
+        return self.text_encoder_2(text_input_ids.to(device), output_hidden_states=False).pooler_output
 
     def encode_prompt(self, image, prompt, prompt_2=None, prompt_template: Dict[str, Any] = DEFAULT_PROMPT_TEMPLATE,
                       num_videos_per_prompt: int = 1, prompt_embeds=None, pooled_prompt_embeds=None,

@@ -119,6 +119,50 @@ def test_clip_vision_matches_transformers(over, tol):
         assert a.dtype == torch.float32 and rel_l2(a, b) < tol, (i, rel_l2(a, b))
 
 
+@pytest.mark.parametrize("over,eos_legacy", [
+    (dict(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=4, vocab_size=1000, eos_token_id=2), True),
+    (dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=2, num_attention_heads=12, vocab_size=49408, eos_token_id=49407), False),
+])
+def test_clip_text_matches_transformers(over, eos_legacy):
+    """HunyuanVideo text_encoder_2 (hy:421-452): ids only (no attention mask), causal, pooled = the EOS token's final-LN state."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from alg_b200 import encoders
+    torch.manual_seed(7)
+    cfg = dict(max_position_embeddings=77, hidden_act="quick_gelu", layer_norm_eps=1e-5, bos_token_id=0, pad_token_id=1)
+    cfg.update(over)
+    hf = CLIPTextModel(CLIPTextConfig(**cfg)).eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                p.copy_(1 + 0.1 * torch.randn_like(p))
+            elif n.endswith("bias"):
+                p.copy_(0.05 * torch.randn_like(p))
+            elif "embedding" in n:
+                p.copy_(0.5 * torch.randn_like(p))
+            else:
+                p.copy_(torch.randn_like(p) * (p.shape[1] ** -0.5))
+    hf = hf.float().cuda()
+    mine = encoders.CLIPTextModel(**cfg).load_state_dict({k: v.detach().clone() for k, v in hf.state_dict().items()})
+    g = torch.Generator().manual_seed(11)
+    eos = cfg["eos_token_id"]
+    hi = cfg["vocab_size"] - 1 if eos_legacy else eos  # legacy pooling = argmax of the ids: keep EOS the largest id only when it is
+    ids = torch.randint(3, hi, (3, 77), generator=g)
+    for b, n in enumerate((9, 77, 40)):  # prompt, EOS, then padding with the EOS id (CLIP tokenizers pad with <|endoftext|>)
+        ids[b, n - 1:] = eos if not eos_legacy else 1
+        if eos_legacy:
+            ids[b, n - 1] = cfg["vocab_size"] - 1
+    ids = ids.cuda()
+    with torch.no_grad():
+        ref = hf(ids, output_hidden_states=True)
+    out = mine(ids, output_hidden_states=True)
+    assert out.pooler_output.shape == ref.pooler_output.shape and out.pooler_output.dtype == torch.float32
+    assert rel_l2(out.pooler_output, ref.pooler_output) < 1e-4, rel_l2(out.pooler_output, ref.pooler_output)
+    assert rel_l2(out.last_hidden_state, ref.last_hidden_state) < 1e-4
+    for i, (a, b) in enumerate(zip(out.hidden_states, ref.hidden_states)):
+        assert rel_l2(a, b) < 1e-4, (i, rel_l2(a, b))
+    assert mine(ids).hidden_states is None
+
+
 def test_small_attention_masks_causal_and_fp32_against_torch():
     """alg_small_attention alone: causal flag (CLIP text towers), key-padding, head_dim 80, fp32 and bf16."""
     import torch.nn.functional as F
