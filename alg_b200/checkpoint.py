@@ -18,10 +18,11 @@ WEIGHTS_NAME = "diffusion_pytorch_model.safetensors"
 INDEX_NAME = WEIGHTS_NAME + ".index.json"
 
 
-def resolve_snapshot(path: str, cache_dir: Optional[str] = None) -> Optional[str]:
-    """A local directory that looks like a diffusers pipeline snapshot, or None.  Accepts the directory itself or a hub id
-    whose snapshot sits in the HF cache layout under ``cache_dir`` (models--org--name/snapshots/<rev>/)."""
-    if os.path.isdir(path) and os.path.isdir(os.path.join(path, "transformer")):
+def resolve_snapshot(path: str, cache_dir: Optional[str] = None, require: str = "transformer") -> Optional[str]:
+    """A local directory that looks like a diffusers pipeline snapshot (it has the ``require`` component folder), or None.
+    Accepts the directory itself or a hub id whose snapshot sits in the HF cache layout under ``cache_dir``
+    (models--org--name/snapshots/<rev>/)."""
+    if os.path.isdir(path) and os.path.isdir(os.path.join(path, require)):
         return path
     if cache_dir:
         repo = os.path.join(cache_dir, "models--" + path.replace("/", "--"))
@@ -35,7 +36,7 @@ def resolve_snapshot(path: str, cache_dir: Optional[str] = None) -> Optional[str
                     revs = [main] + [r for r in revs if r != main]
             for rev in revs:
                 cand = os.path.join(root, rev)
-                if os.path.isdir(os.path.join(cand, "transformer")):
+                if os.path.isdir(os.path.join(cand, require)):
                     return cand
     return None
 

@@ -1,0 +1,250 @@
+// Building blocks of the float32 video VAEs (AutoencoderKLWan: wan:429-434 condition encode, wan:526 per-step encode in
+// pixel-space ALG, wan:959 decode; run.py:51-55 loads it in float32).  Activations are channels-last [T*H*W, C] fp32.  Every
+// convolution is a patch gather that writes the bf16 3-term split [hi | hi | lo] of the fp32 patch directly (the gather and the
+// split are one pass), followed by ONE alg_gemm_bf16 against the weight's [hi | lo | hi] split with fp32 accumulation and fp32
+// output: hi*hi + hi*lo + lo*hi = the fp32 product up to 2^-16 (closer to fp32 than the TF32 convolutions PyTorch runs by default).
+//
+//   alg_im2col_split3_f32   causal (ZERO front padding, WanCausalConv3d) / strided / nearest-x2-upsampled patch gather + split
+//   alg_rms_norm_cl_f32     WanRMS_norm over the channel axis (+ SiLU): x / max(||x||, 1e-12) * sqrt(C) * gamma
+//   alg_softmax_rows_f32    softmax(scale * s) over rows (WanAttentionBlock: one head of C channels, scores via the split GEMM)
+//   alg_nchw_to_cl_f32 / alg_cl_to_nchw_f32   [C, P] <-> [P, ld] layout changes at the VAE boundary (+ clamp on the way out)
+// All HBM-bound streaming kernels; grids sized in multiples of the SM count.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace alg {
+namespace vae32 {
+
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+
+constexpr int kTile = 32;  // output pixels per block
+
+// Vector path (C % 4 == 0): a thread owns one 4-channel group of the K axis (tap decoded once) and walks the tile's pixels;
+// consecutive threads write consecutive 8-byte chunks of a row in each of the three K sections.
+__global__ void __launch_bounds__(256) im2col_split3_vec_kernel(const alg_im2col_f32_t p, int c4, int k4, int ld4, int64_t M) {
+  const float4* __restrict__ x = reinterpret_cast<const float4*>(p.x);
+  uint2* __restrict__ cols = reinterpret_cast<uint2*>(p.cols);
+  const int64_t m0 = (int64_t)blockIdx.x * kTile;
+  const int n = (int)min((int64_t)kTile, M - m0);
+  const int wo0 = (int)(m0 % p.Wo);
+  const int64_t r0 = m0 / p.Wo;
+  const int ho0 = (int)(r0 % p.Ho), to0 = (int)(r0 / p.Ho) + p.to0;
+  const int HL = p.H * p.up, WL = p.W * p.up;  // logical (upsampled) frame
+  for (int kc = threadIdx.x; kc < ld4; kc += blockDim.x) {
+    uint2* dst = cols + m0 * 3 * ld4 + kc;
+    if (kc >= k4) {  // zero tail of a padded row
+      for (int i = 0; i < n; ++i, dst += 3 * ld4) dst[0] = dst[ld4] = dst[2 * ld4] = make_uint2(0u, 0u);
+      continue;
+    }
+    const int tap = kc / c4, cc = kc - tap * c4;
+    const int it = tap / (p.kh * p.kw), r2 = tap - it * (p.kh * p.kw);
+    const int ih = r2 / p.kw, iw = r2 - ih * p.kw;
+    int wo = wo0, ho = ho0, to = to0;
+    for (int i = 0; i < n; ++i, dst += 3 * ld4) {
+      const int t = to * p.st + it - p.pad_t;
+      const int y = ho * p.sh + ih - p.pad_top, xx = wo * p.sw + iw - p.pad_left;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t >= p.t_min && y >= 0 && y < HL && xx >= 0 && xx < WL)
+        v = __ldg(x + (((int64_t)t * p.H + y / p.up) * p.W + xx / p.up) * c4 + cc);
+      uint2 hi, lo;
+      split_pair(v.x, v.y, hi.x, lo.x);
+      split_pair(v.z, v.w, hi.y, lo.y);
+      dst[0] = hi;
+      dst[ld4] = hi;
+      dst[2 * ld4] = lo;
+      if (++wo == p.Wo) {
+        wo = 0;
+        if (++ho == p.Ho) {
+          ho = 0;
+          ++to;
+        }
+      }
+    }
+  }
+}
+
+// Scalar path (any C; the RGB input convolution of the encoder): one thread per (pixel, k) element.
+__global__ void __launch_bounds__(256) im2col_split3_scalar_kernel(const alg_im2col_f32_t p, int K, int64_t M) {
+  const float* __restrict__ x = reinterpret_cast<const float*>(p.x);
+  __nv_bfloat16* __restrict__ cols = reinterpret_cast<__nv_bfloat16*>(p.cols);
+  const int HL = p.H * p.up, WL = p.W * p.up;
+  const int64_t n = M * p.ld;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % p.ld);
+    const int64_t m = i / p.ld;
+    float v = 0.f;
+    if (k < K) {
+      const int tap = k / p.C, c = k - tap * p.C;
+      const int it = tap / (p.kh * p.kw), r2 = tap - it * (p.kh * p.kw);
+      const int ih = r2 / p.kw, iw = r2 - ih * p.kw;
+      const int wo = (int)(m % p.Wo);
+      const int64_t r = m / p.Wo;
+      const int ho = (int)(r % p.Ho), to = (int)(r / p.Ho) + p.to0;
+      const int t = to * p.st + it - p.pad_t;
+      const int y = ho * p.sh + ih - p.pad_top, xx = wo * p.sw + iw - p.pad_left;
+      if (t >= p.t_min && y >= 0 && y < HL && xx >= 0 && xx < WL)
+        v = x[(((int64_t)t * p.H + y / p.up) * p.W + xx / p.up) * p.C + c];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* row = cols + m * 3 * p.ld;
+    row[k] = hi;
+    row[p.ld + k] = hi;
+    row[2 * p.ld + k] = lo;
+  }
+}
+
+// WanRMS_norm on channels-last rows: one warp per pixel row.  F.normalize(x, dim=C) * sqrt(C) * gamma (+ bias) (+ SiLU).
+__global__ void __launch_bounds__(256) rms_norm_cl_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t rows, int C,
+                                                          float scale, const float* __restrict__ gamma,
+                                                          const float* __restrict__ bias, int silu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* xr = x + r * C;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = xr[c];
+      ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    float* orow = out + r * C;
+    for (int c = lane; c < C; c += 32) {
+      float v = __fdiv_rn(xr[c], denom) * scale * gamma[c];
+      if (bias) v += bias[c];
+      if (silu) v = v / (1.0f + expf(-v));
+      orow[c] = v;
+    }
+  }
+}
+
+// in place: row <- softmax(scale * row).  One block per row (6 240 columns at the Wan 480p latent size).
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int cols, int64_t ld, float scale) {
+  __shared__ float red[8];
+  float* row = x + (int64_t)blockIdx.x * ld;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, row[c] * scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    const float e = expf(row[c] * scale - m);
+    row[c] = e;
+    s += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i];
+  const float inv = 1.0f / s;
+  for (int c = threadIdx.x; c < cols; c += 256) row[c] *= inv;
+}
+
+// [C, P] (channel-major: one sample of [B, C, T, H, W]) -> [P, ld] channels-last, columns >= C zeroed
+__global__ void nchw_to_cl_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int64_t P, int ld) {
+  const int64_t n = P * ld;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ld);
+    const int64_t pix = i / ld;
+    out[i] = c < C ? x[(int64_t)c * P + pix] : 0.f;
+  }
+}
+// [P, ld] channels-last -> [C, P]; clamp to [lo, hi] when lo < hi
+__global__ void cl_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int64_t P, int ld, float lo, float hi) {
+  const int64_t n = P * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i % P;
+    const int c = (int)(i / P);
+    float v = x[pix * ld + c];
+    if (lo < hi) v = fminf(fmaxf(v, lo), hi);
+    out[i] = v;
+  }
+}
+
+static int grid_for(int64_t n, int per = 256) { return (int)std::min<int64_t>((n + per - 1) / per, 148 * 16); }
+
+}  // namespace vae32
+}  // namespace alg
+
+using namespace alg;
+
+extern "C" int alg_im2col_split3_f32(const alg_im2col_f32_t* p, void* stream) {
+  ALG_REQUIRE(p && p->x && p->cols, "im2col_split3: null pointer");
+  ALG_REQUIRE(p->T > 0 && p->H > 0 && p->W > 0 && p->C > 0, "im2col_split3: empty input");
+  ALG_REQUIRE(p->kt > 0 && p->kh > 0 && p->kw > 0 && p->st > 0 && p->sh > 0 && p->sw > 0, "im2col_split3: bad kernel / stride");
+  ALG_REQUIRE(p->To > 0 && p->Ho > 0 && p->Wo > 0 && p->to0 >= 0 && p->pad_t >= 0 && p->pad_top >= 0 && p->pad_left >= 0,
+              "im2col_split3: bad output geometry");
+  ALG_REQUIRE(p->up == 1 || p->up == 2, "im2col_split3: up must be 1 or 2");
+  const int64_t K = (int64_t)p->kt * p->kh * p->kw * p->C;
+  ALG_REQUIRE(p->ld >= K && p->ld % 8 == 0, "im2col_split3: ld must be >= kt*kh*kw*C and a multiple of 8");
+  ALG_REQUIRE((int64_t)(p->to0 + p->To - 1) * p->st + p->kt - 1 - p->pad_t < p->T, "im2col_split3: temporal window runs past the last frame");
+  ALG_REQUIRE(((reinterpret_cast<uintptr_t>(p->x) | reinterpret_cast<uintptr_t>(p->cols)) & 15) == 0, "im2col_split3: misaligned pointer");
+  if (int rc = alg_check_device()) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t M = (int64_t)p->To * p->Ho * p->Wo;
+  if (p->C % 4 == 0) {
+    const int ld4 = (int)(p->ld / 4);
+    const int threads = std::min(256, (ld4 + 31) / 32 * 32);
+    const int64_t grid = (M + vae32::kTile - 1) / vae32::kTile;
+    ALG_REQUIRE(grid <= 0x7fffffff, "im2col_split3: too many output pixels");
+    vae32::im2col_split3_vec_kernel<<<(unsigned)grid, threads, 0, st>>>(*p, p->C / 4, (int)(K / 4), ld4, M);
+  } else {
+    vae32::im2col_split3_scalar_kernel<<<vae32::grid_for(M * p->ld), 256, 0, st>>>(*p, (int)K, M);
+  }
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_rms_norm_cl_f32(const float* x, float* out, int64_t rows, int C, const float* gamma, const float* bias, int silu,
+                                   void* stream) {
+  ALG_REQUIRE(x && out && gamma && rows >= 0 && C > 0, "rms_norm_cl: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  if (rows == 0) return 0;
+  vae32::rms_norm_cl_kernel<<<vae32::grid_for(rows, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, out, rows, C, sqrtf((float)C), gamma, bias, silu);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_softmax_rows_f32(float* x, int64_t rows, int cols, int64_t ld, float scale, void* stream) {
+  ALG_REQUIRE(x && rows >= 0 && cols > 0 && ld >= cols, "softmax_rows: bad arguments");
+  ALG_REQUIRE(rows <= 0x7fffffff, "softmax_rows: too many rows");
+  if (int rc = alg_check_device()) return rc;
+  if (rows == 0) return 0;
+  vae32::softmax_rows_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, cols, ld, scale);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_nchw_to_cl_f32(const float* x, float* out, int C, int64_t pixels, int ld, void* stream) {
+  ALG_REQUIRE(x && out && C > 0 && pixels > 0 && ld >= C, "nchw_to_cl: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  vae32::nchw_to_cl_kernel<<<vae32::grid_for(pixels * ld), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, C, pixels, ld);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_cl_to_nchw_f32(const float* x, float* out, int C, int64_t pixels, int ld, float lo, float hi, void* stream) {
+  ALG_REQUIRE(x && out && C > 0 && pixels > 0 && ld >= C, "cl_to_nchw: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  vae32::cl_to_nchw_kernel<<<vae32::grid_for(pixels * C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, C, pixels, ld, lo, hi);
+  ALG_LAUNCH_OK();
+  return 0;
+}

@@ -58,13 +58,20 @@ def split_weight(wt: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
     return out
 
 
+def split_act(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, K] contiguous -> bf16 [rows, 3 K] = [hi | hi | lo] (the activation side of the split product)."""
+    rows, K = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32
+    a3 = torch.empty(rows, 3 * K, device=x.device, dtype=torch.bfloat16)
+    _launch(_lib.lib().alg_split3_bf16, x.device, x.data_ptr(), a3.data_ptr(), rows, K, 0)
+    return a3
+
+
 def linear_f32(x: torch.Tensor, w3: torch.Tensor, bias, act: int = 0, residual=None) -> torch.Tensor:
     """fp32 nn.Linear on the bf16 tensor cores: split the activations [hi | hi | lo], one K-tripled GEMM with fp32
     accumulation and fp32 output, then bias / activation / residual in fp32."""
     rows, K = x.shape
-    a3 = torch.empty(rows, 3 * K, device=x.device, dtype=torch.bfloat16)
-    _launch(_lib.lib().alg_split3_bf16, x.device, x.data_ptr(), a3.data_ptr(), rows, K, 0)
-    y = ops.gemm(a3, w3, None, out_dtype=torch.float32)
+    y = ops.gemm(split_act(x), w3, None, out_dtype=torch.float32)
     if bias is not None or act or residual is not None:
         _launch(_lib.lib().alg_bias_act_f32, x.device, y.data_ptr(), None if bias is None else bias.data_ptr(),
                 None if residual is None else residual.data_ptr(), rows, y.shape[1], act)
@@ -146,7 +153,7 @@ class UMT5EncoderModel:
         import os
 
         from . import checkpoint
-        snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir)
+        snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir, require=subfolder or "transformer")
         if snap is None:
             raise FileNotFoundError(f"no local snapshot for {pretrained_model_name_or_path!r} (there is no network)")
         folder = os.path.join(snap, subfolder) if subfolder else snap
@@ -322,7 +329,7 @@ class CLIPVisionModel:
         import os
 
         from . import checkpoint
-        snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir)
+        snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir, require=subfolder or "transformer")
         if snap is None:
             raise FileNotFoundError(f"no local snapshot for {pretrained_model_name_or_path!r} (there is no network)")
         folder = os.path.join(snap, subfolder) if subfolder else snap
@@ -480,7 +487,7 @@ class CLIPTextModel(CLIPVisionModel):
         import os
 
         from . import checkpoint
-        snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir)
+        snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir, require=subfolder or "transformer")
         if snap is None:
             raise FileNotFoundError(f"no local snapshot for {pretrained_model_name_or_path!r} (there is no network)")
         folder = os.path.join(snap, subfolder) if subfolder else snap

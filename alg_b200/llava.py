@@ -124,7 +124,7 @@ class LlavaForConditionalGeneration:
         import os
 
         from . import checkpoint
-        snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir)
+        snap = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir, require=subfolder or "transformer")
         if snap is None:
             raise FileNotFoundError(f"no local snapshot for {pretrained_model_name_or_path!r} (there is no network)")
         folder = os.path.join(snap, subfolder) if subfolder else snap

@@ -214,7 +214,7 @@ class AutoencoderKLCogVideoX:
         """Weights from a LOCAL diffusers snapshot (``vae/config.json`` + safetensors): encoder and decoder; with ``decoder=``
         given only the encoder keys are read and ``decode`` is delegated."""
         from . import checkpoint
-        root = checkpoint.resolve_snapshot(pretrained_model_name_or_path, cache_dir)
+        root = checkpoint.resolve_snapshot(str(pretrained_model_name_or_path), cache_dir, require=subfolder or "transformer")
         cfg, sd = checkpoint.load_component(root, subfolder, device=device, key_prefix=None if decoder is None else "encoder.")
         known = {k: v for k, v in cfg.items() if k in COGVIDEOX_5B_VAE}
         return cls(decoder=decoder, **known).load_state_dict(sd)

@@ -449,6 +449,43 @@ int alg_upsample_nearest_bf16(const void* x, void* out, int C, int Ti, int Hi, i
 int alg_spatial_norm_apply_bf16(const void* f_norm, const void* yb, void* out, int C, int T, int H, int W, int zt, int zh,
                                 int zw, int silu, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* float32 video VAE (AutoencoderKLWan: wan:429-434 encode of the condition    */
+/* clip, wan:526 per-step encode in pixel-space ALG, wan:959 decode; run.py:   */
+/* 51-55 loads it in float32; network in diffusers@be2fb77 autoencoder_kl_wan).*/
+/* Activations channels-last [T*H*W, C] fp32.  Host sequencing: vae_wan.py.    */
+/* ------------------------------------------------------------------------- */
+
+/* Patch gather + bf16 3-term split in one pass: cols[(to, ho, wo)] = [hi | hi | lo] (three sections of `ld` bf16 each) of the
+ * fp32 patch (it, ih, iw, c) read at frame (to0 + to)*st + it - pad_t, row ho*sh + ih - pad_top, column wo*sw + iw - pad_left of
+ * the LOGICAL frame (H*up) x (W*up), whose pixel (y, x) is x[t][y / up][x / up] (up = 2: nn.Upsample(nearest-exact, x2) fused
+ * into the following convolution).  Frames < t_min (WanCausalConv3d's zero front padding: t_min = 0; WanResample "upsample3d",
+ * whose temporal windows never see frame 0: t_min = 1) and pixels outside the logical frame read as zero.  One alg_gemm_bf16
+ * against the weight's [hi | lo | hi] split (alg_split3_bf16, weight_order 1) then gives the fp32 convolution to 2^-16. */
+typedef struct {
+  const void* x;  /* fp32 [T, H, W, C] */
+  void* cols;     /* bf16 [To*Ho*Wo, 3*ld] */
+  int32_t T, H, W, C;
+  int32_t kt, kh, kw;
+  int32_t st, sh, sw;
+  int32_t pad_t, pad_top, pad_left;
+  int32_t To, Ho, Wo; /* output frames of THIS call, output rows / columns */
+  int32_t to0;        /* index of the first output frame of this call (frame-chunked convolutions) */
+  int32_t up;         /* 1 or 2 */
+  int32_t t_min;
+  int64_t ld;         /* >= kt*kh*kw*C, multiple of 8 */
+} alg_im2col_f32_t;
+int alg_im2col_split3_f32(const alg_im2col_f32_t* p, void* stream);
+/* WanRMS_norm over the channels of each row: out = x / max(||x||_2, 1e-12) * sqrt(C) * gamma (+ bias) (+ SiLU when silu != 0) */
+int alg_rms_norm_cl_f32(const float* x, float* out, int64_t rows, int C, const float* gamma, const float* bias, int silu,
+                        void* stream);
+/* in place: every row <- softmax(scale * row) (WanAttentionBlock scores, one head of C channels per frame) */
+int alg_softmax_rows_f32(float* x, int64_t rows, int cols, int64_t ld, float scale, void* stream);
+/* [C, pixels] (one sample of [B, C, T, H, W]) -> channels-last [pixels, ld] (columns >= C zeroed), and back with an optional
+ * clamp to [lo, hi] (lo < hi; AutoencoderKLWan.decode clamps to [-1, 1]) */
+int alg_nchw_to_cl_f32(const float* x, float* out, int C, int64_t pixels, int ld, void* stream);
+int alg_cl_to_nchw_f32(const float* x, float* out, int C, int64_t pixels, int ld, float lo, float hi, void* stream);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 int64_t alg_launch_count(void);
 

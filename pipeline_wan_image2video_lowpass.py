@@ -107,6 +107,10 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
                 tokenizer, text_encoder = checkpoint.load_text_stack(snap, encoders.UMT5EncoderModel, device, tokenizer)
             if image_encoder is None:  # native CLIP-ViT-H in float32 (run.py:48) + the snapshot's CLIPImageProcessor
                 image_processor, image_encoder = checkpoint.load_image_stack(snap, encoders.CLIPVisionModel, device, image_processor)
+            if vae is None and os.path.isdir(os.path.join(snap, "vae")):  # native AutoencoderKLWan in float32 (run.py:51-55)
+                from alg_b200.vae_wan import AutoencoderKLWan
+
+                vae = AutoencoderKLWan.from_pretrained(snap, device=device)
             if vae is None and not allow_synthetic_aux:
                 raise NotImplementedError(checkpoint.AUX_MESSAGE)
         if transformer is None:
@@ -117,6 +121,10 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
 
             text_encoder = text_encoder or encoders.UMT5EncoderModel.from_synthetic(seed=seed, device=device)
             image_encoder = image_encoder or encoders.CLIPVisionModel.from_synthetic(seed=seed, device=device)
+        if vae is None and synthetic and os.environ.get("ALG_NATIVE_VAE", "0") == "1":
+            from alg_b200.vae_wan import AutoencoderKLWan  # seeded weights at the true Wan2.1 VAE architecture, native kernels
+
+            vae = AutoencoderKLWan.from_synthetic(seed=seed, device=device)
         if vae is None:
             vae = SyntheticVideoVAE(z_dim=16, latents_mean=WAN_VAE_MEAN, latents_std=WAN_VAE_STD, dtype=torch.float32)
         text_dim = transformer.config.text_dim
