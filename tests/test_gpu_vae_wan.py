@@ -156,3 +156,60 @@ def test_from_pretrained_snapshot_and_wan_pipeline_condition(tmp_path):
     assert torch.equal(res[0][0], res[1][0]) and res[0][1].shape == res[1][1].shape == (1, 20, 3, 4, 6)
     assert torch.equal(res[0][1][:, :4], res[1][1][:, :4])  # the first-frame mask
     assert rel_l2(res[0][1][:, 4:], res[1][1][:, 4:]) < 1e-4
+
+
+def test_wan_pipeline_end_to_end_all_native_vs_upstream_modules():
+    """run.py's whole path on tiny shapes -- image + prompt -> tokenizer -> UMT5, CLIP, VAE encode of the condition clip,
+    denoise loop with ALG, VAE decode, post-processing to frames: once with every network native, once with the transformers
+    modules (same weights) and the oracle VAE around the same native DiT.  Frames must agree closely and be valid video."""
+    from types import SimpleNamespace
+    import numpy as np
+    from transformers import CLIPVisionConfig, CLIPVisionModel as HFCLIP
+    from alg_b200 import encoders
+    from alg_b200.pipeline_utils import SyntheticImageProcessor, SyntheticTokenizer
+    from alg_b200.schedulers import UniPCMultistepScheduler
+    from alg_b200.vae_wan import AutoencoderKLWan
+    from oracle import wan_vae_oracle as V
+    from pipeline_wan_image2video_lowpass import WanImageToVideoPipeline
+    import __graft_entry__ as G
+    from test_gpu_encoders import _umt5
+    cfg, dit, _, alg = G.tiny_problem("cuda")
+    base, hf_t = _umt5("UMT5EncoderModel", dict(vocab_size=4096, d_model=64, d_kv=16, d_ff=128))
+    hf_t = hf_t.to(torch.bfloat16).cuda()
+    ccfg = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=2, image_size=224, patch_size=28)
+    torch.manual_seed(5)
+    hf_c = HFCLIP(CLIPVisionConfig(**ccfg)).eval().float().cuda()
+    text = encoders.UMT5EncoderModel(**base).load_state_dict({k: v.clone() for k, v in hf_t.state_dict().items()})
+    clip = encoders.CLIPVisionModel(**ccfg).load_state_dict({k: v.clone() for k, v in hf_c.state_dict().items()})
+    vcfg = dict(V.WAN21_VAE, base_dim=16)
+    sd = V.make_weights(vcfg, seed=11, device="cuda")
+    vae = AutoencoderKLWan(**vcfg).load_state_dict({k: v.clone() for k, v in sd.items()})
+
+    class OracleVAE:
+        dtype = torch.float32
+        temperal_downsample = vcfg["temperal_downsample"]
+        config = SimpleNamespace(**vcfg)
+
+        def encode(self, x):
+            m = V.encode_moments(x.double(), {k: v.double() for k, v in sd.items()}, vcfg, torch.float64).float()
+            return SimpleNamespace(latent_dist=SimpleNamespace(mode=lambda: m[:, :16], sample=lambda generator=None: m[:, :16]))
+
+        def decode(self, z, return_dict=True):
+            v = V.decode(z.double(), {k: v.double() for k, v in sd.items()}, vcfg, torch.float64).float()
+            return SimpleNamespace(sample=v) if return_dict else (v,)
+
+    image = torch.rand(1, 3, 128, 192, generator=torch.Generator().manual_seed(3))
+    frames = []
+    for t, c, v in ((text, clip, vae), (hf_t, hf_c, OracleVAE())):
+        pipe = WanImageToVideoPipeline(tokenizer=SyntheticTokenizer(vocab_size=4096), text_encoder=t, image_encoder=c,
+                                       image_processor=SyntheticImageProcessor(), transformer=dit, vae=v,
+                                       scheduler=UniPCMultistepScheduler(flow_shift=5.0)).to("cuda")
+        out = pipe(image=image, prompt="a red bus turning a corner in the rain", negative_prompt="blurry", height=128, width=192,
+                   num_frames=9, num_inference_steps=3, guidance_scale=5.0, max_sequence_length=32,
+                   generator=torch.Generator(device="cuda").manual_seed(42), output_type="np", **alg)
+        frames.append(np.asarray(out.frames))
+    a, b = frames
+    assert a.shape == b.shape == (1, 9, 128, 192, 3) and np.isfinite(a).all() and a.min() >= 0.0 and a.max() <= 1.0
+    assert a.std() > 1e-3  # not a constant clip
+    err = np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64))
+    assert err < 2e-2, err
