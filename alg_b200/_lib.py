@@ -117,7 +117,8 @@ class Im2colF32(C.Structure):
         ("x", C.c_void_p), ("cols", C.c_void_p), ("T", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
         ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
         ("pad_t", C.c_int32), ("pad_top", C.c_int32), ("pad_left", C.c_int32), ("To", C.c_int32), ("Ho", C.c_int32),
-        ("Wo", C.c_int32), ("to0", C.c_int32), ("up", C.c_int32), ("t_min", C.c_int32), ("ld", C.c_int64),
+        ("Wo", C.c_int32), ("to0", C.c_int32), ("up", C.c_int32), ("t_min", C.c_int32), ("replicate", C.c_int32),
+        ("tdup", C.c_int32), ("ld", C.c_int64),
     ]
 
 
@@ -171,7 +172,9 @@ SIGNATURES = {
     "alg_swiglu_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "alg_im2col_split3_f32": (C.c_int, [C.POINTER(Im2colF32), C.c_void_p]),
     "alg_rms_norm_cl_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "alg_softmax_rows_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_void_p]),
+    "alg_softmax_rows_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_void_p]),
+    "alg_group_norm_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p]),
     "alg_nchw_to_cl_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "alg_cl_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "alg_mul_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -47,11 +47,16 @@ __global__ void __launch_bounds__(256) im2col_split3_vec_kernel(const alg_im2col
     const int ih = r2 / p.kw, iw = r2 - ih * p.kw;
     int wo = wo0, ho = ho0, to = to0;
     for (int i = 0; i < n; ++i, dst += 3 * ld4) {
-      const int t = to * p.st + it - p.pad_t;
-      const int y = ho * p.sh + ih - p.pad_top, xx = wo * p.sw + iw - p.pad_left;
+      int t = to * p.st + it - p.pad_t;
+      int y = ho * p.sh + ih - p.pad_top, xx = wo * p.sw + iw - p.pad_left;
+      if (p.replicate) {  // F.pad(mode="replicate") in all three dimensions (HunyuanVideoCausalConv3d)
+        t = max(t, p.t_min);
+        y = min(max(y, 0), HL - 1);
+        xx = min(max(xx, 0), WL - 1);
+      }
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t >= p.t_min && y >= 0 && y < HL && xx >= 0 && xx < WL)
-        v = __ldg(x + (((int64_t)t * p.H + y / p.up) * p.W + xx / p.up) * c4 + cc);
+        v = __ldg(x + (((int64_t)(p.tdup == 2 ? (t + 1) >> 1 : t) * p.H + y / p.up) * p.W + xx / p.up) * c4 + cc);
       uint2 hi, lo;
       split_pair(v.x, v.y, hi.x, lo.x);
       split_pair(v.z, v.w, hi.y, lo.y);
@@ -86,10 +91,15 @@ __global__ void __launch_bounds__(256) im2col_split3_scalar_kernel(const alg_im2
       const int wo = (int)(m % p.Wo);
       const int64_t r = m / p.Wo;
       const int ho = (int)(r % p.Ho), to = (int)(r / p.Ho) + p.to0;
-      const int t = to * p.st + it - p.pad_t;
-      const int y = ho * p.sh + ih - p.pad_top, xx = wo * p.sw + iw - p.pad_left;
+      int t = to * p.st + it - p.pad_t;
+      int y = ho * p.sh + ih - p.pad_top, xx = wo * p.sw + iw - p.pad_left;
+      if (p.replicate) {
+        t = max(t, p.t_min);
+        y = min(max(y, 0), HL - 1);
+        xx = min(max(xx, 0), WL - 1);
+      }
       if (t >= p.t_min && y >= 0 && y < HL && xx >= 0 && xx < WL)
-        v = x[(((int64_t)t * p.H + y / p.up) * p.W + xx / p.up) * p.C + c];
+        v = x[(((int64_t)(p.tdup == 2 ? (t + 1) >> 1 : t) * p.H + y / p.up) * p.W + xx / p.up) * p.C + c];
     }
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -127,9 +137,13 @@ __global__ void __launch_bounds__(256) rms_norm_cl_kernel(const float* __restric
 }
 
 // in place: row <- softmax(scale * row).  One block per row (6 240 columns at the Wan 480p latent size).
-__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int cols, int64_t ld, float scale) {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int cols_all, int64_t ld, float scale, int block) {
   __shared__ float red[8];
   float* row = x + (int64_t)blockIdx.x * ld;
+  // frame-causal mask (HunyuanVideo VAE mid block): row r of frame r / block sees the columns of frames <= its own; the masked
+  // tail of the row is zeroed
+  const int cols = block > 0 ? min(cols_all, (int)(blockIdx.x / block + 1) * block) : cols_all;
+  for (int c = cols + threadIdx.x; c < cols_all; c += 256) row[c] = 0.f;
   float m = -INFINITY;
   for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, row[c] * scale);
 #pragma unroll
@@ -155,6 +169,60 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x
   for (int i = 0; i < 8; ++i) s += red[i];
   const float inv = 1.0f / s;
   for (int c = threadIdx.x; c < cols; c += 256) row[c] *= inv;
+}
+
+// nn.GroupNorm on channels-last fp32 rows of ONE sample (statistics over rows x channels-of-the-group), + optional SiLU.
+// Pass 1: per-block partial sums per group in fp64 -> global atomics; pass 2: y = (x - mean) * rstd * weight + bias.
+__global__ void __launch_bounds__(256) group_norm_f32_stats_kernel(const float* __restrict__ x, int64_t rows, int C, int cpg,
+                                                                   double* __restrict__ stats) {
+  extern __shared__ double sh[];  // [groups][2]
+  const int groups = C / cpg;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  const int64_t n = rows * C;
+  // a thread keeps one channel (blockDim * gridDim is a multiple of C by construction), so its sums belong to one group
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float s = 0.f, q = 0.f;
+  double ds = 0.0, dq = 0.0;
+  int cnt = 0;
+  for (int64_t i = i0; i < n; i += stride) {
+    const float v = x[i];
+    s += v;
+    q = fmaf(v, v, q);
+    if (++cnt == 64) {  // bound the fp32 partial sums
+      ds += (double)s;
+      dq += (double)q;
+      s = q = 0.f;
+      cnt = 0;
+    }
+  }
+  ds += (double)s;
+  dq += (double)q;
+  if (i0 < n) {
+    const int g = (int)(i0 % C) / cpg;
+    atomicAdd(&sh[2 * g], ds);
+    atomicAdd(&sh[2 * g + 1], dq);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&stats[i], sh[i]);
+}
+__global__ void __launch_bounds__(256) group_norm_f32_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows,
+                                                                   int C, int cpg, float eps, const float* __restrict__ w,
+                                                                   const float* __restrict__ b, int silu,
+                                                                   const double* __restrict__ stats) {
+  const int64_t n = rows * C;
+  const double cnt = (double)rows * (double)cpg;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), g = c / cpg;
+    const double mean = stats[2 * g] / cnt;
+    double var = stats[2 * g + 1] / cnt - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = rsqrtf((float)var + eps);
+    float v = (x[i] - (float)mean) * rstd * (w ? w[c] : 1.f) + (b ? b[c] : 0.f);
+    if (silu) v = v / (1.0f + expf(-v));
+    y[i] = v;
+  }
 }
 
 // [C, P] (channel-major: one sample of [B, C, T, H, W]) -> [P, ld] channels-last, columns >= C zeroed
@@ -194,7 +262,9 @@ extern "C" int alg_im2col_split3_f32(const alg_im2col_f32_t* p, void* stream) {
   ALG_REQUIRE(p->up == 1 || p->up == 2, "im2col_split3: up must be 1 or 2");
   const int64_t K = (int64_t)p->kt * p->kh * p->kw * p->C;
   ALG_REQUIRE(p->ld >= K && p->ld % 8 == 0, "im2col_split3: ld must be >= kt*kh*kw*C and a multiple of 8");
-  ALG_REQUIRE((int64_t)(p->to0 + p->To - 1) * p->st + p->kt - 1 - p->pad_t < p->T, "im2col_split3: temporal window runs past the last frame");
+  ALG_REQUIRE(p->tdup == 1 || p->tdup == 2, "im2col_split3: tdup must be 1 or 2");
+  ALG_REQUIRE((int64_t)(p->to0 + p->To - 1) * p->st + p->kt - 1 - p->pad_t < (p->tdup == 2 ? 2 * p->T - 1 : p->T),
+              "im2col_split3: temporal window runs past the last frame");
   ALG_REQUIRE(((reinterpret_cast<uintptr_t>(p->x) | reinterpret_cast<uintptr_t>(p->cols)) & 15) == 0, "im2col_split3: misaligned pointer");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -223,12 +293,12 @@ extern "C" int alg_rms_norm_cl_f32(const float* x, float* out, int64_t rows, int
   return 0;
 }
 
-extern "C" int alg_softmax_rows_f32(float* x, int64_t rows, int cols, int64_t ld, float scale, void* stream) {
-  ALG_REQUIRE(x && rows >= 0 && cols > 0 && ld >= cols, "softmax_rows: bad arguments");
+extern "C" int alg_softmax_rows_f32(float* x, int64_t rows, int cols, int64_t ld, float scale, int causal_block, void* stream) {
+  ALG_REQUIRE(x && rows >= 0 && cols > 0 && ld >= cols && causal_block >= 0, "softmax_rows: bad arguments");
   ALG_REQUIRE(rows <= 0x7fffffff, "softmax_rows: too many rows");
   if (int rc = alg_check_device()) return rc;
   if (rows == 0) return 0;
-  vae32::softmax_rows_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, cols, ld, scale);
+  vae32::softmax_rows_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, cols, ld, scale, causal_block);
   ALG_LAUNCH_OK();
   return 0;
 }
@@ -245,6 +315,25 @@ extern "C" int alg_cl_to_nchw_f32(const float* x, float* out, int C, int64_t pix
   ALG_REQUIRE(x && out && C > 0 && pixels > 0 && ld >= C, "cl_to_nchw: bad arguments");
   if (int rc = alg_check_device()) return rc;
   vae32::cl_to_nchw_kernel<<<vae32::grid_for(pixels * C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, C, pixels, ld, lo, hi);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_group_norm_f32(const float* x, float* y, int64_t rows, int C, int groups, float eps, const float* weight,
+                                  const float* bias, int silu, double* stats, void* stream) {
+  ALG_REQUIRE(x && y && stats && rows > 0 && C > 0 && groups > 0 && C % groups == 0 && groups <= 1024, "group_norm_f32: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ALG_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups, st));
+  // grid * 256 must be a multiple of C so that a thread's strided elements stay in one channel
+  int64_t unit = C;
+  while (unit % 256) unit += C;  // lcm-ish: smallest multiple of C that is a multiple of 256 (C divides it)
+  const int blocks_unit = (int)(unit / 256);
+  const int64_t want = std::min<int64_t>((rows * C + 255) / 256, 148 * 8);
+  const int grid = (int)std::max<int64_t>(blocks_unit, want / blocks_unit * blocks_unit);
+  vae32::group_norm_f32_stats_kernel<<<grid, 256, sizeof(double) * 2 * groups, st>>>(x, rows, C, C / groups, stats);
+  ALG_LAUNCH_OK();
+  vae32::group_norm_f32_apply_kernel<<<vae32::grid_for(rows * C), 256, 0, st>>>(x, y, rows, C, C / groups, eps, weight, bias, silu, stats);
   ALG_LAUNCH_OK();
   return 0;
 }

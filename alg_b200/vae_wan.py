@@ -141,23 +141,28 @@ class _Act:
         return self.t[i * hw:(i + n) * hw]
 
 
-class AutoencoderKLWan:
-    """Native-kernel ``AutoencoderKLWan``: ``encode(x).latent_dist`` / ``decode(z).sample`` in float32."""
+class SplitConvVAE:
+    """What the float32 video VAEs share: weights as split GEMM operands, the frame-chunked (gather + split, GEMM, bias) convolution,
+    pointwise linears, layout changes, the diffusers-facing ``encode`` / ``decode`` wrappers.  Subclasses provide
+    ``_shapes()``, ``_encode_one`` and ``_decode_one``."""
 
-    def __init__(self, **config):
-        cfg = dict(WAN21_VAE)
-        cfg.update({k: v for k, v in config.items() if k in cfg})
-        if cfg.get("attn_scales"):
-            raise NotImplementedError("attn_scales other than [] (Wan2.1's VAE has attention only in the mid blocks)")
+    Z_KEY = "z_dim"
+    TRUNCATE_FRAMES = True  # AutoencoderKLWan's chunk loop (1 frame, then 4 at a time) drops a trailing partial chunk
+
+    def _init_common(self, cfg: dict):
         self._cfg = cfg
         self.config = SimpleNamespace(**cfg)
-        self.temperal_downsample = list(cfg["temperal_downsample"])  # (sic) wan:180-181 reads it off the module
         self.dtype = torch.float32
         self.device = torch.device("cpu")
         self._w: Dict[str, torch.Tensor] = {}
         self._sd: Dict[str, torch.Tensor] = {}
         self._cols: Optional[torch.Tensor] = None
         self._cols_budget = 6 << 30  # bytes of patch matrix per gather + GEMM call (whole output frames)
+        self._stats: Optional[torch.Tensor] = None
+        self._attn_budget = 48 << 30  # bytes the materialised attention scores may take
+
+    def _shapes(self) -> Dict[str, tuple]:
+        raise NotImplementedError
 
     # ---- construction -------------------------------------------------------------------------------------------------
     @classmethod
@@ -171,12 +176,12 @@ class AutoencoderKLWan:
 
     @classmethod
     def from_synthetic(cls, seed: int = 0, device="cuda", **config):
-        """Seeded weights at the Wan2.1 VAE shape unless ``config`` says otherwise (fan-in scaled: activations stay O(1))."""
+        """Seeded weights at the model's true shape unless ``config`` says otherwise (fan-in scaled: activations stay O(1))."""
         m = cls(**config)
         sd = {}
-        for idx, (name, shape) in enumerate(parameter_shapes(m._cfg).items()):
+        for idx, (name, shape) in enumerate(m._shapes().items()):
             g = torch.Generator(device=device).manual_seed(seed * 1_000_003 + 11_001 + idx)
-            if name.endswith(".gamma"):
+            if name.endswith(".gamma") or ("norm" in name and name.endswith(".weight")):
                 w = 1 + 0.1 * torch.randn(shape, generator=g, device=device)
             elif name.endswith(".bias"):
                 w = 0.05 * torch.randn(shape, generator=g, device=device)
@@ -191,11 +196,11 @@ class AutoencoderKLWan:
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
         """diffusers names.  Convolution weights are re-laid once as split GEMM B operands [Co8, 3 * K8] with
         K = (kt, kh, kw, Ci) flattened (Ci innermost, like the patch rows) and Co / K zero-padded to multiples of 8."""
-        shapes = parameter_shapes(self._cfg)
+        shapes = self._shapes()
         missing = [k for k in shapes if k not in sd]
         if missing:
             raise KeyError(f"missing VAE weights: {missing[:4]}{'...' if len(missing) > 4 else ''}")
-        dev = sd["decoder.norm_out.gamma"].device
+        dev = sd[next(iter(shapes))].device
         if dev.type != "cuda":
             raise RuntimeError("VAE weights must live on a CUDA device (no CPU fallback)")
         self.device = dev
@@ -209,7 +214,7 @@ class AutoencoderKLWan:
             self._sd[name] = t
             if name.endswith(".gamma"):
                 w[name] = t.reshape(-1).contiguous()
-            elif name.endswith(".bias"):
+            elif t.dim() == 1:  # biases (padded like their weight's output channels) and GroupNorm affine parameters
                 co8 = (t.numel() + 7) // 8 * 8
                 w[name] = torch.nn.functional.pad(t, (0, co8 - t.numel())).contiguous()
             else:
@@ -244,7 +249,7 @@ class AutoencoderKLWan:
     def _conv(self, x: _Act, name: str, k: Tuple[int, int, int], *, stride=(1, 1, 1), pad=(None, None, None), up: int = 1,
               t_min: int = 0, frames: Optional[Tuple[int, int]] = None, out_hw: Optional[Tuple[int, int]] = None,
               residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, w_rows: Optional[Tuple[int, int]] = None,
-              out_frame0: int = 0, out_frame_step: int = 1) -> _Act:
+              out_frame0: int = 0, out_frame_step: int = 1, replicate: bool = False, tdup: int = 1) -> _Act:
         """Convolution of the whole clip as frame-chunked (gather + split, GEMM, bias [+ residual]).
 
         ``pad`` = (front frames, top, left), default (kt - 1, kh // 2, kw // 2); ``frames`` = (first output frame, count) of the
@@ -258,7 +263,7 @@ class AutoencoderKLWan:
         pad_top = kh // 2 if pad[1] is None else pad[1]
         pad_left = kw // 2 if pad[2] is None else pad[2]
         Ho, Wo = out_hw if out_hw is not None else (x.H * up, x.W * up)
-        to0, To = frames if frames is not None else (0, x.T)
+        to0, To = frames if frames is not None else (0, x.T if tdup == 1 else 2 * x.T - 1)
         w3, bias = self._w[name + ".weight"], self._w[name + ".bias"]
         if w_rows is not None:
             w3, bias = w3[w_rows[0]:w_rows[1]], bias[w_rows[0]:w_rows[1]]
@@ -281,6 +286,7 @@ class AutoencoderKLWan:
         p.kt, p.kh, p.kw, p.st, p.sh, p.sw = kt, kh, kw, st, sh, sw
         p.pad_t, p.pad_top, p.pad_left = pad_t, pad_top, pad_left
         p.Ho, p.Wo, p.up, p.t_min, p.ld = Ho, Wo, up, t_min, ld
+        p.replicate, p.tdup = int(replicate), tdup
         for f0 in range(0, To, chunk):
             n = min(chunk, To - f0)
             p.To, p.to0 = n, to0 + f0
@@ -306,6 +312,83 @@ class AutoencoderKLWan:
                 self._w[name + ".gamma"].data_ptr(), None, int(silu))
         return out
 
+    def _attention_core(self, y: torch.Tensor, wq3, bq, wk3, bk, wv3, bv, causal_block: int = 0) -> torch.Tensor:
+        """softmax(q k^T / sqrt(C)) v for ONE head of C channels over the rows of y [N, C] (already normalised), fp32 through the
+        split GEMM: scores [N, N] are materialised (like the N x N mask of the reference), V is produced transposed by swapping the
+        GEMM operands, and the value bias is added after P V (softmax rows sum to one).  ``causal_block`` = tokens per frame for the
+        frame-causal mask of the HunyuanVideo VAE."""
+        lib, dev = _lib.lib(), self.device
+        N, Cc = y.shape
+        n8 = (N + 7) // 8 * 8
+        if N * n8 * 10 > self._attn_budget:
+            raise NotImplementedError(
+                f"VAE mid-block attention over {N} tokens needs a {N} x {N} score matrix ({N * n8 * 10 / 2 ** 30:.0f} GiB with its "
+                "split copy); the reference materialises the same N x N mask -- decode a shorter / smaller clip")
+        q = linear_f32(y, wq3, bq)
+        k = linear_f32(y, wk3, bk)
+        # W_v as the swapped GEMM's A operand: its stored [hi | lo | hi] sections reordered to the activation order [hi | hi | lo]
+        wv_a = wv3.reshape(Cc, 3, -1)[:, [0, 2, 1]].reshape(Cc, -1).contiguous()
+        vt = torch.zeros(Cc, n8, device=dev, dtype=torch.float32)  # columns >= N stay zero (K padding of the P V product)
+        ops.gemm(wv_a, split_weight(y), None, out=vt[:, :N], out_dtype=torch.float32)
+        s = torch.zeros(N, n8, device=dev, dtype=torch.float32)
+        ops.gemm(split_act(q), split_weight(k), None, out=s[:, :N], out_dtype=torch.float32)
+        _launch(lib.alg_softmax_rows_f32, dev, s.data_ptr(), N, N, n8, float(Cc) ** -0.5, int(causal_block))
+        return linear_f32(s, split_weight(vt), bv)
+
+    # ---- public surface ---------------------------------------------------------------------------------------------------
+    def _to_cl(self, x: torch.Tensor) -> _Act:
+        Cc, T, H, W = x.shape
+        out = torch.empty(T * H * W, Cc, device=self.device, dtype=torch.float32)
+        _launch(_lib.lib().alg_nchw_to_cl_f32, self.device, x.data_ptr(), out.data_ptr(), Cc, T * H * W, Cc)
+        return _Act(out, T, H, W, Cc)
+
+    def _from_cl(self, a: _Act, Cc: int, clamp: bool) -> torch.Tensor:
+        out = torch.empty(Cc, a.T, a.H, a.W, device=self.device, dtype=torch.float32)
+        lo, hi = (-1.0, 1.0) if clamp else (0.0, 0.0)
+        _launch(_lib.lib().alg_cl_to_nchw_f32, self.device, a.t.data_ptr(), out.data_ptr(), Cc, a.T * a.H * a.W, a.t.shape[1], lo, hi)
+        return out
+
+    def _check(self, x: torch.Tensor, channels: int, what: str) -> torch.Tensor:
+        if not self._w:
+            raise RuntimeError(f"{type(self).__name__} has no weights loaded")
+        if x.dim() != 5 or x.shape[1] != channels:
+            raise ValueError(f"{what}: expected [B, {channels}, T, H, W], got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError(f"{type(self).__name__} runs on CUDA tensors only (no CPU fallback)")
+        return x.to(device=self.device, dtype=torch.float32).contiguous()
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, return_dict: bool = True):
+        """x [B, 3, 1 + 4n, H, W] -> ``.latent_dist`` over [B, 2 z, 1 + n, H/8, W/8] (frames beyond 1 + 4n are dropped like
+        diffusers' chunk loop drops them)."""
+        x = self._check(x, 3, "encode")
+        T = 1 + (x.shape[2] - 1) // 4 * 4 if self.TRUNCATE_FRAMES else x.shape[2]
+        moments = torch.stack([self._encode_one(x[b, :, :T].contiguous()) for b in range(x.shape[0])])
+        dist = DiagonalGaussianDistribution(moments)
+        return SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, return_dict: bool = True):
+        """z [B, z, T, h, w] -> ``.sample`` [B, 3, 4 T - 3, 8 h, 8 w]."""
+        z = self._check(z, self._cfg[self.Z_KEY], "decode")
+        video = torch.stack([self._decode_one(z[b].contiguous()) for b in range(z.shape[0])])
+        return SimpleNamespace(sample=video) if return_dict else (video,)
+
+
+class AutoencoderKLWan(SplitConvVAE):
+    """Native-kernel ``AutoencoderKLWan``: ``encode(x).latent_dist`` / ``decode(z).sample`` in float32."""
+
+    def __init__(self, **config):
+        cfg = dict(WAN21_VAE)
+        cfg.update({k: v for k, v in config.items() if k in cfg})
+        if cfg.get("attn_scales"):
+            raise NotImplementedError("attn_scales other than [] (Wan2.1's VAE has attention only in the mid blocks)")
+        self._init_common(cfg)
+        self.temperal_downsample = list(cfg["temperal_downsample"])  # (sic) wan:180-181 reads it off the module
+
+    def _shapes(self) -> Dict[str, tuple]:
+        return parameter_shapes(self._cfg)
+
     def _res(self, x: _Act, name: str) -> _Act:
         h = x.t
         if name + ".conv_shortcut.weight" in self._w:
@@ -317,27 +400,14 @@ class AutoencoderKLWan:
 
     def _attn(self, x: _Act, name: str) -> _Act:
         """WanAttentionBlock: per frame, ONE head of C channels over the H*W pixels."""
-        lib, dev, Cc, hw = _lib.lib(), self.device, x.C, x.H * x.W
+        Cc, hw = x.C, x.H * x.W
         wq = self._w[name + ".to_qkv.weight"]  # [3C, 3C] split, rows = (q | k | v) output channels
         bq = self._w[name + ".to_qkv.bias"]
         out = torch.empty_like(x.t)
-        hw8 = (hw + 7) // 8 * 8
-        # W_v as the swapped GEMM's A operand: its stored [hi | lo | hi] sections reordered to the activation order [hi | hi | lo]
-        wv_a = wq[2 * Cc:3 * Cc].view(Cc, 3, -1)[:, [0, 2, 1]].reshape(Cc, -1).contiguous()
         for f in range(x.T):
             xf = x.frame(f)
             y = self._norm(xf, name + ".norm", False)
-            q = linear_f32(y, wq[:Cc], bq[:Cc])
-            k = linear_f32(y, wq[Cc:2 * Cc], bq[Cc:2 * Cc])
-            # V^T [C, hw] = W_v y^T: the GEMM with its operands swapped (W_v's [hi | lo | hi] rows against y's split as the "weight");
-            # the value bias is added after P V instead (softmax rows sum to one)
-            y3 = split_weight(y)
-            vt = torch.zeros(Cc, hw8, device=dev, dtype=torch.float32)  # columns >= hw stay zero (K padding of the P V product)
-            ops.gemm(wv_a, y3, None, out=vt[:, :hw], out_dtype=torch.float32)
-            s = torch.zeros(hw, hw8, device=dev, dtype=torch.float32)
-            ops.gemm(split_act(q), split_weight(k), None, out=s[:, :hw], out_dtype=torch.float32)  # scores
-            _launch(lib.alg_softmax_rows_f32, dev, s.data_ptr(), hw, hw, hw8, float(Cc) ** -0.5)
-            o = linear_f32(s, split_weight(vt), bq[2 * Cc:3 * Cc])
+            o = self._attention_core(y, wq[:Cc], bq[:Cc], wq[Cc:2 * Cc], bq[Cc:2 * Cc], wq[2 * Cc:3 * Cc], bq[2 * Cc:3 * Cc])
             out[f * hw:(f + 1) * hw] = self._pointwise(o, name + ".proj", residual=xf)
         return _Act(out, x.T, x.H, x.W, Cc)
 
@@ -369,19 +439,6 @@ class AutoencoderKLWan:
             x = _Act(out, 2 * x.T - 1, x.H, x.W, Cc)
         return self._conv(x, name + ".resample.1", (1, 3, 3), pad=(0, 1, 1), up=2)
 
-    # ---- public surface ---------------------------------------------------------------------------------------------------
-    def _to_cl(self, x: torch.Tensor) -> _Act:
-        Cc, T, H, W = x.shape
-        out = torch.empty(T * H * W, Cc, device=self.device, dtype=torch.float32)
-        _launch(_lib.lib().alg_nchw_to_cl_f32, self.device, x.data_ptr(), out.data_ptr(), Cc, T * H * W, Cc)
-        return _Act(out, T, H, W, Cc)
-
-    def _from_cl(self, a: _Act, Cc: int, clamp: bool) -> torch.Tensor:
-        out = torch.empty(Cc, a.T, a.H, a.W, device=self.device, dtype=torch.float32)
-        lo, hi = (-1.0, 1.0) if clamp else (0.0, 0.0)
-        _launch(_lib.lib().alg_cl_to_nchw_f32, self.device, a.t.data_ptr(), out.data_ptr(), Cc, a.T * a.H * a.W, a.t.shape[1], lo, hi)
-        return out
-
     def _encode_one(self, x: torch.Tensor) -> torch.Tensor:
         enc, _, _, _, _ = _plan(self._cfg)
         a = self._conv(self._to_cl(x), "encoder.conv_in", (3, 3, 3))
@@ -404,29 +461,3 @@ class AutoencoderKLWan:
         a.t = self._norm(a.t, "decoder.norm_out", True)
         a = self._conv(a, "decoder.conv_out", (3, 3, 3))
         return self._from_cl(a, 3, clamp=True)
-
-    def _check(self, x: torch.Tensor, channels: int, what: str) -> torch.Tensor:
-        if not self._w:
-            raise RuntimeError("AutoencoderKLWan has no weights loaded")
-        if x.dim() != 5 or x.shape[1] != channels:
-            raise ValueError(f"{what}: expected [B, {channels}, T, H, W], got {tuple(x.shape)}")
-        if not x.is_cuda:
-            raise RuntimeError("AutoencoderKLWan runs on CUDA tensors only (no CPU fallback)")
-        return x.to(device=self.device, dtype=torch.float32).contiguous()
-
-    @torch.no_grad()
-    def encode(self, x: torch.Tensor, return_dict: bool = True):
-        """x [B, 3, 1 + 4n, H, W] -> ``.latent_dist`` over [B, 2 z, 1 + n, H/8, W/8] (frames beyond 1 + 4n are dropped like
-        diffusers' chunk loop drops them)."""
-        x = self._check(x, 3, "encode")
-        T = 1 + (x.shape[2] - 1) // 4 * 4
-        moments = torch.stack([self._encode_one(x[b, :, :T].contiguous()) for b in range(x.shape[0])])
-        dist = DiagonalGaussianDistribution(moments)
-        return SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
-
-    @torch.no_grad()
-    def decode(self, z: torch.Tensor, return_dict: bool = True):
-        """z [B, z, T, h, w] -> ``.sample`` [B, 3, 4 T - 3, 8 h, 8 w] in [-1, 1]."""
-        z = self._check(z, self._cfg["z_dim"], "decode")
-        video = torch.stack([self._decode_one(z[b].contiguous()) for b in range(z.shape[0])])
-        return SimpleNamespace(sample=video) if return_dict else (video,)

@@ -473,14 +473,23 @@ typedef struct {
   int32_t to0;        /* index of the first output frame of this call (frame-chunked convolutions) */
   int32_t up;         /* 1 or 2 */
   int32_t t_min;
+  int32_t replicate;  /* != 0: F.pad(mode="replicate") instead of zeros, in time (frames < t_min read frame t_min) and space
+                         (HunyuanVideoCausalConv3d) */
+  int32_t tdup;       /* 1, or 2: the LOGICAL clip has 2T - 1 frames, frame t reads source frame (t + 1) / 2 (frame 0 once, every
+                         later frame twice: HunyuanVideoUpsampleCausal3D's temporal nearest upsample fused into its convolution) */
   int64_t ld;         /* >= kt*kh*kw*C, multiple of 8 */
 } alg_im2col_f32_t;
 int alg_im2col_split3_f32(const alg_im2col_f32_t* p, void* stream);
 /* WanRMS_norm over the channels of each row: out = x / max(||x||_2, 1e-12) * sqrt(C) * gamma (+ bias) (+ SiLU when silu != 0) */
 int alg_rms_norm_cl_f32(const float* x, float* out, int64_t rows, int C, const float* gamma, const float* bias, int silu,
                         void* stream);
-/* in place: every row <- softmax(scale * row) (WanAttentionBlock scores, one head of C channels per frame) */
-int alg_softmax_rows_f32(float* x, int64_t rows, int cols, int64_t ld, float scale, void* stream);
+/* in place: every row <- softmax(scale * row) (WanAttentionBlock scores, one head of C channels per frame).  causal_block > 0:
+ * row r only sees columns < (r / causal_block + 1) * causal_block, the rest of the row is zeroed (frame-causal mask of the
+ * HunyuanVideo VAE mid block, diffusers prepare_causal_attention_mask) */
+int alg_softmax_rows_f32(float* x, int64_t rows, int cols, int64_t ld, float scale, int causal_block, void* stream);
+/* nn.GroupNorm (+ SiLU) over channels-last fp32 [rows, C] of one sample; `stats` = scratch of 2*groups doubles (zeroed here) */
+int alg_group_norm_f32(const float* x, float* y, int64_t rows, int C, int groups, float eps, const float* weight, const float* bias,
+                       int silu, double* stats, void* stream);
 /* [C, pixels] (one sample of [B, C, T, H, W]) -> channels-last [pixels, ld] (columns >= C zeroed), and back with an optional
  * clamp to [lo, hi] (lo < hi; AutoencoderKLWan.decode clamps to [-1, 1]) */
 int alg_nchw_to_cl_f32(const float* x, float* out, int C, int64_t pixels, int ld, void* stream);

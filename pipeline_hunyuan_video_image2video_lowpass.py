@@ -160,6 +160,10 @@ class HunyuanVideoImageToVideoPipeline(DiffusionPipelineBase):
                 from transformers import CLIPImageProcessor
 
                 image_processor = CLIPImageProcessor.from_pretrained(os.path.join(snap, "image_processor"))
+            if vae is None and os.path.isdir(os.path.join(snap, "vae")):  # native AutoencoderKLHunyuanVideo (float32 arithmetic)
+                from alg_b200.vae_hunyuan import AutoencoderKLHunyuanVideo
+
+                vae = AutoencoderKLHunyuanVideo.from_pretrained(snap, device=device)
             if (vae is None or text_encoder is None or text_encoder_2 is None or image_processor is None) and not allow_synthetic_aux:
                 raise NotImplementedError(checkpoint.AUX_MESSAGE)
         if transformer is None:
@@ -171,6 +175,10 @@ class HunyuanVideoImageToVideoPipeline(DiffusionPipelineBase):
 
             text_encoder = text_encoder or llava.LlavaForConditionalGeneration.from_synthetic(seed=seed, device=device, torch_dtype=torch_dtype)
             text_encoder_2 = text_encoder_2 or encoders.CLIPTextModel.from_synthetic(seed=seed, device=device, **encoders.CLIP_L_TEXT)
+        if vae is None and synthetic and os.environ.get("ALG_NATIVE_VAE", "0") == "1":
+            from alg_b200.vae_hunyuan import AutoencoderKLHunyuanVideo  # seeded weights at the true architecture, native kernels
+
+            vae = AutoencoderKLHunyuanVideo.from_synthetic(seed=seed, device=device)
         if vae is None:
             vae = SyntheticVideoVAE(z_dim=transformer.config.in_channels, scaling_factor=0.476986, dtype=torch_dtype)
             vae.temporal_compression_ratio, vae.spatial_compression_ratio = 4, 8

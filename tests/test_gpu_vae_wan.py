@@ -38,6 +38,7 @@ def test_im2col_split3_geometries_against_unfold():
         p.x, p.cols, p.T, p.H, p.W, p.C = x.data_ptr(), cols.data_ptr(), T, H, W, Cc
         p.kt, p.kh, p.kw, p.st, p.sh, p.sw = *k, *stride
         p.pad_t, p.pad_top, p.pad_left, p.To, p.Ho, p.Wo, p.to0, p.up, p.t_min, p.ld = *pad, To, Ho, Wo, to0, up, t_min, ld
+        p.replicate, p.tdup = 0, 1
         _lib.check(_lib.lib().alg_im2col_split3_f32(C.byref(p), _lib.stream_ptr(x.device)))
         torch.cuda.synchronize()
         # reference: explicit loops over taps on the (upsampled, zero-padded) clip
