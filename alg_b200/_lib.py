@@ -62,7 +62,7 @@ class Gemm(C.Structure):
         ("ldb", C.c_int64), ("ldd", C.c_int64), ("rows_per_batch", C.c_int64), ("gate_ld", C.c_int64),
         ("epilogue", C.c_int32), ("bias_per_row", C.c_int32), ("out_f32", C.c_int32),
         ("gate_dtype", C.c_int32), ("gate_round", C.c_int32), ("gate_split_row", C.c_int64), ("gate_alt", C.c_void_p),
-        ("a_k_period", C.c_int64),
+        ("a_k_period", C.c_int64), ("a_tap_kblocks", C.c_int32), ("a_n_taps", C.c_int32), ("a_tap_offsets", C.POINTER(C.c_int32)),
     ]
 
 
@@ -177,6 +177,9 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     "alg_nchw_to_cl_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "alg_cl_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "alg_norm_split_pad_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_int, C.c_void_p]),
+    "alg_pad_copy_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "alg_mul_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "alg_patchify_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "alg_clip_embed_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

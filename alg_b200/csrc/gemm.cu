@@ -87,6 +87,9 @@ struct Params {
   int epilogue, bias_per_row, out_f32, gate_bf16, gate_round;
   int m_tiles, n_tiles, k_blocks;
   int a_k_period;  // 0, or the A operand repeats along K with this period (multiple of BK)
+  int a_tap_kb;    // 0, or implicit-convolution mode: K is n_taps groups of a_tap_kb k-blocks; group g reads A columns
+                   // [0, a_tap_kb * BK) at rows shifted by a_tap_off[g] (out-of-range rows are zero-filled by TMA)
+  int a_tap_off[32];
 };
 
 __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
@@ -175,14 +178,20 @@ __global__ void __launch_bounds__(kThreads, 1)
         m_blk = m_blk * CL + (int)crank;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          const int ka = p.a_k_period ? (kb * BK) % p.a_k_period : kb * BK;
+          int ka = p.a_k_period ? (kb * BK) % p.a_k_period : kb * BK;
+          int arow = m_blk * BM;
+          if (p.a_tap_kb) {  // tap g of a convolution: the same activation columns, rows shifted by the tap's raster offset
+            const int g = kb / p.a_tap_kb;
+            ka = (kb - g * p.a_tap_kb) * BK;
+            arow += p.a_tap_off[g];
+          }
           if (CL > 1) {  // own A rows + own half of the B tile; the bytes of both CTAs complete on the leader's barrier
             if (crank == 0) mbar_arrive_expect_tx(&full[stage], CL * (C::kBytesA + C::kBytesB));
-            tma_load_2d_pair(sA + stage * C::kBytesA, &tmA, &full[stage], ka, m_blk * BM);
+            tma_load_2d_pair(sA + stage * C::kBytesA, &tmA, &full[stage], ka, arow);
             tma_load_2d_pair(sB + stage * C::kBytesB, &tmB, &full[stage], kb * BK, n_blk * BN + (int)crank * (BN / CL));
           } else {
             mbar_arrive_expect_tx(&full[stage], C::kBytesA + C::kBytesB);
-            tma_load_2d(sA + stage * C::kBytesA, &tmA, &full[stage], ka, m_blk * BM);
+            tma_load_2d(sA + stage * C::kBytesA, &tmA, &full[stage], ka, arow);
             tma_load_2d(sB + stage * C::kBytesB, &tmB, &full[stage], kb * BK, n_blk * BN);
           }
           if (++stage == C::kStages) {
@@ -428,6 +437,7 @@ static int launch(const alg_gemm_t* g, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)(g->a_k_period ? g->a_k_period : g->K), (uint64_t)g->M}, strides[2] = {1, (uint64_t)g->lda};
+    if (g->a_tap_kblocks) dims[0] = (uint64_t)g->a_tap_kblocks * BK;
     uint32_t box[2] = {BK, BM};
     if (int rc = make_tmap_bf16(&tmA, g->A, 2, dims, strides, box)) return rc;
   }
@@ -458,6 +468,8 @@ static int launch(const alg_gemm_t* g, cudaStream_t st) {
   p.n_tiles = (int)((g->N + BN - 1) / BN);
   p.k_blocks = (int)((g->K + BK - 1) / BK);
   p.a_k_period = (int)g->a_k_period;
+  p.a_tap_kb = g->a_tap_kblocks;
+  for (int i = 0; i < 32; ++i) p.a_tap_off[i] = (g->a_tap_kblocks && i < g->a_n_taps) ? g->a_tap_offsets[i] : 0;
   const int units = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
   if (CL == 1) {
     const int grid = std::min(units, num_sms());
@@ -492,6 +504,12 @@ extern "C" int alg_gemm_bf16(const alg_gemm_t* g, void* stream) {
   ALG_REQUIRE(g->a_k_period >= 0 && g->a_k_period < (int64_t(1) << 30) &&
                   (g->a_k_period == 0 || (g->a_k_period % 64 == 0 && g->K % g->a_k_period == 0)),
               "gemm: a_k_period must be a multiple of 64 that divides K");
+  if (g->a_tap_kblocks) {
+    ALG_REQUIRE(g->a_tap_kblocks > 0 && g->a_n_taps > 0 && g->a_n_taps <= 32 && g->a_tap_offsets && g->a_k_period == 0 &&
+                    (int64_t)g->a_n_taps * g->a_tap_kblocks * 64 == g->K,
+                "gemm: implicit-convolution mode needs 1..32 taps, K = taps * a_tap_kblocks * 64 and no a_k_period");
+    ALG_REQUIRE(g->lda >= (int64_t)g->a_tap_kblocks * 64 && g->ldb >= g->K && g->ldd >= g->N, "gemm: leading dimension too small");
+  } else
   ALG_REQUIRE(g->lda >= (g->a_k_period ? g->a_k_period : g->K) && g->ldb >= g->K && g->ldd >= g->N,
               "gemm: leading dimension too small");
   ALG_REQUIRE(g->ldd % (g->out_f32 ? 4 : 8) == 0, "gemm: ldd must keep rows 16-byte aligned");
@@ -530,6 +548,8 @@ extern "C" int alg_gemm_bf16(const alg_gemm_t* g, void* stream) {
     if (cluster == 2 && g->M > pair_min_m) return gemm::launch<256, 2>(g, st);
     return gemm::launch<256, 1>(g, st);
   }
-  if (g->N % 128 == 0 || g->N > 128) return gemm::launch<128, 1>(g, st);
+  // 64 < N < 128 (the 96-channel level of the Wan VAE) takes the 128-wide tile too: a 128 x 64 x 16 SS MMA is operand-fetch
+  // bound (48 cycles for 32 cycles of math), so one 3/4-used 128-wide tile beats a 64 + a half-used 64 tile
+  if (g->N % 128 == 0 || g->N > 64) return gemm::launch<128, 1>(g, st);
   return gemm::launch<64, 1>(g, st);
 }

@@ -225,6 +225,65 @@ __global__ void __launch_bounds__(256) group_norm_f32_apply_kernel(const float* 
   }
 }
 
+// ---- implicit-convolution operand (no patch matrix) ----------------------------------------------------------------------
+// The stride-1 3x3x3 convolutions read their input as a ZERO-PADDED channels-last clip in split form: S3P = bf16
+// [(T + pt) * (H + 2) * (W + 2), Cs], row of pixel (t, y, x) = ((t + pt) * (H + 2) + y + 1) * (W + 2) + x + 1, columns
+// [hi(C) | hi(C) | lo(C) | 0...] (Cs = 3C rounded up to 64).  alg_gemm_bf16's tap mode then walks the 27 taps as row-shifted
+// reads of this one buffer.  This kernel is the producer: (optional WanRMS_norm) (+ SiLU) + split of every interior pixel, read
+// from a compact [T*H*W, C] or a padded-raster [(T+pt)(H+2)(W+2), C] fp32 activation; the padding rows / columns of the output
+// are never written (the buffer is zeroed once).
+__global__ void __launch_bounds__(256) norm_split_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int T, int H,
+                                                             int W, int C, int pt, int in_padded, int Cs, float scale,
+                                                             const float* __restrict__ gamma, int silu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pixels = (int64_t)T * H * W;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t pix = warp; pix < pixels; pix += nwarps) {
+    const int xx = (int)(pix % W);
+    const int64_t r = pix / W;
+    const int y = (int)(r % H), t = (int)(r / H);
+    const int64_t prow = ((int64_t)(t + pt) * (H + 2) + y + 1) * (W + 2) + xx + 1;
+    const float* xr = x + (in_padded ? prow : pix) * C;
+    float mul = 1.f;
+    if (gamma) {
+      float ss = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float v = xr[c];
+        ss = fmaf(v, v, ss);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      mul = fmaxf(sqrtf(ss), 1e-12f);
+    }
+    __nv_bfloat16* orow = out + prow * Cs;
+    for (int c = lane; c < C; c += 32) {
+      float v = xr[c];
+      if (gamma) v = __fdiv_rn(v, mul) * scale * gamma[c];
+      if (silu) v = v / (1.0f + expf(-v));
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      orow[c] = hi;
+      orow[C + c] = hi;
+      orow[2 * C + c] = lo;
+    }
+  }
+}
+// interior pixels of a compact [T*H*W, C] clip <-> the padded raster [(T+pt)(H+2)(W+2), C] (fp32); padding is not touched
+__global__ void pad_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int H, int W, int C, int pt,
+                                int to_padded) {
+  const int64_t n = (int64_t)T * H * W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t pix = i / C;
+    const int xx = (int)(pix % W);
+    const int64_t r = pix / W;
+    const int y = (int)(r % H), t = (int)(r / H);
+    const int64_t j = (((int64_t)(t + pt) * (H + 2) + y + 1) * (W + 2) + xx + 1) * C + c;
+    if (to_padded) dst[j] = src[i];
+    else dst[i] = src[j];
+  }
+}
+
 // [C, P] (channel-major: one sample of [B, C, T, H, W]) -> [P, ld] channels-last, columns >= C zeroed
 __global__ void nchw_to_cl_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int64_t P, int ld) {
   const int64_t n = P * ld;
@@ -334,6 +393,26 @@ extern "C" int alg_group_norm_f32(const float* x, float* y, int64_t rows, int C,
   vae32::group_norm_f32_stats_kernel<<<grid, 256, sizeof(double) * 2 * groups, st>>>(x, rows, C, C / groups, stats);
   ALG_LAUNCH_OK();
   vae32::group_norm_f32_apply_kernel<<<vae32::grid_for(rows * C), 256, 0, st>>>(x, y, rows, C, C / groups, eps, weight, bias, silu, stats);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_norm_split_pad_f32(const float* x, void* out, int T, int H, int W, int C, int front_pad, int in_padded, int Cs,
+                                      const float* gamma, int silu, void* stream) {
+  ALG_REQUIRE(x && out && T > 0 && H > 0 && W > 0 && C > 0 && front_pad >= 0 && Cs >= 3 * C && Cs % 8 == 0, "norm_split_pad: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  const int64_t pixels = (int64_t)T * H * W;
+  vae32::norm_split_pad_kernel<<<vae32::grid_for(pixels, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), T, H, W, C, front_pad, in_padded, Cs, sqrtf((float)C), gamma, silu);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_pad_copy_f32(const float* src, float* dst, int T, int H, int W, int C, int front_pad, int to_padded, void* stream) {
+  ALG_REQUIRE(src && dst && T > 0 && H > 0 && W > 0 && C > 0 && front_pad >= 0, "pad_copy: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  vae32::pad_copy_kernel<<<vae32::grid_for((int64_t)T * H * W * C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, dst, T, H, W, C, front_pad, to_padded);
   ALG_LAUNCH_OK();
   return 0;
 }

@@ -129,12 +129,17 @@ def parameter_shapes(cfg: dict) -> Dict[str, tuple]:
     return s
 
 
-class _Act:
-    """One sample's activation, channels-last: ``t`` is [T*H*W, C] fp32 contiguous."""
-    __slots__ = ("t", "T", "H", "W", "C")
+FRONT_PAD = 2  # zero frames in front of a clip in the padded raster (kt - 1 of the causal 3x3x3 convolutions)
 
-    def __init__(self, t, T, H, W, C_):
-        self.t, self.T, self.H, self.W, self.C = t, T, H, W, C_
+
+class _Act:
+    """One sample's activation, channels-last fp32: ``t`` is [T*H*W, C] (compact), or, with ``padded``, the zero-padded raster
+    [(T + FRONT_PAD) * (H + 2) * (W + 2), C] in which the implicit convolutions produce their output (pixel (t, y, x) sits in row
+    ((t + FRONT_PAD) * (H + 2) + y + 1) * (W + 2) + x + 1; the padding rows hold don't-care values)."""
+    __slots__ = ("t", "T", "H", "W", "C", "padded")
+
+    def __init__(self, t, T, H, W, C_, padded=False):
+        self.t, self.T, self.H, self.W, self.C, self.padded = t, T, H, W, C_, padded
 
     def frame(self, i, n=1):
         hw = self.H * self.W
@@ -147,6 +152,7 @@ class SplitConvVAE:
     ``_shapes()``, ``_encode_one`` and ``_decode_one``."""
 
     Z_KEY = "z_dim"
+    BUILD_TAPS = False      # also lay the 3x3x3 weights out tap-major for the implicit (zero-padded) convolution
     TRUNCATE_FRAMES = True  # AutoencoderKLWan's chunk loop (1 frame, then 4 at a time) drops a trailing partial chunk
 
     def _init_common(self, cfg: dict):
@@ -160,6 +166,9 @@ class SplitConvVAE:
         self._cols_budget = 6 << 30  # bytes of patch matrix per gather + GEMM call (whole output frames)
         self._stats: Optional[torch.Tensor] = None
         self._attn_budget = 48 << 30  # bytes the materialised attention scores may take
+        self._s3p: Dict[tuple, torch.Tensor] = {}  # zero-padded split operands of the implicit convolutions, by geometry
+        import os
+        self.implicit = os.environ.get("ALG_VAE_IMPLICIT", "1") == "1"
 
     def _shapes(self) -> Dict[str, tuple]:
         raise NotImplementedError
@@ -224,6 +233,15 @@ class SplitConvVAE:
                 if co8 != co:
                     m = torch.cat([m, m.new_zeros(co8 - co, m.shape[1])])
                 w[name] = split_weight(m.contiguous(), k8)
+                if self.BUILD_TAPS and t.dim() == 5 and tuple(t.shape[2:]) == (3, 3, 3) and t.shape[1] % 2 == 0:
+                    # implicit convolution: per tap [w_hi | w_lo | w_hi | 0] padded to a multiple of 64 columns, taps along K
+                    ci = t.shape[1]
+                    cs = (3 * ci + 63) // 64 * 64
+                    taps = t.permute(0, 2, 3, 4, 1).reshape(co, 27, ci)
+                    if co8 != co:
+                        taps = torch.cat([taps, taps.new_zeros(co8 - co, 27, ci)])
+                    w3 = split_weight(taps.reshape(co8 * 27, ci).contiguous()).view(co8, 27, 3 * ci)
+                    w[name + "_taps"] = torch.nn.functional.pad(w3, (0, cs - 3 * ci)).reshape(co8, 27 * cs).contiguous()
         self._w = w
         self._cols = None
         return self
@@ -257,6 +275,7 @@ class SplitConvVAE:
         ``out`` / ``out_frame0`` / ``out_frame_step`` scatter output frame i to frame ``out_frame0 + i * out_frame_step`` of an
         existing clip (the two channel halves of "upsample3d" become alternating frames)."""
         lib, dev = _lib.lib(), self.device
+        x = self._to_compact(x)
         kt, kh, kw = k
         st, sh, sw = stride
         pad_t = kt - 1 if pad[0] is None else pad[0]
@@ -311,6 +330,50 @@ class SplitConvVAE:
         _launch(_lib.lib().alg_rms_norm_cl_f32, self.device, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
                 self._w[name + ".gamma"].data_ptr(), None, int(silu))
         return out
+
+    # ---- implicit (patch-matrix-free) 3x3x3 stride-1 convolution -----------------------------------------------------------------
+    def _to_padded(self, x: _Act) -> _Act:
+        if x.padded:
+            return x
+        out = torch.zeros((x.T + FRONT_PAD) * (x.H + 2) * (x.W + 2), x.C, device=self.device, dtype=torch.float32)
+        _launch(_lib.lib().alg_pad_copy_f32, self.device, x.t.data_ptr(), out.data_ptr(), x.T, x.H, x.W, x.C, FRONT_PAD, 1)
+        return _Act(out, x.T, x.H, x.W, x.C, padded=True)
+
+    def _to_compact(self, x: _Act) -> _Act:
+        if not x.padded:
+            return x
+        out = torch.empty(x.T * x.H * x.W, x.C, device=self.device, dtype=torch.float32)
+        _launch(_lib.lib().alg_pad_copy_f32, self.device, x.t.data_ptr(), out.data_ptr(), x.T, x.H, x.W, x.C, FRONT_PAD, 0)
+        return _Act(out, x.T, x.H, x.W, x.C)
+
+    def _split_pad(self, x: _Act, gamma: Optional[torch.Tensor], silu: bool) -> torch.Tensor:
+        """(WanRMS_norm) (+ SiLU) + bf16 split of ``x`` into the zero-padded operand buffer of its geometry (reused by every
+        convolution of that geometry: only interior pixels are rewritten, the padding stays zero)."""
+        cs = (3 * x.C + 63) // 64 * 64
+        key = (x.T, x.H, x.W, cs)
+        buf = self._s3p.get(key)
+        if buf is None or buf.device != self.device:
+            buf = self._s3p[key] = torch.zeros((x.T + FRONT_PAD) * (x.H + 2) * (x.W + 2), cs, device=self.device, dtype=torch.bfloat16)
+        _launch(_lib.lib().alg_norm_split_pad_f32, self.device, x.t.data_ptr(), buf.data_ptr(), x.T, x.H, x.W, x.C, FRONT_PAD,
+                int(x.padded), cs, None if gamma is None else gamma.data_ptr(), int(silu))
+        return buf
+
+    def _conv_taps(self, s3p: torch.Tensor, geom: Tuple[int, int, int], name: str, residual: Optional[torch.Tensor] = None) -> _Act:
+        """The 27 taps as row-shifted reads of ONE padded operand (alg_gemm_bf16 tap mode): out = padded raster [P_pad, Co8]."""
+        T, H, W = geom
+        w3, bias = self._w[name + ".weight_taps"], self._w[name + ".bias"]
+        cs = s3p.shape[1]
+        plane, row = (H + 2) * (W + 2), W + 2
+        offs = [(it - FRONT_PAD) * plane + (ih - 1) * row + (iw - 1) for it in range(3) for ih in range(3) for iw in range(3)]
+        out = torch.empty(s3p.shape[0], w3.shape[0], device=self.device, dtype=torch.float32)
+        ops.gemm(s3p, w3, None, out=out, out_dtype=torch.float32, a_tap_kblocks=cs // 64, a_tap_offsets=offs)
+        _launch(_lib.lib().alg_bias_act_f32, self.device, out.data_ptr(), bias.data_ptr(), None if residual is None else residual.data_ptr(),
+                out.shape[0], out.shape[1], 0)
+        return _Act(out, T, H, W, out.shape[1], padded=True)
+
+    def _release_operands(self):
+        self._s3p.clear()
+        self._cols = None
 
     def _attention_core(self, y: torch.Tensor, wq3, bq, wk3, bk, wv3, bv, causal_block: int = 0) -> torch.Tensor:
         """softmax(q k^T / sqrt(C)) v for ONE head of C channels over the rows of y [N, C] (already normalised), fp32 through the
@@ -378,6 +441,8 @@ class SplitConvVAE:
 class AutoencoderKLWan(SplitConvVAE):
     """Native-kernel ``AutoencoderKLWan``: ``encode(x).latent_dist`` / ``decode(z).sample`` in float32."""
 
+    BUILD_TAPS = True
+
     def __init__(self, **config):
         cfg = dict(WAN21_VAE)
         cfg.update({k: v for k, v in config.items() if k in cfg})
@@ -389,7 +454,26 @@ class AutoencoderKLWan(SplitConvVAE):
     def _shapes(self) -> Dict[str, tuple]:
         return parameter_shapes(self._cfg)
 
+    def _fits_implicit(self, x: _Act, c_out: int) -> bool:
+        """The implicit path keeps the padded input, two padded outputs and the split operands of a whole level resident; when that
+        does not fit next to what is already allocated (720p clips beside a resident DiT), fall back to the frame-chunked gather."""
+        rows = (x.T + FRONT_PAD) * (x.H + 2) * (x.W + 2)
+        cs_in, cs_out = (3 * x.C + 63) // 64 * 64, (3 * c_out + 63) // 64 * 64
+        need = rows * (2 * (cs_in + cs_out) + 4 * (x.C + 3 * c_out))
+        free, _ = torch.cuda.mem_get_info(self.device)
+        free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        return need < 0.8 * free
+
     def _res(self, x: _Act, name: str) -> _Act:
+        if self.implicit and self._fits_implicit(x, self._w[name + ".conv1.bias"].numel()):
+            # norm + SiLU + split straight into the padded operand; both convolutions without a patch matrix
+            x = self._to_padded(x)
+            geom = (x.T, x.H, x.W)
+            h = x.t
+            if name + ".conv_shortcut.weight" in self._w:
+                h = self._pointwise(x.t, name + ".conv_shortcut")
+            y = self._conv_taps(self._split_pad(x, self._w[name + ".norm1.gamma"], True), geom, name + ".conv1")
+            return self._conv_taps(self._split_pad(y, self._w[name + ".norm2.gamma"], True), geom, name + ".conv2", residual=h)
         h = x.t
         if name + ".conv_shortcut.weight" in self._w:
             h = self._pointwise(x.t, name + ".conv_shortcut")
@@ -400,6 +484,7 @@ class AutoencoderKLWan(SplitConvVAE):
 
     def _attn(self, x: _Act, name: str) -> _Act:
         """WanAttentionBlock: per frame, ONE head of C channels over the H*W pixels."""
+        x = self._to_compact(x)
         Cc, hw = x.C, x.H * x.W
         wq = self._w[name + ".to_qkv.weight"]  # [3C, 3C] split, rows = (q | k | v) output channels
         bq = self._w[name + ".to_qkv.bias"]
@@ -417,6 +502,7 @@ class AutoencoderKLWan(SplitConvVAE):
         return self._res(x, name + ".resnets.1")
 
     def _down(self, x: _Act, name: str, kind: str) -> _Act:
+        x = self._to_compact(x)
         Ho, Wo = (x.H + 1 - 3) // 2 + 1, (x.W + 1 - 3) // 2 + 1  # ZeroPad2d((0, 1, 0, 1)) + Conv2d(3, stride 2)
         y = self._conv(x, name + ".resample.1", (1, 3, 3), stride=(1, 2, 2), pad=(0, 0, 0), out_hw=(Ho, Wo))
         if kind == "down3d" and y.T > 1:
@@ -429,6 +515,7 @@ class AutoencoderKLWan(SplitConvVAE):
         return y
 
     def _up(self, x: _Act, name: str, kind: str) -> _Act:
+        x = self._to_compact(x)
         if kind == "up3d" and x.T > 1:
             hw, Cc = x.H * x.W, x.C
             out = torch.empty((2 * x.T - 1) * hw, Cc, device=self.device, dtype=torch.float32)
@@ -439,25 +526,37 @@ class AutoencoderKLWan(SplitConvVAE):
             x = _Act(out, 2 * x.T - 1, x.H, x.W, Cc)
         return self._conv(x, name + ".resample.1", (1, 3, 3), pad=(0, 1, 1), up=2)
 
+    def _conv3(self, a: _Act, name: str, norm: Optional[str] = None) -> _Act:
+        """A causal 3x3x3 convolution, optionally behind ``norm`` (WanRMS_norm) + SiLU: implicit when its tap-major weight exists."""
+        gamma = None if norm is None else self._w[norm + ".gamma"]
+        if self.implicit and name + ".weight_taps" in self._w and self._fits_implicit(a, self._w[name + ".bias"].numel()):
+            return self._conv_taps(self._split_pad(a, gamma, norm is not None), (a.T, a.H, a.W), name)
+        a = self._to_compact(a)
+        if norm is not None:
+            a = _Act(self._norm(a.t, norm, True), a.T, a.H, a.W, a.C)
+        return self._conv(a, name, (3, 3, 3))
+
     def _encode_one(self, x: torch.Tensor) -> torch.Tensor:
         enc, _, _, _, _ = _plan(self._cfg)
-        a = self._conv(self._to_cl(x), "encoder.conv_in", (3, 3, 3))
+        a = self._conv3(self._to_cl(x), "encoder.conv_in")
         for name, kind, ci, co in enc:
             a = self._res(a, name) if kind == "res" else self._down(a, name, kind)
         a = self._mid(a, "encoder.mid_block")
-        a.t = self._norm(a.t, "encoder.norm_out", True)
-        a = self._conv(a, "encoder.conv_out", (3, 3, 3))
+        a = self._to_compact(self._conv3(a, "encoder.conv_out", norm="encoder.norm_out"))
         a.t = self._pointwise(a.t, "quant_conv")
-        return self._from_cl(a, 2 * self._cfg["z_dim"], clamp=False)
+        out = self._from_cl(a, 2 * self._cfg["z_dim"], clamp=False)
+        self._release_operands()
+        return out
 
     def _decode_one(self, z: torch.Tensor) -> torch.Tensor:
         _, dec, _, _, _ = _plan(self._cfg)
         a = self._to_cl(z)
         a.t = self._pointwise(a.t, "post_quant_conv")[:, :self._cfg["z_dim"]].contiguous()
-        a = self._conv(a, "decoder.conv_in", (3, 3, 3))
+        a = self._conv3(a, "decoder.conv_in")
         a = self._mid(a, "decoder.mid_block")
         for name, kind, ci, co in dec:
             a = self._res(a, name) if kind == "res" else self._up(a, name, kind)
-        a.t = self._norm(a.t, "decoder.norm_out", True)
-        a = self._conv(a, "decoder.conv_out", (3, 3, 3))
-        return self._from_cl(a, 3, clamp=True)
+        a = self._to_compact(self._conv3(a, "decoder.conv_out", norm="decoder.norm_out"))
+        out = self._from_cl(a, 3, clamp=True)
+        self._release_operands()
+        return out

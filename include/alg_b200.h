@@ -165,6 +165,14 @@ typedef struct {
                                 (multiple of 64 dividing K; lda >= period).  A causal 3-D convolution on ONE frame reads
                                 the same [kh, kw, C] patch for each of its kt temporal taps, so the patch matrix is
                                 gathered once and only the weights differ along K                                  */
+  /* --- ABI 5: implicit convolution --- */
+  int32_t a_tap_kblocks;     /* 0, or K = a_n_taps groups of a_tap_kblocks * 64 columns: group g multiplies A columns
+                                [0, a_tap_kblocks * 64) of the rows SHIFTED by a_tap_offsets[g] against B columns of group g.  With
+                                A = a zero-padded channels-last clip [(T+pt) * (H+2) * (W+2), C] and offsets = the taps' raster
+                                distances, D row m is the stride-1 convolution at padded-raster pixel m: no patch matrix exists;
+                                rows outside [0, M) read as zero (TMA out-of-bounds fill)                              */
+  int32_t a_n_taps;          /* <= 32 */
+  const int32_t* a_tap_offsets; /* HOST array of a_n_taps row offsets */
 } alg_gemm_t;
 
 /* D = epilogue(A * B^T + bias): every nn.Linear of the DiT (SURVEY kernel K6). */
@@ -494,6 +502,15 @@ int alg_group_norm_f32(const float* x, float* y, int64_t rows, int C, int groups
  * clamp to [lo, hi] (lo < hi; AutoencoderKLWan.decode clamps to [-1, 1]) */
 int alg_nchw_to_cl_f32(const float* x, float* out, int C, int64_t pixels, int ld, void* stream);
 int alg_cl_to_nchw_f32(const float* x, float* out, int C, int64_t pixels, int ld, float lo, float hi, void* stream);
+
+/* Operand of the implicit (patch-matrix-free) stride-1 convolution, see alg_gemm_t.a_tap_kblocks: every interior pixel of a
+ * clip -- x fp32 [T*H*W, C] compact, or the padded raster [(T+front_pad)(H+2)(W+2), C] when in_padded -- goes through the optional
+ * WanRMS_norm (gamma != NULL) and SiLU and is written as bf16 [hi | hi | lo] into row ((t+front_pad)(H+2) + y+1)(W+2) + x+1 of
+ * out [(T+front_pad)(H+2)(W+2), Cs] (Cs >= 3C).  Padding rows and columns >= 3C are not written: zero the buffer once. */
+int alg_norm_split_pad_f32(const float* x, void* out, int T, int H, int W, int C, int front_pad, int in_padded, int Cs,
+                           const float* gamma, int silu, void* stream);
+/* interior pixels of compact [T*H*W, C] fp32 -> padded raster (to_padded != 0) or back; padding is not touched */
+int alg_pad_copy_f32(const float* src, float* dst, int T, int H, int W, int C, int front_pad, int to_padded, void* stream);
 
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 int64_t alg_launch_count(void);

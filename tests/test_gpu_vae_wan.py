@@ -214,3 +214,36 @@ def test_wan_pipeline_end_to_end_all_native_vs_upstream_modules():
     assert a.std() > 1e-3  # not a constant clip
     err = np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64))
     assert err < 2e-2, err
+
+
+def test_gemm_tap_mode_is_a_stride1_convolution():
+    """alg_gemm_bf16's implicit-convolution mode alone (bf16): 27 row-shifted reads of a zero-padded channels-last clip equal
+    F.conv3d with causal zero padding; rows of the padded raster that are padding are don't-care."""
+    import torch.nn.functional as F
+    from alg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    T, H, W, Ci, Co = 3, 5, 7, 64, 96
+    x = torch.randn(T, H, W, Ci, generator=g, device="cuda").bfloat16()
+    w = (torch.randn(Co, Ci, 3, 3, 3, generator=g, device="cuda") * (27 * Ci) ** -0.5).bfloat16()
+    pad = torch.zeros(T + 2, H + 2, W + 2, Ci, device="cuda", dtype=torch.bfloat16)
+    pad[2:, 1:-1, 1:-1] = x
+    a = pad.view(-1, Ci)
+    wt = w.permute(0, 2, 3, 4, 1).reshape(Co, 27 * Ci).contiguous()
+    plane, row = (H + 2) * (W + 2), W + 2
+    offs = [(it - 2) * plane + (ih - 1) * row + (iw - 1) for it in range(3) for ih in range(3) for iw in range(3)]
+    out = ops.gemm(a, wt, None, out_dtype=torch.float32, a_tap_kblocks=Ci // 64, a_tap_offsets=offs)
+    got = out.view(T + 2, H + 2, W + 2, Co)[2:, 1:-1, 1:-1]
+    ref = F.conv3d(F.pad(x.float().permute(3, 0, 1, 2)[None], (1, 1, 1, 1, 2, 0)), w.float())[0].permute(1, 2, 3, 0)
+    assert rel_l2(got, ref) < 1e-5, rel_l2(got, ref)
+
+
+def test_implicit_and_patch_matrix_paths_agree():
+    """ALG_VAE_IMPLICIT=0 (gather + split patch matrix) and the default implicit convolutions give the same clip / moments."""
+    vae, sd, ocfg = _pair(dict(TINY, z_dim=16), seed=5)
+    z = torch.randn(1, 16, 3, 4, 6, generator=torch.Generator(device="cuda").manual_seed(7), device="cuda")
+    x = torch.rand(1, 3, 5, 32, 48, generator=torch.Generator(device="cuda").manual_seed(8), device="cuda") * 2 - 1
+    assert vae.implicit
+    a, ma = vae.decode(z).sample, vae.encode(x).latent_dist.parameters
+    vae.implicit = False
+    b, mb = vae.decode(z).sample, vae.encode(x).latent_dist.parameters
+    assert rel_l2(a, b) < 2e-5 and rel_l2(ma, mb) < 2e-5, (rel_l2(a, b), rel_l2(ma, mb))
