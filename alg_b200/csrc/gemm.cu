@@ -437,7 +437,10 @@ static int launch(const alg_gemm_t* g, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)(g->a_k_period ? g->a_k_period : g->K), (uint64_t)g->M}, strides[2] = {1, (uint64_t)g->lda};
-    if (g->a_tap_kblocks) dims[0] = (uint64_t)g->a_tap_kblocks * BK;
+    if (g->a_tap_kblocks) {
+      dims[0] = (uint64_t)g->a_tap_kblocks * BK;
+      if (g->a_rows > 0) dims[1] = (uint64_t)g->a_rows;
+    }
     uint32_t box[2] = {BK, BM};
     if (int rc = make_tmap_bf16(&tmA, g->A, 2, dims, strides, box)) return rc;
   }

@@ -195,6 +195,60 @@ __global__ void __launch_bounds__(256) spatial_norm_apply_kernel(const uint4* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Spatially zero-padded raster for the implicit (patch-matrix-free) convolution, see alg_gemm_t.a_tap_kblocks:
+// frames [F, H + 2, W + 2, C] with the image in [1, H] x [1, W].  to_padded: compact [n*H*W, C] -> interior of padded frames
+// (borders are not written: zero the buffer once); else padded rows of `ld` elements -> compact [n*H*W, C] (+ bf16 residual:
+// dst = bf16(float(src) + float(residual)), the rounding chain of the GEMM's residual epilogue).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pad_frames_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                         const __nv_bfloat16* __restrict__ res, int n, int H, int W, int C, int ld,
+                                                         int to_padded) {
+  const int64_t total = (int64_t)n * H * W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t pix = i / C;
+    const int xx = (int)(pix % W);
+    const int64_t r = pix / W;
+    const int y = (int)(r % H), t = (int)(r / H);
+    const int64_t prow = ((int64_t)t * (H + 2) + y + 1) * (W + 2) + xx + 1;
+    if (to_padded) {
+      dst[prow * ld + c] = src[i];
+    } else {
+      float v = __bfloat162float(src[prow * ld + c]);
+      if (res) v += __bfloat162float(res[i]);
+      dst[i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) pad_frames_vec_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                             const uint4* __restrict__ res, int n, int H, int W, int c8, int ld8,
+                                                             int to_padded) {
+  const int64_t total = (int64_t)n * H * W * c8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8);
+    const int64_t pix = i / c8;
+    const int xx = (int)(pix % W);
+    const int64_t r = pix / W;
+    const int y = (int)(r % H), t = (int)(r / H);
+    const int64_t prow = ((int64_t)t * (H + 2) + y + 1) * (W + 2) + xx + 1;
+    if (to_padded) {
+      dst[prow * ld8 + c] = __ldg(src + i);
+    } else {
+      uint4 v = __ldg(src + prow * ld8 + c);
+      if (res) {
+        float a[8], b[8];
+        unpack8(v, a);
+        unpack8(__ldg(res + i), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] += b[e];
+        v = pack8(a);
+      }
+      dst[i] = v;
+    }
+  }
+}
+
 }  // namespace vae
 }  // namespace alg
 
@@ -268,6 +322,26 @@ extern "C" int alg_spatial_norm_apply_bf16(const void* f_norm, const void* yb, v
   alg::vae::spatial_norm_apply_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(f_norm), reinterpret_cast<const uint4*>(yb), reinterpret_cast<uint4*>(out), C / 8, T, H, W, zt,
       zh, zw, silu, n);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_pad_frames_bf16(const void* src, void* dst, const void* residual, int frames, int H, int W, int C, int64_t ld,
+                                   int to_padded, void* stream) {
+  ALG_REQUIRE(src && dst && frames > 0 && H > 0 && W > 0 && C > 0 && ld >= C, "pad_frames: bad arguments");
+  ALG_REQUIRE(!(residual && to_padded), "pad_frames: the residual belongs to the padded -> compact direction");
+  if (int rc = alg_check_device()) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec = C % 8 == 0 && ld % 8 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0;
+  const int64_t n = (int64_t)frames * H * W * (vec ? C / 8 : C);
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  if (vec)
+    alg::vae::pad_frames_vec_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst),
+                                                          reinterpret_cast<const uint4*>(residual), frames, H, W, C / 8, (int)(ld / 8), to_padded);
+  else
+    alg::vae::pad_frames_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst),
+                                                      reinterpret_cast<const __nv_bfloat16*>(residual), frames, H, W, C, (int)ld, to_padded);
   ALG_LAUNCH_OK();
   return 0;
 }

@@ -54,7 +54,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
          bias_per_row: bool = False, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
          gate_alt: Optional[torch.Tensor] = None, gate_split_row: int = 0, gate_round: bool = False,
-         a_k_period: int = 0, a_tap_kblocks: int = 0, a_tap_offsets=None) -> torch.Tensor:
+         a_k_period: int = 0, a_tap_kblocks: int = 0, a_tap_offsets=None, m_rows: int = 0) -> torch.Tensor:
     """``epilogue(a @ w.T + bias)``: a [M, K] bf16, w [N, K] bf16 (nn.Linear layout).  See alg_gemm_bf16.
 
     ``a_k_period``: a is [M, period] and repeats along K (``a.repeat(1, K // period)`` without materialising it).
@@ -64,7 +64,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     _lib.require_cuda(a, w, bias, residual, gate, out, gate_alt)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == (a_k_period or a_tap_kblocks * 64 or w.shape[1])
-    M, K = a.shape[0], w.shape[1]
+    M, K = (int(m_rows) if (a_tap_kblocks and m_rows) else a.shape[0]), w.shape[1]
     N = w.shape[0]
     if out is None:
         ldd = (N + 7) // 8 * 8
@@ -87,6 +87,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if a_tap_kblocks:  # implicit convolution: K groups read row-shifted copies of the same A columns (see alg_gemm_t)
         offs = (C.c_int32 * len(a_tap_offsets))(*[int(o) for o in a_tap_offsets])
         g.a_tap_kblocks, g.a_n_taps, g.a_tap_offsets = int(a_tap_kblocks), len(a_tap_offsets), offs
+        g.a_rows = a.shape[0]  # the offsets may reach past the last output row (m_rows < rows of a)
     if gate is not None:
         assert gate.dtype in (torch.float32, torch.bfloat16) and gate.stride(-1) == 1
         g.gate_dtype = _lib.dtype_code(gate.dtype)

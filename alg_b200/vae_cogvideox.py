@@ -194,6 +194,9 @@ class AutoencoderKLCogVideoX:
         self._cols: Optional[torch.Tensor] = None
         self._cols_budget = 3 << 30  # bytes of patch matrix per im2col + GEMM call (whole frames)
         self.num_latent_frames_batch_size = 2
+        import os
+        self.implicit = os.environ.get("ALG_VAE_IMPLICIT", "1") == "1"  # 3x3x3 decoder convolutions without a patch matrix
+        self._padded: Dict[tuple, torch.Tensor] = {}
         self.decoder = decoder
         self.has_decoder = False
         self.dtype = torch.bfloat16
@@ -275,6 +278,22 @@ class AutoencoderKLCogVideoX:
         """CogVideoXCausalConv3d(k=3) on one frame: [H*W, Ci] -> [H*W, Co]."""
         wt, b = self._w[name + ".conv.weight"], self._w[name + ".conv.bias"]
         Cc = x.shape[1]
+        if self.implicit and Cc % 64 == 0 and wt.shape[0] % 8 == 0:
+            # no patch matrix: the frame is laid out once with a zero border; the GEMM's tap mode reads it at the 9 spatial
+            # offsets, three times over (on one frame the three temporal taps of the replicate-padded clip are the same frame)
+            lib, dev, plane, row = _lib.lib(), x.device, (H + 2) * (W + 2), W + 2
+            xp = self._padded.get((1, H, W, Cc))
+            if xp is None or xp.device != dev:
+                xp = self._padded[(1, H, W, Cc)] = torch.zeros(plane, Cc, device=dev, dtype=torch.bfloat16)
+            with torch.cuda.device(dev):
+                _lib.check(lib.alg_pad_frames_bf16(x.data_ptr(), xp.data_ptr(), None, 1, H, W, Cc, Cc, 1, _lib.stream_ptr(dev)))
+            offs = [(ih - 1) * row + (iw - 1) for _ in range(3) for ih in range(3) for iw in range(3)]
+            d = ops.gemm(xp, wt, b, a_tap_kblocks=Cc // 64, a_tap_offsets=offs)
+            out = torch.empty(H * W, wt.shape[0], device=dev, dtype=torch.bfloat16)
+            with torch.cuda.device(dev):
+                _lib.check(lib.alg_pad_frames_bf16(d.data_ptr(), out.data_ptr(), None if residual is None else residual.data_ptr(), 1, H, W,
+                                                   wt.shape[0], d.stride(0), 0, _lib.stream_ptr(dev)))
+            return out
         if (9 * Cc) % 64 == 0:
             # one frame: the three temporal taps read the same [3, 3, C] patch, so it is gathered once and the GEMM walks
             # it three times along K (a_k_period) against the three temporal weight slices
@@ -350,6 +369,8 @@ class AutoencoderKLCogVideoX:
         the previous chunk (``conv_cache``) or replicate frame 0; the last two input frames are kept for the next chunk."""
         wt, b = self._w[name + ".conv.weight"], self._w[name + ".conv.bias"]
         Ci, HW = x.shape[1], H * W
+        if self.implicit and Ci % 64 == 0:
+            return self._conv3_implicit(x, T, H, W, name, cache, residual)
         xin = torch.empty((T + 2) * HW, Ci, device=x.device, dtype=torch.bfloat16)
         prev = cache.get(name)
         if prev is None:
@@ -374,6 +395,46 @@ class AutoencoderKLCogVideoX:
             else:
                 outs.append(ops.gemm(cols, wt, b, **kw))
         return out if out is not None else torch.cat(outs)
+
+    def _conv3_implicit(self, x, T, H, W, name, cache, residual=None):
+        """The same convolution without a patch matrix: the chunk (with its two cached / replicated frames in front) is laid out once
+        as spatially zero-padded frames [(T + 2), H + 2, W + 2, Ci]; the GEMM's tap mode reads it 27 times at row offsets
+        (it * plane + (ih - 1) * row + (iw - 1)); the bf16 result comes back from the padded raster with the residual added in the
+        same pass (the rounding chain of the GEMM's residual epilogue: bf16(R + bf16(acc + bias)))."""
+        lib, dev = _lib.lib(), x.device
+        wt, b = self._w[name + ".conv.weight"], self._w[name + ".conv.bias"]
+        Ci, HW, plane, row = x.shape[1], H * W, (H + 2) * (W + 2), W + 2
+        key = (T, H, W, Ci)
+        xp = self._padded.get(key)
+        if xp is None or xp.device != dev:  # borders are zeroed once; every use rewrites all interiors
+            xp = self._padded[key] = torch.zeros((T + 2) * plane, Ci, device=dev, dtype=torch.bfloat16)
+        prev = cache.get(name)
+
+        def pad_in(src, frame0, n):
+            with torch.cuda.device(dev):
+                _lib.check(lib.alg_pad_frames_bf16(src.data_ptr(), xp[frame0 * plane:].data_ptr(), None, n, H, W, Ci, Ci, 1,
+                                                   _lib.stream_ptr(dev)))
+        if prev is None:
+            pad_in(x[:HW], 0, 1)
+            pad_in(x[:HW], 1, 1)
+        else:
+            pad_in(prev, 0, 2)
+        pad_in(x, 2, T)
+        keep = torch.empty(2 * HW, Ci, device=dev, dtype=torch.bfloat16)  # the last two frames of (front frames + chunk)
+        if T >= 2:
+            ops.copy_rows(x[(T - 2) * HW:], keep)
+        else:
+            ops.copy_rows(prev[HW:] if prev is not None else x[:HW], keep[:HW])
+            ops.copy_rows(x, keep[HW:])
+        cache[name] = keep
+        offs = [it * plane + (ih - 1) * row + (iw - 1) for it in range(3) for ih in range(3) for iw in range(3)]
+        d = ops.gemm(xp, wt, b, a_tap_kblocks=Ci // 64, a_tap_offsets=offs, m_rows=T * plane)  # padded raster [T * plane, Co]
+        Co = wt.shape[0]
+        out = torch.empty(T * HW, Co, device=dev, dtype=torch.bfloat16)
+        with torch.cuda.device(dev):
+            _lib.check(lib.alg_pad_frames_bf16(d.data_ptr(), out.data_ptr(), None if residual is None else residual.data_ptr(), T, H, W, Co,
+                                               d.stride(0), 0, _lib.stream_ptr(dev)))
+        return out
 
     def _spatial_norm(self, f, T, H, W, z, zt, zh, zw, name, silu=True):
         """CogVideoXSpatialNorm3D: GroupNorm(f) * conv_y(zq') + conv_b(zq') (+ SiLU); f [T*H*W, C], z [zt*zh*zw, zc]."""
@@ -472,6 +533,7 @@ class AutoencoderKLCogVideoX:
             videos.append(torch.cat(parts, dim=1))
         video = torch.stack(videos).to(z.dtype)
         self._cols = None  # the patch-matrix workspace is large at 480 x 720: give it back once the video is decoded
+        self._padded.clear()
         if not return_dict:
             return (video,)
         return SimpleNamespace(sample=video)

@@ -173,6 +173,7 @@ typedef struct {
                                 rows outside [0, M) read as zero (TMA out-of-bounds fill)                              */
   int32_t a_n_taps;          /* <= 32 */
   const int32_t* a_tap_offsets; /* HOST array of a_n_taps row offsets */
+  int64_t a_rows;            /* rows of A in tap mode when it has more than M (offsets reach past the last output row); 0 = M */
 } alg_gemm_t;
 
 /* D = epilogue(A * B^T + bias): every nn.Linear of the DiT (SURVEY kernel K6). */
@@ -511,6 +512,13 @@ int alg_norm_split_pad_f32(const float* x, void* out, int T, int H, int W, int C
                            const float* gamma, int silu, void* stream);
 /* interior pixels of compact [T*H*W, C] fp32 -> padded raster (to_padded != 0) or back; padding is not touched */
 int alg_pad_copy_f32(const float* src, float* dst, int T, int H, int W, int C, int front_pad, int to_padded, void* stream);
+
+/* bf16 frames <-> their spatially zero-padded raster [frames, H+2, W+2, ld] (image in [1,H] x [1,W]) for the implicit convolution:
+ * to_padded != 0: src compact [frames*H*W, C] -> interior of dst (borders untouched: zero the buffer once);
+ * to_padded == 0: src padded -> dst compact [frames*H*W, C], plus an optional bf16 residual [frames*H*W, C]:
+ * dst = bf16(float(src) + float(residual)) */
+int alg_pad_frames_bf16(const void* src, void* dst, const void* residual, int frames, int H, int W, int C, int64_t ld, int to_padded,
+                        void* stream);
 
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 int64_t alg_launch_count(void);
