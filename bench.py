@@ -575,6 +575,43 @@ def run_reference(args):
 # ======================================================================================================
 # this repo's arm
 # ======================================================================================================
+def vae_sample(wl, device, fps):
+    """AutoencoderKLWan at the workload's size (alg_b200/vae_wan.py, float32 through the bf16 3-term split): decode of one clip of
+    latents and encode of the [image, zeros...] condition clip, CUDA-event timed, outside the timed regions."""
+    from alg_b200.vae_wan import AutoencoderKLWan
+    if hasattr(wl, "pipe"):
+        del wl.pipe
+    if hasattr(wl, "transformer"):
+        del wl.transformer
+    torch.cuda.empty_cache()
+    vae = AutoencoderKLWan.from_synthetic(seed=0, device=device)
+    z = torch.randn(1, 16, *wl.lat0.shape[2:], generator=torch.Generator(device=device).manual_seed(3), device=device)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return out, a.elapsed_time(b)
+    with torch.no_grad():
+        vae.decode(z[:, :, :2])  # warm-up (tensor maps, allocator)
+        video, ms_dec = timed(lambda: vae.decode(z).sample)
+        clip = torch.zeros(1, 3, video.shape[2], video.shape[3], video.shape[4], device=device)
+        clip[:, :, 0] = video[:, :, 0]
+        finite, shape = bool(torch.isfinite(video).all()), list(video.shape)
+        del video
+        lat, ms_enc = timed(lambda: vae.encode(clip).latent_dist.mode())
+    loop_s = wl.frames / fps
+    return {"what": "native AutoencoderKLWan, seeded weights at the Wan2.1 VAE architecture, float32 via the bf16 3-term split; "
+                    "NOT inside the metric's timed region (the denoise loop)",
+            "decode_ms": ms_dec, "decoded": shape, "decode_finite": finite, "encode_condition_ms": ms_enc, "latent": list(lat.shape),
+            "encode_finite": bool(torch.isfinite(lat).all()),
+            "frames_per_s_loop_plus_encode_decode": wl.frames / (loop_s + (ms_dec + ms_enc) / 1e3),
+            "peak_mem_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from alg_b200 import _lib
@@ -726,6 +763,14 @@ def run_ours(args):
                               "max_latent_rel_l2": res.get("max_latent_rel_l2")}
                 except Exception as ex:  # pragma: no cover
                     parity = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        vae_leg = None
+        if not FAST and args.vae and world == 1 and wl.key == "wan":
+            # informational leg, OUTSIDE every timed region: what turns the loop's latents into the frames the metric counts
+            # (wan:959) and what built the condition (wan:429-434), on the native float32 VAE at the config size
+            try:
+                vae_leg = vae_sample(wl, device, fps)
+            except Exception as ex:  # pragma: no cover
+                vae_leg = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         line = {
             "metric": wl.metric, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
@@ -745,6 +790,8 @@ def run_ours(args):
             line["parity_at_config"] = parity
         if full is not None:
             line["full_video"] = full
+        if vae_leg is not None:
+            line["vae"] = vae_leg
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -764,6 +811,9 @@ def main():
     ap.add_argument("--parity", type=int, default=int(os.environ.get("ALG_BENCH_PARITY", "1")),
                     help="1 (default, N = 1 only): after the timed regions, run one teacher-forced step of each kind at full depth "
                          "against the eager bf16 oracle on the GPU and report parity_at_config + eager_gpu")
+    ap.add_argument("--vae", type=int, default=int(os.environ.get("ALG_BENCH_VAE", "1")),
+                    help="1 (default, N = 1, Wan configs): after the timed regions, decode one clip of latents and encode the condition "
+                         "clip on the native AutoencoderKLWan (seeded weights at the true architecture) and report the times")
     args = ap.parse_args()
     if args.config is None:
         args.config = "wan720" if args.resolution == "720p" else "wan480"
