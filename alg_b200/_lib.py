@@ -190,6 +190,7 @@ SIGNATURES = {
     "alg_wan_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int]),
     "alg_wan_weights_complete": (C.c_int, [C.c_void_p]),
     "alg_wan_set_debug_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "alg_wan_context_cache": (C.c_int, [C.c_void_p, C.c_int]),
     "alg_wan_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "alg_wan_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int]),
     "alg_wan_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),

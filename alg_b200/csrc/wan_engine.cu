@@ -48,6 +48,21 @@ struct alg_wan_engine {
   size_t ev_used = 0;
   struct Span { int cls; cudaEvent_t a, b; };
   std::vector<Span> spans;
+  // Step-invariant cross-attention context (text / image embedders and the K, V^T projections of all layers): memoised per
+  // (prompt pointers, image pointer, pass layout) when the caller enables it -- the conditioning does not change between the
+  // denoise steps of one video (wan:844-944), so steps after the first of each pass layout skip ~10 TFLOP of projections.
+  struct CtxSlot {
+    const void* text[3] = {nullptr, nullptr, nullptr};
+    const void* image = nullptr;
+    int n_pass = 0, n_img = 0;
+    bool valid = false;
+    char* buf = nullptr;  // [layers] x (k_text | vt_text | k_img | vt_img)
+    size_t bytes = 0;
+    uint64_t stamp = 0;
+  };
+  bool ctx_caching = false;
+  CtxSlot ctx_slots[2];  // the three-pass and the two-pass layouts of one video
+  uint64_t ctx_clock = 0;
   int dim() const { return cfg.num_heads * cfg.head_dim; }
 };
 
@@ -315,6 +330,7 @@ extern "C" void alg_wan_destroy(alg_wan_engine_t* e) {
   cudaFree(e->rope_t);
   cudaFree(e->rope_h);
   cudaFree(e->rope_w);
+  for (auto& s : e->ctx_slots) cudaFree(s.buf);
   delete e;
 }
 
@@ -417,13 +433,51 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
   ALG_TRY(gemm(st, Apatch, pk, e->patch_w, pk, x, d, M, d, pk, e->patch_b));
   debug_dump(x, (size_t)M * d * 2);
 
+  // ---- context cache lookup (see alg_wan_engine::CtxSlot) ---------------------------------------------------
+  const size_t kt_elems = (size_t)n_pass * txt * d, vtt_elems = (size_t)n_pass * d * txt_pad;
+  const size_t ki_elems = n_img > 0 ? (size_t)n_pass * ni * d : 0, vti_elems = n_img > 0 ? (size_t)n_pass * d * ni_pad : 0;
+  auto al = [](size_t n) { return (n + 127) & ~size_t(127); };  // 256-byte aligned sections (bf16 elements)
+  const size_t layer_elems = al(kt_elems) + al(vtt_elems) + al(ki_elems) + al(vti_elems);
+  alg_wan_engine::CtxSlot* slot = nullptr;
+  bool ctx_hit = false;
+  if (e->ctx_caching) {
+    for (auto& s : e->ctx_slots) {
+      bool same = s.valid && s.n_pass == n_pass && s.n_img == n_img && s.image == image;
+      for (int p = 0; same && p < n_pass; ++p) same = s.text[p] == text[p];
+      if (same) {
+        slot = &s;
+        ctx_hit = true;
+      }
+    }
+    if (!slot) {  // miss: take the least recently used slot and fill it during this forward
+      slot = e->ctx_slots[0].stamp <= e->ctx_slots[1].stamp ? &e->ctx_slots[0] : &e->ctx_slots[1];
+      const size_t want = layer_elems * c.num_layers * sizeof(bf16);
+      if (slot->bytes < want) {
+        if (slot->buf) {
+          ALG_CUDA_OK(cudaStreamSynchronize(st));
+          ALG_CUDA_OK(cudaFree(slot->buf));
+          slot->buf = nullptr;
+          slot->bytes = 0;
+        }
+        ALG_CUDA_OK(cudaMalloc(&slot->buf, want));
+        slot->bytes = want;
+      }
+      slot->valid = false;  // becomes valid once every layer has been written (below)
+      slot->n_pass = n_pass;
+      slot->n_img = n_img;
+      slot->image = image;
+      for (int p = 0; p < 3; ++p) slot->text[p] = p < n_pass ? text[p] : nullptr;
+    }
+    slot->stamp = ++e->ctx_clock;
+  }
+
   // ---- 2. condition embedder --------------------------------------------------------------------------
   ALG_TRY_EW(dit::timestep_sinusoid((float)timestep, c.freq_dim, sinus, st));
   ALG_TRY_EW(dit::gemv_f32(e->te1_w, e->te1_b, sinus, te_h, (int)d, c.freq_dim, 1, st));
   ALG_TRY_EW(dit::gemv_f32(e->te2_w, e->te2_b, te_h, te_o, (int)d, (int)d, 0, st));
   ALG_TRY_EW(dit::temb_finish(te_o, temb, silu_temb, (int)d, st));
   ALG_TRY(gemm(st, silu_temb, d, e->tp_w, d, tproj, 6 * d, 1, 6 * d, d, e->tp_b));
-  for (int p = 0; p < n_pass; ++p) {
+  for (int p = 0; p < n_pass && !ctx_hit; ++p) {
     int same = -1;
     for (int r = 0; r < p; ++r)
       if (text[r] == text[p]) same = r;
@@ -435,7 +489,7 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
       ALG_TRY(gemm(st, txt_h, d, e->tx2_w, d, dst, d, txt, d, d, e->tx2_b));
     }
   }
-  if (n_img > 0) {
+  if (n_img > 0 && !ctx_hit) {
     ALG_TRY_EW(layer_norm(st, (const bf16*)image, img_n, ni, c.image_dim, 1e-5f, e->in1_w, e->in1_b, nullptr, nullptr));
     ALG_TRY(gemm(st, img_n, c.image_dim, e->if1_w, c.image_dim, img_h, c.image_dim, ni, c.image_dim, c.image_dim,
                  e->if1_b, ALG_EPI_GELU_ERF));
@@ -452,6 +506,13 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
   // ---- 3. transformer blocks --------------------------------------------------------------------------
   for (int l = 0; l < c.num_layers; ++l) {
     const BlockW& b = e->blocks[l];
+    if (slot) {  // this layer's context K / V^T live in the cache slot instead of the workspace
+      bf16* base = reinterpret_cast<bf16*>(slot->buf) + (size_t)l * layer_elems;
+      k_text = base;
+      vt_text = k_text + al(kt_elems);
+      k_img = vt_text + al(vtt_elems);
+      vt_img = k_img + al(ki_elems);
+    }
     ALG_TRY_EW(dit::add_table(b.table, tproj, mod, 6, (int)d, 0, st));
     const float *shift = mod, *scale = mod + d, *gate = mod + 2 * d, *c_shift = mod + 3 * d, *c_scale = mod + 4 * d,
                 *c_gate = mod + 5 * d;
@@ -470,17 +531,21 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
     ALG_TRY_EW(layer_norm(st, x, h, M, (int)d, c.eps, b.norm2_w, b.norm2_b, nullptr, nullptr));
     ALG_TRY(gemm(st, h, d, b.attn2.q_w, d, q, d, M, d, d, b.attn2.q_b));
     ALG_TRY_EW(dit::rms_norm_rope(q, M, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_q, nullptr, st));
-    ALG_TRY(gemm(st, ctx_text, d, b.attn2.k_w, d, k_text, d, n_pass * txt, d, d, b.attn2.k_b));
-    ALG_TRY_EW(dit::rms_norm_rope(k_text, n_pass * txt, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_k, nullptr, st));
-    for (int p = 0; p < n_pass; ++p)
-      ALG_TRY(gemm(st, b.attn2.v_w, d, ctx_text + (int64_t)p * txt * d, d, vt_text + (int64_t)p * d * txt_pad, txt_pad, d,
-                   txt, d, b.attn2.v_b, ALG_EPI_NONE, nullptr, nullptr, 1));
-    if (n_img > 0) {
-      ALG_TRY(gemm(st, ctx_img, d, b.attn2.add_k_w, d, k_img, d, n_pass * ni, d, d, b.attn2.add_k_b));
-      ALG_TRY_EW(dit::rms_norm_rope(k_img, n_pass * ni, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_added_k, nullptr, st));
+    if (!ctx_hit) {
+      ALG_TRY(gemm(st, ctx_text, d, b.attn2.k_w, d, k_text, d, n_pass * txt, d, d, b.attn2.k_b));
+      ALG_TRY_EW(dit::rms_norm_rope(k_text, n_pass * txt, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_k, nullptr, st));
       for (int p = 0; p < n_pass; ++p)
-        ALG_TRY(gemm(st, b.attn2.add_v_w, d, ctx_img + (int64_t)p * ni * d, d, vt_img + (int64_t)p * d * ni_pad, ni_pad, d,
-                     ni, d, b.attn2.add_v_b, ALG_EPI_NONE, nullptr, nullptr, 1));
+        ALG_TRY(gemm(st, b.attn2.v_w, d, ctx_text + (int64_t)p * txt * d, d, vt_text + (int64_t)p * d * txt_pad, txt_pad, d,
+                     txt, d, b.attn2.v_b, ALG_EPI_NONE, nullptr, nullptr, 1));
+    }
+    if (n_img > 0) {
+      if (!ctx_hit) {
+        ALG_TRY(gemm(st, ctx_img, d, b.attn2.add_k_w, d, k_img, d, n_pass * ni, d, d, b.attn2.add_k_b));
+        ALG_TRY_EW(dit::rms_norm_rope(k_img, n_pass * ni, (int)d, hd, c.eps, (const bf16*)b.attn2.norm_added_k, nullptr, st));
+        for (int p = 0; p < n_pass; ++p)
+          ALG_TRY(gemm(st, b.attn2.add_v_w, d, ctx_img + (int64_t)p * ni * d, d, vt_img + (int64_t)p * d * ni_pad, ni_pad, d,
+                       ni, d, b.attn2.add_v_b, ALG_EPI_NONE, nullptr, nullptr, 1));
+      }
       ALG_TRY(attention(st, q, k_img, vt_img, ao, n_pass, heads, hd, N, ni, ni_pad, 0));
     }
     ALG_TRY(attention(st, q, k_text, vt_text, ao, n_pass, heads, hd, N, txt, txt_pad, n_img > 0 ? 1 : 0));
@@ -492,11 +557,21 @@ extern "C" int alg_wan_forward(alg_wan_engine_t* e, const float* const* latents,
     debug_dump(x, (size_t)M * d * 2);
   }
 
+  if (slot && !ctx_hit) slot->valid = true;  // every layer's context K / V^T is in the slot now
+
   // ---- 4. output norm, projection, unpatchify ------------------------------------------------------------
   ALG_TRY_EW(dit::add_table(e->head_table, temb, mod, 2, (int)d, 1, st));
   ALG_TRY_EW(layer_norm(st, x, h, M, (int)d, c.eps, nullptr, nullptr, mod + d, mod));
   ALG_TRY(gemm(st, h, d, e->proj_w, d, proj, pop, M, po, d, e->proj_b));
   ALG_TRY_EW(dit::unpatchify(proj, (bf16*)noise_out, n_pass, c.out_channels, T, H, W, st));
+  return 0;
+}
+
+extern "C" int alg_wan_context_cache(alg_wan_engine_t* e, int enable) {
+  using namespace alg;
+  ALG_REQUIRE(e, "wan_context_cache: null engine");
+  e->ctx_caching = enable != 0;
+  for (auto& s : e->ctx_slots) s.valid = false;  // enabling, disabling and re-enabling all drop what was memoised
   return 0;
 }
 

@@ -281,6 +281,20 @@ def copy_rows(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def pad_frames(src: torch.Tensor, dst: torch.Tensor, frames: int, H: int, W: int, *, to_padded: bool,
+               residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 frames <-> their zero-bordered raster [frames, H + 2, W + 2, ld] (alg_pad_frames_bf16, operand / result of the implicit
+    convolution).  ``to_padded``: src compact [frames*H*W, C] -> interior of dst (borders untouched); else src padded (row length
+    ``src.stride(0)``) -> dst compact [frames*H*W, C] (+ bf16 ``residual``: dst = bf16(float(src) + float(residual)))."""
+    _lib.require_cuda(src, dst, residual)
+    assert src.dtype == dst.dtype == torch.bfloat16 and src.stride(1) == dst.stride(1) == 1
+    Cc = dst.shape[1] if not to_padded else src.shape[1]
+    ld = dst.stride(0) if to_padded else src.stride(0)
+    _launch(_lib.lib().alg_pad_frames_bf16, src.device, src.data_ptr(), dst.data_ptr(), None if residual is None else residual.data_ptr(),
+            frames, H, W, Cc, ld, int(to_padded))
+    return dst
+
+
 def im2col(x: torch.Tensor, T: int, H: int, W: int, *, kernel, stride=(1, 1, 1), pad_t: int = 0, pad_top: int = 0,
            pad_left: int = 0, out_hw=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Patch gather for a (causal 3-D / strided 2-D) convolution on channels-last x [T*H*W, C] bf16.  See alg_im2col_bf16.

@@ -281,19 +281,15 @@ class AutoencoderKLCogVideoX:
         if self.implicit and Cc % 64 == 0 and wt.shape[0] % 8 == 0:
             # no patch matrix: the frame is laid out once with a zero border; the GEMM's tap mode reads it at the 9 spatial
             # offsets, three times over (on one frame the three temporal taps of the replicate-padded clip are the same frame)
-            lib, dev, plane, row = _lib.lib(), x.device, (H + 2) * (W + 2), W + 2
+            dev, plane, row = x.device, (H + 2) * (W + 2), W + 2
             xp = self._padded.get((1, H, W, Cc))
             if xp is None or xp.device != dev:
                 xp = self._padded[(1, H, W, Cc)] = torch.zeros(plane, Cc, device=dev, dtype=torch.bfloat16)
-            with torch.cuda.device(dev):
-                _lib.check(lib.alg_pad_frames_bf16(x.data_ptr(), xp.data_ptr(), None, 1, H, W, Cc, Cc, 1, _lib.stream_ptr(dev)))
+            ops.pad_frames(x, xp, 1, H, W, to_padded=True)
             offs = [(ih - 1) * row + (iw - 1) for _ in range(3) for ih in range(3) for iw in range(3)]
             d = ops.gemm(xp, wt, b, a_tap_kblocks=Cc // 64, a_tap_offsets=offs)
             out = torch.empty(H * W, wt.shape[0], device=dev, dtype=torch.bfloat16)
-            with torch.cuda.device(dev):
-                _lib.check(lib.alg_pad_frames_bf16(d.data_ptr(), out.data_ptr(), None if residual is None else residual.data_ptr(), 1, H, W,
-                                                   wt.shape[0], d.stride(0), 0, _lib.stream_ptr(dev)))
-            return out
+            return ops.pad_frames(d, out, 1, H, W, to_padded=False, residual=residual)
         if (9 * Cc) % 64 == 0:
             # one frame: the three temporal taps read the same [3, 3, C] patch, so it is gathered once and the GEMM walks
             # it three times along K (a_k_period) against the three temporal weight slices
@@ -401,7 +397,7 @@ class AutoencoderKLCogVideoX:
         as spatially zero-padded frames [(T + 2), H + 2, W + 2, Ci]; the GEMM's tap mode reads it 27 times at row offsets
         (it * plane + (ih - 1) * row + (iw - 1)); the bf16 result comes back from the padded raster with the residual added in the
         same pass (the rounding chain of the GEMM's residual epilogue: bf16(R + bf16(acc + bias)))."""
-        lib, dev = _lib.lib(), x.device
+        dev = x.device
         wt, b = self._w[name + ".conv.weight"], self._w[name + ".conv.bias"]
         Ci, HW, plane, row = x.shape[1], H * W, (H + 2) * (W + 2), W + 2
         key = (T, H, W, Ci)
@@ -411,9 +407,7 @@ class AutoencoderKLCogVideoX:
         prev = cache.get(name)
 
         def pad_in(src, frame0, n):
-            with torch.cuda.device(dev):
-                _lib.check(lib.alg_pad_frames_bf16(src.data_ptr(), xp[frame0 * plane:].data_ptr(), None, n, H, W, Ci, Ci, 1,
-                                                   _lib.stream_ptr(dev)))
+            ops.pad_frames(src, xp[frame0 * plane:(frame0 + n) * plane], n, H, W, to_padded=True)
         if prev is None:
             pad_in(x[:HW], 0, 1)
             pad_in(x[:HW], 1, 1)
@@ -431,10 +425,7 @@ class AutoencoderKLCogVideoX:
         d = ops.gemm(xp, wt, b, a_tap_kblocks=Ci // 64, a_tap_offsets=offs, m_rows=T * plane)  # padded raster [T * plane, Co]
         Co = wt.shape[0]
         out = torch.empty(T * HW, Co, device=dev, dtype=torch.bfloat16)
-        with torch.cuda.device(dev):
-            _lib.check(lib.alg_pad_frames_bf16(d.data_ptr(), out.data_ptr(), None if residual is None else residual.data_ptr(), T, H, W, Co,
-                                               d.stride(0), 0, _lib.stream_ptr(dev)))
-        return out
+        return ops.pad_frames(d, out, T, H, W, to_padded=False, residual=residual)
 
     def _spatial_norm(self, f, T, H, W, z, zt, zh, zw, name, silu=True):
         """CogVideoXSpatialNorm3D: GroupNorm(f) * conv_y(zq') + conv_b(zq') (+ SiLU); f [T*H*W, C], z [zt*zh*zw, zc]."""

@@ -191,6 +191,13 @@ class WanTransformer3DModel:
 
     PROFILE_CLASSES = ("self_attention", "cross_attention", "gemm", "elementwise")
 
+    def context_cache(self, enable: bool = True):
+        """Memoise the step-invariant cross-attention context (text / image embedders + K, V^T of all layers) across forwards that
+        receive the SAME prompt / image tensors (alg_wan_context_cache: keyed on their addresses).  Calling this -- with either
+        value -- drops what was memoised: call it again whenever the contents of those tensors change."""
+        _lib.check(_lib.lib().alg_wan_context_cache(self._handle, int(enable)))
+        self._ctx_cache_on = bool(enable)
+
     def profile(self, enable: bool = True):
         """Per-kernel-class device timing of the forwards that follow (CUDA events on the launching stream)."""
         _lib.check(_lib.lib().alg_wan_profile(self._handle, int(enable)))
@@ -242,6 +249,13 @@ class WanTransformer3DModel:
         text_p = (C.c_void_p * 3)(*[prep(t.reshape(-1, t.shape[-1]), torch.bfloat16) for t in text])
         n_img = 0 if image is None else image.reshape(-1, image.shape[-1]).shape[0]
         img_ptr = None if image is None else prep(image.reshape(-1, image.shape[-1]), torch.bfloat16)
+        if getattr(self, "_ctx_cache_on", False):
+            # the context cache is keyed on addresses: a conditioning tensor that had to be cast / compacted lives in a temporary whose
+            # address the allocator will reuse for other contents, so such a call must not hit (re-arming drops the memo)
+            src = [t.reshape(-1, t.shape[-1]) for t in text] + ([] if image is None else [image.reshape(-1, image.shape[-1])])
+            ptrs = list(text_p[:n_pass]) + ([] if image is None else [img_ptr])
+            if any(t.data_ptr() != p_ for t, p_ in zip(src, ptrs)):
+                self.context_cache(True)
         if out is None:
             out = torch.empty(n_pass, self._cfg["out_channels"], T, H, W, device=self.device, dtype=torch.bfloat16)
         L = _lib.lib()

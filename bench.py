@@ -171,6 +171,7 @@ class WanWorkload:
         self.pipe.to(device)
         self.pipe.set_progress_bar_config(disable=True)
         self.pipe._guidance_scale = GUIDANCE
+        self.transformer.context_cache(True)  # like pipe.__call__: the conditioning is fixed over the steps of a video
         self.sched = self.pipe.scheduler
         self.sched.set_timesteps(self.steps_per_video, device=device)
         self.ts = self.sched.timesteps.tolist()

@@ -405,6 +405,12 @@ int alg_wan_rms_norm_rope(void* x, int64_t rows, int d, int head_dim, float eps,
  * [n_pass*N, d] bf16 after each block.  Pass NULL to switch it off. */
 int alg_wan_set_debug_buffer(alg_wan_engine_t* e, void* buf, size_t bytes);
 
+/* Step-invariant context memoisation (SURVEY 7 "hoist", wan:844-944: prompt / image conditioning is fixed for the whole video):
+ * with enable != 0, alg_wan_forward remembers the text / image embedder outputs' K and V^T projections of all layers per
+ * (text pointers, image pointer, n_pass, n_img) -- two layouts are kept, the three-pass and the two-pass one -- and later forwards
+ * with the same key skip those projections (~0.2 % of a step; results are bit-identical).  The KEY IS THE POINTERS: call again
+ * (enable or disable) whenever the CONTENTS behind them change, which also drops what was memoised.  Default: off. */
+int alg_wan_context_cache(alg_wan_engine_t* e, int enable);
 /* Device timing per kernel class, measured with CUDA events on the launching stream around every launch of the
  * forward (classes: 0 self-attention, 1 cross-attention, 2 GEMM, 3 HBM-bound elementwise).  Enable, run forwards,
  * then read: the read synchronises on the recorded events, returns summed milliseconds + launch counts and resets. */

@@ -27,9 +27,18 @@ def _r(x):  # round to bf16, keep fp32 container
 
 
 def gemm(a, w, bias=None, *, epilogue=EPI_NONE, residual=None, gate=None, rows_per_batch=0, bias_per_row=False, out=None,
-         out_dtype=torch.bfloat16, gate_alt=None, gate_split_row=0, gate_round=False, a_k_period=0):
+         out_dtype=torch.bfloat16, gate_alt=None, gate_split_row=0, gate_round=False, a_k_period=0, a_tap_kblocks=0,
+         a_tap_offsets=None, m_rows=0):
     if a_k_period:
         a = a.repeat(1, w.shape[1] // a_k_period)
+    if a_tap_kblocks:  # implicit convolution: K group g = the same columns of a, rows shifted by offsets[g] (zero outside)
+        rows, m = a.shape[0], int(m_rows or a.shape[0])
+        cols = []
+        for off in a_tap_offsets:
+            idx = torch.arange(m, device=a.device) + int(off)
+            ok = (idx >= 0) & (idx < rows)
+            cols.append(a[idx.clamp(0, rows - 1)] * ok[:, None].to(a.dtype))
+        a = torch.cat(cols, dim=1)
     M, N = a.shape[0], w.shape[0]
     acc = a.float() @ w.float().t()
     if bias is not None:
@@ -178,6 +187,20 @@ def silu(a, out=None):
 
 def mean_rows(x):
     return x.float().mean(0).to(torch.bfloat16)
+
+
+def pad_frames(src, dst, frames, H, W, *, to_padded, residual=None):
+    """alg_pad_frames_bf16: compact [frames*H*W, C] <-> zero-bordered raster [frames, H + 2, W + 2, ld]."""
+    if to_padded:
+        Cc = src.shape[1]
+        dst.view(frames, H + 2, W + 2, -1)[:, 1:H + 1, 1:W + 1, :Cc] = src.view(frames, H, W, Cc)
+    else:
+        Cc = dst.shape[1]
+        v = src.reshape(frames, H + 2, W + 2, -1)[:, 1:H + 1, 1:W + 1, :Cc].reshape(frames * H * W, Cc).float()
+        if residual is not None:
+            v = v + residual.float()
+        dst.copy_(v.to(dst.dtype))
+    return dst
 
 
 def copy_rows(src, dst):

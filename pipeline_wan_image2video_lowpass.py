@@ -468,6 +468,11 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
 
         num_warmup_steps = len(timesteps) - num_inference_steps * self.scheduler.order
         self._num_timesteps = len(timesteps)
+        # the prompt / image conditioning is fixed for the whole loop: let the engine memoise its cross-attention K / V (re-armed
+        # whenever a callback may have touched the embeddings, dropped when the loop ends)
+        ctx_cache = getattr(self.transformer, "context_cache", None)
+        if ctx_cache is not None:
+            ctx_cache(True)
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t_host in enumerate(timesteps_host):
                 if self.interrupt:
@@ -482,9 +487,13 @@ class WanImageToVideoPipeline(DiffusionPipelineBase):
                     latents = outputs.pop("latents", latents)
                     prompt_embeds = outputs.pop("prompt_embeds", prompt_embeds)
                     negative_prompt_embeds = outputs.pop("negative_prompt_embeds", negative_prompt_embeds)
+                    if ctx_cache is not None:
+                        ctx_cache(True)  # the callback saw (and may have edited in place) the embeddings
                 if i == len(timesteps) - 1 or ((i + 1) > num_warmup_steps and (i + 1) % self.scheduler.order == 0):
                     progress_bar.update()
         self._current_timestep = None
+        if ctx_cache is not None:
+            ctx_cache(False)
 
         if output_type != "latent":
             z = latents.to(self.vae.dtype)

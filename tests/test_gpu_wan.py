@@ -272,3 +272,44 @@ def test_rope_double_float_equals_complex128_on_gpu():
     z = torch.view_as_complex(normed.view(B, N, heads, hd // 2, 2).to(torch.float64))
     ref = torch.view_as_real(z * freqs).flatten(3, 4).to(torch.bfloat16).view(B * N, d)
     assert torch.equal(rotated, ref), (rotated.float() - ref.float()).abs().max()
+
+
+def test_context_cache_is_bit_identical_and_invalidates():
+    """alg_wan_context_cache: forwards with memoised cross-attention K / V equal the uncached ones bit for bit (two- and
+    three-pass layouts interleaved like a video's steps), new prompt tensors miss, and re-arming drops the memo when the
+    CONTENTS behind the same addresses change."""
+    import __graft_entry__ as G
+    cfg, model, inp, _ = G.tiny_problem("cuda")
+    lat, cond = inp["latents"][0], inp["condition"][0]
+    pos, neg, img = inp["prompt_embeds"][0], inp["negative_prompt_embeds"][0], inp["image_embeds"][0]
+    lp = cond * 0.5
+
+    def run(t, three, p=pos):
+        conds = [cond, lp, lp] if three else [cond, cond]
+        texts = [neg, neg, p] if three else [neg, p]
+        return model.forward_passes([lat] * len(conds), conds, texts, img, t).clone()
+
+    ref = [run(900, True), run(800, False), run(700, True), run(600, False)]
+    model.context_cache(True)
+    got = [run(900, True), run(800, False), run(700, True), run(600, False)]  # steps 3 and 4 hit both slots
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
+    other = torch.randn_like(pos)
+    model.context_cache(False)
+    want = run(500, False, other)
+    model.context_cache(True)
+    run(600, False)
+    assert torch.equal(run(500, False, other), want)      # another prompt tensor: a miss, not the memo of `pos`
+    pos_backup = pos.clone()
+    pos.copy_(other)                                       # same address, new contents
+    model.context_cache(True)                              # ... so the caller re-arms (the pipeline does after every callback)
+    assert torch.equal(run(500, False), want)
+    pos.copy_(pos_backup)
+    model.context_cache(False)
+    assert torch.equal(run(600, False), ref[3])
+    # a conditioning tensor that needs a cast lives in a temporary: such calls never hit
+    model.context_cache(True)
+    a = model.forward_passes([lat, lat], [cond, cond], [neg.float(), pos.float()], img, 600)
+    b = model.forward_passes([lat, lat], [cond, cond], [neg.float(), (pos * 2).float()], img, 600)
+    model.context_cache(False)
+    assert torch.equal(a, ref[3]) and not torch.equal(a, b)
