@@ -191,3 +191,80 @@ def test_hunyuan_pipeline_conditioning_through_native_encoders():
     assert e0.shape == e1.shape and torch.equal(m0, m1)
     keep = m0.bool()
     assert rel_l2(e0[keep], e1[keep]) < 2e-4 and rel_l2(p0, p1) < 1e-4
+
+
+def test_hunyuan_pipeline_end_to_end_all_native_vs_upstream_modules():
+    """run.py's HunyuanVideo path on tiny shapes -- image + prompt -> template tokenizer -> LLaVA, CLIP text, VAE encode of the
+    first frame, ALG loop (true CFG: three-pass then two-pass steps), VAE decode, frames: once with every network native, once
+    with the transformers modules and the oracle VAE around the same native DiT."""
+    from types import SimpleNamespace
+    import numpy as np
+    from transformers import CLIPTextConfig, CLIPTextModel as HFCLIPText, CLIPVisionConfig, LlamaConfig, LlavaConfig
+    from transformers import LlavaForConditionalGeneration as HFLlava
+    from alg_b200 import encoders, hunyuan, llava
+    from alg_b200.schedulers import FlowMatchEulerDiscreteScheduler
+    from alg_b200.vae_hunyuan import AutoencoderKLHunyuanVideo
+    from oracle import hunyuan_vae_oracle as V
+    from oracle.stub_text import IMAGE_TOKEN, PAD as TPAD, TemplateTokenizer, WordTokenizer
+    import pipeline_hunyuan_video_image2video_lowpass as P
+    dit = hunyuan.HunyuanVideoTransformer3DModel.from_synthetic(seed=0, device="cuda", num_attention_heads=2, attention_head_dim=128,
+                                                                num_layers=2, num_single_layers=2, num_refiner_layers=1,
+                                                                text_embed_dim=64, pooled_projection_dim=32)
+    text = dict(TEXT, vocab_size=128320, hidden_size=64, intermediate_size=128, num_hidden_layers=4)
+    torch.manual_seed(9)
+    hf = HFLlava(LlavaConfig(vision_config=CLIPVisionConfig(**VISION), text_config=LlamaConfig(rope_theta=500000.0, **text),
+                             image_token_index=IMAGE_TOKEN, pad_token_id=TPAD)).eval().float().cuda()
+    ccfg = dict(vocab_size=49408, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2,
+                max_position_embeddings=77, hidden_act="quick_gelu", layer_norm_eps=1e-5, eos_token_id=49407, bos_token_id=49406, pad_token_id=49407)
+    hf_c = HFCLIPText(CLIPTextConfig(**ccfg)).eval().float().cuda()
+    mine = llava.LlavaForConditionalGeneration(text_config=dict(text, rope_theta=500000.0), vision_config=VISION, image_token_index=IMAGE_TOKEN,
+                                               pad_token_id=TPAD).load_state_dict({k: v.detach().clone() for k, v in hf.state_dict().items()})
+    mine_c = encoders.CLIPTextModel(**ccfg).load_state_dict({k: v.detach().clone() for k, v in hf_c.state_dict().items()})
+    vcfg = dict(V.HUNYUAN_VAE, block_out_channels=(32, 64, 64, 64))
+    sd = V.make_weights(vcfg, seed=4, device="cuda")
+    vae = AutoencoderKLHunyuanVideo(block_out_channels=(32, 64, 64, 64)).load_state_dict({k: v.clone() for k, v in sd.items()})
+    sd64 = {k: v.double() for k, v in sd.items()}
+
+    class OracleVAE:
+        dtype = torch.float32
+        config = SimpleNamespace(**vcfg)
+        temporal_compression_ratio, spatial_compression_ratio = 4, 8
+
+        def encode(self, x):
+            m = V.encode_moments(x.double(), sd64, vcfg, torch.float64).float()
+            return SimpleNamespace(latent_dist=SimpleNamespace(mode=lambda: m[:, :16], sample=lambda generator=None: m[:, :16]))
+
+        def decode(self, z, return_dict=True):
+            v = V.decode(z.double(), sd64, vcfg, torch.float64).float()
+            return SimpleNamespace(sample=v) if return_dict else (v,)
+
+    class Proc:
+        def __call__(self, image, return_tensors="pt", **kw):
+            x = torch.as_tensor(np.asarray(image), dtype=torch.float32)
+            x = x.permute(2, 0, 1)[None] / 255.0 if x.dim() == 3 and x.shape[-1] == 3 else (x[None] if x.dim() == 3 else x)
+            return SimpleNamespace(pixel_values=torch.nn.functional.interpolate(x, size=(VISION["image_size"],) * 2, mode="bilinear"))
+
+    tok = TemplateTokenizer()
+    n_img = (VISION["image_size"] // VISION["patch_size"]) ** 2
+    tmpl = dict(P.DEFAULT_PROMPT_TEMPLATE)
+    tmpl["crop_start"] = len(tok.encode(tmpl["template"].split("<|start_header_id|>user")[0]))
+    tmpl["image_emb_len"], tmpl["image_emb_end"] = n_img, 5 + n_img
+    alg = dict(use_low_pass_guidance=True, lp_filter_type="down_up", lp_filter_in_latent=True, lp_blur_sigma=15.0,
+               lp_blur_kernel_size=0.02734375, lp_resize_factor=0.625, lp_strength_schedule_type="interval",
+               schedule_blur_kernel_size=False, schedule_interval_start_time=0.0, schedule_interval_end_time=0.4,
+               schedule_linear_start_weight=1.0, schedule_linear_end_weight=0.0, schedule_linear_end_time=0.5,
+               schedule_exp_decay_rate=10.0)
+    image = torch.rand(1, 3, 64, 96, generator=torch.Generator().manual_seed(3))
+    frames = []
+    for te, te2, v in ((mine, mine_c, vae), (hf, hf_c, OracleVAE())):
+        pipe = P.HunyuanVideoImageToVideoPipeline(text_encoder=te, tokenizer=tok, transformer=dit, vae=v,
+                                                  scheduler=FlowMatchEulerDiscreteScheduler(shift=7.0), text_encoder_2=te2,
+                                                  tokenizer_2=WordTokenizer(), image_processor=Proc()).to("cuda")
+        out = pipe(image=image, prompt="a red bus turning a corner in the rain", negative_prompt="blurry", height=64, width=96,
+                   num_frames=5, num_inference_steps=3, guidance_scale=6.0, true_cfg_scale=4.0, prompt_template=tmpl,
+                   max_sequence_length=32, generator=torch.Generator(device="cuda").manual_seed(42), output_type="np", **alg)
+        frames.append(np.asarray(out.frames))
+    a, b = frames
+    assert a.shape == b.shape == (1, 5, 64, 96, 3) and np.isfinite(a).all() and a.min() >= 0.0 and a.max() <= 1.0 and a.std() > 1e-3
+    err = np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64))
+    assert err < 2e-2, err
