@@ -47,6 +47,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef ALG_ATTN_PAIR_DEFAULT
 #define ALG_ATTN_PAIR_DEFAULT 0
 #endif
+#ifndef ALG_ATTN_S128_DEFAULT
+#define ALG_ATTN_S128_DEFAULT 0
+#endif
 
 // PAIR = 1: the CTA is one half of a CTA pair (cta_group::2 MMAs, see attention_kernel): a K stage holds this CTA's 32 of
 // the step's 64 keys and a V^T stage this CTA's half of the head_dim rows.
@@ -70,6 +73,7 @@ struct Params {
   int n_q, n_kv, heads;
   float scale_log2;  // scale * log2(e)
   int accumulate;
+  int stagger;  // S128: cycles tile 1's issuer waits before its first S (experiment knob ALG_ATTN_STAGGER)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -110,9 +114,11 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 struct MmaCtx {
   uint32_t tmem, tmem_o, bar, q_lo, k_lo, v_lo;  // tmem_o = first O column (behind the S buffers of all tiles)
   int n_steps;
+  int stagger;
 };
 constexpr int kBarKFull = 1, kBarKEmpty = 1 + kStages, kBarVFull = 1 + 2 * kStages, kBarVEmpty = 1 + 3 * kStages,
-              kBarSFull = 1 + 4 * kStages, kBarPFull = kBarSFull + 4, kBarODone = kBarPFull + 4, kBarOFull = kBarODone + 2;
+              kBarSFull = 1 + 4 * kStages, kBarPFull = kBarSFull + 4, kBarODone = kBarPFull + 4, kBarOFull = kBarODone + 2,
+              kBarTurn = kBarOFull + 2;  // S128: the two tiles' issuers take turns with their PV + S blocks
 static_assert(kStages == 4, "the issuer's compile-time parities assume a four-step unroll");
 // MmaCtx::tiles = query tiles of the CTA: O accumulators start behind the S buffers of all tiles
 
@@ -201,6 +207,94 @@ __device__ __forceinline__ void mma_tile_loop(const MmaCtx& c) {
   }
 }
 
+// ---- S128: one 128-key S MMA per PAIR of steps ---------------------------------------------------------------------------
+// The two S buffers of a tile are adjacent TMEM columns, so S(j) and S(j + 1) can be ONE 128 x 128 x 16 MMA chain over a 128-key K
+// stage: it runs at the 32-cycle-per-64-keys floor instead of the 48 cycles of the operand-fetch-bound 128 x 64 x 16 shape (tensor
+// work per 128 keys and tile: 1 024 instead of 1 280 cycles, i.e. the structural cap of the tensor pipe goes from 80 % to 100 %).
+// The softmax side is unchanged: it still consumes 64-key buffers with per-buffer barriers, and P(j) / P(j + 1) are released and
+// multiplied separately.  What changes is the issue order of a tile -- PV(j), PV(j + 1), then S(j + 2, j + 3) -- so a tile's softmax
+// warpgroup idles while its own PV + S block runs.  K stages hold 128 keys (two per ring, same 64 KB), V^T stages stay 64 keys.
+// MEASURED SLOWER (r02, profiles/r02_attention_s128.md): 1 100 vs 1 285 TFLOP/s at the Wan shape, tensor pipe 49 % active
+// instead of 78 %, and insensitive to the softmax speed (POLY 0 / 4 / 8, one or two threads per row), to taking turns between the
+// tiles and to an initial stagger: with S single-buffered per pair, every S -> softmax -> P -> PV -> S hand-over (commit, mbarrier
+// wake-up, tcgen05.ld / st round trips) sits on the critical path, ~1 500 cycles per 128 keys that the 64-key double-buffered
+// schedule hides by keeping S two steps ahead.  512 TMEM columns cannot hold two 128-key S buffers next to O for two tiles, so the
+// 64-key schedule stays the default; this variant is kept behind ALG_ATTN_S128=1.
+template <int D, int I, int KST>
+__device__ __forceinline__ void issue_s128(const MmaCtx& c) {  // S_I(j, j + 1) = Q_I K^T (128-key stage KST) into both S buffers
+  constexpr uint32_t idesc_s = make_idesc_bf16(BQ, 2 * BKV);
+  constexpr int kBytesQ = BQ * D * 2, kBytesK = 2 * BKV * D * 2, kSub = 2 * BKV * 128;  // K slab: [128 keys][64 elem]
+  const uint32_t d = c.tmem + I * 128;
+#pragma unroll
+  for (int ks = 0; ks < D / 16; ++ks) {
+    const uint32_t qoff = (I * kBytesQ + (ks >> 2) * (BQ * 128) + (ks & 3) * 32) >> 4;
+    const uint32_t koff = (KST * kBytesK + (ks >> 2) * kSub + (ks & 3) * 32) >> 4;
+    mma_ss_lo(d, c.q_lo + qoff, c.k_lo + koff, idesc_s, ks != 0);
+  }
+  tc_commit_a(c.bar + 8 * (kBarSFull + I * 2 + 0));
+  tc_commit_a(c.bar + 8 * (kBarSFull + I * 2 + 1));
+}
+// pair jp = 2 m + PP of query tile I (steps j = 2 jp, 2 jp + 1); ph = m & 1 (parity of the V ring and, with PP, of the K ring)
+template <int D, int I, int PP>
+__device__ __forceinline__ void mma_tile_pair(const MmaCtx& c, const int jp, const uint32_t ph) {
+  constexpr int VS0 = 2 * PP, VS1 = 2 * PP + 1, KSTN = (PP + 1) & 1;
+  const uint32_t p_par = PP;                      // p_full[buf] completes once per pair: parity = jp & 1
+  const uint32_t k_phn = PP ? (ph ^ 1u) : ph;     // pair jp + 1 is the ((jp + 1) >> 1)-th use of its K stage
+  const int j = 2 * jp;
+  mbar_wait_a(c.bar + 8 * (kBarPFull + I * 2 + 0), p_par);
+  mbar_wait_a(c.bar + 8 * (kBarVFull + VS0), ph);
+  tc_fence_after();
+  issue_pv<D, I, 0, VS0, 0>(c, j > 0);
+  tc_commit_a(c.bar + 8 * (kBarVEmpty + VS0));
+  if (j == c.n_steps - 1) tc_commit_a(c.bar + 8 * (kBarOFull + I));
+  if (j + 1 < c.n_steps) {
+    mbar_wait_a(c.bar + 8 * (kBarPFull + I * 2 + 1), p_par);
+    mbar_wait_a(c.bar + 8 * (kBarVFull + VS1), ph);
+  }
+  if (j + 2 < c.n_steps) mbar_wait_a(c.bar + 8 * (kBarKFull + KSTN), k_phn);
+  // The PV(j + 1) + S(j + 2, j + 3) block is 768 tensor-pipe cycles during which this tile's softmax warps have nothing to do.
+  // Two tiles that reach their blocks together interleave them MMA by MMA, finish together and stay in lockstep: every block
+  // then takes twice as long (measured: 3 100 cycles per pair instead of ~2 200).  So the tiles take turns: tile 0 issues its
+  // n-th block, hands the turn to tile 1, and waits for tile 1's n-th block to be ISSUED before its (n + 1)-th -- after the first
+  // round the tiles run half a period apart and one tile's block covers the other tile's softmax.
+  if (I == 0) {
+    if (jp > 0) mbar_wait_a(c.bar + 8 * (kBarTurn + 0), (uint32_t)(jp - 1) & 1u);
+  } else {
+    mbar_wait_a(c.bar + 8 * (kBarTurn + 1), (uint32_t)jp & 1u);
+  }
+  tc_fence_after();
+  if (j + 1 < c.n_steps) {
+    issue_pv<D, I, 1, VS1, 0>(c, 1u);
+    tc_commit_a(c.bar + 8 * (kBarVEmpty + VS1));
+    if (j + 1 == c.n_steps - 1) tc_commit_a(c.bar + 8 * (kBarOFull + I));
+  }
+  if (j + 2 < c.n_steps) {
+    issue_s128<D, I, KSTN>(c);  // both S buffers are free: their P was consumed by the two PVs just issued (in-order pipe)
+    tc_commit_a(c.bar + 8 * (kBarKEmpty + KSTN));
+  }
+  mbar_arrive_a(c.bar + 8 * (kBarTurn + (I ^ 1)));
+}
+template <int D, int I>
+__device__ __forceinline__ void mma_tile_loop128(const MmaCtx& c) {
+  mbar_wait_a(c.bar, 0);  // q_full
+  mbar_wait_a(c.bar + 8 * (kBarKFull + 0), 0);
+  if (I == 1 && c.stagger > 0) {  // start tile 1 half a period behind tile 0 (see mma_tile_pair)
+    const long long t0 = clock64();
+    while (clock64() - t0 < c.stagger) {
+    }
+  }
+  tc_fence_after();
+  issue_s128<D, I, 0>(c);
+  tc_commit_a(c.bar + 8 * (kBarKEmpty + 0));
+  const int n_pairs = (c.n_steps + 1) >> 1;
+  uint32_t ph = 0;
+#pragma unroll 1
+  for (int jp = 0; jp < n_pairs; jp += 2, ph ^= 1u) {
+    mma_tile_pair<D, I, 0>(c, jp, ph);
+    if (jp + 1 < n_pairs) mma_tile_pair<D, I, 1>(c, jp + 1, ph);
+  }
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -224,7 +318,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 //            128 x 64 x 16 S MMA, which at 6 KB of operands per 32 cycles out-runs the 128 B/clk shared-memory port, drops to
 //            5 KB).  K/V "full" barriers live in the leader (both CTAs' TMA bytes complete there), "P ready" collects the
 //            softmax warps of both CTAs by remote arrives, everything the issuer signals is a multicast commit.
-template <int D, int POLY, int SPLIT, int TILES, int STAGES, int PAIR>
+template <int D, int POLY, int SPLIT, int TILES, int STAGES, int PAIR, int S128 = 0>
 __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TILES == 1 ? 2 : 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Params p) {
@@ -250,7 +344,8 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
                                                // the MMA warp's wait: one barrier per S buffer keeps the parity unambiguous)
   uint64_t* o_done = p_full + 4;               // 2: committed behind every PV (the rare O-rescale path waits on it)
   uint64_t* o_full = o_done + 2;               // 2: committed behind the last PV only (epilogue)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* turn = o_full + 2;                 // 2 (S128 only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
   float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // SPLIT only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -276,6 +371,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
     for (int i = 0; i < 2; ++i) {
       mbar_init(&o_done[i], 1);
       mbar_init(&o_full[i], 1);
+      mbar_init(&turn[i], 1);
     }
     fence_barrier_init();
   }
@@ -320,11 +416,29 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
         if (crank == 0) mbar_arrive_expect_tx(&v_full[st], C::kCtas * C::kBytesV);
         load(sV + st * C::kBytesV, &tmV, &v_full[st], j * BKV, head * D + (int)crank * (D / C::kCtas), batch);
       };
-      load_k(0);
-      if (n_steps > 1) load_k(1);
-      for (int j = 0; j < n_steps; ++j) {
-        load_v(j);
-        if (j + 2 < n_steps) load_k(j + 2);
+      if constexpr (S128) {  // K stages of 128 keys (two per ring); consumption order: K(0) | V(0) V(1) K(1) | V(2) V(3) K(2) | ...
+        static_assert(!S128 || (TILES == 2 && STAGES == 4 && !PAIR), "S128 is a variant of the long layout");
+        const int n_pairs = (n_steps + 1) >> 1;
+        auto load_k128 = [&](int jp) {
+          const int st = jp & 1;
+          mbar_wait(&k_empty[st], ((jp >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], 2 * C::kBytesK);
+          for (int s = 0; s < D / 64; ++s)
+            tma_load_3d(sK + st * 2 * C::kBytesK + s * (2 * BKV * 128), &tmK, &k_full[st], head * D + s * 64, jp * 2 * BKV, batch);
+        };
+        load_k128(0);
+        for (int jp = 0; jp < n_pairs; ++jp) {
+          load_v(2 * jp);
+          if (2 * jp + 1 < n_steps) load_v(2 * jp + 1);
+          if (jp + 1 < n_pairs) load_k128(jp + 1);
+        }
+      } else {
+        load_k(0);
+        if (n_steps > 1) load_k(1);
+        for (int j = 0; j < n_steps; ++j) {
+          load_v(j);
+          if (j + 2 < n_steps) load_k(j + 2);
+        }
       }
     }
   } else if (warp >= kMmaWarp) {
@@ -338,8 +452,14 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       c.k_lo = smem_desc_lo_sw128(smem_u32(sK));
       c.v_lo = smem_desc_lo_sw128(smem_u32(sV));
       c.n_steps = n_steps;
-      if (warp == kMmaWarp) mma_tile_loop<D, 0, STAGES, PAIR>(c);
-      else if constexpr (TILES == 2) mma_tile_loop<D, 1, STAGES, PAIR>(c);
+      c.stagger = p.stagger;
+      if constexpr (S128) {
+        if (warp == kMmaWarp) mma_tile_loop128<D, 0>(c);
+        else mma_tile_loop128<D, 1>(c);
+      } else {
+        if (warp == kMmaWarp) mma_tile_loop<D, 0, STAGES, PAIR>(c);
+        else if constexpr (TILES == 2) mma_tile_loop<D, 1, STAGES, PAIR>(c);
+      }
     }
   } else {  // ===== softmax warps =====
     constexpr int W = SPLIT ? BKV / 2 : BKV;      // key columns of a step owned by this thread
@@ -516,7 +636,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
   }
 }
 
-template <int D, int POLY, int SPLIT, int TILES, int STAGES, int PAIR = 0>
+template <int D, int POLY, int SPLIT, int TILES, int STAGES, int PAIR = 0, int S128 = 0>
 static int launch(const alg_attention_t* a, cudaStream_t st) {
   using C = Cfg<D, PAIR>;
   constexpr int kThreads = ((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32;
@@ -525,7 +645,7 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   int dev = 0;
   ALG_CUDA_OK(cudaGetDevice(&dev));
   if (dev >= 64 || !(attr_done.load(std::memory_order_relaxed) >> dev & 1)) {
-    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR, S128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     if (dev < 64) attr_done.fetch_or(uint64_t(1) << dev, std::memory_order_relaxed);
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -537,7 +657,7 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   }
   {
     uint64_t dims[3] = {hd, (uint64_t)a->n_kv, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->k_rs, (uint64_t)a->k_bs};
-    uint32_t box[3] = {64, BKV / C::kCtas, 1};
+    uint32_t box[3] = {64, S128 ? 2 * BKV : BKV / C::kCtas, 1};
     if (int rc = make_tmap_bf16(&tmK, a->K, 3, dims, strides, box)) return rc;
   }
   {
@@ -554,6 +674,14 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   p.heads = a->heads;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
+  {
+    static int stagger = -1;
+    if (stagger < 0) {
+      const char* e = getenv("ALG_ATTN_STAGGER");
+      stagger = e ? atoi(e) : 0;
+    }
+    p.stagger = stagger;
+  }
   dim3 grid((unsigned)((a->n_q + TILES * BQ - 1) / (TILES * BQ)), (unsigned)a->heads, (unsigned)a->batch);
   if constexpr (PAIR) {
     grid.x = (grid.x + 1) / 2 * 2;  // whole pairs: a CTA past the last query rows loads zero-filled tiles and stores nothing
@@ -571,7 +699,7 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
     cfg.numAttrs = 1;
     ALG_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR>, tmQ, tmK, tmV, p));
   } else {
-    attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR><<<grid, kThreads, kSmem, st>>>(tmQ, tmK, tmV, p);
+    attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR, S128><<<grid, kThreads, kSmem, st>>>(tmQ, tmK, tmV, p);
   }
   ALG_LAUNCH_OK();
   return 0;
@@ -593,7 +721,7 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   ALG_REQUIRE((reinterpret_cast<uintptr_t>(a->O) & 15) == 0, "attention: O must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static int poly = -1, split = -1, short_max = -1, pair = 0;  // tuning knobs; defaults from profiling
+  static int poly = -1, split = -1, short_max = -1, pair = 0, s128 = 0;  // tuning knobs; defaults from profiling
   if (poly < 0) {
     const char* e = getenv("ALG_ATTN_POLY");
     poly = e ? atoi(e) : ALG_ATTN_POLY_DEFAULT;
@@ -603,10 +731,28 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
     short_max = e ? atoi(e) : ALG_ATTN_SHORT_MAX_DEFAULT;
     e = getenv("ALG_ATTN_PAIR");  // CTA pairs (cta_group::2 MMAs) for the long variant
     pair = e ? atoi(e) : ALG_ATTN_PAIR_DEFAULT;
+    e = getenv("ALG_ATTN_S128");  // one 128-key S MMA per pair of steps (long variant, one thread per row)
+    s128 = e ? atoi(e) : ALG_ATTN_S128_DEFAULT;
   }
   const bool use_short = a->n_kv <= short_max;
 #define ALG_ATTN_DISPATCH(DD)                                                        \
   if (use_short) return attn::launch<DD, 8, 0, 1, 2>(a, st);                         \
+  if (s128 && !pair && split) {                                                      \
+    switch (poly) {                                                                  \
+      case 0: return attn::launch<DD, 0, 1, 2, 4, 0, 1>(a, st);                      \
+      case 4: return attn::launch<DD, 4, 1, 2, 4, 0, 1>(a, st);                      \
+      default: return attn::launch<DD, 8, 1, 2, 4, 0, 1>(a, st);                     \
+    }                                                                                \
+  }                                                                                  \
+  if (s128 && !pair && !split) {                                                     \
+    switch (poly) {                                                                  \
+      case 0: return attn::launch<DD, 0, 0, 2, 4, 0, 1>(a, st);                      \
+      case 2: return attn::launch<DD, 2, 0, 2, 4, 0, 1>(a, st);                      \
+      case 3: return attn::launch<DD, 3, 0, 2, 4, 0, 1>(a, st);                      \
+      case 4: return attn::launch<DD, 4, 0, 2, 4, 0, 1>(a, st);                      \
+      default: return attn::launch<DD, 8, 0, 2, 4, 0, 1>(a, st);                     \
+    }                                                                                \
+  }                                                                                  \
   if (pair && !split) {                                                              \
     switch (poly) {                                                                  \
       case 0: return attn::launch<DD, 0, 0, 2, 4, 1>(a, st);                         \
