@@ -517,7 +517,11 @@ extern "C" int alg_small_attention(const alg_small_attention_t* a, void* stream)
   p.key_mask = a->key_mask;
   ALG_REQUIRE(a->heads % p.kv_group == 0, "small_attention: heads must be a multiple of kv_group");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p.kv_group > 1 || p.key_mask || a->n_kv > 768) {  // streamed-key variant: grouped K/V heads, general key mask, long prompts
+  const size_t elem = a->dtype == ALG_BF16 ? 2 : 4;
+  const size_t small_smem = 2 * (size_t)p.D * p.Lp * elem + (size_t)enc::kWarps * enc::kRowsPerWarp * (p.D + p.Lp) * sizeof(float);
+  // streamed-key variant: grouped K/V heads, general key mask, long prompts, or all keys of a head do not fit in shared memory
+  // (CLIP-ViT-L/14-336 inside LLaVA: 577 tokens x 64 in fp32)
+  if (p.kv_group > 1 || p.key_mask || a->n_kv > 768 || (small_smem > 227 * 1024 && !a->rel_bias)) {
     ALG_REQUIRE(!a->rel_bias, "small_attention: rel_bias needs n_kv <= 768, kv_group 1 and no key_mask");
     if (a->dtype == ALG_BF16) return enc::launch_tiled_attention<__nv_bfloat16>(p, a->batch, a->heads, st);
     return enc::launch_tiled_attention<float>(p, a->batch, a->heads, st);

@@ -90,6 +90,8 @@ def test_relative_position_buckets_match_transformers():
     (dict(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=4, image_size=56, patch_size=14), 1e-4),
     (dict(hidden_size=96, intermediate_size=200, num_hidden_layers=2, num_attention_heads=2, image_size=28, patch_size=14, hidden_act="quick_gelu"), 1e-4),
     (dict(hidden_size=1280, intermediate_size=5120, num_hidden_layers=2, num_attention_heads=16, image_size=224, patch_size=14), 1e-4),
+    # CLIP-ViT-L/14-336 geometry (LLaVA's tower): 577 tokens x head_dim 64 in fp32 does not fit one head in shared memory -> streamed keys
+    (dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, image_size=336, patch_size=14, hidden_act="quick_gelu"), 1e-4),
 ])
 def test_clip_vision_matches_transformers(over, tol):
     from transformers import CLIPVisionConfig, CLIPVisionModel
