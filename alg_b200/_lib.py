@@ -63,7 +63,7 @@ class Gemm(C.Structure):
         ("epilogue", C.c_int32), ("bias_per_row", C.c_int32), ("out_f32", C.c_int32),
         ("gate_dtype", C.c_int32), ("gate_round", C.c_int32), ("gate_split_row", C.c_int64), ("gate_alt", C.c_void_p),
         ("a_k_period", C.c_int64), ("a_tap_kblocks", C.c_int32), ("a_n_taps", C.c_int32), ("a_tap_offsets", C.POINTER(C.c_int32)),
-        ("a_rows", C.c_int64),
+        ("a_rows", C.c_int64), ("bias_f32", C.c_void_p), ("residual_f32", C.c_void_p),
     ]
 
 

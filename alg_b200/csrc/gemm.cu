@@ -90,6 +90,8 @@ struct Params {
   int a_tap_kb;    // 0, or implicit-convolution mode: K is n_taps groups of a_tap_kb k-blocks; group g reads A columns
                    // [0, a_tap_kb * BK) at rows shifted by a_tap_off[g] (out-of-range rows are zero-filled by TMA)
   int a_tap_off[32];
+  const float* bias32;  // out_f32 only: fp32 bias [N] and fp32 residual [M, ldd] added in fp32 (the float32 VAE / encoder linears)
+  const float* R32;
 };
 
 __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
@@ -369,6 +371,31 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ---- store ------------------------------------------------------------------------
         if (p.out_f32) {
           float* drow = reinterpret_cast<float*>(p.D) + row * p.ldd + col0;
+          if (p.bias32) {
+            if (full_chunk) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias32 + col0) + g);
+                v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] += p.bias32[col0 + j];
+            }
+          }
+          if (p.R32) {
+            const float* rrow32 = p.R32 + row * p.ldd + col0;
+            if (full_chunk) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rrow32 + g * 4);
+                v[4 * g] += r4.x; v[4 * g + 1] += r4.y; v[4 * g + 2] += r4.z; v[4 * g + 3] += r4.w;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] += rrow32[j];
+            }
+          }
           if (full_chunk) {
 #pragma unroll
             for (int g = 0; g < 8; ++g)
@@ -471,6 +498,8 @@ static int launch(const alg_gemm_t* g, cudaStream_t st) {
   p.n_tiles = (int)((g->N + BN - 1) / BN);
   p.k_blocks = (int)((g->K + BK - 1) / BK);
   p.a_k_period = (int)g->a_k_period;
+  p.bias32 = g->out_f32 ? g->bias_f32 : nullptr;
+  p.R32 = g->out_f32 ? g->residual_f32 : nullptr;
   p.a_tap_kb = g->a_tap_kblocks;
   for (int i = 0; i < 32; ++i) p.a_tap_off[i] = (g->a_tap_kblocks && i < g->a_n_taps) ? g->a_tap_offsets[i] : 0;
   const int units = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
@@ -532,6 +561,11 @@ extern "C" int alg_gemm_bf16(const alg_gemm_t* g, void* stream) {
   }
   if (g->bias && !g->bias_per_row)
     ALG_REQUIRE((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  if (g->bias_f32 || g->residual_f32) {
+    ALG_REQUIRE(g->out_f32 && !g->bias && g->epilogue == ALG_EPI_NONE, "gemm: bias_f32 / residual_f32 need out_f32, no bf16 bias and no epilogue");
+    ALG_REQUIRE(((reinterpret_cast<uintptr_t>(g->bias_f32) | reinterpret_cast<uintptr_t>(g->residual_f32)) & 15) == 0,
+                "gemm: bias_f32 / residual_f32 must be 16-byte aligned");
+  }
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static int force_bn = -1, cluster = -1;  // experiment knobs

@@ -235,36 +235,54 @@ __global__ void __launch_bounds__(256) group_norm_f32_apply_kernel(const float* 
 __global__ void __launch_bounds__(256) norm_split_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int T, int H,
                                                              int W, int C, int pt, int in_padded, int Cs, float scale,
                                                              const float* __restrict__ gamma, int silu) {
+  // one warp per pixel; a lane owns channel PAIRS (2 lane + 64 k, + 1): 8-byte loads, 4-byte bf16x2 stores, the row stays in
+  // registers between the reduction and the write (C <= 512)
   const int lane = threadIdx.x & 31;
   const int64_t pixels = (int64_t)T * H * W;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int kIters = 8;
   for (int64_t pix = warp; pix < pixels; pix += nwarps) {
     const int xx = (int)(pix % W);
     const int64_t r = pix / W;
     const int y = (int)(r % H), t = (int)(r / H);
     const int64_t prow = ((int64_t)(t + pt) * (H + 2) + y + 1) * (W + 2) + xx + 1;
     const float* xr = x + (in_padded ? prow : pix) * C;
+    float2 v[kIters];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kIters; ++k) {
+      const int c = 2 * lane + 64 * k;
+      v[k] = c < C ? *reinterpret_cast<const float2*>(xr + c) : make_float2(0.f, 0.f);
+      ss = fmaf(v[k].x, v[k].x, ss);
+      ss = fmaf(v[k].y, v[k].y, ss);
+    }
     float mul = 1.f;
     if (gamma) {
-      float ss = 0.f;
-      for (int c = lane; c < C; c += 32) {
-        const float v = xr[c];
-        ss = fmaf(v, v, ss);
-      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
       mul = fmaxf(sqrtf(ss), 1e-12f);
     }
     __nv_bfloat16* orow = out + prow * Cs;
-    for (int c = lane; c < C; c += 32) {
-      float v = xr[c];
-      if (gamma) v = __fdiv_rn(v, mul) * scale * gamma[c];
-      if (silu) v = v / (1.0f + expf(-v));
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-      orow[c] = hi;
-      orow[C + c] = hi;
-      orow[2 * C + c] = lo;
+#pragma unroll
+    for (int k = 0; k < kIters; ++k) {
+      const int c = 2 * lane + 64 * k;
+      if (c < C) {
+        float a = v[k].x, b = v[k].y;
+        if (gamma) {
+          const float2 g = *reinterpret_cast<const float2*>(gamma + c);
+          a = __fdiv_rn(a, mul) * scale * g.x;
+          b = __fdiv_rn(b, mul) * scale * g.y;
+        }
+        if (silu) {
+          a = a / (1.0f + expf(-a));
+          b = b / (1.0f + expf(-b));
+        }
+        uint32_t hi, lo;
+        split_pair(a, b, hi, lo);
+        *reinterpret_cast<uint32_t*>(orow + c) = hi;
+        *reinterpret_cast<uint32_t*>(orow + C + c) = hi;
+        *reinterpret_cast<uint32_t*>(orow + 2 * C + c) = lo;
+      }
     }
   }
 }
@@ -400,6 +418,9 @@ extern "C" int alg_group_norm_f32(const float* x, float* y, int64_t rows, int C,
 extern "C" int alg_norm_split_pad_f32(const float* x, void* out, int T, int H, int W, int C, int front_pad, int in_padded, int Cs,
                                       const float* gamma, int silu, void* stream) {
   ALG_REQUIRE(x && out && T > 0 && H > 0 && W > 0 && C > 0 && front_pad >= 0 && Cs >= 3 * C && Cs % 8 == 0, "norm_split_pad: bad arguments");
+  ALG_REQUIRE(C % 2 == 0 && C <= 512, "norm_split_pad: C must be even and <= 512");
+  ALG_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma)) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+              "norm_split_pad: misaligned pointer");
   if (int rc = alg_check_device()) return rc;
   const int64_t pixels = (int64_t)T * H * W;
   vae32::norm_split_pad_kernel<<<vae32::grid_for(pixels, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

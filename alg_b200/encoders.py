@@ -71,6 +71,9 @@ def linear_f32(x: torch.Tensor, w3: torch.Tensor, bias, act: int = 0, residual=N
     """fp32 nn.Linear on the bf16 tensor cores: split the activations [hi | hi | lo], one K-tripled GEMM with fp32
     accumulation and fp32 output, then bias / activation / residual in fp32."""
     rows, K = x.shape
+    if not act and (w3.shape[0] % 8 == 0) and (residual is None or (residual.is_contiguous() and residual.shape[1] == w3.shape[0])):
+        # no activation: bias and residual ride in the GEMM epilogue (one pass less over the output)
+        return ops.gemm(split_act(x), w3, None, out_dtype=torch.float32, bias_f32=bias, residual_f32=residual)
     y = ops.gemm(split_act(x), w3, None, out_dtype=torch.float32)
     if bias is not None or act or residual is not None:
         _launch(_lib.lib().alg_bias_act_f32, x.device, y.data_ptr(), None if bias is None else bias.data_ptr(),

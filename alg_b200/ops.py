@@ -54,14 +54,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
          bias_per_row: bool = False, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
          gate_alt: Optional[torch.Tensor] = None, gate_split_row: int = 0, gate_round: bool = False,
-         a_k_period: int = 0, a_tap_kblocks: int = 0, a_tap_offsets=None, m_rows: int = 0) -> torch.Tensor:
+         a_k_period: int = 0, a_tap_kblocks: int = 0, a_tap_offsets=None, m_rows: int = 0,
+         bias_f32: Optional[torch.Tensor] = None, residual_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``epilogue(a @ w.T + bias)``: a [M, K] bf16, w [N, K] bf16 (nn.Linear layout).  See alg_gemm_bf16.
 
     ``a_k_period``: a is [M, period] and repeats along K (``a.repeat(1, K // period)`` without materialising it).
 
     ``gate`` fp32 or bf16, [N] or [batches, N]; ``gate_alt`` replaces it for rows whose index inside their sample is
     below ``gate_split_row``; ``gate_round`` rounds ``gate * y`` to bf16 before the residual add (eager bf16 chain)."""
-    _lib.require_cuda(a, w, bias, residual, gate, out, gate_alt)
+    _lib.require_cuda(a, w, bias, residual, gate, out, gate_alt, bias_f32, residual_f32)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == (a_k_period or a_tap_kblocks * 64 or w.shape[1])
     M, K = (int(m_rows) if (a_tap_kblocks and m_rows) else a.shape[0]), w.shape[1]
@@ -84,6 +85,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     g.bias_per_row = int(bias_per_row)
     g.out_f32 = int(out.dtype == torch.float32)
     g.a_k_period = int(a_k_period)
+    if bias_f32 is not None:  # fp32 output only: fp32 bias / residual added in the epilogue (no extra pass over D)
+        assert bias_f32.dtype == torch.float32 and bias_f32.numel() >= N and out.dtype == torch.float32
+        g.bias_f32 = bias_f32.data_ptr()
+    if residual_f32 is not None:
+        assert residual_f32.dtype == torch.float32 and residual_f32.stride(0) == out.stride(0) and out.dtype == torch.float32
+        g.residual_f32 = residual_f32.data_ptr()
     if a_tap_kblocks:  # implicit convolution: K groups read row-shifted copies of the same A columns (see alg_gemm_t)
         offs = (C.c_int32 * len(a_tap_offsets))(*[int(o) for o in a_tap_offsets])
         g.a_tap_kblocks, g.a_n_taps, g.a_tap_offsets = int(a_tap_kblocks), len(a_tap_offsets), offs

@@ -233,7 +233,7 @@ class SplitConvVAE:
                 if co8 != co:
                     m = torch.cat([m, m.new_zeros(co8 - co, m.shape[1])])
                 w[name] = split_weight(m.contiguous(), k8)
-                if self.BUILD_TAPS and t.dim() == 5 and tuple(t.shape[2:]) == (3, 3, 3) and t.shape[1] % 2 == 0:
+                if self.BUILD_TAPS and t.dim() == 5 and tuple(t.shape[2:]) == (3, 3, 3) and t.shape[1] % 2 == 0 and t.shape[1] <= 512:
                     # implicit convolution: per tap [w_hi | w_lo | w_hi | 0] padded to a multiple of 64 columns, taps along K
                     ci = t.shape[1]
                     cs = (3 * ci + 63) // 64 * 64
@@ -313,9 +313,8 @@ class SplitConvVAE:
             a = cols[:n * hw * 3 * ld].view(n * hw, 3 * ld)
             r0 = (out_frame0 + f0 * out_frame_step) * hw
             y = out[r0:r0 + n * hw]
-            ops.gemm(a, w3, None, out=y, out_dtype=torch.float32)
             rs = None if residual is None else residual[r0:r0 + n * hw]
-            _launch(lib.alg_bias_act_f32, dev, y.data_ptr(), bias.data_ptr(), None if rs is None else rs.data_ptr(), n * hw, N, 0)
+            ops.gemm(a, w3, None, out=y, out_dtype=torch.float32, bias_f32=bias, residual_f32=rs)
         return res
 
     def _pointwise(self, x: torch.Tensor, name: str, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -366,9 +365,8 @@ class SplitConvVAE:
         plane, row = (H + 2) * (W + 2), W + 2
         offs = [(it - FRONT_PAD) * plane + (ih - 1) * row + (iw - 1) for it in range(3) for ih in range(3) for iw in range(3)]
         out = torch.empty(s3p.shape[0], w3.shape[0], device=self.device, dtype=torch.float32)
-        ops.gemm(s3p, w3, None, out=out, out_dtype=torch.float32, a_tap_kblocks=cs // 64, a_tap_offsets=offs)
-        _launch(_lib.lib().alg_bias_act_f32, self.device, out.data_ptr(), bias.data_ptr(), None if residual is None else residual.data_ptr(),
-                out.shape[0], out.shape[1], 0)
+        ops.gemm(s3p, w3, None, out=out, out_dtype=torch.float32, a_tap_kblocks=cs // 64, a_tap_offsets=offs, bias_f32=bias,
+                 residual_f32=residual)  # bias and the block's residual ride in the GEMM epilogue
         return _Act(out, T, H, W, out.shape[1], padded=True)
 
     def _release_operands(self):

@@ -174,6 +174,8 @@ typedef struct {
   int32_t a_n_taps;          /* <= 32 */
   const int32_t* a_tap_offsets; /* HOST array of a_n_taps row offsets */
   int64_t a_rows;            /* rows of A in tap mode when it has more than M (offsets reach past the last output row); 0 = M */
+  const float* bias_f32;     /* out_f32 only (no bf16 bias, no epilogue): D = acc + bias_f32[col] + residual_f32[row, col], all in */
+  const float* residual_f32; /* fp32; residual_f32 has D's leading dimension.  The float32 VAE / encoder linears.  May be NULL. */
 } alg_gemm_t;
 
 /* D = epilogue(A * B^T + bias): every nn.Linear of the DiT (SURVEY kernel K6). */

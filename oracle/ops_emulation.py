@@ -28,7 +28,7 @@ def _r(x):  # round to bf16, keep fp32 container
 
 def gemm(a, w, bias=None, *, epilogue=EPI_NONE, residual=None, gate=None, rows_per_batch=0, bias_per_row=False, out=None,
          out_dtype=torch.bfloat16, gate_alt=None, gate_split_row=0, gate_round=False, a_k_period=0, a_tap_kblocks=0,
-         a_tap_offsets=None, m_rows=0):
+         a_tap_offsets=None, m_rows=0, bias_f32=None, residual_f32=None):
     if a_k_period:
         a = a.repeat(1, w.shape[1] // a_k_period)
     if a_tap_kblocks:  # implicit convolution: K group g = the same columns of a, rows shifted by offsets[g] (zero outside)
@@ -43,6 +43,10 @@ def gemm(a, w, bias=None, *, epilogue=EPI_NONE, residual=None, gate=None, rows_p
     acc = a.float() @ w.float().t()
     if bias is not None:
         acc = acc + (bias.float()[:, None] if bias_per_row else bias.float()[None, :])
+    if bias_f32 is not None:
+        acc = acc + bias_f32[None, :acc.shape[1]]
+    if residual_f32 is not None:
+        acc = acc + residual_f32
     if epilogue != EPI_NONE:
         y = _r(acc)
         if epilogue == EPI_GELU_TANH:
