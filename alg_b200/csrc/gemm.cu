@@ -72,8 +72,9 @@ template <int BN, int CL = 1>
 struct Cfg {
   static constexpr int kBytesA = BM * BK * 2;
   static constexpr int kBytesB = (BN / CL) * BK * 2;  // CL = 2: each CTA of the pair holds half of the B tile
-  static constexpr int kStages = CL == 2 ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32)
+  static constexpr int kStages = CL == 2 ? 6 : (BN == 256 ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : (BN == 96 ? 7 : 8))));
+  // two accumulator stages at columns 0 and BN; the allocation is the next power of two >= 32
+  static constexpr int kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int kSmemBytes = kStages * (kBytesA + kBytesB) + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -587,6 +588,10 @@ extern "C" int alg_gemm_bf16(const alg_gemm_t* g, void* stream) {
   }
   // 64 < N < 128 (the 96-channel level of the Wan VAE) takes the 128-wide tile too: a 128 x 64 x 16 SS MMA is operand-fetch
   // bound (48 cycles for 32 cycles of math), so one 3/4-used 128-wide tile beats a 64 + a half-used 64 tile
+  // tiles as wide as the problem for the 96- and 192-channel levels of the float32 VAEs (N = 96: one 96-wide tile instead of a
+  // 3/4-used 128-wide one; N = 192: one 192-wide tile instead of 128 + a half-used 128), which also reads A once
+  if (g->N > 64 && g->N <= 96) return gemm::launch<96, 1>(g, st);
+  if ((g->N > 128 && g->N <= 192) || (g->N > 256 && g->N <= 384)) return gemm::launch<192, 1>(g, st);
   if (g->N % 128 == 0 || g->N > 64) return gemm::launch<128, 1>(g, st);
   return gemm::launch<64, 1>(g, st);
 }

@@ -268,3 +268,42 @@ def test_hunyuan_pipeline_end_to_end_all_native_vs_upstream_modules():
     assert a.shape == b.shape == (1, 5, 64, 96, 3) and np.isfinite(a).all() and a.min() >= 0.0 and a.max() <= 1.0 and a.std() > 1e-3
     err = np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64))
     assert err < 2e-2, err
+
+
+def test_llama_stack_at_true_width_two_layers():
+    """Llama-3-8B geometry (hidden 4096, 32 query heads on 8 K/V heads of 128, SwiGLU 14336, rope_theta 5e5) on two layers and a
+    900-token prompt -- the head_dim / group / key-count combination the HunyuanVideo encoder really runs."""
+    from transformers import CLIPVisionConfig, LlamaConfig, LlavaConfig, LlavaForConditionalGeneration
+    from alg_b200 import llava
+    text = dict(vocab_size=2048, hidden_size=4096, intermediate_size=14336, num_hidden_layers=2, num_attention_heads=32,
+                num_key_value_heads=8, rms_norm_eps=1e-5, max_position_embeddings=8192)
+    torch.manual_seed(11)
+    hf = LlavaForConditionalGeneration(LlavaConfig(vision_config=CLIPVisionConfig(**VISION), text_config=LlamaConfig(rope_theta=500000.0, **text),
+                                                   image_token_index=2040, pad_token_id=2041)).eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                p.copy_(1 + 0.1 * torch.randn_like(p))
+            elif "embed" in n:
+                p.copy_(0.5 * torch.randn_like(p))
+            elif p.dim() >= 2:
+                p.copy_(torch.randn_like(p) * (p[0].numel() ** -0.5))
+            p.copy_(p.half().float())
+    hf = hf.cuda()
+    mine = llava.LlavaForConditionalGeneration(text_config=dict(text, rope_theta=500000.0), vision_config=VISION, image_token_index=2040,
+                                               pad_token_id=2041).load_state_dict({k: v.detach().clone() for k, v in hf.state_dict().items()})
+    L, n = 900, 731
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(3, 2000, (1, L), generator=g)
+    mask = torch.zeros(1, L, dtype=torch.int64)
+    mask[:, :n] = 1
+    ids[:, n:] = 2041
+    pos = (mask.cumsum(-1) - 1).masked_fill_(mask == 0, 1)
+    ids, mask, pos = ids.cuda(), mask.cuda(), pos.cuda()
+    with torch.no_grad():
+        ref = hf(input_ids=ids, attention_mask=mask, position_ids=pos, output_hidden_states=True).hidden_states
+        ref16 = hf.half()(input_ids=ids, attention_mask=mask, position_ids=pos, output_hidden_states=True).hidden_states
+    out = mine(input_ids=ids, attention_mask=mask, position_ids=pos).hidden_states
+    for i, (a, r, r16) in enumerate(zip(out, ref, ref16)):
+        e = rel_l2(a[0, :n], r[0, :n])
+        assert e < 2e-4 and e <= rel_l2(r16[0, :n].float(), r[0, :n]) + 1e-6, (i, e)

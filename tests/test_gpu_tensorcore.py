@@ -139,3 +139,24 @@ def test_attention_full_size_properties():
     assert rel_l2(o1, o2) < TOL
     ref = _attn_ref(q[:, :512], k, v)
     assert rel_l2(o1[:, :512], ref) < TOL
+
+
+@pytest.mark.parametrize("N", [72, 96, 160, 192, 320, 384])
+def test_gemm_narrow_tiles_96_and_192(N):
+    """The 96- and 192-wide tiles (N of the float32 VAE levels): plain and fp32-output GEMMs with fp32 bias / residual."""
+    import torch
+    from alg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(N)
+    M, K = 1000, 448
+    a = torch.randn(M, K, generator=g, device="cuda").bfloat16()
+    w = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).bfloat16()
+    b = torch.randn(N, generator=g, device="cuda")
+    r = torch.randn(M, N, generator=g, device="cuda")
+    ref = a.float() @ w.float().t()
+    out = ops.gemm(a, w, None, out_dtype=torch.float32)
+    assert float((out - ref).abs().max()) < 1e-3 * float(ref.abs().max())
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(a, w, None, out=out, out_dtype=torch.float32, bias_f32=b, residual_f32=r)
+    assert float((out - (ref + b + r)).abs().max()) < 1e-3 * float(ref.abs().max())
+    out16 = ops.gemm(a, w, b.bfloat16())
+    assert float((out16.float() - (ref + b.bfloat16().float())).abs().max()) < 2 ** -7 * float(ref.abs().max())

@@ -247,3 +247,19 @@ def test_implicit_and_patch_matrix_paths_agree():
     vae.implicit = False
     b, mb = vae.decode(z).sample, vae.encode(x).latent_dist.parameters
     assert rel_l2(a, b) < 2e-5 and rel_l2(ma, mb) < 2e-5, (rel_l2(a, b), rel_l2(ma, mb))
+
+
+def test_full_width_small_clip():
+    """The real Wan2.1 VAE widths (96 / 192 / 384 channels, z = 16: the 320-column operand rows, the 96-wide GEMM tiles) on a small
+    clip, encode and decode, implicit path."""
+    from oracle import wan_vae_oracle as V
+    vae, sd, ocfg = _pair(dict(V.WAN21_VAE), seed=9)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    z = torch.randn(1, 16, 3, 6, 10, generator=torch.Generator(device="cuda").manual_seed(1), device="cuda")
+    out = vae.decode(z).sample
+    ref = V.decode(z.double(), sd64, ocfg, torch.float64)
+    assert out.shape == ref.shape == (1, 3, 9, 48, 80) and rel_l2(out, ref) < 1e-4, rel_l2(out, ref)
+    x = torch.rand(1, 3, 5, 48, 80, generator=torch.Generator(device="cuda").manual_seed(2), device="cuda") * 2 - 1
+    m = vae.encode(x).latent_dist.parameters
+    mref = V.encode_moments(x.double(), sd64, ocfg, torch.float64)
+    assert rel_l2(m, mref) < 1e-4, rel_l2(m, mref)
