@@ -216,7 +216,12 @@ class UniPCMultistepScheduler(_ConfigMixin):
 
 # =====================================================================================================
 class CogVideoXDDIMScheduler(_ConfigMixin):
-    """CogVideoX DDIM, v-prediction, trailing spacing, zero-terminal-SNR.  SURVEY Appendix B.2."""
+    """CogVideoX DDIM, v-prediction, trailing spacing, zero-terminal-SNR.  SURVEY Appendix B.2.
+
+    ``_defaults`` are NOT diffusers' class defaults (epsilon / leading / snr_shift_scale 3.0 ...) but the values of the
+    ``scheduler/scheduler_config.json`` THUDM/CogVideoX-5b-I2V ships (v_prediction, trailing, rescale_betas_zero_snr, snr_shift_scale
+    1.0): the only configuration this class builds -- anything else raises below -- and what the synthetic pipelines must reproduce.
+    Real snapshots carry every value explicitly (``from_config`` / ``checkpoint.scheduler_config``)."""
 
     order = 1
     init_noise_sigma = 1.0
