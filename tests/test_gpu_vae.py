@@ -197,3 +197,57 @@ def test_cog_pipeline_decodes_through_the_native_vae():
                negative_prompt_embeds=torch.randn(1, 16, 64, generator=g, device="cuda").bfloat16(), height=64, width=96,
                num_frames=9, num_inference_steps=2, guidance_scale=6.0, generator=g, output_type="pt")
     assert out.frames.shape == (1, 9, 3, 64, 96) and torch.isfinite(out.frames).all()
+
+
+def test_cog_pipeline_end_to_end_all_native_vs_upstream_modules():
+    """run.py's CogVideoX path on tiny shapes with pixel-space ALG (configs/cogvideox_alg.yaml: Gaussian blur of the image, then a VAE
+    encode + sample EVERY step): prompt -> tokenizer -> T5, VAE encode, ALG loop, VAE decode, frames -- once with every network
+    native, once with the transformers T5 and the eager oracle VAE around the same native DiT."""
+    from types import SimpleNamespace
+    import numpy as np
+    from alg_b200 import cogvideox, encoders, vae_cogvideox as V
+    from alg_b200.pipeline_utils import SyntheticTokenizer
+    from alg_b200.schedulers import CogVideoXDDIMScheduler
+    from oracle import vae_oracle as Vo
+    from pipeline_cogvideox_image2video_lowpass import CogVideoXImageToVideoPipeline
+    from test_gpu_encoders import _umt5
+    tiny = dict(num_attention_heads=2, attention_head_dim=64, time_embed_dim=64, text_embed_dim=64, num_layers=2, sample_width=12,
+                sample_height=8, sample_frames=9, max_text_seq_length=16)
+    dit = cogvideox.CogVideoXTransformer3DModel.from_synthetic(seed=0, device="cuda", **tiny)
+    base, hf_t = _umt5("T5EncoderModel", dict(vocab_size=4096, d_model=64, d_kv=16, d_ff=128))
+    hf_t = hf_t.to(torch.bfloat16).cuda()
+    text = encoders.T5EncoderModel(**base).load_state_dict({k: v.clone() for k, v in hf_t.state_dict().items()})
+    vae = V.AutoencoderKLCogVideoX.from_synthetic(seed=3, device="cuda", with_decoder=True, **TINY_VAE)
+    sd = {k: v for k, v in V.synthetic_state_dict(vae._cfg, seed=3, device="cuda").items()}
+    sd.update(V.synthetic_decoder_state_dict(vae._cfg, seed=3, device="cuda"))
+
+    class OracleVAE:
+        dtype = torch.bfloat16
+        config = vae.config
+
+        def encode(self, x):
+            m = Vo.encode_moments(x, sd, vae._cfg, dtype=torch.bfloat16)
+            return SimpleNamespace(latent_dist=V.DiagonalGaussianDistribution(m))
+
+        def decode(self, z, return_dict=True):
+            v = Vo.decode(z, sd, vae._cfg, dtype=torch.bfloat16)
+            return SimpleNamespace(sample=v) if return_dict else (v,)
+
+    alg = dict(use_low_pass_guidance=True, lp_filter_type="gaussian_blur", lp_filter_in_latent=False, lp_blur_sigma=3.0,
+               lp_blur_kernel_size=5, lp_resize_factor=0.25, lp_strength_schedule_type="interval", schedule_blur_kernel_size=False,
+               schedule_interval_start_time=0.0, schedule_interval_end_time=0.4, schedule_linear_start_weight=1.0,
+               schedule_linear_end_weight=0.0, schedule_linear_end_time=0.5, schedule_exp_decay_rate=10.0)
+    image = torch.rand(1, 3, 64, 96, generator=torch.Generator().manual_seed(3))
+    frames = []
+    for t, v in ((text, vae), (hf_t, OracleVAE())):
+        pipe = CogVideoXImageToVideoPipeline(tokenizer=SyntheticTokenizer(vocab_size=4096), text_encoder=t, vae=v, transformer=dit,
+                                             scheduler=CogVideoXDDIMScheduler()).to("cuda")
+        pipe.set_progress_bar_config(disable=True)
+        out = pipe(image=image, prompt="a red bus turning a corner in the rain", negative_prompt="blurry", height=64, width=96,
+                   num_frames=9, num_inference_steps=3, guidance_scale=6.0, max_sequence_length=16,
+                   generator=torch.Generator(device="cuda").manual_seed(42), output_type="np", **alg)
+        frames.append(np.asarray(out.frames))
+    a, b = frames
+    assert a.shape == b.shape == (1, 9, 64, 96, 3) and np.isfinite(a).all() and a.min() >= 0.0 and a.max() <= 1.0 and a.std() > 1e-3
+    err = np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64))
+    assert err < 5e-2, err  # bf16 VAE + bf16 T5 on both sides
