@@ -6,8 +6,10 @@
 `diffusers` is not a dependency: the pipeline classes come from this repo's drop-in modules (same module and class
 names as the reference's imports at run.py:15-19) and the scheduler classes from ``alg_b200.schedulers``.  Offline
 there are no checkpoints: with ``ALG_SYNTHETIC=1`` the ``model.path`` of the config only selects the architecture
-(seeded random weights, synthetic encoders / VAE); without it ``from_pretrained`` raises the checkpoint-loader
-NotImplementedError.
+(seeded random weights; ``ALG_NATIVE_ENCODERS=1`` / ``ALG_NATIVE_VAE=1`` add seeded encoders / VAE at their true architectures
+instead of the shape-only stand-ins); with a local diffusers snapshot (a directory, or the hub id under ``--model_cache_dir``)
+every component -- DiT, scheduler config, text / image encoders, VAE -- loads into the native engines like run.py:46-81 does;
+without either ``from_pretrained`` raises FileNotFoundError.
 """
 import argparse
 import logging
@@ -40,16 +42,31 @@ def main(args):
         raise RuntimeError("the ALG engine is sm_100a CUDA only: there is no CPU fallback")
 
     # 2. Pipeline preparation (run.py:45-87)
+    from alg_b200 import checkpoint
+    have_snapshot = checkpoint.resolve_snapshot(str(model_path), args.model_cache_dir) is not None  # else: ALG_SYNTHETIC=1 (seeded weights)
     if "Wan" in model_path:
-        pipe = WanImageToVideoPipeline.from_pretrained(model_path, torch_dtype=model_dtype, cache_dir=args.model_cache_dir)
+        extra = {}
+        if have_snapshot:  # run.py:46-55: the image encoder and the VAE are loaded in float32 and handed to the pipeline
+            from alg_b200.encoders import CLIPVisionModel
+            from alg_b200.vae_wan import AutoencoderKLWan
+            extra["image_encoder"] = CLIPVisionModel.from_pretrained(model_path, subfolder="image_encoder", torch_dtype=torch.float32,
+                                                                     cache_dir=args.model_cache_dir)
+            extra["vae"] = AutoencoderKLWan.from_pretrained(model_path, subfolder="vae", torch_dtype=torch.float32,
+                                                            cache_dir=args.model_cache_dir)
+        pipe = WanImageToVideoPipeline.from_pretrained(model_path, torch_dtype=model_dtype, cache_dir=args.model_cache_dir, **extra)
         # run.py:63 compares the YAML int 480 with the string '480', so flow_shift is always 5.0 (quirk q1): kept as shipped
         pipe.scheduler = UniPCMultistepScheduler.from_config(
             pipe.scheduler.config, flow_shift=3.0 if config['generation']['height'] == '480' else 5.0)
     elif "CogVideoX" in model_path:
         pipe = CogVideoXImageToVideoPipeline.from_pretrained(model_path, torch_dtype=model_dtype, cache_dir=args.model_cache_dir)
     elif "HunyuanVideo" in model_path:
+        extra = {}
+        if have_snapshot:  # run.py:71-76: the transformer is loaded in bfloat16 on its own, the rest of the pipeline in float16
+            from alg_b200.hunyuan import HunyuanVideoTransformer3DModel
+            extra["transformer"] = HunyuanVideoTransformer3DModel.from_pretrained(model_path, subfolder="transformer",
+                                                                                  torch_dtype=torch.bfloat16, cache_dir=args.model_cache_dir)
         pipe = HunyuanVideoImageToVideoPipeline.from_pretrained(model_path, torch_dtype=torch.float16,
-                                                                cache_dir=args.model_cache_dir)
+                                                                cache_dir=args.model_cache_dir, **extra)
         pipe.scheduler = FlowMatchEulerDiscreteScheduler.from_config(
             pipe.scheduler.config, flow_shift=config['model']['flow_shift'], invert_sigmas=config['model']['flow_reverse'])
     else:

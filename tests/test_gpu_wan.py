@@ -313,3 +313,60 @@ def test_context_cache_is_bit_identical_and_invalidates():
     b = model.forward_passes([lat, lat], [cond, cond], [neg.float(), (pos * 2).float()], img, 600)
     model.context_cache(False)
     assert torch.equal(a, ref[3]) and not torch.equal(a, b)
+
+
+def test_run_py_on_a_local_snapshot_all_native(tmp_path, monkeypatch):
+    """run.py:26-146 on a LOCAL diffusers snapshot of a tiny Wan model: transformer/, scheduler/, text_encoder/, image_encoder/, vae/
+    all load into the native engines (run.py:46-61: CLIPVisionModel and AutoencoderKLWan in float32, handed to from_pretrained),
+    the YAML drives pipe(**kwargs), an mp4 lands on disk.  Only the tokenizer / image-processor FILES (vocabulary, preprocessing
+    json: data, not code) are stand-ins."""
+    import json
+    import os
+    import types
+    import transformers
+    import yaml
+    from PIL import Image
+    from alg_b200 import checkpoint, encoders, wan
+    from alg_b200.pipeline_utils import SyntheticImageProcessor, SyntheticTokenizer
+    from alg_b200.vae_wan import AutoencoderKLWan
+    import __graft_entry__ as G
+    import run
+    cfg, model, _, _ = G.tiny_problem("cuda")
+    snap = str(tmp_path / "Wan-AI--Wan2.1-I2V-tiny")
+    checkpoint.save_transformer(snap, dict(wan.WAN_I2V_14B, **cfg), model.state_dict(), "WanTransformer3DModel")
+    os.makedirs(os.path.join(snap, "scheduler"))
+    json.dump(dict(_class_name="UniPCMultistepScheduler", flow_shift=3.0, prediction_type="flow_prediction", use_flow_sigmas=True,
+                   solver_order=2, num_train_timesteps=1000), open(os.path.join(snap, "scheduler", "scheduler_config.json"), "w"))
+    tcfg = dict(vocab_size=512, d_model=64, d_kv=16, d_ff=128, num_layers=2, num_heads=4, relative_attention_num_buckets=32,
+                relative_attention_max_distance=128, layer_norm_epsilon=1e-6, model_type="umt5", feed_forward_proj="gated-gelu")
+    text = encoders.UMT5EncoderModel.from_synthetic(seed=1, **{k: v for k, v in tcfg.items() if k != "model_type"})
+    ccfg = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2, image_size=224, patch_size=28,
+                hidden_act="gelu", layer_norm_eps=1e-5, num_channels=3)
+    clip = encoders.CLIPVisionModel.from_synthetic(seed=2, **ccfg)
+    vae = AutoencoderKLWan.from_synthetic(seed=3, base_dim=16)
+    checkpoint.save_component(snap, "text_encoder", tcfg, text.state_dict())
+    checkpoint.save_component(snap, "image_encoder", ccfg, clip.state_dict())
+    checkpoint.save_component(snap, "vae", dict(vae._cfg, _class_name="AutoencoderKLWan"), vae.state_dict())
+    for d in ("tokenizer", "image_processor"):
+        os.makedirs(os.path.join(snap, d))
+    monkeypatch.setattr(transformers.AutoTokenizer, "from_pretrained", classmethod(lambda cls, p, **kw: SyntheticTokenizer(vocab_size=512)))
+    monkeypatch.setattr(transformers.CLIPImageProcessor, "from_pretrained", classmethod(lambda cls, p, **kw: SyntheticImageProcessor()))
+    conf = yaml.safe_load(open("configs/wan_alg.yaml"))
+    conf["model"]["path"] = snap
+    conf["generation"].update(num_frames=9, num_inference_steps=3, height=128, width=192)
+    conf["generation"]["max_sequence_length"] = 32
+    cpath, ipath, opath = tmp_path / "c.yaml", tmp_path / "i.png", tmp_path / "o.mp4"
+    cpath.write_text(yaml.safe_dump(conf))
+    Image.new("RGB", (200, 140), (30, 90, 200)).save(ipath)
+    seen = {}
+    orig = run.WanImageToVideoPipeline.from_pretrained.__func__
+
+    def spy(cls, path, **kw):
+        pipe = orig(cls, path, **kw)
+        seen.update(vae=type(pipe.vae).__name__, text=type(pipe.text_encoder).__name__, image=type(pipe.image_encoder).__name__,
+                    passed=sorted(k for k in kw if k in ("vae", "image_encoder")))
+        return pipe
+    monkeypatch.setattr(run.WanImageToVideoPipeline, "from_pretrained", classmethod(spy))
+    run.main(types.SimpleNamespace(config=str(cpath), image_path=str(ipath), prompt="a red bus", output_path=str(opath), model_cache_dir=None))
+    assert seen == dict(vae="AutoencoderKLWan", text="UMT5EncoderModel", image="CLIPVisionModel", passed=["image_encoder", "vae"])
+    assert opath.exists() and opath.stat().st_size > 1000
