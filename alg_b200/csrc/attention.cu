@@ -47,6 +47,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef ALG_ATTN_PAIR_DEFAULT
 #define ALG_ATTN_PAIR_DEFAULT 0
 #endif
+#ifndef ALG_ATTN_PS_DEFAULT
+#define ALG_ATTN_PS_DEFAULT 0
+#endif
 #ifndef ALG_ATTN_S128_DEFAULT
 #define ALG_ATTN_S128_DEFAULT 0
 #endif
@@ -705,6 +708,433 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   return 0;
 }
 
+
+// ====================================================================================================================
+// PS variant (head_dim 128, long sequences): P travels through SHARED memory, S is a full-rate 128-key MMA, and S stays one
+// step AHEAD of the softmax.
+//
+// Why: the default kernel's 128 x 64 x 16 S MMAs are operand-fetch bound (80 % structural cap, and it sits there); the S128
+// variant above runs them at full rate but exposes the S -> softmax -> P -> PV -> S hand-over chain, because with P aliased
+// onto S in TMEM an S buffer is only free once PV has CONSUMED P.  Here the softmax copies S(j) (128 keys, 128 fp32 per
+// row) into registers and releases the buffer at once -- S(j+1) is issued while the softmax of step j is still running -- and P is
+// written as bf16 into a small shared-memory operand (SW128 K-major rows, two 32-key slots per tile) from which PV runs as an SS
+// MMA.  LSU stores do not slow the tensor core's operand fetch (scripts/microbench/mma_smem_contention.cu: 64 -> 65 cycles per
+// 128 x 128 x 16 MMA under 60 B/clk of st.shared), and every MMA of the kernel is now a full-rate N = 128 shape.
+//
+//   TMEM: S0 [0,128)  S1 [128,256)  O0 [256,384)  O1 [384,512)          (one S buffer per tile)
+//   smem: Q0 Q1 (64 KB) | K ring 2 x 128 keys (64 KB) | V^T ring 4 x 64 keys (64 KB) | P0 P1 (2 x 16 KB: [128 rows][2 slots x 32 keys])
+//   per step j and tile:  issuer: wait s_free(j) -> S(j+1);  for quarter q = 0..3: wait p_ready[q] -> PV(j, q) (2 MMAs) -> commit p_free[q]
+//                         softmax: wait s_full(j) -> ld S -> arrive s_free -> row max (lazy O rescale) -> for q: 32 exps -> wait
+//                                  p_free[q - 2] (slot reuse) -> st.shared (swizzled) -> fence.proxy.async -> arrive p_ready[q]
+// ====================================================================================================================
+namespace ps {
+constexpr int BK = 128, QK = 32;  // keys per step, keys per P quarter
+constexpr int kBytesQ = BQ * 128 * 2, kBytesK = BK * 128 * 2, kBytesV = 128 * 64 * 2, kBytesP = BQ * 64 * 2;
+constexpr int kSmem = 2 * kBytesQ + 2 * kBytesK + 4 * kBytesV + 2 * kBytesP + 512 + 2048;  // + barriers + SPLIT's exchange
+constexpr int bQFull = 0, bKFull = 1, bKEmpty = 3, bVFull = 5, bVEmpty = 9, bSFull = 13, bSFree = 15, bPReady = 17, bPFree = 25,
+              bOFull = 33, bCount = 35;
+
+struct Ctx {
+  uint32_t tmem, bar, q_lo, k_lo, v_lo, p_lo;
+  int n_steps;
+};
+
+template <int I, int KST>
+__device__ __forceinline__ void issue_s(const Ctx& c) {  // S_I = Q_I K^T over the 128-key stage KST
+  constexpr uint32_t idesc = make_idesc_bf16(BQ, BK);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint32_t qoff = (I * kBytesQ + (ks >> 2) * (BQ * 128) + (ks & 3) * 32) >> 4;
+    const uint32_t koff = (KST * kBytesK + (ks >> 2) * (BK * 128) + (ks & 3) * 32) >> 4;
+    mma_ss_lo(c.tmem + I * 128, c.q_lo + qoff, c.k_lo + koff, idesc, ks != 0);
+  }
+  tc_commit_a(c.bar + 8 * (bSFull + I));
+  tc_commit_a(c.bar + 8 * (bKEmpty + KST));
+}
+// PV quarter Q of a step whose V^T stages are VS0 (keys 0-63) and VS0 + 1 (keys 64-127)
+template <int I, int Q, int VS0>
+__device__ __forceinline__ void issue_pv(const Ctx& c, uint32_t acc_first) {
+  constexpr uint32_t idesc = make_idesc_bf16(BQ, 128);
+  constexpr int VS = VS0 + (Q >> 1), SLOT = Q & 1;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const uint32_t poff = (I * kBytesP + (SLOT * 2 + ks) * 32) >> 4;
+    const uint32_t voff = (VS * kBytesV + (SLOT * 2 + ks) * 32) >> 4;
+    mma_ss_lo(c.tmem + 256 + I * 128, c.p_lo + poff, c.v_lo + voff, idesc, ks == 0 ? acc_first : 1u);
+  }
+  tc_commit_a(c.bar + 8 * (bPFree + I * 4 + Q));
+  if (Q & 1) tc_commit_a(c.bar + 8 * (bVEmpty + VS));
+}
+// step j = 2 m + JJ of tile I; ph = m & 1
+template <int I, int JJ>
+__device__ __forceinline__ void issuer_step(const Ctx& c, const int j, const uint32_t ph) {
+  constexpr int KSTN = (JJ + 1) & 1, VS0 = 2 * JJ;
+  const uint32_t par = JJ;                          // barriers that complete once per step: parity j & 1
+  const uint32_t k_phn = JJ ? (ph ^ 1u) : ph;       // step j + 1 is the ((j + 1) >> 1)-th use of its K stage
+  if (j + 1 < c.n_steps) {  // S runs one step ahead: as soon as the softmax has copied S(j) out of TMEM
+    mbar_wait_a(c.bar + 8 * (bSFree + I), par);
+    mbar_wait_a(c.bar + 8 * (bKFull + KSTN), k_phn);
+    tc_fence_after();
+    issue_s<I, KSTN>(c);
+  }
+  const bool last = j == c.n_steps - 1;
+  mbar_wait_a(c.bar + 8 * (bPReady + I * 4 + 0), par);
+  mbar_wait_a(c.bar + 8 * (bVFull + VS0), ph);
+  tc_fence_after();
+  issue_pv<I, 0, VS0>(c, j > 0);
+  mbar_wait_a(c.bar + 8 * (bPReady + I * 4 + 1), par);
+  tc_fence_after();
+  issue_pv<I, 1, VS0>(c, 1u);
+  mbar_wait_a(c.bar + 8 * (bPReady + I * 4 + 2), par);
+  mbar_wait_a(c.bar + 8 * (bVFull + VS0 + 1), ph);
+  tc_fence_after();
+  issue_pv<I, 2, VS0>(c, 1u);
+  mbar_wait_a(c.bar + 8 * (bPReady + I * 4 + 3), par);
+  tc_fence_after();
+  issue_pv<I, 3, VS0>(c, 1u);
+  if (last) tc_commit_a(c.bar + 8 * (bOFull + I));
+}
+template <int I>
+__device__ __forceinline__ void issuer_loop(const Ctx& c) {
+  mbar_wait_a(c.bar + 8 * bQFull, 0);
+  mbar_wait_a(c.bar + 8 * (bKFull + 0), 0);
+  tc_fence_after();
+  issue_s<I, 0>(c);
+  uint32_t ph = 0;
+#pragma unroll 1
+  for (int j = 0; j < c.n_steps; j += 2, ph ^= 1u) {
+    issuer_step<I, 0>(c, j, ph);
+    if (j + 1 < c.n_steps) issuer_step<I, 1>(c, j + 1, ph);
+  }
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float bf16_ceil(float x) {  // smallest bf16 >= x (x finite or -inf)
+  const float r = __bfloat162float(__float2bfloat16_rd(x)), u = __bfloat162float(__float2bfloat16_ru(x));
+  return x > r ? u : r;
+}
+
+// SPLIT = 1: TWO threads per query row (16 softmax warps, 4 per SM sub-partition): warps w and w + 4 of a tile own the same 32
+// TMEM lanes and take the keys [0, 64) / [64, 128) of every step, i.e. the P quarters {0, 1} / {2, 3}.  The softmax of this kernel is
+// bound by the instruction issue of its warps (ncu: 1 460 warp instructions per sub-partition and step at 0.40 IPC with two warps
+// per sub-partition), so doubling the warps doubles the latency hiding.  The halves agree on the row maximum by exchanging their
+// partial maxima ROUNDED UP to bf16 through 2 KB of shared memory (any common upper bound of the row works as the softmax shift).
+template <int POLY, int SPLIT>
+__global__ void __launch_bounds__((SPLIT ? 19 : 11) * 32, 1)
+    attention_ps_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const Params p) {
+  constexpr int kSoftmaxWarps = SPLIT ? 16 : 8, kTmaWarp = kSoftmaxWarps, kMmaWarp = kSoftmaxWarps + 1;
+  constexpr int kWarpsPerTile = kSoftmaxWarps / 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023u) __trap();  // the SW128 tiles need 1 KB alignment; dynamic shared memory starts 1 KB-aligned
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * kBytesQ;
+  uint8_t* sV = sK + 2 * kBytesK;
+  uint8_t* sP = sV + 4 * kBytesV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kBytesP);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
+  __nv_bfloat16* xch = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(bars) + 512);  // SPLIT: [tile][parity][half][row]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * BQ;
+  const int n_steps = (p.n_kv + BK - 1) / BK;
+
+  if (warp == kTmaWarp && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    mbar_init(&bars[bQFull], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[bKFull + i], 1);
+      mbar_init(&bars[bKEmpty + i], 2);  // one commit per issuer
+      mbar_init(&bars[bSFull + i], 1);
+      mbar_init(&bars[bSFree + i], kWarpsPerTile);  // every softmax warp of the tile has copied S out of TMEM
+      mbar_init(&bars[bOFull + i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bars[bVFull + i], 1);
+      mbar_init(&bars[bVEmpty + i], 2);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&bars[bPReady + i], 4);  // a quarter is written by four warps in both layouts
+      mbar_init(&bars[bPFree + i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kTmaWarp) {
+    if (elect_one()) {  // ===== TMA producer: Q0 Q1 | K(0) K(1) | V(0) V(1) K(2) | V(2) V(3) K(3) | ... =====
+      mbar_arrive_expect_tx(&bars[bQFull], 2 * kBytesQ);
+      for (int i = 0; i < 2; ++i)
+        for (int s = 0; s < 2; ++s)
+          tma_load_3d(sQ + i * kBytesQ + s * (BQ * 128), &tmQ, &bars[bQFull], head * 128 + s * 64, q0 + i * BQ, batch);
+      auto load_k = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&bars[bKEmpty + st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[bKFull + st], kBytesK);
+        for (int s = 0; s < 2; ++s)
+          tma_load_3d(sK + st * kBytesK + s * (BK * 128), &tmK, &bars[bKFull + st], head * 128 + s * 64, j * BK, batch);
+      };
+      auto load_v = [&](int h) {  // h = index of the 64-key half
+        const int st = h & 3;
+        mbar_wait(&bars[bVEmpty + st], ((h >> 2) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[bVFull + st], kBytesV);
+        tma_load_3d(sV + st * kBytesV, &tmV, &bars[bVFull + st], h * 64, head * 128, batch);
+      };
+      load_k(0);
+      if (n_steps > 1) load_k(1);
+      for (int j = 0; j < n_steps; ++j) {
+        load_v(2 * j);
+        load_v(2 * j + 1);
+        if (j + 2 < n_steps) load_k(j + 2);
+      }
+    }
+  } else if (warp >= kMmaWarp) {
+    if (elect_one()) {  // ===== MMA issuers, one per query tile =====
+      Ctx c;
+      c.tmem = tmem_base;
+      c.bar = smem_u32(bars);
+      c.q_lo = smem_desc_lo_sw128(smem_u32(sQ));
+      c.k_lo = smem_desc_lo_sw128(smem_u32(sK));
+      c.v_lo = smem_desc_lo_sw128(smem_u32(sV));
+      c.p_lo = smem_desc_lo_sw128(smem_u32(sP));
+      c.n_steps = n_steps;
+      if (warp == kMmaWarp) issuer_loop<0>(c);
+      else issuer_loop<1>(c);
+    }
+  } else {  // ===== softmax warps =====
+    constexpr int W = SPLIT ? 64 : 128;             // keys of a step owned by this thread
+    constexpr int NQ = W / QK;                      // P quarters it produces
+    constexpr int OC = SPLIT ? 64 : 128;            // O columns it rescales / writes
+    const int i = warp / kWarpsPerTile, quad = warp & 3;
+    const int hh = SPLIT ? (warp >> 2) & 1 : 0;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + i * 128 + hh * W;
+    const uint32_t t_o = tmem_base + lane_base + 256 + i * 128 + hh * OC;
+    const int row_in_tile = quad * 32 + lane;
+    const int row = q0 + i * BQ + row_in_tile;
+    const uint32_t p_row = smem_u32(sP) + i * kBytesP + row_in_tile * 128;  // this row of the tile's P operand (2 slots x 32 keys)
+    const int sw = row_in_tile & 7;                                          // SWIZZLE_128B: chunk c of row r sits at c ^ (r & 7)
+    const uint32_t bar = smem_u32(bars);
+    float m_used = -INFINITY, l = 0.f;
+    const float c = p.scale_log2;
+#pragma unroll 1
+    for (int j = 0; j < n_steps; ++j) {
+      const uint32_t par = (uint32_t)j & 1u;
+      mbar_wait_a(bar + 8 * (bSFull + i), par);
+      tc_fence_after();
+      float s[W];
+#pragma unroll
+      for (int g = 0; g < W / 32; ++g) tmem_ld32(t_s + g * 32, reinterpret_cast<uint32_t*>(s) + g * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(bar + 8 * (bSFree + i));  // S(j) is in registers: the issuer may overwrite the buffer with S(j+1)
+      if (j == n_steps - 1) {  // TMA zero-filled the tail of the last K tile: mask it out
+        const int valid = p.n_kv - j * BK - hh * W;
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+          if (k >= valid) s[k] = -INFINITY;
+      }
+      if (p.stagger & 1) {  // DEBUG (ALG_ATTN_STAGGER=1): skeleton only -- no softmax arithmetic, P slots published untouched
+#pragma unroll
+        for (int qq = 0; qq < NQ; ++qq) {
+          const int q = hh * NQ + qq;
+          if (q >= 2) mbar_wait_a(bar + 8 * (bPFree + i * 4 + q - 2), par);
+          else if (j > 0) mbar_wait_a(bar + 8 * (bPFree + i * 4 + q + 2), par ^ 1u);
+          l += s[qq];
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(bar + 8 * (bPReady + i * 4 + q));
+        }
+        continue;
+      }
+      float mc[W / 16];
+#pragma unroll
+      for (int g = 0; g < W / 16; ++g) {
+        float m = s[g * 16];
+#pragma unroll
+        for (int k = 1; k + 1 < 16; k += 2) m = max3(m, s[g * 16 + k], s[g * 16 + k + 1]);
+        mc[g] = fmaxf(m, s[g * 16 + 15]);
+      }
+      float mraw = fmaxf(max3(mc[0], mc[1], mc[2]), mc[3]);
+      if constexpr (!SPLIT) mraw = fmaxf(mraw, fmaxf(max3(mc[W / 16 - 4], mc[W / 16 - 3], mc[W / 16 - 2]), mc[W / 16 - 1]));
+      if constexpr (SPLIT) {
+        // the two halves of a row agree on a common upper bound: each partial maximum rounded UP to bf16
+        __nv_bfloat16* slot = xch + ((i * 2 + (int)par) * 2) * BQ;
+        const float mine = bf16_ceil(mraw);
+        slot[hh * BQ + row_in_tile] = __float2bfloat16_rn(mine);  // exact: already a bf16 value
+        named_bar_sync(1 + i, kWarpsPerTile * 32);
+        mraw = fmaxf(mine, __bfloat162float(slot[(hh ^ 1) * BQ + row_in_tile]));
+      }
+      const float mx = mraw * c;
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const float m_new = fmaxf(m_used, mx);
+        const bool need = (m_new - m_used) > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {  // warp-uniform, and identical in both halves (same rows, same maxima)
+          // every PV of step j - 1 must have landed in O; none of step j is issued before P(j) is published
+          mbar_wait_a(bar + 8 * (bPFree + i * 4 + 3), par ^ 1u);
+          tc_fence_after();
+          const float f = ex2(m_used - m_new);
+          l *= f;
+          m_used = m_new;
+#pragma unroll 1
+          for (int ch = 0; ch < OC / 16; ++ch) {
+            uint32_t o[16];
+            tmem_ld16(t_o + ch * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * f);
+            tmem_st16(t_o + ch * 16, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+      }
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_used, -m_used);
+      float2 sum0 = make_float2(0.f, 0.f), sum1 = sum0;
+#pragma unroll
+      for (int qq = 0; qq < NQ; ++qq) {
+        const int q = hh * NQ + qq;  // quarter of the step (compile-time when !SPLIT; hh * 2 + qq otherwise)
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float2 x = __ffma2_rn(make_float2(s[qq * 32 + 2 * k], s[qq * 32 + 2 * k + 1]), c2, nm2);
+          float2 e;
+          if (POLY > 0 && (k % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
+            e = ex2_poly2(x);
+          } else {
+            e.x = ex2(x.x);
+            e.y = ex2(x.y);
+          }
+          if (k & 1) sum1 = __fadd2_rn(sum1, e);
+          else sum0 = __fadd2_rn(sum0, e);
+          __nv_bfloat162 h = __floats2bfloat162_rn(e.x, e.y);
+          pk[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        // slot q & 1 was last read by PV quarter q - 2 (this step) or q + 2 (previous step)
+        if (q >= 2) mbar_wait_a(bar + 8 * (bPFree + i * 4 + q - 2), par);
+        else if (j > 0) mbar_wait_a(bar + 8 * (bPFree + i * 4 + q + 2), par ^ 1u);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = ((qq & 1) * 4 + ch) ^ sw;  // q & 1 == qq & 1 (NQ is even)
+          st_shared_v4(p_row + chunk * 16, pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy operand reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(bar + 8 * (bPReady + i * 4 + q));
+      }
+      l += (sum0.x + sum0.y) + (sum1.x + sum1.y);
+    }
+    // ---- epilogue: O / l -> bf16 -> global ----
+    mbar_wait_a(bar + 8 * (bOFull + i), 0);
+    tc_fence_after();
+    if constexpr (SPLIT) {  // row sum = the two halves' partial sums, exchanged through the (now idle) P operand of the tile
+      float* lx = reinterpret_cast<float*>(sP + i * kBytesP);
+      lx[hh * BQ + row_in_tile] = l;
+      named_bar_sync(1 + i, kWarpsPerTile * 32);
+      l += lx[(hh ^ 1) * BQ + row_in_tile];
+    }
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = p.O + (int64_t)batch * p.o_bs + (int64_t)row * p.o_rs + head * 128 + hh * OC;
+#pragma unroll
+    for (int ch = 0; ch < OC / 32; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(t_o + ch * 32, o);
+      tmem_ld_wait();
+      if (row < p.n_q) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+          uint4 prev;
+          if (p.accumulate) prev = *reinterpret_cast<const uint4*>(orow + ch * 32 + g * 8);
+          const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(o[g * 8 + 2 * e]) * inv;
+            float y = __uint_as_float(o[g * 8 + 2 * e + 1]) * inv;
+            if (p.accumulate) {
+              float2 qv = __bfloat1622float2(ph[e]);
+              x = bf16_round(x) + qv.x;
+              y = bf16_round(y) + qv.y;
+            }
+            h[e] = __floats2bfloat162_rn(x, y);
+          }
+          *reinterpret_cast<uint4*>(orow + ch * 32 + g * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int POLY, int SPLIT>
+static int launch(const alg_attention_t* a, cudaStream_t st) {
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  ALG_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 64 || !(attr_done.load(std::memory_order_relaxed) >> dev & 1)) {
+    ALG_CUDA_OK(cudaFuncSetAttribute(attention_ps_kernel<POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    if (dev < 64) attr_done.fetch_or(uint64_t(1) << dev, std::memory_order_relaxed);
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t hd = (uint64_t)a->heads * 128;
+  {
+    uint64_t dims[3] = {hd, (uint64_t)a->n_q, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->q_rs, (uint64_t)a->q_bs};
+    uint32_t box[3] = {64, BQ, 1};
+    if (int rc = make_tmap_bf16(&tmQ, a->Q, 3, dims, strides, box)) return rc;
+  }
+  {
+    uint64_t dims[3] = {hd, (uint64_t)a->n_kv, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->k_rs, (uint64_t)a->k_bs};
+    uint32_t box[3] = {64, BK, 1};
+    if (int rc = make_tmap_bf16(&tmK, a->K, 3, dims, strides, box)) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a->n_kv, hd, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->v_rs, (uint64_t)a->v_bs};
+    uint32_t box[3] = {64, 128, 1};
+    if (int rc = make_tmap_bf16(&tmV, a->Vt, 3, dims, strides, box)) return rc;
+  }
+  Params p;
+  p.O = reinterpret_cast<__nv_bfloat16*>(a->O);
+  p.o_bs = a->o_bs;
+  p.o_rs = a->o_rs;
+  p.n_q = (int)a->n_q;
+  p.n_kv = (int)a->n_kv;
+  p.heads = a->heads;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.accumulate = a->accumulate;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("ALG_ATTN_STAGGER");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.stagger = dbg;
+  }
+  dim3 grid((unsigned)((a->n_q + 2 * BQ - 1) / (2 * BQ)), (unsigned)a->heads, (unsigned)a->batch);
+  attention_ps_kernel<POLY, SPLIT><<<grid, (SPLIT ? 19 : 11) * 32, kSmem, st>>>(tmQ, tmK, tmV, p);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+}  // namespace ps
+
 }  // namespace attn
 }  // namespace alg
 
@@ -721,7 +1151,7 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   ALG_REQUIRE((reinterpret_cast<uintptr_t>(a->O) & 15) == 0, "attention: O must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static int poly = -1, split = -1, short_max = -1, pair = 0, s128 = 0;  // tuning knobs; defaults from profiling
+  static int poly = -1, split = -1, short_max = -1, pair = 0, s128 = 0, ps = 0;  // tuning knobs; defaults from profiling
   if (poly < 0) {
     const char* e = getenv("ALG_ATTN_POLY");
     poly = e ? atoi(e) : ALG_ATTN_POLY_DEFAULT;
@@ -733,8 +1163,24 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
     pair = e ? atoi(e) : ALG_ATTN_PAIR_DEFAULT;
     e = getenv("ALG_ATTN_S128");  // one 128-key S MMA per pair of steps (long variant, one thread per row)
     s128 = e ? atoi(e) : ALG_ATTN_S128_DEFAULT;
+    e = getenv("ALG_ATTN_PS");  // P through shared memory, 128-key S one step ahead (head_dim 128, long variant)
+    ps = e ? atoi(e) : ALG_ATTN_PS_DEFAULT;
   }
   const bool use_short = a->n_kv <= short_max;
+  if (ps && !use_short && a->head_dim == 128) {
+    if (ps == 2) {  // two threads per row
+      switch (poly) {
+        case 0: return attn::ps::launch<0, 1>(a, st);
+        case 4: return attn::ps::launch<4, 1>(a, st);
+        default: return attn::ps::launch<8, 1>(a, st);
+      }
+    }
+    switch (poly) {
+      case 0: return attn::ps::launch<0, 0>(a, st);
+      case 4: return attn::ps::launch<4, 0>(a, st);
+      default: return attn::ps::launch<8, 0>(a, st);
+    }
+  }
 #define ALG_ATTN_DISPATCH(DD)                                                        \
   if (use_short) return attn::launch<DD, 8, 0, 1, 2>(a, st);                         \
   if (s128 && !pair && split) {                                                      \

@@ -160,3 +160,27 @@ def test_gemm_narrow_tiles_96_and_192(N):
     assert float((out - (ref + b + r)).abs().max()) < 1e-3 * float(ref.abs().max())
     out16 = ops.gemm(a, w, b.bfloat16())
     assert float((out16.float() - (ref + b.bfloat16().float())).abs().max()) < 2 ** -7 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("env", [dict(ALG_ATTN_S128="1"), dict(ALG_ATTN_PS="1"), dict(ALG_ATTN_PS="2"), dict(ALG_ATTN_PAIR="1")])
+def test_attention_experimental_variants_keep_parity(env):
+    """The schedules kept behind knobs (profiles/r02_attention_s128.md, r02_pair_mma.md) stay correct: each runs in a fresh process
+    (the knobs are read once per process) on a long ragged head_dim-128 problem against fp32 SDPA."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, torch.nn.functional as F\n"
+        "from alg_b200 import ops\n"
+        "torch.manual_seed(0)\n"
+        "B, H, D, Nq, Nkv = 1, 3, 128, 700, 2500\n"
+        "q = (torch.randn(B, Nq, H, D, device='cuda') * 3).bfloat16(); k = torch.randn(B, Nkv, H, D, device='cuda').bfloat16()\n"
+        "v = torch.randn(B, Nkv, H, D, device='cuda').bfloat16()\n"
+        "pad = (Nkv + 7) // 8 * 8\n"
+        "vt = torch.zeros(B, H, D, pad, device='cuda', dtype=torch.bfloat16); vt[..., :Nkv] = v.permute(0, 2, 3, 1)\n"
+        "o = ops.attention(q, k, vt, n_kv=Nkv)\n"
+        "ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)).transpose(1, 2)\n"
+        "e = float((o.float() - ref).norm() / ref.norm()); print('REL', e); assert e < 2 ** -8, e\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "REL" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
