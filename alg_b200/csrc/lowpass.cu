@@ -341,17 +341,20 @@ struct DownUpGeom {
 };
 
 template <int DT>
-__global__ void __launch_bounds__(256) down_up_fused_kernel(const void* __restrict__ in, void* __restrict__ out,
+__global__ void __launch_bounds__(256, 5) down_up_fused_kernel(const void* __restrict__ in, void* __restrict__ out,
                                                             int64_t planes, int H, int W, int h1, int w1,
                                                             const int* __restrict__ ints,
                                                             const float* __restrict__ weights, DownUpGeom g,
-                                                            int bufA_elems, int bufB_elems, int vec) {
+                                                            int bufA_elems, int bufB_elems, int vec, int prefetch) {
   using T = typename Elem<DT>::type;
   using S = typename Stage<DT>::type;
   constexpr int VW = 16 / (int)sizeof(S);  // columns per 16-byte shared-memory vector
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  S* A = reinterpret_cast<S*>(smem_raw);     // in [H, W]      -> small [h1, w1]
-  S* B = A + bufA_elems;                     // t1 [H, w1]     -> t2 [h1, W]     (bufA_elems, bufB_elems: multiples of 8)
+  // prefetch: TWO input stages A0 | A1 -- while plane i is filtered out of one, cp.async streams plane i + gridDim.x into the other,
+  // so the global-load latency (the largest stall of the single-stage version: long_scoreboard 2.5 cycles per issued
+  // instruction, profiles/r01_lowpass_norm_ncu.txt) is off the critical path
+  S* A0 = reinterpret_cast<S*>(smem_raw);    // in [H, W]      -> small [h1, w1]
+  S* B = A0 + (prefetch ? 2 : 1) * bufA_elems;  // t1 [H, w1]   -> t2 [h1, W]     (bufA_elems, bufB_elems: multiples of 8)
   float* sw = reinterpret_cast<float*>(B + bufB_elems);  // operator taps
   int* si = reinterpret_cast<int*>(sw + g.n_weights);    // operator starts / counts
   for (int i = threadIdx.x; i < g.n_weights; i += blockDim.x) sw[i] = weights[i];
@@ -361,16 +364,37 @@ __global__ void __launch_bounds__(256) down_up_fused_kernel(const void* __restri
   BandPtr bw_up{si + g.s_off[2], si + g.c_off[2], sw + g.w_off[2], g.stride[2]};
   BandPtr bh_up{si + g.s_off[3], si + g.c_off[3], sw + g.w_off[3], g.stride[3]};
   const int HW = H * W;
+  auto stage_async = [&](int64_t plane, S* dstA) {  // prefetch mode only: planes are 16-byte aligned and HW % VW == 0
+    const char* src = reinterpret_cast<const char*>(reinterpret_cast<const T*>(in) + plane * HW);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dstA);
+    for (int i = threadIdx.x; i < HW / VW; i += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(src + (size_t)i * 16) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if (prefetch && (int64_t)blockIdx.x < planes) stage_async(blockIdx.x, A0);
   for (int64_t plane = blockIdx.x; plane < planes; plane += gridDim.x) {
-    const T* src = reinterpret_cast<const T*>(in) + plane * HW;
+    S* A = A0 + (prefetch ? buf * bufA_elems : 0);
     T* dst = reinterpret_cast<T*>(out) + plane * HW;
-    // ---- stage the plane: 16-byte vector loads when the plane start is aligned (S == T: a plain copy) -------------
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (HW % VW) == 0) {
-      const uint4* s4 = reinterpret_cast<const uint4*>(src);
-      uint4* a4 = reinterpret_cast<uint4*>(A);
-      for (int i = threadIdx.x; i < HW / VW; i += blockDim.x) a4[i] = __ldg(s4 + i);
+    if (prefetch) {
+      const int64_t next = plane + gridDim.x;
+      if (next < planes) {
+        stage_async(next, A0 + (buf ^ 1) * bufA_elems);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      buf ^= 1;
     } else {
-      for (int i = threadIdx.x; i < HW; i += blockDim.x) A[i] = src[i];
+      const T* src = reinterpret_cast<const T*>(in) + plane * HW;
+      // ---- stage the plane: 16-byte vector loads when the plane start is aligned (S == T: a plain copy) -------------
+      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (HW % VW) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* a4 = reinterpret_cast<uint4*>(A);
+        for (int i = threadIdx.x; i < HW / VW; i += blockDim.x) a4[i] = __ldg(s4 + i);
+      } else {
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) A[i] = src[i];
+      }
     }
     __syncthreads();
     if (vec) {  // W % VW == 0 and 16-byte aligned planes: H-passes run one 16-byte vector of columns per thread
@@ -461,8 +485,20 @@ static int down_up_dispatch(const void* in, void* out, int64_t planes, int H, in
   const int w1p = vec ? (w1 + VW - 1) / VW * VW : w1;
   const int64_t a_elems = (std::max<int64_t>((int64_t)H * W, (int64_t)h1 * w1p) + 7) & ~(int64_t)7;
   const int64_t b_elems = (std::max<int64_t>((int64_t)H * w1p, (int64_t)h1 * W) + 7) & ~(int64_t)7;
-  const size_t smem = (size_t)(a_elems + b_elems) * kStageBytes + (size_t)(t.n_weights + t.n_ints) * sizeof(float);
+  size_t smem = (size_t)(a_elems + b_elems) * kStageBytes + (size_t)(t.n_weights + t.n_ints) * sizeof(float);
   if (smem > 200 * 1024) return down_up_generic<DT>(in, out, planes, H, W, h1, w1, t, st);
+  // second input stage for the cp.async prefetch of the next plane: when planes are 16-byte aligned, there is more than one plane
+  // per CTA to overlap, and two stages still leave >= 3 CTAs per SM (measured: 60 x 104 fp32, 8 192 planes 141 -> 137 us; with only
+  // 2 CTAs left -- 90 x 160 bf16 -- the lost occupancy costs more than the hidden load latency gains: 133 -> 141 us)
+  static int prefetch_knob = -1;
+  if (prefetch_knob < 0) {
+    const char* e = getenv("ALG_DOWNUP_PREFETCH");
+    prefetch_knob = e ? atoi(e) : 1;
+  }
+  const size_t smem2 = smem + (size_t)a_elems * kStageBytes;
+  const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && ((int64_t)H * W) % VW == 0;
+  const int prefetch = prefetch_knob && aligned && smem2 <= 72 * 1024 /* >= 3 CTAs per SM */ && planes > (int64_t)148 * ((220 * 1024) / (smem2 + 1024));
+  if (prefetch) smem = smem2;
   // once per denoise step: set every time (the attribute is per-device state; no per-process cache to go stale)
   ALG_CUDA_OK(cudaFuncSetAttribute(down_up_fused_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
@@ -478,7 +514,7 @@ static int down_up_dispatch(const void* in, void* out, int64_t planes, int H, in
   g.n_ints = t.n_ints;
   g.n_weights = t.n_weights;
   down_up_fused_kernel<DT><<<grid, 256, smem, st>>>(in, out, planes, H, W, h1, w1, t.ints, t.weights, g, (int)a_elems,
-                                                    (int)b_elems, vec);
+                                                    (int)b_elems, vec, prefetch);
   ALG_LAUNCH_OK();
   return 0;
 }
