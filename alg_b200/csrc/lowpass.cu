@@ -650,12 +650,128 @@ __global__ void __launch_bounds__(256) gaussian_kernel(const void* __restrict__ 
   }
 }
 
+// float32 tensors (Wan's pixel-space ALG filters the fp32 image, wan:500-506) take the SEPARABLE form: a row pass into shared
+// memory, then a column pass -- 2 k FMAs per output instead of k * k.  torchvision multiplies the two 1-D kernels into a dense
+// [k, k] matrix first; in fp32 that product carries one more rounding (6e-8) than the separable evaluation, far inside the 2e-6 the
+// fp32 filters are held to, so only the 16-bit dtypes (whose taps round to 8 / 11 bits and must be reproduced product by product)
+// keep the dense kernel above.
+__global__ void __launch_bounds__(256) gaussian_sep_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                               int k, Taps taps) {
+  extern __shared__ __align__(16) float smem[];
+  const int r = k / 2;
+  const int th = GT_H + k - 1, tw = (GT_W + k - 1 + 3) & ~3;
+  float* tile = smem;           // [th][tw]  reflect-padded input tile
+  float* tmp = smem + th * tw;  // [th][GT_W] row-filtered
+  const int64_t plane = blockIdx.z;
+  const int x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
+  const size_t base = (size_t)plane * H * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int ty = warp; ty < th; ty += 8) {
+    int y = y0 + ty - r;
+    y = y < 0 ? -y : y;
+    y = y >= H ? 2 * H - 2 - y : y;
+    y = min(max(y, 0), H - 1);
+    const float* rsrc = in + base + (size_t)y * W;
+    float* trow = tile + ty * tw;
+    for (int tx = lane; tx < tw; tx += 32) {
+      int x = x0 + tx - r;
+      x = x < 0 ? -x : x;
+      x = x >= W ? 2 * W - 2 - x : x;
+      x = min(max(x, 0), W - 1);
+      trow[tx] = __ldg(rsrc + x);
+    }
+  }
+  __syncthreads();
+  const int kg = k >> 2, rem = k & 3;
+  // row pass: a work item = 8 consecutive columns of one tile row, 12-float sliding register window (16-byte shared loads)
+  for (int item = threadIdx.x; item < th * (GT_W / 8); item += blockDim.x) {
+    const int ty = item / (GT_W / 8), xs = (item - ty * (GT_W / 8)) * 8;
+    const uint32_t row_s = (uint32_t)__cvta_generic_to_shared(tile + ty * tw + xs);
+    float a[12], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    lds128(a, row_s);
+    lds128(a + 4, row_s + 16);
+    int off = 32;
+    for (int g = 0; g < kg; ++g, off += 16) {
+      lds128(a + 8, row_s + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float w = taps.w[4 * g + q];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, a[i + q], acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = a[i + 4];
+    }
+    if (rem) {
+      if (xs + 8 + 4 * kg < tw) lds128(a + 8, row_s + off);  // the last window may end exactly at the tile edge
+      for (int q = 0; q < rem; ++q) {
+        const float w = taps.w[4 * kg + q];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, a[i + q], acc[i]);
+      }
+    }
+    float4* d = reinterpret_cast<float4*>(tmp + ty * GT_W + xs);
+    d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  __syncthreads();
+  // column pass: thread = 8 consecutive columns of one output row
+  const int xt = (threadIdx.x & 7) * 8, yy = threadIdx.x >> 3;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  uint32_t col_s = (uint32_t)__cvta_generic_to_shared(tmp + yy * GT_W + xt);
+  for (int dy = 0; dy < k; ++dy, col_s += GT_W * 4) {
+    float v[8];
+    lds128(v, col_s);
+    lds128(v + 4, col_s + 16);
+    const float w = taps.w[dy];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+  }
+  const int y = y0 + yy;
+  if (y < H) {
+    float* orow = out + base + (size_t)y * W + x0 + xt;
+    if (x0 + xt + 8 <= W && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
+      reinterpret_cast<float4*>(orow)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(orow)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (x0 + xt + i < W) orow[i] = acc[i];
+    }
+  }
+}
+
 template <int DT>
 static int gaussian_dispatch(const void* in, void* out, int64_t planes, int H, int W, int k, double sigma,
                              cudaStream_t st) {
   Taps taps;
   memset(&taps, 0, sizeof(taps));
   gaussian_taps(k, sigma, DT, taps.w);
+  if (DT == ALG_F32) {
+    static int dense = -1;
+    if (dense < 0) {
+      const char* e = getenv("ALG_GAUSS_DENSE");
+      dense = e ? atoi(e) : 0;
+    }
+    if (!dense) {
+      const int th = GT_H + k - 1, tw = (GT_W + k - 1 + 3) & ~3;
+      const size_t smem_sep = ((size_t)th * tw + (size_t)th * GT_W) * sizeof(float);
+      ALG_CUDA_OK(cudaFuncSetAttribute(gaussian_sep_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      for (int64_t p0 = 0; p0 < planes; p0 += 65535) {
+        const int64_t np = std::min<int64_t>(65535, planes - p0);
+        dim3 grid((W + GT_W - 1) / GT_W, (H + GT_H - 1) / GT_H, (unsigned)np);
+        const size_t off = (size_t)p0 * H * W;
+        gaussian_sep_f32_kernel<<<grid, 256, smem_sep, st>>>(reinterpret_cast<const float*>(in) + off, reinterpret_cast<float*>(out) + off,
+                                                             H, W, k, taps);
+        ALG_LAUNCH_OK();
+      }
+      return 0;
+    }
+  }
   const size_t smem = ((size_t)gauss_tile_w(k) * (GT_H + k - 1) + (size_t)k * ((k + 3) & ~3)) * sizeof(float);
   ALG_CUDA_OK(cudaFuncSetAttribute(gaussian_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   for (int64_t p0 = 0; p0 < planes; p0 += 65535) {

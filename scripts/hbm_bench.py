@@ -50,6 +50,9 @@ report("down_up f=0.625 4096 planes 90x160 bf16", 2 * x.numel() * 2, timed(lambd
 for planes, tag in ((3, "Cog config [1,3,480,720] bf16"), (768, "768 planes 480x720 bf16")):
     x = torch.randn(1, planes, 480, 720, device=dev).bfloat16()
     report(f"gaussian k=13 sigma=15 {tag}", 2 * x.numel() * 2, timed(lambda: lp_utils.apply_low_pass_filter(x, "gaussian_blur", 15.0, 0.02734375, 0.25)))
+x = torch.randn(1, 768, 480, 832, device=dev)  # fp32 (Wan's pixel-space ALG filters the fp32 image): the separable kernel
+report("gaussian k=13 sigma=15 768 planes 480x832 fp32 (separable)", 2 * x.numel() * 4, timed(lambda: lp_utils.apply_low_pass_filter(x, "gaussian_blur", 15.0, 0.02734375, 0.25)))
+del x
 # ---- fused CFG + UniPC step (wan:919-927): E = 2 096 640 (config) and 64x that
 for mult, tag in ((1, "Wan config E=2.1M"), (64, "E=134M")):
     E = 2096640 * mult

@@ -123,3 +123,17 @@ def test_edge_cases():
     assert rel_l2(y, lp_utils.apply_low_pass_filter(nc.contiguous(), "down_up", 0, 0, 0.5)) == 0
     with pytest.raises(RuntimeError, match="reflect padding"):
         lp_utils.apply_low_pass_filter(torch.randn(1, 1, 4, 4, device="cuda"), "gaussian_blur", 1.0, 9, 0.5)
+
+
+@pytest.mark.parametrize("H,W,k,sigma", [(480, 832, 13, 15.0), (33, 70, 5, 1.3), (64, 64, 31, 7.0), (40, 19, 3, 0.8), (130, 200, 63, 20.0)])
+def test_gaussian_fp32_separable_matches_torchvision(H, W, k, sigma):
+    """fp32 tensors take the separable kernel (row pass + column pass): within 2e-6 of torchvision's dense [k, k] depthwise
+    convolution with reflect padding, on ragged sizes, tile-edge windows (k % 4 = 1, 3), the largest kernel, several planes."""
+    import torchvision.transforms.functional as tvF
+    import lp_utils
+    g = torch.Generator(device="cuda").manual_seed(H * W + k)
+    x = torch.randn(2, 3, H, W, generator=g, device="cuda")
+    out = lp_utils.apply_low_pass_filter(x, "gaussian_blur", sigma, k, 0.25)
+    ref = tvF.gaussian_blur(x.double(), kernel_size=[k, k], sigma=[sigma, sigma])
+    assert out.dtype == torch.float32 and out.shape == x.shape
+    assert rel_l2(out, ref) < 2e-6, rel_l2(out, ref)
