@@ -323,6 +323,12 @@ __global__ void cl_to_nchw_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+// out = wa * a + wb * b (fp32): the linear cross-fade between overlapping temporal tiles of a decoded clip (blend_t)
+__global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n, float wa, float wb) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(__fmul_rn(a[i], wa), __fmul_rn(b[i], wb));
+}
+
 static int grid_for(int64_t n, int per = 256) { return (int)std::min<int64_t>((n + per - 1) / per, 148 * 16); }
 
 }  // namespace vae32
@@ -434,6 +440,15 @@ extern "C" int alg_pad_copy_f32(const float* src, float* dst, int T, int H, int 
   if (int rc = alg_check_device()) return rc;
   vae32::pad_copy_kernel<<<vae32::grid_for((int64_t)T * H * W * C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, dst, T, H, W, C, front_pad, to_padded);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_axpby_f32(const float* a, const float* b, float* out, int64_t n, float wa, float wb, void* stream) {
+  ALG_REQUIRE(a && b && out && n >= 0, "axpby: bad arguments");
+  if (int rc = alg_check_device()) return rc;
+  if (n == 0) return 0;
+  vae32::axpby_kernel<<<vae32::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, out, n, wa, wb);
   ALG_LAUNCH_OK();
   return 0;
 }

@@ -14,8 +14,11 @@ parity unpinned; ``oracle/hunyuan_vae_oracle.py`` restates it, ``tests/test_gpu_
     GroupNorm(32) (+ SiLU)            alg_group_norm_f32
     mid-block attention               one head of C channels over ALL T*H*W tokens, frame-causal: scores and P V through the split
                                       GEMM, alg_softmax_rows_f32 with causal_block = H*W.  The score matrix is materialised, as
-                                      the reference materialises the N x N mask: a 129 x 720 x 1280 clip (475 200 latent tokens)
-                                      is out of reach for both without tiling; the single-frame encode (14 400 tokens) is not.
+                                      the reference materialises the N x N mask; diffusers' default temporal tiling (below) keeps
+                                      N at 5 latent frames: 72 000 tokens at 720 x 1280.
+    _temporal_tiled_decode / blend_t  clips of more than 4 latent frames: overlapping tiles of 5 latent frames (stride 3), each
+                                      decoded on its own, cross-faded over 4 frames with alg_axpby_f32 (diffusers' default
+                                      use_framewise_decoding; 129 x 720 x 1280 = 11 tiles, 23.4 s)
 """
 from __future__ import annotations
 
@@ -114,6 +117,15 @@ class AutoencoderKLHunyuanVideo(SplitConvVAE):
         self._init_common(cfg)
         self.temporal_compression_ratio = cfg["temporal_compression_ratio"]  # hy:277-278 read these off the module
         self.spatial_compression_ratio = cfg["spatial_compression_ratio"]
+        # diffusers decodes long clips in overlapping TEMPORAL tiles by default (use_framewise_decoding = True: 16-frame tiles, stride
+        # 12, linear cross-fade over the 4 shared frames) -- that is what hy:1292 runs for 129 frames, and it is what bounds the
+        # mid-block attention to 5 latent frames.  Spatial tiling is opt-in there (enable_tiling) and run.py never opts in.
+        self.use_framewise_decoding = True
+        self.tile_sample_min_num_frames, self.tile_sample_stride_num_frames = 16, 12
+        self._attn_budget = 64 << 30
+
+    def enable_tiling(self, *a, **k):
+        raise NotImplementedError("spatial VAE tiling is not built (run.py does not enable it); temporal tiling is always on, like diffusers' default")
 
     def _shapes(self) -> Dict[str, tuple]:
         return parameter_shapes(self._cfg)
@@ -175,6 +187,35 @@ class AutoencoderKLHunyuanVideo(SplitConvVAE):
         return self._from_cl(a, 2 * self._cfg["latent_channels"], clamp=False)
 
     def _decode_one(self, z: torch.Tensor) -> torch.Tensor:
+        """``AutoencoderKLHunyuanVideo._decode``: clips longer than one temporal tile go through ``_temporal_tiled_decode``."""
+        r = self._cfg["temporal_compression_ratio"]
+        t_min, t_stride = self.tile_sample_min_num_frames // r, self.tile_sample_stride_num_frames // r
+        T = z.shape[1]
+        if not (self.use_framewise_decoding and T > t_min):
+            return self._decode_tile(z)
+        lib, dev = _lib.lib(), self.device
+        blend = self.tile_sample_min_num_frames - self.tile_sample_stride_num_frames
+        stride_f = self.tile_sample_stride_num_frames
+        tiles = []
+        for i in range(0, T, t_stride):  # tiles of t_min + 1 latent frames; every tile but the first drops its first decoded frame
+            d = self._decode_tile(z[:, i:i + t_min + 1].contiguous())
+            tiles.append(d if i == 0 else d[:, 1:].contiguous())
+        out = []
+        for i, tile in enumerate(tiles):
+            if i > 0:  # blend_t: the first frames of this tile cross-fade from the last frames of the previous one
+                prev = tiles[i - 1]
+                n = min(prev.shape[1], tile.shape[1], blend)
+                for x in range(n):
+                    a_, b_ = prev[:, prev.shape[1] - n + x].contiguous(), tile[:, x].contiguous()
+                    mixed = torch.empty_like(b_)
+                    _launch(lib.alg_axpby_f32, dev, a_.data_ptr(), b_.data_ptr(), mixed.data_ptr(), b_.numel(), 1.0 - x / n, x / n)
+                    tile[:, x] = mixed
+                out.append(tile[:, :stride_f])
+            else:
+                out.append(tile[:, :stride_f + 1])
+        return torch.cat(out, dim=1)[:, :(T - 1) * r + 1].contiguous()
+
+    def _decode_tile(self, z: torch.Tensor) -> torch.Tensor:
         _, dec = _stages(self._cfg)
         a = self._to_cl(z)
         a.t = self._pointwise(a.t, "post_quant_conv")[:, :self._cfg["latent_channels"]].contiguous()

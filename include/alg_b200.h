@@ -528,6 +528,10 @@ int alg_pad_copy_f32(const float* src, float* dst, int T, int H, int W, int C, i
 int alg_pad_frames_bf16(const void* src, void* dst, const void* residual, int frames, int H, int W, int C, int64_t ld, int to_padded,
                         void* stream);
 
+/* out = wa * a + wb * b over n fp32 elements (each product rounded, then the sum): the cross-fade of overlapping temporal tiles in
+ * AutoencoderKLHunyuanVideo._temporal_tiled_decode (blend_t); out may alias a or b */
+int alg_axpby_f32(const float* a, const float* b, float* out, int64_t n, float wa, float wb, void* stream);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 int64_t alg_launch_count(void);
 

@@ -168,8 +168,37 @@ def encode_moments(x, sd, cfg, dtype=torch.float32):
     return F.conv3d(h, net.p("quant_conv.weight"), net.p("quant_conv.bias"))
 
 
-def decode(z, sd, cfg, dtype=torch.float32):
-    """z [B, z, T, h, w] -> [B, 3, 4 (T - 1) + 1, 8 h, 8 w]."""
+def decode(z, sd, cfg, dtype=torch.float32, tile_min_frames=16, tile_stride_frames=12, framewise=True):
+    """``AutoencoderKLHunyuanVideo._decode``: z [B, z, T, h, w] -> [B, 3, 4 (T - 1) + 1, 8 h, 8 w].  With diffusers' default
+    ``use_framewise_decoding`` a clip of more than 4 latent frames is decoded in overlapping temporal tiles of 5 latent frames
+    (stride 3) and cross-faded over 4 frames (``_temporal_tiled_decode`` + ``blend_t``)."""
+    r = cfg["temporal_compression_ratio"]
+    t_min, t_stride = tile_min_frames // r, tile_stride_frames // r
+    T = z.shape[2]
+    if not (framewise and T > t_min):
+        return decode_tile(z, sd, cfg, dtype)
+    blend = tile_min_frames - tile_stride_frames
+    row = []
+    for i in range(0, T, t_stride):
+        d = decode_tile(z[:, :, i:i + t_min + 1], sd, cfg, dtype)
+        row.append(d if i == 0 else d[:, :, 1:])
+    out = []
+    for i, tile in enumerate(row):
+        if i > 0:
+            a = row[i - 1]
+            n = min(a.shape[2], tile.shape[2], blend)
+            tile = tile.clone()
+            for x in range(n):
+                tile[:, :, x] = a[:, :, -n + x] * (1 - x / n) + tile[:, :, x] * (x / n)
+            row[i] = tile
+            out.append(tile[:, :, :tile_stride_frames])
+        else:
+            out.append(tile[:, :, :tile_stride_frames + 1])
+    return torch.cat(out, dim=2)[:, :, :(T - 1) * r + 1]
+
+
+def decode_tile(z, sd, cfg, dtype=torch.float32):
+    """One temporal tile: post_quant_conv + decoder."""
     net = _Net(sd, cfg, dtype)
     _, dec = stage_plan(cfg)
     h = F.conv3d(z.to(dtype), net.p("post_quant_conv.weight"), net.p("post_quant_conv.bias"))

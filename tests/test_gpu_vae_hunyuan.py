@@ -140,3 +140,20 @@ def test_pipeline_image_latents_and_attention_budget():
     vae._attn_budget = 1 << 20
     with pytest.raises(NotImplementedError, match="score matrix"):
         vae.decode(torch.randn(1, 16, 3, 16, 16, device="cuda"))
+
+
+@pytest.mark.parametrize("T", [5, 9, 8])
+def test_temporal_tiled_decode_matches_oracle(T):
+    """hy:1292 on clips longer than one temporal tile: diffusers' default ``use_framewise_decoding`` decodes overlapping tiles of 5
+    latent frames (stride 3) and cross-fades 4 frames (``_temporal_tiled_decode`` / ``blend_t``); T = 5 is the first tiled length,
+    T = 8 ends on a short last tile."""
+    from oracle import hunyuan_vae_oracle as V
+    vae, sd, ocfg = _pair(seed=6)
+    z = torch.randn(1, 4, T, 4, 4, generator=torch.Generator(device="cuda").manual_seed(T), device="cuda")
+    out = vae.decode(z).sample
+    ref = V.decode(z.double(), {k: v.double() for k, v in sd.items()}, ocfg, torch.float64)
+    assert out.shape == ref.shape == (1, 3, 4 * (T - 1) + 1, 32, 32) and rel_l2(out, ref) < 1e-4, rel_l2(out, ref)
+    whole = V.decode(z.double(), {k: v.double() for k, v in sd.items()}, ocfg, torch.float64, framewise=False)
+    assert rel_l2(ref, whole) > 1e-3  # tiling is not a no-op: the tiles lose their causal context, which is why it must be reproduced
+    with pytest.raises(NotImplementedError, match="spatial"):
+        vae.enable_tiling()
