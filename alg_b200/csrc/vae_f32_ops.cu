@@ -286,6 +286,24 @@ __global__ void __launch_bounds__(256) norm_split_pad_kernel(const float* __rest
     }
   }
 }
+// F.pad(mode="replicate") of the padded split operand (HunyuanVideoCausalConv3d): every PADDING pixel of the raster
+// [(T + pt), H + 2, W + 2, Cs] -- the pt front frames and the one-pixel border -- takes the row of the nearest interior pixel
+// (all three coordinates clamped, so sources are always interior pixels written by alg_norm_split_pad_f32).
+__global__ void __launch_bounds__(256) replicate_border_kernel(uint4* __restrict__ buf, int T, int H, int W, int pt, int cs8) {
+  const int64_t pixels = (int64_t)(T + pt) * (H + 2) * (W + 2);
+  const int64_t n = pixels * cs8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cs8);
+    const int64_t pix = i / cs8;
+    const int xx = (int)(pix % (W + 2));
+    const int64_t r = pix / (W + 2);
+    const int y = (int)(r % (H + 2)), t = (int)(r / (H + 2));
+    const int ts = max(t, pt), ys = min(max(y, 1), H), xs = min(max(xx, 1), W);
+    if (ts == t && ys == y && xs == xx) continue;  // interior
+    buf[i] = buf[(((int64_t)ts * (H + 2) + ys) * (W + 2) + xs) * cs8 + c];
+  }
+}
+
 // interior pixels of a compact [T*H*W, C] clip <-> the padded raster [(T+pt)(H+2)(W+2), C] (fp32); padding is not touched
 __global__ void pad_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int H, int W, int C, int pt,
                                 int to_padded) {
@@ -449,6 +467,17 @@ extern "C" int alg_axpby_f32(const float* a, const float* b, float* out, int64_t
   if (int rc = alg_check_device()) return rc;
   if (n == 0) return 0;
   vae32::axpby_kernel<<<vae32::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, out, n, wa, wb);
+  ALG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int alg_replicate_border_bf16(void* buf, int T, int H, int W, int front_pad, int Cs, void* stream) {
+  ALG_REQUIRE(buf && T > 0 && H > 0 && W > 0 && front_pad >= 0 && Cs > 0 && Cs % 8 == 0, "replicate_border: bad arguments");
+  ALG_REQUIRE((reinterpret_cast<uintptr_t>(buf) & 15) == 0, "replicate_border: misaligned pointer");
+  if (int rc = alg_check_device()) return rc;
+  const int64_t n = (int64_t)(T + front_pad) * (H + 2) * (W + 2) * (Cs / 8);
+  vae32::replicate_border_kernel<<<vae32::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<uint4*>(buf), T, H, W, front_pad, Cs / 8);
   ALG_LAUNCH_OK();
   return 0;
 }

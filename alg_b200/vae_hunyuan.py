@@ -6,8 +6,10 @@ first-frame latent every step's model input carries) and hy:1292 (``decode``).  
 arithmetic here is float32 (a superset).  The network is diffusers@be2fb77 ``autoencoder_kl_hunyuan_video.py`` (absent offline:
 parity unpinned; ``oracle/hunyuan_vae_oracle.py`` restates it, ``tests/test_gpu_vae_hunyuan.py`` compares).
 
-    HunyuanVideoCausalConv3d          alg_im2col_split3_f32 with replicate = 1 (F.pad(mode="replicate") in time and space is
-                                      index clamping inside the gather) + alg_gemm_bf16 + alg_bias_act_f32
+    HunyuanVideoCausalConv3d          multi-frame stride-1: implicit -- alg_norm_split_pad_f32 (split only) + alg_replicate_border_bf16
+                                      (F.pad(mode="replicate") = the padding of the operand raster filled from the nearest interior
+                                      pixel) + tap-mode alg_gemm_bf16; otherwise alg_im2col_split3_f32 with replicate = 1 (index
+                                      clamping inside the gather) + alg_gemm_bf16
     HunyuanVideoDownsampleCausal3D    the same gather with stride (1|2, 2, 2)
     HunyuanVideoUpsampleCausal3D      the same gather with up = 2 / tdup = 2: frame 0 once, later frames twice, pixels x2 -- the
                                       nearest-neighbour resize is addressing, never materialised
@@ -18,7 +20,7 @@ parity unpinned; ``oracle/hunyuan_vae_oracle.py`` restates it, ``tests/test_gpu_
                                       N at 5 latent frames: 72 000 tokens at 720 x 1280.
     _temporal_tiled_decode / blend_t  clips of more than 4 latent frames: overlapping tiles of 5 latent frames (stride 3), each
                                       decoded on its own, cross-faded over 4 frames with alg_axpby_f32 (diffusers' default
-                                      use_framewise_decoding; 129 x 720 x 1280 = 11 tiles, 23.4 s)
+                                      use_framewise_decoding; 129 x 720 x 1280 = 11 tiles, 17.0 s)
 """
 from __future__ import annotations
 
@@ -107,6 +109,7 @@ class AutoencoderKLHunyuanVideo(SplitConvVAE):
 
     Z_KEY = "latent_channels"
     TRUNCATE_FRAMES = False
+    BUILD_TAPS = True
 
     def __init__(self, **config):
         cfg = dict(HUNYUAN_VAE)
@@ -141,7 +144,31 @@ class AutoencoderKLHunyuanVideo(SplitConvVAE):
         return out
 
     def _cconv(self, x: _Act, name: str, **kw) -> _Act:
+        """HunyuanVideoCausalConv3d.  Stride-1 convolutions at the input resolution take the implicit path: the input split into the
+        padded raster (alg_norm_split_pad_f32 without a norm), its padding filled by replication (alg_replicate_border_bf16), the
+        27 taps as row-shifted reads in ONE GEMM with bias / residual in the epilogue, the result copied back out of the padded
+        raster.  Strided and upsampling convolutions gather patches (the resize and the padding are addressing there)."""
+        plain = not kw.get("stride") and not kw.get("up") and kw.get("tdup", 1) == 1 and not kw.get("frames") and not kw.get("out_hw")
+        # (a single frame -- the pipeline's encode -- is faster through the patch gather: 84 vs 103 ms at 720 x 1280)
+        if self.implicit and plain and x.T > 1 and name + ".conv.weight_taps" in self._w and self._fits_implicit_hy(x, self._w[name + ".conv.bias"].numel()):
+            x = self._to_compact(x)
+            s3p = self._split_pad(x, None, False)
+            _launch(_lib.lib().alg_replicate_border_bf16, self.device, s3p.data_ptr(), x.T, x.H, x.W, 2, s3p.shape[1])
+            res = kw.get("residual")
+            if res is not None:  # the residual lives in the compact layout: add it after un-padding (one fused pass)
+                y = self._to_compact(self._conv_taps(s3p, (x.T, x.H, x.W), name + ".conv"))
+                _launch(_lib.lib().alg_axpby_f32, self.device, y.t.data_ptr(), res.data_ptr(), y.t.data_ptr(), y.t.numel(), 1.0, 1.0)
+                return y
+            return self._to_compact(self._conv_taps(s3p, (x.T, x.H, x.W), name + ".conv"))
         return self._conv(x, name + ".conv", (3, 3, 3), replicate=True, **kw)
+
+    def _fits_implicit_hy(self, x: _Act, c_out: int) -> bool:
+        rows = (x.T + 2) * (x.H + 2) * (x.W + 2)
+        cs = (3 * x.C + 63) // 64 * 64
+        need = rows * (2 * cs + 4 * c_out) + x.T * x.H * x.W * 4 * c_out
+        free, _ = torch.cuda.mem_get_info(self.device)
+        free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        return need < 0.8 * free
 
     def _res(self, x: _Act, name: str) -> _Act:
         h = x.t
@@ -184,7 +211,9 @@ class AutoencoderKLHunyuanVideo(SplitConvVAE):
         a.t = self._gn(a.t, "encoder.conv_norm_out", True)
         a = self._cconv(a, "encoder.conv_out")
         a.t = self._pointwise(a.t, "quant_conv")
-        return self._from_cl(a, 2 * self._cfg["latent_channels"], clamp=False)
+        out = self._from_cl(a, 2 * self._cfg["latent_channels"], clamp=False)
+        self._release_operands()
+        return out
 
     def _decode_one(self, z: torch.Tensor) -> torch.Tensor:
         """``AutoencoderKLHunyuanVideo._decode``: clips longer than one temporal tile go through ``_temporal_tiled_decode``."""
@@ -228,4 +257,6 @@ class AutoencoderKLHunyuanVideo(SplitConvVAE):
                 a = self._up(a, f"decoder.up_blocks.{i}.upsamplers.0.conv", sp, tp)
         a.t = self._gn(a.t, "decoder.conv_norm_out", True)
         a = self._cconv(a, "decoder.conv_out")
-        return self._from_cl(a, self._cfg["out_channels"], clamp=False)
+        out = self._from_cl(a, self._cfg["out_channels"], clamp=False)
+        self._release_operands()
+        return out

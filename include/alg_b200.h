@@ -518,6 +518,9 @@ int alg_cl_to_nchw_f32(const float* x, float* out, int C, int64_t pixels, int ld
  * out [(T+front_pad)(H+2)(W+2), Cs] (Cs >= 3C).  Padding rows and columns >= 3C are not written: zero the buffer once. */
 int alg_norm_split_pad_f32(const float* x, void* out, int T, int H, int W, int C, int front_pad, int in_padded, int Cs,
                            const float* gamma, int silu, void* stream);
+/* F.pad(mode="replicate") of a padded split operand [(T+front_pad)(H+2)(W+2), Cs] bf16 in place: every padding pixel (front frames,
+ * one-pixel border) takes the row of the nearest interior pixel (HunyuanVideoCausalConv3d) */
+int alg_replicate_border_bf16(void* buf, int T, int H, int W, int front_pad, int Cs, void* stream);
 /* interior pixels of compact [T*H*W, C] fp32 -> padded raster (to_padded != 0) or back; padding is not touched */
 int alg_pad_copy_f32(const float* src, float* dst, int T, int H, int W, int C, int front_pad, int to_padded, void* stream);
 
