@@ -255,6 +255,27 @@ class CogVideoXImageToVideoPipeline(DiffusionPipelineBase):
                                  f" got: `prompt_embeds` {prompt_embeds.shape} != `negative_prompt_embeds`"
                                  f" {negative_prompt_embeds.shape}.")
 
+    def fuse_qkv_projections(self) -> None:
+        """cog:527-530.  The native engine always evaluates q|k|v as ONE tensor-core GEMM per block (the weights are
+        packed at load time), so there is no slower unfused state to leave; the flag keeps the reference's bookkeeping."""
+        self.fusing_transformer = True
+        fuse = getattr(self.transformer, "fuse_qkv_projections", None)
+        if fuse is not None:
+            fuse()
+
+    def unfuse_qkv_projections(self) -> None:
+        """cog:533-539: warn when fusion was never requested, else clear the flag."""
+        if not getattr(self, "fusing_transformer", False):
+            import logging
+
+            logging.getLogger(__name__).warning(
+                "The Transformer was not initially fused for QKV projections. Doing nothing.")
+            return
+        unfuse = getattr(self.transformer, "unfuse_qkv_projections", None)
+        if unfuse is not None:
+            unfuse()
+        self.fusing_transformer = False
+
     def _prepare_rotary_positional_embeddings(self, height: int, width: int, num_frames: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
         """cog:542-584, CogVideoX 1.0 branch (patch_size_t is None)."""
         cfg = self.transformer.config

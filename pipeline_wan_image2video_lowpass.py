@@ -33,10 +33,9 @@ WAN_VAE_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743, 3
                1.1253, 2.8251, 1.9160]
 
 
-def prompt_clean(text: str) -> str:
-    """wan:96-110: ftfy.fix_text (when ftfy is installed), double html.unescape, whitespace collapse."""
+def basic_clean(text: str) -> str:
+    """wan:97-101: ftfy.fix_text (when ftfy is installed), two rounds of html.unescape, strip."""
     import html
-    import re
 
     try:
         import ftfy
@@ -44,8 +43,19 @@ def prompt_clean(text: str) -> str:
         text = ftfy.fix_text(text)
     except ImportError:
         pass
-    text = html.unescape(html.unescape(text)).strip()
+    return html.unescape(html.unescape(text)).strip()
+
+
+def whitespace_clean(text: str) -> str:
+    """wan:104-107: every whitespace run becomes one space."""
+    import re
+
     return re.sub(r"\s+", " ", text).strip()
+
+
+def prompt_clean(text: str) -> str:
+    """wan:110-112."""
+    return whitespace_clean(basic_clean(text))
 
 
 def retrieve_latents(encoder_output, generator=None, sample_mode: str = "sample"):

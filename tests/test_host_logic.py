@@ -307,3 +307,35 @@ def test_ddim_coefficients_against_fp64_closed_forms():
         want = math.sqrt(a_p) * x0 + math.sqrt(1 - a_p) * eps
         got = a * x + b * (sa * x - sb * v)
         assert abs(got - want) < 2e-6 * max(1.0, abs(want)), (t, got, want)
+
+
+def test_pipeline_module_helpers_and_qkv_fusion_bookkeeping(caplog):
+    """Reference module-level helpers (wan:97-112) and the Cog pipeline's fuse/unfuse bookkeeping (cog:527-539)."""
+    import logging
+
+    import pipeline_cogvideox_image2video_lowpass as cog
+    import pipeline_wan_image2video_lowpass as wan
+
+    assert wan.basic_clean("  a &amp;amp; b  ") == "a & b"
+    assert wan.whitespace_clean(" a \n\t b   c ") == "a b c"
+    assert wan.prompt_clean("  x &amp;lt;  \n y ") == "x < y"
+    assert cog.get_resize_crop_region_for_grid((30, 45), 45, 30) == ((0, 0), (30, 45))
+
+    class _T:
+        fused = 0
+
+        def fuse_qkv_projections(self):
+            self.fused += 1
+
+        def unfuse_qkv_projections(self):
+            self.fused -= 1
+
+    pipe = cog.CogVideoXImageToVideoPipeline.__new__(cog.CogVideoXImageToVideoPipeline)
+    pipe.transformer = _T()
+    with caplog.at_level(logging.WARNING):
+        pipe.unfuse_qkv_projections()
+    assert "not initially fused" in caplog.text and pipe.transformer.fused == 0
+    pipe.fuse_qkv_projections()
+    assert pipe.fusing_transformer and pipe.transformer.fused == 1
+    pipe.unfuse_qkv_projections()
+    assert not pipe.fusing_transformer and pipe.transformer.fused == 0
