@@ -739,11 +739,12 @@ def run_ours(args):
             roofline["gemm_tflops_in_step"] = gemm_flops / (prof["gemm"]["ms"] / 1e3) / 1e12
         cpu = parity = eager = None
         if not FAST:
-            try:
-                c_fps, c_dt, c_desc, c_thr = cpu_sample(wl, steps=1, warmup=0, budget_s=45.0)
-                cpu = {"value": c_fps, "unit": "frames/s", "cores": c_thr, "kind": "port", "sample": c_desc}
-            except Exception as ex:  # pragma: no cover
-                cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+            if world == 1:  # the CPU baseline is an N = 1 leg (rank 0's host cores); N > 1 lines carry null
+                try:
+                    c_fps, c_dt, c_desc, c_thr = cpu_sample(wl, steps=1, warmup=0, budget_s=45.0)
+                    cpu = {"value": c_fps, "unit": "frames/s", "cores": c_thr, "kind": "port", "sample": c_desc}
+                except Exception as ex:  # pragma: no cover
+                    cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
             if args.parity and world == 1:
                 # checker leg, OUTSIDE every timed region: a teacher-forced step of each kind at the config size and FULL depth,
                 # engine vs the eager bf16 oracle on this GPU (scripts/parity_fullsize.py); the eager step time is the GPU bar
