@@ -80,25 +80,32 @@ __device__ __forceinline__ float block_sum_t(float v, float* red) {
   return t;
 }
 
-template <int TH, int CH>
+// HD > 0: head_dim is the compile-time HD (the rotary-pair index of a chunk is a mask, not an integer division per chunk);
+// EXACT: d == TH * CH * 8, so no chunk is ever out of range.  The instruction count matters: with RoPE the kernel is
+// issue-bound (profiles/r01_lowpass_norm_ncu.txt norm_r41: 549 M warp instructions, 0.50 of the HBM peak against 0.93 without
+// RoPE), and a third of its instructions were bf16 <-> fp32 repacking, runtime `% head_dim` and range guards.
+// `bf16(bf16(x * rstd) * w)`: the second product is ONE packed bf16 multiply (HMUL2.BF16: exact 16-bit product, one rounding --
+// the same value as the fp32 multiply + cast it replaces).
+template <int TH, int CH, int HD, bool EXACT>
 __global__ void __launch_bounds__(TH)
-    rms_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int d, int head_dim, float eps,
+    rms_norm_rope_kernel(__nv_bfloat16* __restrict__ x, int d, int head_dim_rt, float eps,
                          const __nv_bfloat16* __restrict__ w, RopeTables rope, int use_rope) {
   __shared__ float red[TH / 32];
   // per rotary pair p: (cos_hi, cos_hi, cos_lo, cos_lo) and (sin_hi, sin_hi, sin_lo, sin_lo), the packed operands as stored,
   // at slot p + (p >> 3): consecutive threads read pairs 4 apart, and the one-in-eight padding spreads a quarter warp's
   // eight 16-byte reads over all 32 banks (a dense [pair] layout is 4-way conflicted, an interleaved one 8-way)
   __shared__ float4 cs_c[72], cs_s[72];
+  const int head_dim = HD > 0 ? HD : head_dim_rt;
   const int64_t row = blockIdx.x;
   uint4* xr = reinterpret_cast<uint4*>(x + row * d);
   const uint4* wr = reinterpret_cast<const uint4*>(w);
-  const int chunks = d / 8;
+  const int chunks = EXACT ? TH * CH : d / 8;
   float2 v[CH][4];
   float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     const int ci = threadIdx.x + c * TH;
-    if (ci < chunks) {
+    if (EXACT || ci < chunks) {
       const uint4 u = xr[ci];
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -111,13 +118,13 @@ __global__ void __launch_bounds__(TH)
   // the row's head_dim / 2 (cos, sin) pairs are the same for every head: stage them once per block in shared memory
   // (the fp64 table reads were 4x the activation bytes when every head re-read them), split into fp32 hi + lo
   if (use_rope) {
-    const int64_t N = (int64_t)rope.ppf * rope.pph * rope.ppw;
-    const int n = (int)(row % N);
-    const int t = n / (rope.pph * rope.ppw);
-    const int rem = n - t * rope.pph * rope.ppw;
-    const int y = rem / rope.ppw, xx = rem - y * rope.ppw;
     const int pi = threadIdx.x;
     if (pi < head_dim / 2) {
+      const int64_t N = (int64_t)rope.ppf * rope.pph * rope.ppw;
+      const int n = (int)(row % N);
+      const int t = n / (rope.pph * rope.ppw);
+      const int rem = n - t * rope.pph * rope.ppw;
+      const int y = rem / rope.ppw, xx = rem - y * rope.ppw;
       const double* cs;
       if (pi < rope.n_t) cs = rope.t + ((int64_t)t * rope.n_t + pi) * 2;
       else if (pi < rope.n_t + rope.n_h) cs = rope.h + ((int64_t)y * rope.n_h + (pi - rope.n_t)) * 2;
@@ -134,32 +141,29 @@ __global__ void __launch_bounds__(TH)
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     const int ci = threadIdx.x + c * TH;
-    if (ci < chunks) {
+    if (EXACT || ci < chunks) {
       const uint4 wu = __ldg(wr + ci);
       const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wu);
-      float2 o[4];
+      uint4 u;
+      __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 h = bf16x2_round(__fmul2_rn(v[c][e], rstd2));            // hidden_states.to(weight.dtype)
-        o[e] = bf16x2_round(__fmul2_rn(h, __bfloat1622float2(wh[e])));         // * weight (bf16 tensor op)
-      }
+      for (int e = 0; e < 4; ++e)  // hidden_states.to(weight.dtype) * weight: two bf16 roundings
+        ob[e] = __hmul2(__float22bfloat162_rn(__fmul2_rn(v[c][e], rstd2)), wh[e]);
       if (use_rope) {
         const int pair0 = ((ci * 8) % head_dim) >> 1;  // 4 complex pairs per chunk, never straddling a head
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int slot = pair0 + q + ((pair0 + q) >> 3);
           const float4 tc = cs_c[slot], ts = cs_s[slot];
-          const float re = o[q].x, im = o[q].y;
+          const float2 o = __bfloat1622float2(ob[q]);
+          const float re = o.x, im = o.y;
           // (re, im) * (cos, cos) + (-im, re) * (sin, sin): lane 0 = re*cos - im*sin, lane 1 = im*cos + re*sin; rounded to
           // bf16 (.type_as) by the pack below
-          o[q] = dd_dot2(o[q], make_float2(-re, -im), make_float2(tc.x, tc.y), make_float2(tc.z, tc.w), make_float2(-im, re),
-                         make_float2(im, -re), make_float2(ts.x, ts.y), make_float2(ts.z, ts.w));
+          ob[q] = __float22bfloat162_rn(dd_dot2(o, make_float2(-re, -im), make_float2(tc.x, tc.y), make_float2(tc.z, tc.w),
+                                                make_float2(-im, re), make_float2(im, -re), make_float2(ts.x, ts.y),
+                                                make_float2(ts.z, ts.w)));
         }
       }
-      uint4 u;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = __float22bfloat162_rn(o[e]);
       xr[ci] = u;
     }
   }
@@ -173,9 +177,11 @@ int rms_norm_rope(__nv_bfloat16* x, int64_t rows, int d, int head_dim, float eps
   RopeTables r{};
   if (rope) r = *rope;
   const int chunks = d / 8;
-  if (chunks <= 128 * 3) rms_norm_rope_kernel<128, 3><<<(unsigned)rows, 128, 0, st>>>(x, d, head_dim, eps, w, r, rope != nullptr);
-  else if (chunks <= 128 * 5) rms_norm_rope_kernel<128, 5><<<(unsigned)rows, 128, 0, st>>>(x, d, head_dim, eps, w, r, rope != nullptr);
-  else rms_norm_rope_kernel<128, 8><<<(unsigned)rows, 128, 0, st>>>(x, d, head_dim, eps, w, r, rope != nullptr);
+  const int ur = rope != nullptr;
+  if (head_dim == 128 && chunks == 128 * 5) rms_norm_rope_kernel<128, 5, 128, true><<<(unsigned)rows, 128, 0, st>>>(x, d, head_dim, eps, w, r, ur);
+  else if (chunks <= 128 * 3) rms_norm_rope_kernel<128, 3, 0, false><<<(unsigned)rows, 128, 0, st>>>(x, d, head_dim, eps, w, r, ur);
+  else if (chunks <= 128 * 5) rms_norm_rope_kernel<128, 5, 0, false><<<(unsigned)rows, 128, 0, st>>>(x, d, head_dim, eps, w, r, ur);
+  else rms_norm_rope_kernel<128, 8, 0, false><<<(unsigned)rows, 128, 0, st>>>(x, d, head_dim, eps, w, r, ur);
   ALG_LAUNCH_OK();
   return 0;
 }

@@ -65,7 +65,10 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // the register file is sized for the actual width (d = 5120: 84 registers at 128 x 5, 6 blocks per SM, against 64 registers
 // x 256 threads = 4 blocks for the first version): 3.47 -> 3.94 TB/s.  A cp.async row-streaming variant (persistent blocks,
 // 4-stage shared-memory ring, 120 KB in flight per SM) was slower (3.2 TB/s): the per-row block reductions, not the bytes in
-// flight, pace this kernel.
+// flight, pace this kernel.  Also measured and dropped in round 2 (profiles/hbm_r02.log notes): a warp-per-row variant with the
+// row packed in registers (no barrier at all; 0.56-0.65 of the HBM peak against 0.72: 130-230 registers per thread) and
+// single-barrier statistics by Chan's pairwise (count, mean, M2) combination (0.63: ~75 more instructions per thread-row than the
+// two plain reductions).  The kernel is bound by its ~650 instructions per thread-row, not by barriers or bytes in flight.
 template <int TH>
 __device__ __forceinline__ float block_sum_t(float v, float* red) {
 #pragma unroll

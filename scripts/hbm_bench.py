@@ -40,35 +40,37 @@ def report(name, nbytes, ms):
 
 
 dev = "cuda"
-# ---- down_up (lp_utils.py:49-54): Wan config shape, and 8192 planes
-for planes, tag in ((420, "Wan config [1,20,21,60,104] fp32"), (8192, "8192 planes 60x104 fp32")):
-    x = torch.randn(1, planes, 1, 60, 104, device=dev)
-    report(f"down_up f=0.4 {tag}", 2 * x.numel() * 4, timed(lambda: lp_utils.apply_low_pass_filter(x, "down_up", 0.0, 0.0, 0.4)))
-x = torch.randn(1, 4096, 1, 90, 160, device=dev).bfloat16()
-report("down_up f=0.625 4096 planes 90x160 bf16", 2 * x.numel() * 2, timed(lambda: lp_utils.apply_low_pass_filter(x, "down_up", 0.0, 0.0, 0.625)))
-# ---- gaussian_blur (lp_utils.py:40-47): Cog config shape, and 768 planes
-for planes, tag in ((3, "Cog config [1,3,480,720] bf16"), (768, "768 planes 480x720 bf16")):
-    x = torch.randn(1, planes, 480, 720, device=dev).bfloat16()
-    report(f"gaussian k=13 sigma=15 {tag}", 2 * x.numel() * 2, timed(lambda: lp_utils.apply_low_pass_filter(x, "gaussian_blur", 15.0, 0.02734375, 0.25)))
-x = torch.randn(1, 768, 480, 832, device=dev)  # fp32 (Wan's pixel-space ALG filters the fp32 image): the separable kernel
-report("gaussian k=13 sigma=15 768 planes 480x832 fp32 (separable)", 2 * x.numel() * 4, timed(lambda: lp_utils.apply_low_pass_filter(x, "gaussian_blur", 15.0, 0.02734375, 0.25)))
-del x
-# ---- fused CFG + UniPC step (wan:919-927): E = 2 096 640 (config) and 64x that
-for mult, tag in ((1, "Wan config E=2.1M"), (64, "E=134M")):
-    E = 2096640 * mult
-    s = S.UniPCMultistepScheduler(flow_shift=5.0)
-    s.set_timesteps(50, device=dev)
-    x = torch.randn(E, device=dev)
-    noise = torch.randn(3, E, device=dev).bfloat16()
-    for _ in range(3):
-        s.step_cfg(noise, 5.0, x)  # reach the order-2 + corrector steady state
+ONLY = os.environ.get("HBM_ONLY", "")  # "norms": only the DiT norm lines
+if ONLY != "norms":
+  # ---- down_up (lp_utils.py:49-54): Wan config shape, and 8192 planes
+  for planes, tag in ((420, "Wan config [1,20,21,60,104] fp32"), (8192, "8192 planes 60x104 fp32")):
+      x = torch.randn(1, planes, 1, 60, 104, device=dev)
+      report(f"down_up f=0.4 {tag}", 2 * x.numel() * 4, timed(lambda: lp_utils.apply_low_pass_filter(x, "down_up", 0.0, 0.0, 0.4)))
+  x = torch.randn(1, 4096, 1, 90, 160, device=dev).bfloat16()
+  report("down_up f=0.625 4096 planes 90x160 bf16", 2 * x.numel() * 2, timed(lambda: lp_utils.apply_low_pass_filter(x, "down_up", 0.0, 0.0, 0.625)))
+  # ---- gaussian_blur (lp_utils.py:40-47): Cog config shape, and 768 planes
+  for planes, tag in ((3, "Cog config [1,3,480,720] bf16"), (768, "768 planes 480x720 bf16")):
+      x = torch.randn(1, planes, 480, 720, device=dev).bfloat16()
+      report(f"gaussian k=13 sigma=15 {tag}", 2 * x.numel() * 2, timed(lambda: lp_utils.apply_low_pass_filter(x, "gaussian_blur", 15.0, 0.02734375, 0.25)))
+  x = torch.randn(1, 768, 480, 832, device=dev)  # fp32 (Wan's pixel-space ALG filters the fp32 image): the separable kernel
+  report("gaussian k=13 sigma=15 768 planes 480x832 fp32 (separable)", 2 * x.numel() * 4, timed(lambda: lp_utils.apply_low_pass_filter(x, "gaussian_blur", 15.0, 0.02734375, 0.25)))
+  del x
+  # ---- fused CFG + UniPC step (wan:919-927): E = 2 096 640 (config) and 64x that
+  for mult, tag in ((1, "Wan config E=2.1M"), (64, "E=134M")):
+      E = 2096640 * mult
+      s = S.UniPCMultistepScheduler(flow_shift=5.0)
+      s.set_timesteps(50, device=dev)
+      x = torch.randn(E, device=dev)
+      noise = torch.randn(3, E, device=dev).bfloat16()
+      for _ in range(3):
+          s.step_cfg(noise, 5.0, x)  # reach the order-2 + corrector steady state
 
-    def step():
-        s._step_index = 10
-        s.step_cfg(noise, 5.0, x)
+      def step():
+          s._step_index = 10
+          s.step_cfg(noise, 5.0, x)
 
-    report(f"CFG + UniPC step 3-pass order-2 {tag}", (3 * 2 + 4 * 4 + 3 * 4) * E, timed(step))
-    del x, noise, s
+      report(f"CFG + UniPC step 3-pass order-2 {tag}", (3 * 2 + 4 * 4 + 3 * 4) * E, timed(step))
+      del x, noise, s
 # ---- DiT norms at the Wan 3-pass shape
 M, d = 98280, 5120
 x = torch.randn(M, d, device=dev).bfloat16()
@@ -80,7 +82,23 @@ ang = torch.rand(32760, 64, device=dev) * 6.28
 cos, sin = ang.cos().repeat_interleave(2, dim=1).contiguous(), ang.sin().repeat_interleave(2, dim=1).contiguous()
 report("head RMSNorm + RoPE 98280 x (40 x 128) bf16", 2 * x.numel() * 2,
        timed(lambda: ops.head_norm_rope(x, 40, 128, norm_kind=1, weight=w, cos=cos, sin=sin, rows_per_batch=32760)))
+# the Wan engine's RMSNorm across heads (+ RoPE from the fp64 axis tables), in place (alg_wan_rms_norm_rope)
+import ctypes as C
+from alg_b200 import _lib
+L = _lib.lib()
+wd = torch.randn(d, device=dev).bfloat16()
+tabs = [torch.stack([a.cos(), a.sin()], dim=-1).contiguous() for a in
+        (torch.rand(21, 22, device=dev, dtype=torch.float64) * 6.28, torch.rand(30, 21, device=dev, dtype=torch.float64) * 6.28,
+         torch.rand(52, 21, device=dev, dtype=torch.float64) * 6.28)]
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+for rope in (True, False):
+    ptrs = [C.c_void_p(t.data_ptr()) for t in tabs] if rope else [None, None, None]
+    fn = lambda: L.alg_wan_rms_norm_rope(C.c_void_p(x.data_ptr()), M, d, 128, C.c_float(1e-6), C.c_void_p(wd.data_ptr()), *ptrs,
+                                         22, 21, 21, 21, 30, 52, st)
+    report(f"Wan RMSNorm across heads{' + RoPE' if rope else ''} 98280x5120 bf16", 2 * x.numel() * 2, timed(fn))
 del x, out
+if ONLY == "norms":
+    sys.exit(0)
 # ---- CogVideoX VAE encoder blocks at its 128-channel level (480x720 frame)
 H, W, Cc = 480, 720, 128
 a = torch.randn(H * W, Cc, device=dev).bfloat16()
