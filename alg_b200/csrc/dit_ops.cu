@@ -85,7 +85,9 @@ __device__ __forceinline__ float block_sum_t(float v, float* red) {
 
 __device__ __forceinline__ float2 bf16x2_round(float2 x) { return __bfloat1622float2(__float22bfloat162_rn(x)); }
 
-template <bool CHAIN, int TH, int CH>
+// FAST: the launch covers the common shape exactly -- d == TH * CH * 8 (no range guards), fp32 affine / modulation vectors (no
+// dtype branches per chunk), one modulation set for all rows (no per-row batch / split arithmetic).
+template <bool CHAIN, int TH, int CH, bool FAST = false>
 __global__ void __launch_bounds__(TH) layer_norm_kernel(const alg_layer_norm_t p) {
   constexpr int kRowThreads = TH, kMaxChunks = CH;
   __shared__ float red[TH / 32];
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(TH) layer_norm_kernel(const alg_layer_norm_t p
   const int d = p.d;
   const uint4* xr = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * d);
   uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * d);
-  const int chunks = d >> 3;
+  const int chunks = FAST ? TH * CH : d >> 3;
   // Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2: IEEE rn per lane, same results as the scalar ops): the kernel is
   // instruction-issue bound (ncu ln_r29: 21 instructions per element, issue slots 57 % busy, DRAM 60 %), not DRAM-bound.
   float2 v[kMaxChunks][4];
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(TH) layer_norm_kernel(const alg_layer_norm_t p
 #pragma unroll
   for (int c = 0; c < kMaxChunks; ++c) {
     const int ci = threadIdx.x + c * kRowThreads;
-    if (ci < chunks) {
+    if (FAST || ci < chunks) {
       const uint4 u = xr[ci];
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -113,7 +115,10 @@ __global__ void __launch_bounds__(TH) layer_norm_kernel(const alg_layer_norm_t p
   }
   // modulation vectors of this row (resolved while the loads are in flight)
   const void *scale = nullptr, *shift = nullptr;
-  if (p.scale) {
+  if constexpr (FAST) {
+    scale = p.scale;
+    shift = p.shift;
+  } else if (p.scale) {
     const uint32_t rpb = (uint32_t)min(p.rows_per_batch, (int64_t)0x7fffffff);  // rows <= 2^31 - 1 (grid size)
     const uint32_t b = (uint32_t)row / rpb, r_in = (uint32_t)row - b * rpb;
     const bool alt = (int64_t)r_in < p.split_row;
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(TH) layer_norm_kernel(const alg_layer_norm_t p
 #pragma unroll
   for (int c = 0; c < kMaxChunks; ++c) {
     const int ci = threadIdx.x + c * kRowThreads;
-    if (ci < chunks) {
+    if (FAST || ci < chunks) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         v[c][e] = __fadd2_rn(v[c][e], nmean2);  // x - mean, kept for the normalisation below
@@ -140,22 +145,22 @@ __global__ void __launch_bounds__(TH) layer_norm_kernel(const alg_layer_norm_t p
 #pragma unroll
   for (int c = 0; c < kMaxChunks; ++c) {
     const int ci = threadIdx.x + c * kRowThreads;
-    if (ci < chunks) {
+    if (FAST || ci < chunks) {
       float2 o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = __fmul2_rn(v[c][e], rstd2);
       if (p.weight) {
         float w[8], b[8];
-        load_vec8(p.weight, p.affine_dtype, ci, w);
-        load_vec8(p.bias, p.affine_dtype, ci, b);
+        load_vec8(p.weight, FAST ? (int)ALG_F32 : p.affine_dtype, ci, w);
+        load_vec8(p.bias, FAST ? (int)ALG_F32 : p.affine_dtype, ci, b);
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           o[e] = __fadd2_rn(__fmul2_rn(o[e], make_float2(w[2 * e], w[2 * e + 1])), make_float2(b[2 * e], b[2 * e + 1]));
       }
       if (scale) {
         float sc[8], sh[8];
-        load_vec8(scale, p.mod_dtype, ci, sc);
-        load_vec8(shift, p.mod_dtype, ci, sh);
+        load_vec8(scale, FAST ? (int)ALG_F32 : p.mod_dtype, ci, sc);
+        load_vec8(shift, FAST ? (int)ALG_F32 : p.mod_dtype, ci, sh);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 s1 = __fadd2_rn(one2, make_float2(sc[2 * e], sc[2 * e + 1]));
@@ -457,6 +462,13 @@ extern "C" int alg_layer_norm(const alg_layer_norm_t* p, void* stream) {
   if (th_knob < 0) {
     const char* e = getenv("ALG_LN_THREADS");
     th_knob = e ? atoi(e) : 128;
+  }
+  const bool f32_vectors = (!p->weight || p->affine_dtype == ALG_F32) && (!p->scale || p->mod_dtype == ALG_F32);
+  const bool one_mod_set = !p->scale || (p->rows_per_batch >= p->rows && p->split_row == 0);
+  if (th_knob != 256 && p->d == 128 * 5 * 8 && f32_vectors && one_mod_set && !p->chain_bf16) {  // Wan's d = 5120, fp32 chain
+    ops::layer_norm_kernel<false, 128, 5, true><<<(unsigned)p->rows, 128, 0, st>>>(*p);
+    ALG_LAUNCH_OK();
+    return 0;
   }
 #define ALG_LN(TH, CH)                                                                         \
   do {                                                                                         \
