@@ -70,6 +70,21 @@ struct Cfg {
   static constexpr int kSubK = BKV * 128 / kCtas;  // bytes of one [64 (32) keys][64 elem] sub-tile of K
 };
 
+// Timeline probe (scripts/attn_trace.py builds a second library with -DALG_ATTN_TRACE): clock64() stamps of one CTA's phases,
+// 32 slots per CTA.  Compiled out of the product library.
+#ifdef ALG_ATTN_TRACE
+__device__ long long* g_attn_trace = nullptr;
+#define ATTN_TRACE(slot)                                                                                                     \
+  do {                                                                                                                       \
+    if (g_attn_trace)                                                                                                        \
+      g_attn_trace[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] = clock64();      \
+  } while (0)
+#else
+#define ATTN_TRACE(slot) \
+  do {                   \
+  } while (0)
+#endif
+
 struct Params {
   __nv_bfloat16* O;
   int64_t o_bs, o_rs;
@@ -83,6 +98,14 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
@@ -190,10 +213,12 @@ __device__ __forceinline__ void mma_tile_step(const MmaCtx& c, const int j, uint
 template <int D, int I, int STAGES, int PAIR>
 __device__ __forceinline__ void mma_tile_loop(const MmaCtx& c) {
   mbar_wait_a(c.bar, 0);  // q_full
+  if (I == 0) ATTN_TRACE(4);
   mbar_wait_a(c.bar + 8 * (kBarKFull + 0), 0);
   tc_fence_after();
   issue_s<D, I, 0, 0, PAIR>(c);
   commit<PAIR>(c.bar + 8 * (kBarKEmpty + 0));
+  if (I == 0) ATTN_TRACE(5);
   if (c.n_steps > 1) {
     mbar_wait_a(c.bar + 8 * (kBarKFull + 1), 0);
     tc_fence_after();
@@ -208,6 +233,7 @@ __device__ __forceinline__ void mma_tile_loop(const MmaCtx& c) {
     if (j0 + 2 < c.n_steps) mma_tile_step<D, I, 2, STAGES, PAIR>(c, j0 + 2, ph);
     if (j0 + 3 < c.n_steps) mma_tile_step<D, I, 3, STAGES, PAIR>(c, j0 + 3, ph);
   }
+  if (I == 0) ATTN_TRACE(6);
 }
 
 // ---- S128: one 128-key S MMA per PAIR of steps ---------------------------------------------------------------------------
@@ -355,6 +381,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
   const int head = blockIdx.y, batch = blockIdx.z;
   const int q0 = blockIdx.x * TILES * BQ;
   const int n_steps = (p.n_kv + BKV - 1) / BKV;
+  if (threadIdx.x == 0) ATTN_TRACE(0);
 
   if (warp == kTmaWarp && lane == 0) {
     prefetch_tmap(&tmQ);
@@ -377,6 +404,20 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       mbar_init(&turn[i], 1);
     }
     fence_barrier_init();
+    if constexpr (!PAIR && !S128) {
+      // Q and the first two K stages go out BEFORE the CTA-wide setup barrier: the TMEM allocation and the barrier cost ~550
+      // cycles that the ~1 900-cycle load latency can overlap (scripts/attn_trace.py; it matters for the SHORT variant, whose
+      // CTAs live ~20 000 cycles).  Only this thread has touched the barriers so far, and nothing else uses sQ / sK yet.
+      mbar_arrive_expect_tx(q_full, TILES * C::kBytesQ);
+      for (int i = 0; i < TILES; ++i)
+        for (int s = 0; s < D / 64; ++s)
+          tma_load_3d(sQ + i * C::kBytesQ + s * C::kSubQ, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
+      for (int j = 0; j < 2 && j < n_steps; ++j) {
+        mbar_arrive_expect_tx(&k_full[j], C::kBytesK);
+        for (int s = 0; s < D / 64; ++s)
+          tma_load_3d(sK + j * C::kBytesK + s * C::kSubK, &tmK, &k_full[j], head * D + s * 64, j * BKV, batch);
+      }
+    }
   }
   if (warp == kMmaWarp) {
     if constexpr (PAIR) {
@@ -392,6 +433,14 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
   if constexpr (PAIR) cluster_sync_all();  // the peer's barriers exist before anything completes / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    ATTN_TRACE(1);
+#ifdef ALG_ATTN_TRACE
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    if (g_attn_trace) g_attn_trace[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + 2] = smid;
+#endif
+  }
 
   if (warp == kTmaWarp) {
     if (elect_one()) {  // ===== TMA producer: Q0 Q1 | K0 K1 | V0 K2 | V1 K3 | ... (the order the MMA warp consumes) =====
@@ -401,10 +450,12 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
         if constexpr (PAIR) tma_load_3d_pair(dst, m, bar, c0, c1, c2);
         else tma_load_3d(dst, m, bar, c0, c1, c2);
       };
-      if (crank == 0) mbar_arrive_expect_tx(q_full, C::kCtas * TILES * C::kBytesQ);
-      for (int i = 0; i < TILES; ++i)
-        for (int s = 0; s < D / 64; ++s)
-          load(sQ + i * C::kBytesQ + s * C::kSubQ, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
+      if constexpr (PAIR || S128) {  // (otherwise issued before the setup barrier, above)
+        if (crank == 0) mbar_arrive_expect_tx(q_full, C::kCtas * TILES * C::kBytesQ);
+        for (int i = 0; i < TILES; ++i)
+          for (int s = 0; s < D / 64; ++s)
+            load(sQ + i * C::kBytesQ + s * C::kSubQ, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
+      }
       auto load_k = [&](int j) {
         const int st = j % STAGES;
         mbar_wait(&k_empty[st], ((j / STAGES) & 1) ^ 1);
@@ -436,8 +487,10 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
           if (jp + 1 < n_pairs) load_k128(jp + 1);
         }
       } else {
-        load_k(0);
-        if (n_steps > 1) load_k(1);
+        if constexpr (PAIR) {
+          load_k(0);
+          if (n_steps > 1) load_k(1);
+        }
         for (int j = 0; j < n_steps; ++j) {
           load_v(j);
           if (j + 2 < n_steps) load_k(j + 2);
@@ -477,6 +530,13 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
     const int row = q0 + i * BQ + row_in_tile;
     float m_used = -INFINITY, l = 0.f;
     const float c = p.scale_log2;
+    if (p.accumulate && row < p.n_q) {
+      // the epilogue reads this tile's previous O rows (written by the launch before: HBM by now): pull them into L2 while the
+      // warpgroup waits for Q and S(0) anyway -- no registers held, and the epilogue's 16 loads per lane then hit L2
+      const char* prow = reinterpret_cast<const char*>(p.O + (int64_t)batch * p.o_bs + (int64_t)row * p.o_rs + head * D);
+#pragma unroll
+      for (int b = 0; b < D * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + b));
+    }
     // one 64-key step of online softmax; `ragged` (compile-time) is the last, partially filled step -- kept out of the
     // main loop body, where the compiler would otherwise if-convert the mask into always-executed selects
     // barrier addresses of this tile's two S buffers; the loop is unrolled by two so the buffer index is compile-time
@@ -486,6 +546,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       const uint32_t t_sj = t_s + BUF * 64;
       mbar_wait_a(bar_s0 + 8 * BUF, (j >> 1) & 1);
       tc_fence_after();
+      if (j == 0 && warp == 0 && lane == 0) ATTN_TRACE(7);
       float s[W];
       tmem_ld32(t_sj + hh * W, reinterpret_cast<uint32_t*>(s));
       if constexpr (W == 64) tmem_ld32(t_sj + 32, reinterpret_cast<uint32_t*>(s) + 32);
@@ -571,6 +632,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       if (lane == 0) {
         if constexpr (PAIR) mbar_arrive_remote_a(bar_p0 + 8 * BUF, 0);  // the leader's issuer waits for both CTAs' P
         else mbar_arrive_a(bar_p0 + 8 * BUF);
+        if (j == 0 && warp == 0) ATTN_TRACE(8);
       }
     };
     const int n_full = p.n_kv / BKV;
@@ -595,9 +657,78 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       l += slot[(hh ^ 1) * BQ + row_in_tile];
     }
     // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------------
+    if (warp == 0 && lane == 0) ATTN_TRACE(9);
+    // coalesced write-back geometry (see below): lane -> (row rl of RPI, 16-byte chunk cl) of each store instruction
+    constexpr int RB = D * 2, CPR = RB / 16, RPI = 32 / CPR;  // row bytes, chunks per row, rows per warp instruction
+    constexpr int NIT = 32 / RPI;                              // store instructions per warp (its 32 rows)
+    const int rl = lane / CPR, cl = lane % CPR;
+    const int r0 = quad * 32 + rl;                              // this lane's row in iteration 0; + RPI per iteration
+    const int n_live = p.n_q - (q0 + i * BQ + r0);              // rows r0 + it * RPI with it * RPI < n_live exist
+    uint4* dst0 = reinterpret_cast<uint4*>(p.O + (int64_t)batch * p.o_bs + (int64_t)(q0 + i * BQ + r0) * p.o_rs + head * D + cl * 8);
+    const int64_t dstep = (int64_t)RPI * p.o_rs / 8;            // uint4 units (o_rs % 8 == 0)
+    [[maybe_unused]] uint4 prev[NIT];
+    if constexpr (!SPLIT) {
+      if (p.accumulate) {  // the previous O rows: all loads in flight while the last PV drains and the rows are staged
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+          if (it * RPI < n_live) prev[it] = __ldcs(dst0 + it * dstep);
+      }
+    }
     mbar_wait(&o_full[i], 0);
     tc_fence_after();
+    if (warp == 0 && lane == 0) ATTN_TRACE(10);
     const float inv = 1.0f / l;
+    if constexpr (!SPLIT) {
+      // Staged epilogue.  A thread owns one O row, so storing straight from its registers makes every 16-byte store of a warp hit
+      // 32 different rows: 2 048 L1 wavefronts per tile instead of 256, measured at 4 400 cycles per CTA (11 400 with the
+      // read-modify-write of `accumulate`) -- a quarter to 40 % of a SHORT CTA's life (scripts/attn_trace.py).  The tile's Q
+      // region is dead by now (every S MMA completed before the commit behind the last PV), so each warp parks its 32 rows
+      // there as bf16 (16-byte chunks XOR-swizzled by the row, conflict-free both ways) and writes them back out with
+      // 32 / CPR whole rows per instruction.
+      const uint32_t stage = smem_u32(sQ + i * C::kBytesQ);       // explicit shared-space accesses (a generic pointer costs
+                                                                 // ~70 instructions per 16 bytes here and serialises the loop)
+#pragma unroll
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(t_o + ch * 32, o);
+        tmem_ld_wait();
+        if (ch == 0 && warp == 0 && lane == 0) ATTN_TRACE(14);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            h[e] = __floats2bfloat162_rn(__uint_as_float(o[g * 8 + 2 * e]) * inv, __uint_as_float(o[g * 8 + 2 * e + 1]) * inv);
+          const int c16 = ch * 4 + g;
+          sts_v4(stage + row_in_tile * RB + ((c16 ^ (row_in_tile & (CPR - 1))) << 4), u);
+        }
+      }
+      __syncwarp();  // a warp re-reads only the 32 rows it wrote
+      if (warp == 0 && lane == 0) ATTN_TRACE(13);
+      uint4 u[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int r_t = r0 + it * RPI;
+        u[it] = lds_v4(stage + r_t * RB + ((cl ^ (r_t & (CPR - 1))) << 4));
+      }
+      if (p.accumulate) {  // hidden_states(text) + hidden_states_img: both already bf16 tensors
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev[it]);
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u[it]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = __bfloat1622float2(h[e]), b = __bfloat1622float2(ph[e]);
+            h[e] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+          }
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it)
+        if (it * RPI < n_live) dst0[it * dstep] = u[it];
+      if (warp == 0 && lane == 0) ATTN_TRACE(11);
+    } else {
     __nv_bfloat16* orow = p.O + (int64_t)batch * p.o_bs + (int64_t)row * p.o_rs + head * D + hh * OC;
 #pragma unroll
     for (int ch = 0; ch < OC / 32; ++ch) {
@@ -627,10 +758,13 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
         }
       }
     }
+    if (warp == 0 && lane == 0) ATTN_TRACE(11);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) ATTN_TRACE(12);
   if constexpr (PAIR) cluster_sync_all();  // no CTA leaves while the pair's MMAs / commits / remote arrives may touch it
   if (warp == kMmaWarp) {
     tc_fence_after();
@@ -1137,6 +1271,12 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
 
 }  // namespace attn
 }  // namespace alg
+
+#ifdef ALG_ATTN_TRACE
+extern "C" int alg_attention_trace_buffer(void* buf) {  // device buffer of 32 x int64 per CTA of the next launches (NULL = off)
+  return cudaMemcpyToSymbol(alg::attn::g_attn_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   using namespace alg;
