@@ -53,6 +53,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef ALG_ATTN_S128_DEFAULT
 #define ALG_ATTN_S128_DEFAULT 0
 #endif
+#ifndef ALG_ATTN_MC_DEFAULT
+#define ALG_ATTN_MC_DEFAULT 1  // r02: +0.7 % (Wan) / +1.0 % (Hunyuan shape) alone, neutral to +0.5 % in the step; half the L2 -> SM reads
+#endif
 
 // PAIR = 1: the CTA is one half of a CTA pair (cta_group::2 MMAs, see attention_kernel): a K stage holds this CTA's 32 of
 // the step's 64 keys and a V^T stage this CTA's half of the head_dim rows.
@@ -158,6 +161,17 @@ __device__ __forceinline__ void commit(uint32_t bar_addr) {  // PAIR: the arrive
   if constexpr (PAIR) tc_commit_pair_a(bar_addr, 3);
   else tc_commit_a(bar_addr);
 }
+// K / V stage release.  MC (TMA-multicast cluster of two independent CTAs): a stage is refilled by BOTH CTAs' producers (each
+// multicasts half of the tile into both shared memories), so the release has to reach both CTAs' `empty` barriers.
+template <int PAIR, int MC>
+__device__ __forceinline__ void commit_ring(uint32_t bar_addr) {
+  if constexpr (MC) {  // own barrier + the peer's (shared-window addresses of a 2-CTA cluster differ in the rank bit, 1 << 24)
+    tc_commit_a(bar_addr);
+    tc_commit_a(bar_addr ^ 0x01000000u);
+  } else {
+    commit<PAIR>(bar_addr);
+  }
+}
 template <int D, int I, int BUF, int ST, int PAIR>
 __device__ __forceinline__ void issue_s(const MmaCtx& c) {  // S_I = Q_I K^T (stage ST) into S buffer BUF
   using C = Cfg<D, PAIR>;
@@ -187,7 +201,7 @@ __device__ __forceinline__ void issue_pv(const MmaCtx& c, uint32_t acc_first) { 
 // step j = 4 m + JJ of query tile I; ph = m & 1 (parity of the K/V stage ring at this step).  Each tile has its OWN issuer
 // warp: one thread issuing for both tiles still needed ~230 instructions (~1 000+ cycles) per step; two threads halve that,
 // and the tiles' MMA streams are independent (disjoint TMEM), sharing only the K/V stage barriers (two arrivals each).
-template <int D, int I, int JJ, int STAGES, int PAIR>
+template <int D, int I, int JJ, int STAGES, int PAIR, int MC = 0>
 __device__ __forceinline__ void mma_tile_step(const MmaCtx& c, const int j, uint32_t ph) {
   constexpr int BUF = JJ & 1, ST = JJ % STAGES, STN = (JJ + 2) % STAGES;
   constexpr uint32_t p_par = (JJ >> 1) & 1;                      // ((4 m + JJ) >> 1) & 1
@@ -201,37 +215,37 @@ __device__ __forceinline__ void mma_tile_step(const MmaCtx& c, const int j, uint
   mbar_wait_a(c.bar + 8 * (kBarVFull + ST), ph);
   tc_fence_after();
   issue_pv<D, I, BUF, ST, PAIR>(c, j > 0);
-  commit<PAIR>(c.bar + 8 * (kBarVEmpty + ST));
+  commit_ring<PAIR, MC>(c.bar + 8 * (kBarVEmpty + ST));
   if (last) commit<PAIR>(c.bar + 8 * (kBarOFull + I));
   if (has_next) {
     mbar_wait_a(c.bar + 8 * (kBarKFull + STN), phn);
     tc_fence_after();
     issue_s<D, I, BUF, STN, PAIR>(c);  // reuses the S buffer whose P was consumed by the PV just issued (in-order tensor pipe)
-    commit<PAIR>(c.bar + 8 * (kBarKEmpty + STN));
+    commit_ring<PAIR, MC>(c.bar + 8 * (kBarKEmpty + STN));
   }
 }
-template <int D, int I, int STAGES, int PAIR>
+template <int D, int I, int STAGES, int PAIR, int MC = 0>
 __device__ __forceinline__ void mma_tile_loop(const MmaCtx& c) {
   mbar_wait_a(c.bar, 0);  // q_full
   if (I == 0) ATTN_TRACE(4);
   mbar_wait_a(c.bar + 8 * (kBarKFull + 0), 0);
   tc_fence_after();
   issue_s<D, I, 0, 0, PAIR>(c);
-  commit<PAIR>(c.bar + 8 * (kBarKEmpty + 0));
+  commit_ring<PAIR, MC>(c.bar + 8 * (kBarKEmpty + 0));
   if (I == 0) ATTN_TRACE(5);
   if (c.n_steps > 1) {
     mbar_wait_a(c.bar + 8 * (kBarKFull + 1), 0);
     tc_fence_after();
     issue_s<D, I, 1, 1, PAIR>(c);
-    commit<PAIR>(c.bar + 8 * (kBarKEmpty + 1));
+    commit_ring<PAIR, MC>(c.bar + 8 * (kBarKEmpty + 1));
   }
   uint32_t ph = 0;
 #pragma unroll 1
   for (int j0 = 0; j0 < c.n_steps; j0 += 4, ph ^= 1u) {
-    mma_tile_step<D, I, 0, STAGES, PAIR>(c, j0, ph);
-    if (j0 + 1 < c.n_steps) mma_tile_step<D, I, 1, STAGES, PAIR>(c, j0 + 1, ph);
-    if (j0 + 2 < c.n_steps) mma_tile_step<D, I, 2, STAGES, PAIR>(c, j0 + 2, ph);
-    if (j0 + 3 < c.n_steps) mma_tile_step<D, I, 3, STAGES, PAIR>(c, j0 + 3, ph);
+    mma_tile_step<D, I, 0, STAGES, PAIR, MC>(c, j0, ph);
+    if (j0 + 1 < c.n_steps) mma_tile_step<D, I, 1, STAGES, PAIR, MC>(c, j0 + 1, ph);
+    if (j0 + 2 < c.n_steps) mma_tile_step<D, I, 2, STAGES, PAIR, MC>(c, j0 + 2, ph);
+    if (j0 + 3 < c.n_steps) mma_tile_step<D, I, 3, STAGES, PAIR, MC>(c, j0 + 3, ph);
   }
   if (I == 0) ATTN_TRACE(6);
 }
@@ -347,12 +361,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 //            128 x 64 x 16 S MMA, which at 6 KB of operands per 32 cycles out-runs the 128 B/clk shared-memory port, drops to
 //            5 KB).  K/V "full" barriers live in the leader (both CTAs' TMA bytes complete there), "P ready" collects the
 //            softmax warps of both CTAs by remote arrives, everything the issuer signals is a multicast commit.
-template <int D, int POLY, int SPLIT, int TILES, int STAGES, int PAIR, int S128 = 0>
+// MC = 1: the kernel runs as clusters of TWO INDEPENDENT CTAs (neighbouring query-tile pairs of one head: same K / V^T).  Each
+//            CTA's producer fetches HALF of every K / V^T stage and TMA-multicasts it into both shared memories, so the L2 -> SM
+//            traffic of the K / V stream (5 TB/s at the Wan shape: every CTA streams the whole head) halves; MMAs stay
+//            cta_group::1, every CTA keeps its own barriers, only the stage releases are multicast commits (see commit_ring).
+template <int D, int POLY, int SPLIT, int TILES, int STAGES, int PAIR, int S128 = 0, int MC = 0>
 __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TILES == 1 ? 2 : 1)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Params p) {
+  static_assert(!MC || (!PAIR && !S128 && TILES == 2), "MC is a variant of the long layout");
   using C = Cfg<D, PAIR>;
-  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const uint32_t crank = (PAIR || MC) ? cluster_ctarank() : 0u;
   constexpr int kSoftmaxWarps = (SPLIT ? 8 : 4) * TILES;
   constexpr int kTmaWarp = kSoftmaxWarps, kMmaWarp = kSoftmaxWarps + 1;  // MMA issuers: kMmaWarp (tile 0), kMmaWarp + 1 (tile 1)
   constexpr int kWarpsPerTile = kSoftmaxWarps / TILES;
@@ -390,9 +409,9 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
     mbar_init(q_full, 1);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], TILES);  // one commit per issuer warp
+      mbar_init(&k_empty[i], TILES * (MC ? 2 : 1));  // one commit per issuer warp (MC: of both CTAs)
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], TILES);
+      mbar_init(&v_empty[i], TILES * (MC ? 2 : 1));
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -412,7 +431,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       for (int i = 0; i < TILES; ++i)
         for (int s = 0; s < D / 64; ++s)
           tma_load_3d(sQ + i * C::kBytesQ + s * C::kSubQ, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
-      for (int j = 0; j < 2 && j < n_steps; ++j) {
+      for (int j = 0; j < 2 && j < n_steps && !MC; ++j) {  // (MC: the peer's barriers must exist first)
         mbar_arrive_expect_tx(&k_full[j], C::kBytesK);
         for (int s = 0; s < D / 64; ++s)
           tma_load_3d(sK + j * C::kBytesK + s * C::kSubK, &tmK, &k_full[j], head * D + s * 64, j * BKV, batch);
@@ -430,7 +449,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers exist before anything completes / arrives on them
+  if constexpr (PAIR || MC) cluster_sync_all();  // the peer's barriers exist before anything completes / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) {
@@ -456,9 +475,23 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
           for (int s = 0; s < D / 64; ++s)
             load(sQ + i * C::kBytesQ + s * C::kSubQ, &tmQ, q_full, head * D + s * 64, q0 + i * BQ, batch);
       }
+      auto load_mc = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], "
+            "[%2], %6;" ::"r"(smem_u32(dst)),
+            "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"((uint16_t)3)
+            : "memory");
+      };
       auto load_k = [&](int j) {
         const int st = j % STAGES;
         mbar_wait(&k_empty[st], ((j / STAGES) & 1) ^ 1);
+        if constexpr (MC) {  // my 32 keys of the tile, into both CTAs; each CTA's barrier expects the whole stage
+          mbar_arrive_expect_tx(&k_full[st], C::kBytesK);
+          for (int s = 0; s < D / 64; ++s)
+            load_mc(sK + st * C::kBytesK + s * C::kSubK + (int)crank * (BKV / 2) * 128, &tmK, &k_full[st], head * D + s * 64,
+                    j * BKV + (int)crank * (BKV / 2), batch);
+          return;
+        }
         if (crank == 0) mbar_arrive_expect_tx(&k_full[st], C::kCtas * C::kBytesK);
         for (int s = 0; s < D / 64; ++s)
           load(sK + st * C::kBytesK + s * C::kSubK, &tmK, &k_full[st], head * D + s * 64,
@@ -467,6 +500,11 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       auto load_v = [&](int j) {
         const int st = j % STAGES;
         mbar_wait(&v_empty[st], ((j / STAGES) & 1) ^ 1);
+        if constexpr (MC) {  // my half of the head_dim rows of the V^T tile
+          mbar_arrive_expect_tx(&v_full[st], C::kBytesV);
+          load_mc(sV + st * C::kBytesV + (int)crank * (D / 2) * 128, &tmV, &v_full[st], j * BKV, head * D + (int)crank * (D / 2), batch);
+          return;
+        }
         if (crank == 0) mbar_arrive_expect_tx(&v_full[st], C::kCtas * C::kBytesV);
         load(sV + st * C::kBytesV, &tmV, &v_full[st], j * BKV, head * D + (int)crank * (D / C::kCtas), batch);
       };
@@ -487,7 +525,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
           if (jp + 1 < n_pairs) load_k128(jp + 1);
         }
       } else {
-        if constexpr (PAIR) {
+        if constexpr (PAIR || MC) {
           load_k(0);
           if (n_steps > 1) load_k(1);
         }
@@ -498,7 +536,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
       }
     }
   } else if (warp >= kMmaWarp) {
-    if (crank == 0 && elect_one()) {  // ===== MMA issuers (of the leader CTA when PAIR).  elect.sync (not `lane == 0`) tells ptxas that a single lane runs this region, so
+    if ((!PAIR || crank == 0) && elect_one()) {  // ===== MMA issuers (of the leader CTA when PAIR).  elect.sync (not `lane == 0`) tells ptxas that a single lane runs this region, so
                         // the descriptors stay in uniform registers; otherwise every UTCHMMA is wrapped in an ELECT / R2UR loop =====
       MmaCtx c;
       c.tmem = tmem_base;
@@ -513,8 +551,8 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
         if (warp == kMmaWarp) mma_tile_loop128<D, 0>(c);
         else mma_tile_loop128<D, 1>(c);
       } else {
-        if (warp == kMmaWarp) mma_tile_loop<D, 0, STAGES, PAIR>(c);
-        else if constexpr (TILES == 2) mma_tile_loop<D, 1, STAGES, PAIR>(c);
+        if (warp == kMmaWarp) mma_tile_loop<D, 0, STAGES, PAIR, MC>(c);
+        else if constexpr (TILES == 2) mma_tile_loop<D, 1, STAGES, PAIR, MC>(c);
       }
     }
   } else {  // ===== softmax warps =====
@@ -765,7 +803,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) ATTN_TRACE(12);
-  if constexpr (PAIR) cluster_sync_all();  // no CTA leaves while the pair's MMAs / commits / remote arrives may touch it
+  if constexpr (PAIR || MC) cluster_sync_all();  // no CTA leaves while the pair's MMAs / commits / remote arrives may touch it
   if (warp == kMmaWarp) {
     tc_fence_after();
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
@@ -773,7 +811,7 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
   }
 }
 
-template <int D, int POLY, int SPLIT, int TILES, int STAGES, int PAIR = 0, int S128 = 0>
+template <int D, int POLY, int SPLIT, int TILES, int STAGES, int PAIR = 0, int S128 = 0, int MC = 0>
 static int launch(const alg_attention_t* a, cudaStream_t st) {
   using C = Cfg<D, PAIR>;
   constexpr int kThreads = ((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32;
@@ -782,7 +820,7 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   int dev = 0;
   ALG_CUDA_OK(cudaGetDevice(&dev));
   if (dev >= 64 || !(attr_done.load(std::memory_order_relaxed) >> dev & 1)) {
-    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR, S128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    ALG_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR, S128, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     if (dev < 64) attr_done.fetch_or(uint64_t(1) << dev, std::memory_order_relaxed);
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -794,12 +832,12 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
   }
   {
     uint64_t dims[3] = {hd, (uint64_t)a->n_kv, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->k_rs, (uint64_t)a->k_bs};
-    uint32_t box[3] = {64, S128 ? 2 * BKV : BKV / C::kCtas, 1};
+    uint32_t box[3] = {64, S128 ? 2 * BKV : BKV / (MC ? 2 : C::kCtas), 1};
     if (int rc = make_tmap_bf16(&tmK, a->K, 3, dims, strides, box)) return rc;
   }
   {
     uint64_t dims[3] = {(uint64_t)a->n_kv, hd, (uint64_t)a->batch}, strides[3] = {1, (uint64_t)a->v_rs, (uint64_t)a->v_bs};
-    uint32_t box[3] = {BKV, (uint32_t)D / C::kCtas, 1};
+    uint32_t box[3] = {BKV, (uint32_t)D / (MC ? 2 : C::kCtas), 1};
     if (int rc = make_tmap_bf16(&tmV, a->Vt, 3, dims, strides, box)) return rc;
   }
   Params p;
@@ -820,7 +858,7 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
     p.stagger = stagger;
   }
   dim3 grid((unsigned)((a->n_q + TILES * BQ - 1) / (TILES * BQ)), (unsigned)a->heads, (unsigned)a->batch);
-  if constexpr (PAIR) {
+  if constexpr (PAIR || MC) {
     grid.x = (grid.x + 1) / 2 * 2;  // whole pairs: a CTA past the last query rows loads zero-filled tiles and stores nothing
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
@@ -834,7 +872,7 @@ static int launch(const alg_attention_t* a, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ALG_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR>, tmQ, tmK, tmV, p));
+    ALG_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR, S128, MC>, tmQ, tmK, tmV, p));
   } else {
     attention_kernel<D, POLY, SPLIT, TILES, STAGES, PAIR, S128><<<grid, kThreads, kSmem, st>>>(tmQ, tmK, tmV, p);
   }
@@ -1291,7 +1329,7 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   ALG_REQUIRE((reinterpret_cast<uintptr_t>(a->O) & 15) == 0, "attention: O must be 16-byte aligned");
   if (int rc = alg_check_device()) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static int poly = -1, split = -1, short_max = -1, pair = 0, s128 = 0, ps = 0;  // tuning knobs; defaults from profiling
+  static int poly = -1, split = -1, short_max = -1, pair = 0, s128 = 0, ps = 0, mc = 0;  // tuning knobs; defaults from profiling
   if (poly < 0) {
     const char* e = getenv("ALG_ATTN_POLY");
     poly = e ? atoi(e) : ALG_ATTN_POLY_DEFAULT;
@@ -1305,6 +1343,8 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
     s128 = e ? atoi(e) : ALG_ATTN_S128_DEFAULT;
     e = getenv("ALG_ATTN_PS");  // P through shared memory, 128-key S one step ahead (head_dim 128, long variant)
     ps = e ? atoi(e) : ALG_ATTN_PS_DEFAULT;
+    e = getenv("ALG_ATTN_MC");  // long variant: two-CTA clusters that TMA-multicast the K / V^T stream (half the L2 reads)
+    mc = e ? atoi(e) : ALG_ATTN_MC_DEFAULT;
   }
   const bool use_short = a->n_kv <= short_max;
   if (ps && !use_short && a->head_dim == 128) {
@@ -1323,6 +1363,13 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   }
 #define ALG_ATTN_DISPATCH(DD)                                                        \
   if (use_short) return attn::launch<DD, 8, 0, 1, 2>(a, st);                         \
+  if (mc && !s128 && !pair && !split) {                                              \
+    switch (poly) {                                                                  \
+      case 0: return attn::launch<DD, 0, 0, 2, 4, 0, 0, 1>(a, st);                   \
+      case 4: return attn::launch<DD, 4, 0, 2, 4, 0, 0, 1>(a, st);                   \
+      default: return attn::launch<DD, 8, 0, 2, 4, 0, 0, 1>(a, st);                  \
+    }                                                                                \
+  }                                                                                  \
   if (s128 && !pair && split) {                                                      \
     switch (poly) {                                                                  \
       case 0: return attn::launch<DD, 0, 1, 2, 4, 0, 1>(a, st);                      \

@@ -89,7 +89,7 @@ def _vt(v, pad_to=8):
 @pytest.mark.parametrize("B,H,D,Nq,Nkv,sq", [(1, 1, 128, 256, 128, 1.0), (2, 3, 128, 512, 1024, 1.0), (1, 2, 128, 300, 257, 1.0),
                                              (1, 2, 128, 100, 77, 1.0), (1, 2, 128, 1000, 2000, 4.0), (1, 2, 64, 256, 256, 1.0),
                                              (2, 3, 64, 700, 1000, 1.0), (1, 4, 128, 4096, 4096, 3.0), (3, 2, 128, 1, 512, 1.0),
-                                             (1, 48, 64, 520, 1226, 2.0)])
+                                             (1, 48, 64, 520, 1226, 2.0), (2, 2, 128, 600, 1500, 1.0), (1, 3, 64, 1300, 1100, 1.0)])
 def test_attention(B, H, D, Nq, Nkv, sq):
     from alg_b200 import ops
     torch.manual_seed(Nq + Nkv)
@@ -162,7 +162,8 @@ def test_gemm_narrow_tiles_96_and_192(N):
     assert float((out16.float() - (ref + b.bfloat16().float())).abs().max()) < 2 ** -7 * float(ref.abs().max())
 
 
-@pytest.mark.parametrize("env", [dict(ALG_ATTN_S128="1"), dict(ALG_ATTN_PS="1"), dict(ALG_ATTN_PS="2"), dict(ALG_ATTN_PAIR="1")])
+@pytest.mark.parametrize("env", [dict(ALG_ATTN_S128="1"), dict(ALG_ATTN_PS="1"), dict(ALG_ATTN_PS="2"), dict(ALG_ATTN_PAIR="1"),
+                                 dict(ALG_ATTN_MC="0"), dict(ALG_ATTN_MC="1")])
 def test_attention_experimental_variants_keep_parity(env):
     """The schedules kept behind knobs (profiles/r02_attention_s128.md, r02_pair_mma.md) stay correct: each runs in a fresh process
     (the knobs are read once per process) on a long ragged head_dim-128 problem against fp32 SDPA."""
