@@ -1347,6 +1347,9 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
     mc = e ? atoi(e) : ALG_ATTN_MC_DEFAULT;
   }
   const bool use_short = a->n_kv <= short_max;
+  // the cluster variant pads an odd grid with one CTA that does a whole CTA's work for nothing: only where that is < 2 %
+  const int64_t gx = (a->n_q + 2 * attn::BQ - 1) / (2 * attn::BQ);
+  const bool mc_ok = mc == 2 || (mc && (gx % 2 == 0 || gx >= 64));  // ALG_ATTN_MC=2 forces it (tests of the padded grid)
   if (ps && !use_short && a->head_dim == 128) {
     if (ps == 2) {  // two threads per row
       switch (poly) {
@@ -1363,7 +1366,7 @@ extern "C" int alg_attention_bf16(const alg_attention_t* a, void* stream) {
   }
 #define ALG_ATTN_DISPATCH(DD)                                                        \
   if (use_short) return attn::launch<DD, 8, 0, 1, 2>(a, st);                         \
-  if (mc && !s128 && !pair && !split) {                                              \
+  if (mc_ok && !s128 && !pair && !split) {                                           \
     switch (poly) {                                                                  \
       case 0: return attn::launch<DD, 0, 0, 2, 4, 0, 0, 1>(a, st);                   \
       case 4: return attn::launch<DD, 4, 0, 2, 4, 0, 0, 1>(a, st);                   \
