@@ -163,7 +163,7 @@ def test_gemm_narrow_tiles_96_and_192(N):
 
 
 @pytest.mark.parametrize("env", [dict(ALG_ATTN_S128="1"), dict(ALG_ATTN_PS="1"), dict(ALG_ATTN_PS="2"), dict(ALG_ATTN_PAIR="1"),
-                                 dict(ALG_ATTN_MC="0"), dict(ALG_ATTN_MC="2")])
+                                 dict(ALG_ATTN_MC="0"), dict(ALG_ATTN_MC="2"), dict(ALG_ATTN_FX="1", ALG_ATTN_MC="0")])
 def test_attention_experimental_variants_keep_parity(env):
     """The schedules kept behind knobs (profiles/r02_attention_s128.md, r02_pair_mma.md) stay correct: each runs in a fresh process
     (the knobs are read once per process) on a long ragged head_dim-128 problem against fp32 SDPA."""
