@@ -646,30 +646,55 @@ __global__ void __launch_bounds__(((SPLIT ? 8 : 4) * TILES + 1 + TILES) * 32, TI
         }
       }
       }
-      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_used, -m_used);
-      float2 sum0 = make_float2(0.f, 0.f), sum1 = sum0;
+      float l_step;
+      for (;;) {
+        const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_used, -m_used);
+        float2 sum0 = make_float2(0.f, 0.f), sum1 = sum0;
 #pragma unroll
-      for (int ch = 0; ch < W / 32; ++ch) {
-        uint32_t pk[16];
+        for (int ch = 0; ch < W / 32; ++ch) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float2 x = __ffma2_rn(make_float2(s[ch * 32 + 2 * k], s[ch * 32 + 2 * k + 1]), c2, nm2);
-          float2 e;
-          if (POLY > 0 && (k % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
-            e = ex2_poly2(x);
-          } else {
-            e.x = ex2(x.x);
-            e.y = ex2(x.y);
+          for (int k = 0; k < 16; ++k) {
+            const float2 x = __ffma2_rn(make_float2(s[ch * 32 + 2 * k], s[ch * 32 + 2 * k + 1]), c2, nm2);
+            float2 e;
+            if (POLY > 0 && (k % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
+              // FX: the exponent patch of the polynomial wraps past 2^128 instead of saturating; 2^128 patches to 3.4e38
+              e = ex2_poly2(FX ? make_float2(fminf(x.x, 128.f), fminf(x.y, 128.f)) : x);
+            } else {
+              e.x = ex2(x.x);
+              e.y = ex2(x.y);
+            }
+            if (k & 1) sum1 = __fadd2_rn(sum1, e);
+            else sum0 = __fadd2_rn(sum0, e);
+            __nv_bfloat162 h = __floats2bfloat162_rn(e.x, e.y);
+            pk[k] = *reinterpret_cast<uint32_t*>(&h);
           }
-          if (k & 1) sum1 = __fadd2_rn(sum1, e);
-          else sum0 = __fadd2_rn(sum0, e);
-          __nv_bfloat162 h = __floats2bfloat162_rn(e.x, e.y);
-          pk[k] = *reinterpret_cast<uint32_t*>(&h);
+          // P (bf16 pairs) overwrites the first 32 columns of this S buffer: 16 columns per 32 keys
+          tmem_st16(t_sj + hh * 16 + ch * 16, pk);
         }
-        // P (bf16 pairs) overwrites the first 32 columns of this S buffer: 16 columns per 32 keys
-        tmem_st16(t_sj + hh * 16 + ch * 16, pk);
+        l_step = (sum0.x + sum0.y) + (sum1.x + sum1.y);
+        if (!FX || !__any_sync(0xffffffffu, l_step > 7.9228163e28f)) break;
+        // Range guard of the fixed reference (cold): a step whose probabilities sum past 2^96 (or overflowed to inf) raises the
+        // reference by exactly 96 log2 units -- O and l scale by the exact power of two -- and the step's P is computed again
+        // from the scores still in registers, by the same code; repeated until the step fits.
+        constexpr float kDown = 1.2621774e-29f;  // 2^-96
+        if (j > 0) {
+          mbar_wait(&o_done[i], (j - 1) & 1);  // O_i may still be receiving P_i(j-1) V_(j-1)
+          tc_fence_after();
+#pragma unroll 1
+          for (int ch = 0; ch < OC / 16; ++ch) {
+            uint32_t o[16];
+            tmem_ld16(t_o + ch * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * kDown);
+            tmem_st16(t_o + ch * 16, o);
+          }
+        }
+        l *= kDown;
+        m_used += 96.f;
       }
-      l += (sum0.x + sum0.y) + (sum1.x + sum1.y);
+      l += l_step;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

@@ -185,3 +185,31 @@ def test_attention_experimental_variants_keep_parity(env):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "REL" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
+
+
+@pytest.mark.parametrize("amp", [1.5, 2.0, 3.0])
+def test_attention_fixed_reference_range_guard(amp):
+    """ALG_ATTN_FX=1 (fixed softmax reference): rows whose later scores tower over the first 64 keys by 100-400 log2 units must hit
+    the range guard (reference raised by exact powers of two, step recomputed) and still match fp32 SDPA; in a fresh process
+    because the knob is read once."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, torch.nn.functional as F\n"
+        "from alg_b200 import ops\n"
+        "torch.manual_seed(1)\n"
+        f"B, H, D, Nq, Nkv, amp = 1, 2, 128, 300, 2000, {amp}\n"
+        "q = (4 + 0.25 * torch.randn(B, Nq, H, D, device='cuda')).bfloat16()\n"
+        "k = (0.25 * torch.randn(B, Nkv, H, D, device='cuda')); k[:, :64] -= amp; k[:, 64:1000] += 0.2 * amp; k[:, 1000:] += amp\n"
+        "k = k.bfloat16(); v = torch.randn(B, Nkv, H, D, device='cuda').bfloat16()\n"
+        "pad = (Nkv + 7) // 8 * 8\n"
+        "vt = torch.zeros(B, H, D, pad, device='cuda', dtype=torch.bfloat16); vt[..., :Nkv] = v.permute(0, 2, 3, 1)\n"
+        "o = ops.attention(q, k, vt, n_kv=Nkv)\n"
+        "ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)).transpose(1, 2)\n"
+        "assert torch.isfinite(o.float()).all()\n"
+        "e = float((o.float() - ref).norm() / ref.norm()); print('REL', e); assert e < 2 ** -7, e\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ALG_ATTN_FX="1", ALG_ATTN_MC="0")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "REL" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
