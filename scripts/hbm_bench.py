@@ -41,36 +41,42 @@ def report(name, nbytes, ms):
 
 dev = "cuda"
 ONLY = os.environ.get("HBM_ONLY", "")  # "norms": only the DiT norm lines
+
+
+def filters_and_scheduler():
+    # ---- down_up (lp_utils.py:49-54): Wan config shape, and 8192 planes
+    for planes, tag in ((420, "Wan config [1,20,21,60,104] fp32"), (8192, "8192 planes 60x104 fp32")):
+        x = torch.randn(1, planes, 1, 60, 104, device=dev)
+        report(f"down_up f=0.4 {tag}", 2 * x.numel() * 4, timed(lambda: lp_utils.apply_low_pass_filter(x, "down_up", 0.0, 0.0, 0.4)))
+    x = torch.randn(1, 4096, 1, 90, 160, device=dev).bfloat16()
+    report("down_up f=0.625 4096 planes 90x160 bf16", 2 * x.numel() * 2, timed(lambda: lp_utils.apply_low_pass_filter(x, "down_up", 0.0, 0.0, 0.625)))
+    # ---- gaussian_blur (lp_utils.py:40-47): Cog config shape, and 768 planes
+    for planes, tag in ((3, "Cog config [1,3,480,720] bf16"), (768, "768 planes 480x720 bf16")):
+        x = torch.randn(1, planes, 480, 720, device=dev).bfloat16()
+        report(f"gaussian k=13 sigma=15 {tag}", 2 * x.numel() * 2, timed(lambda: lp_utils.apply_low_pass_filter(x, "gaussian_blur", 15.0, 0.02734375, 0.25)))
+    x = torch.randn(1, 768, 480, 832, device=dev)  # fp32 (Wan's pixel-space ALG filters the fp32 image): the separable kernel
+    report("gaussian k=13 sigma=15 768 planes 480x832 fp32 (separable)", 2 * x.numel() * 4, timed(lambda: lp_utils.apply_low_pass_filter(x, "gaussian_blur", 15.0, 0.02734375, 0.25)))
+    del x
+    # ---- fused CFG + UniPC step (wan:919-927): E = 2 096 640 (config) and 64x that
+    for mult, tag in ((1, "Wan config E=2.1M"), (64, "E=134M")):
+        E = 2096640 * mult
+        s = S.UniPCMultistepScheduler(flow_shift=5.0)
+        s.set_timesteps(50, device=dev)
+        x = torch.randn(E, device=dev)
+        noise = torch.randn(3, E, device=dev).bfloat16()
+        for _ in range(3):
+            s.step_cfg(noise, 5.0, x)  # reach the order-2 + corrector steady state
+
+        def step():
+            s._step_index = 10
+            s.step_cfg(noise, 5.0, x)
+
+        report(f"CFG + UniPC step 3-pass order-2 {tag}", (3 * 2 + 4 * 4 + 3 * 4) * E, timed(step))
+        del x, noise, s
+
+
 if ONLY != "norms":
-  # ---- down_up (lp_utils.py:49-54): Wan config shape, and 8192 planes
-  for planes, tag in ((420, "Wan config [1,20,21,60,104] fp32"), (8192, "8192 planes 60x104 fp32")):
-      x = torch.randn(1, planes, 1, 60, 104, device=dev)
-      report(f"down_up f=0.4 {tag}", 2 * x.numel() * 4, timed(lambda: lp_utils.apply_low_pass_filter(x, "down_up", 0.0, 0.0, 0.4)))
-  x = torch.randn(1, 4096, 1, 90, 160, device=dev).bfloat16()
-  report("down_up f=0.625 4096 planes 90x160 bf16", 2 * x.numel() * 2, timed(lambda: lp_utils.apply_low_pass_filter(x, "down_up", 0.0, 0.0, 0.625)))
-  # ---- gaussian_blur (lp_utils.py:40-47): Cog config shape, and 768 planes
-  for planes, tag in ((3, "Cog config [1,3,480,720] bf16"), (768, "768 planes 480x720 bf16")):
-      x = torch.randn(1, planes, 480, 720, device=dev).bfloat16()
-      report(f"gaussian k=13 sigma=15 {tag}", 2 * x.numel() * 2, timed(lambda: lp_utils.apply_low_pass_filter(x, "gaussian_blur", 15.0, 0.02734375, 0.25)))
-  x = torch.randn(1, 768, 480, 832, device=dev)  # fp32 (Wan's pixel-space ALG filters the fp32 image): the separable kernel
-  report("gaussian k=13 sigma=15 768 planes 480x832 fp32 (separable)", 2 * x.numel() * 4, timed(lambda: lp_utils.apply_low_pass_filter(x, "gaussian_blur", 15.0, 0.02734375, 0.25)))
-  del x
-  # ---- fused CFG + UniPC step (wan:919-927): E = 2 096 640 (config) and 64x that
-  for mult, tag in ((1, "Wan config E=2.1M"), (64, "E=134M")):
-      E = 2096640 * mult
-      s = S.UniPCMultistepScheduler(flow_shift=5.0)
-      s.set_timesteps(50, device=dev)
-      x = torch.randn(E, device=dev)
-      noise = torch.randn(3, E, device=dev).bfloat16()
-      for _ in range(3):
-          s.step_cfg(noise, 5.0, x)  # reach the order-2 + corrector steady state
-
-      def step():
-          s._step_index = 10
-          s.step_cfg(noise, 5.0, x)
-
-      report(f"CFG + UniPC step 3-pass order-2 {tag}", (3 * 2 + 4 * 4 + 3 * 4) * E, timed(step))
-      del x, noise, s
+    filters_and_scheduler()
 # ---- DiT norms at the Wan 3-pass shape
 M, d = 98280, 5120
 x = torch.randn(M, d, device=dev).bfloat16()
